@@ -1,0 +1,315 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python -m oracle.make_golden            # needs /root/reference
+
+Every fixture holds seeded, float32-representable inputs together with what the
+reference's own code returned for them, so the oracle (and through it the CUDA
+path) can be pinned on machines where the reference tree does not exist.
+Reference entry points exercised:
+  MCMC/potential.py:3-29, 55-116; MCMC/simulation_box.py:19-65;
+  MCMC/energy_calculator.py:48-203; MCMC/monte_carlo.py:146-303, 375-403;
+  NF/normflows/core.py:178-214 with flows built exactly like
+  hybrid_NF_MCMC/main_algorithm_1.py:277-284.
+"""
+import logging
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import _refimport  # noqa: E402
+from oracle import energy_ref as er  # noqa: E402
+from oracle.mc_ref import SpyRNG  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+POT = dict(num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15)
+
+
+def quiet_logger():
+    lg = logging.getLogger("fs_golden")
+    lg.setLevel(logging.CRITICAL)
+    lg.addHandler(logging.NullHandler())
+    return lg
+
+
+# ---------------------------------------------------------------------------
+def gen_energy(ref):
+    SB = ref["simulation_box"].SimulationBox
+    EC = ref["energy_calculator"].EnergyCalculator
+    pot = ref["potential"]
+    out = {}
+    # Known-answer inputs of SURVEY.md Appendix B
+    r = np.array([0.5, 1.0, 2 ** (1 / 6), 2.0, 2.5, 2.5000001, 3.0])
+    e, w = pot.lennard_jones_energy_virial(r)
+    out["kat_lj_r"], out["kat_lj_e"], out["kat_lj_w"] = r, e, w
+    P = np.array([[2.5, 5], [7.5, 5], [5, 5], [0, 0], [3.7, 5], [9.9, 5]], dtype=np.float64)
+    out["kat_dw_pos"] = P
+    out["kat_dw_v"] = pot.double_well_potential(P, 10, 10, [-10, -10.5], 1.2, 15, 2)
+    box = SB(10.0)
+    out["kat_pbc_in"] = np.array([[-0.1, 10.0], [10.3, -1e-17]])
+    out["kat_pbc_out"] = np.array([box.apply_pbc(p) for p in out["kat_pbc_in"]])
+
+    cases = []
+    # (name, positions float32-exact, L, wells on?)
+    cases.append(("kat3", np.array([[2.0, 5.0], [3.5, 5.0], [2.75, 6.3]], np.float32), 10.0, True))
+    cases.append(("kat3_nowell", np.array([[0.2, 0.3], [9.7, 9.9], [5, 5]], np.float32), 10.0, False))
+    cases.append(("kat3_overlap", np.array([[1, 1], [1.3, 1], [5, 5]], np.float32), 10.0, True))
+    for n in (3, 32, 64, 256):
+        for rho in (0.03, 0.5):
+            for seed in (0, 1):
+                p, L = er.jittered_lattice(n, rho, 1000 * n + seed)
+                cases.append(("lat_n%d_rho%g_s%d" % (n, rho, seed), p, L, True))
+    # denser, cancellation-heavy and a clustered init (spacing 1.5 around a well)
+    p, L = er.jittered_lattice(64, 0.8, 7, jitter=0.3)
+    cases.append(("dense_n64", p, L, True))
+    L = er.box_length(32, 0.03)
+    g = np.array([(i, j) for i in range(6) for j in range(6)][:32], dtype=np.float64)
+    clus = (g - g.mean(0)) * 1.5 + np.array([L / 4, L / 2])
+    clus += (np.random.default_rng(5).random((32, 2)) - 0.5) * 0.2
+    cases.append(("cluster_n32", clus.astype(np.float32), L, True))
+    # one particle copied to within 0.3 of another -> inf
+    p, L = er.jittered_lattice(32, 0.5, 99)
+    p = p.copy()
+    p[5] = p[17] + np.float32(0.2)
+    cases.append(("overlap_n32", p, L, True))
+    # pair straddling the periodic boundary
+    L = 12.0
+    p = np.array([[0.1, 6.0], [11.6, 6.2], [6.0, 0.2], [6.3, 11.7], [3.0, 6.0]], np.float32)
+    cases.append(("wrap_n5", p, L, True))
+
+    names = []
+    for name, p32, L, wells in cases:
+        n = len(p32)
+        kw = dict(POT) if wells else dict(num_wells=0, V0_list=[0, 0], r0=1.2, k=15)
+        for mode, arr in (("f64", p32.astype(np.float64)), ("f32", p32.copy())):
+            ec = EC(n, arr, SB(L), timing=False, **kw)
+            E, W = ec.total_energy, ec.total_virial
+            idx = sorted(set([0, n // 2, n - 1]))
+            pe = np.array([ec.calculate_particle_energy_virial(arr, i) for i in idx], dtype=np.float64)
+            out["%s__%s_E" % (name, mode)] = np.float64(E)
+            out["%s__%s_W" % (name, mode)] = np.float64(W)
+            out["%s__%s_pe" % (name, mode)] = pe
+        out[name + "__pos"] = p32
+        out[name + "__L"] = np.float64(L)
+        out[name + "__wells"] = np.int64(1 if wells else 0)
+        out[name + "__pidx"] = np.array(idx)
+        names.append(name)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "energy_cases.npz"), **out)
+    print("energy_cases: %d cases" % len(names))
+
+
+# ---------------------------------------------------------------------------
+def gen_mc(ref):
+    SB = ref["simulation_box"].SimulationBox
+    MC = ref["monte_carlo"].MonteCarlo
+    lg = quiet_logger()
+    out = {}
+    names = []
+    specs = [("n3", 3, 0.03, 400, 0.65), ("n32", 32, 0.5, 300, 0.65), ("n64", 64, 0.5, 200, 0.4),
+             ("n256", 256, 0.5, 60, 0.3)]
+    for tag, n, rho, steps, md in specs:
+        for mode in ("f32", "f64"):
+            for seed in (42, 43):
+                if n == 3:
+                    # clustered start near the left / right well like initialise_low_*
+                    L = er.box_length(n, rho)
+                    cx = L / 4 if seed % 2 == 0 else 3 * L / 4
+                    p32 = (np.array([[cx - 0.8, L / 2], [cx + 0.8, L / 2], [cx, L / 2 + 1.3]])).astype(np.float32)
+                else:
+                    p32, L = er.jittered_lattice(n, rho, seed)
+                arr = p32.astype(np.float64) if mode == "f64" else p32.copy()
+                mc = MC(arr, SB(L), 1.0, n, initial_max_displacement=md, target_acceptance=0.5,
+                        timing=False, checking=False, logger=lg, seed=seed, **POT)
+                spy = SpyRNG(mc.rng)
+                mc.rng = spy
+                E0 = mc.energy_calculator.total_energy
+                # wrap particle energy to record (eno, enn) per step
+                rec = []
+                orig = mc.energy_calculator.calculate_particle_energy_virial
+
+                def wrapped(pos, i, _o=orig, _r=rec):
+                    v = _o(pos, i)
+                    _r.append(v)
+                    return v
+                mc.energy_calculator.calculate_particle_energy_virial = wrapped
+                acc = np.zeros(steps, np.uint8)
+                half = steps // 2
+                md_mid = None
+                for s in range(steps):
+                    a0 = mc.accepted_displacement
+                    mc.particle_displacement()
+                    acc[s] = mc.accepted_displacement - a0
+                    if s + 1 == half:
+                        mc.adjust_displacement()
+                        md_mid = mc.max_displacement
+                mc.adjust_displacement()
+                key = "%s_%s_s%d" % (tag, mode, seed)
+                names.append(key)
+                ee = np.array(rec, dtype=np.float64).reshape(steps, 2, 2)
+                out[key + "__pos0"] = p32
+                out[key + "__L"] = np.float64(L)
+                out[key + "__seed"] = np.int64(seed)
+                out[key + "__steps"] = np.int64(steps)
+                out[key + "__md0"] = np.float64(md)
+                out[key + "__E0"] = np.float64(E0)
+                out[key + "__idx"] = np.array(spy.ints, np.int64)
+                out[key + "__u"] = np.array(spy.uniforms, np.float64)
+                out[key + "__eno"] = ee[:, 0, 0]
+                out[key + "__enn"] = ee[:, 1, 0]
+                out[key + "__viro"] = ee[:, 0, 1]
+                out[key + "__virn"] = ee[:, 1, 1]
+                out[key + "__acc"] = acc
+                out[key + "__posF"] = np.asarray(mc.particles, dtype=np.float64)
+                out[key + "__EF"] = np.float64(mc.energy_calculator.total_energy)
+                out[key + "__WF"] = np.float64(mc.energy_calculator.total_virial)
+                out[key + "__md_mid"] = np.float64(md_mid)
+                out[key + "__mdF"] = np.float64(mc.max_displacement)
+                out[key + "__attempts"] = np.int64(mc.attempts_displacement)
+                out[key + "__accepted"] = np.int64(mc.accepted_displacement)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "mc_local.npz"), **out)
+    print("mc_local: %d traces" % len(names))
+
+
+# ---------------------------------------------------------------------------
+def build_ref_flow(ref, n, K, blocks, H, nb, bound, seed, sigma):
+    """Constructor call of main_algorithm_1.py:277-284, then the SURVEY 8(d)
+    perturbation so the flow is not the identity."""
+    NF = ref["normflows"]
+    torch.manual_seed(seed)
+    with ref["quiet"]():
+        base = NF.Energy.UniformParticle(n, 2, bound, device="cpu")
+        layers = [NF.flows.CircularCoupledRationalQuadraticSpline(
+            n * 2, blocks, H, range(n * 2), num_bins=nb, tail_bound=bound) for _ in range(K)]
+        model = NF.NormalizingFlow(base, layers)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            prm.add_(sigma * torch.randn(prm.shape, generator=g))
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn(buf.shape, generator=g))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+    model.eval()
+    return model
+
+
+FLOW_SPECS = [
+    # tag, n, K, blocks, H, nb, rho, sigma, B
+    ("n3_k3", 3, 3, 2, 32, 8, 0.03, 0.05, 64),        # odd N: couplings alternate (A.4-Q2)
+    ("n4_k4", 4, 4, 2, 32, 15, 0.03, 0.05, 64),       # even N: x only element-wise
+    ("n32_k2", 32, 2, 3, 64, 32, 0.03, 0.02, 48),     # Alg-1 bins (32) at N=32, cut-down width
+    ("n4_k23", 4, 23, 2, 32, 15, 0.03, 0.05, 32),     # Alg-2 depth and bins (K=23, nb=15), cut-down width
+]
+
+
+def gen_flow(ref):
+    for tag, n, K, blocks, H, nb, rho, sigma, B in FLOW_SPECS:
+        bound = er.box_length(n, rho) / 2
+        model = build_ref_flow(ref, n, K, blocks, H, nb, bound, seed=11, sigma=sigma)
+        g = torch.Generator().manual_seed(3)
+        x = (torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound
+        x[0, 0] = bound            # exactly on the upper edge: last bin (A.4-Q13)
+        x[1, 1] = -bound
+        x[2, 3] = bound * 1.25     # outside: passes through, base log-prob -inf
+        z0 = (torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound
+        with torch.no_grad():
+            lp = model.log_prob(x.clone())
+            zi, ldi = model.inverse_and_log_det(x.clone())
+            xf, ldf = model.forward_and_log_det(z0.clone())
+            first, ld_first = model.flows[K - 1].inverse(x.clone())
+        out = {"sd__" + k: v.numpy() for k, v in model.state_dict().items()}
+        out.update(n=np.int64(n), K=np.int64(K), blocks=np.int64(blocks), H=np.int64(H), nb=np.int64(nb),
+                   bound=np.float64(bound), x=x.numpy(), z0=z0.numpy(), log_prob=lp.numpy(),
+                   inv_z=zi.numpy(), inv_ld=ldi.numpy(), fwd_x=xf.numpy(), fwd_ld=ldf.numpy(),
+                   lastlayer_inv=first.numpy(), lastlayer_ld=ld_first.numpy())
+        np.savez_compressed(os.path.join(GOLD, "flow_%s.npz" % tag), **out)
+        print("flow_%s: params %d" % (tag, sum(p.numel() for p in model.parameters())))
+
+
+# ---------------------------------------------------------------------------
+def gen_global(ref):
+    """nf_big_move traces (monte_carlo.py:235-303) with a small perturbed flow."""
+    SB = ref["simulation_box"].SimulationBox
+    MC = ref["monte_carlo"].MonteCarlo
+    lg = quiet_logger()
+    out = {}
+    names = []
+    for tag, n, rho, K, blocks, H, nb, sigma in (("n3", 3, 0.03, 3, 2, 32, 8, 0.05),
+                                                 ("n8", 8, 0.03, 4, 2, 32, 15, 0.05)):
+        L = er.box_length(n, rho)
+        bound = L / 2
+        model = build_ref_flow(ref, n, K, blocks, H, nb, bound, seed=21, sigma=sigma)
+        for k, v in model.state_dict().items():
+            out["%s__sd__%s" % (tag, k)] = v.numpy()
+        out[tag + "__bound"] = np.float64(bound)
+        out[tag + "__L"] = np.float64(L)
+        torch.manual_seed(5)
+        for seed in (42, 43, 44):
+            if n == 3:
+                cx = L / 4 if seed % 2 == 0 else 3 * L / 4
+                p32 = (np.array([[cx - 0.8, L / 2], [cx + 0.8, L / 2], [cx, L / 2 + 1.3]])).astype(np.float32)
+            else:
+                p32, _ = er.jittered_lattice(n, rho, seed)
+            mc = MC(p32.astype(np.float64), SB(L), 1.0, n, initial_max_displacement=0.65,
+                    timing=False, checking=False, logger=lg, seed=seed, device=torch.device("cpu"), **POT)
+            mc.set_nf_model(model)
+            spy = SpyRNG(mc.rng)
+            mc.rng = spy
+            rounds, local = 12, 25
+            with torch.no_grad():
+                props = model.sample(rounds).reshape(rounds, n, 2).numpy() + bound   # main_algorithm_2.py:479-482
+            # make some proposals near the current state so a few get accepted
+            rec = dict(acc=[], eno=[], enn=[], pos_before=[], E_after=[])
+            for r in range(rounds):
+                for _ in range(local):
+                    mc.particle_displacement()
+                cfg = props[r].copy()
+                if r % 3 == 2:
+                    cfg = (np.asarray(mc.particles, dtype=np.float32)
+                           + np.float32(0.01) * (r + 1)).astype(np.float32) % np.float32(L)
+                    props[r] = cfg
+                rec["pos_before"].append(np.asarray(mc.particles, dtype=np.float64).copy())
+                rec["eno"].append(mc.energy_calculator.total_energy)
+                a = mc.nf_big_move(cfg)
+                rec["acc"].append(1 if a else 0)
+                rec["E_after"].append(mc.energy_calculator.total_energy)
+            key = "%s_s%d" % (tag, seed)
+            names.append(key)
+            out[key + "__pos0"] = p32
+            out[key + "__seed"] = np.int64(seed)
+            out[key + "__rounds"] = np.int64(rounds)
+            out[key + "__local"] = np.int64(local)
+            out[key + "__props"] = props.astype(np.float32)
+            out[key + "__acc"] = np.array(rec["acc"], np.uint8)
+            out[key + "__eno"] = np.array(rec["eno"], np.float64)
+            out[key + "__E_after"] = np.array(rec["E_after"], np.float64)
+            out[key + "__pos_before"] = np.array(rec["pos_before"], np.float64)
+            out[key + "__idx"] = np.array(spy.ints, np.int64)
+            out[key + "__u"] = np.array(spy.uniforms, np.float64)
+            out[key + "__posF"] = np.asarray(mc.particles, dtype=np.float64)
+            out[key + "__attempts"] = np.int64(mc.attempts_displacement)
+            out[key + "__accepted"] = np.int64(mc.accepted_displacement)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "mc_global.npz"), **out)
+    print("mc_global: %d traces" % len(names))
+
+
+def main():
+    ref = _refimport.load()
+    os.makedirs(GOLD, exist_ok=True)
+    gen_energy(ref)
+    gen_mc(ref)
+    gen_flow(ref)
+    gen_global(ref)
+
+
+if __name__ == "__main__":
+    main()

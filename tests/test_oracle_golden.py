@@ -1,0 +1,152 @@
+"""Pins the oracle (oracle/*.py) on outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py running
+the reference's own code (the reference holds no golden vectors
+for this path, so parity is pinned by executing it)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import energy_ref as er
+from oracle import flow_ref as fr
+from oracle import mc_ref as mr
+
+POT = er.Potential(2, [-10.0, -10.5], 1.2, 15.0)
+NOPOT = er.Potential(0, [0, 0], 1.2, 15.0)
+
+
+def _close(a, b, rtol):
+    if np.isinf(b):
+        return np.isinf(a) and a > 0
+    return abs(a - b) <= rtol * max(1.0, abs(b))
+
+
+def test_known_answers(golden_dir):
+    g = np.load(os.path.join(golden_dir, "energy_cases.npz"))
+    e, w = er.lj_energy_virial(g["kat_lj_r"])
+    np.testing.assert_allclose(e, g["kat_lj_e"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(w, g["kat_lj_w"], rtol=1e-14, atol=1e-14)
+    # Appendix B values, typed in independently of the fixture
+    np.testing.assert_allclose(e[:3], [16128.016316891137, 0.016316891136000006, -0.983683108864], rtol=1e-13)
+    assert e[4] == 0.0 and w[4] != 0.0 and e[5] == 0.0 and w[5] == 0.0
+    v = er.double_well(g["kat_dw_pos"], 10, 10, POT)
+    np.testing.assert_allclose(v, g["kat_dw_v"], rtol=1e-13, atol=1e-14)
+    for pin, pout in zip(g["kat_pbc_in"], g["kat_pbc_out"]):
+        np.testing.assert_array_equal(er.apply_pbc(pin, 10.0, 10.0), pout)
+    assert er.apply_pbc(np.array([10.3, -1e-17]), 10.0, 10.0)[1] == 10.0
+
+
+def test_energy_cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "energy_cases.npz"))
+    for name in g["names"]:
+        p32 = g[name + "__pos"]
+        L = float(g[name + "__L"])
+        pot = POT if int(g[name + "__wells"]) else NOPOT
+        for mode, rtol in (("f64", 1e-12), ("f32", 2e-6)):
+            arr = p32.astype(np.float64) if mode == "f64" else p32
+            E, W = er.total_energy_virial(arr, L, L, pot)
+            assert _close(E, float(g["%s__%s_E" % (name, mode)]), rtol), (name, mode, E)
+            assert _close(W, float(g["%s__%s_W" % (name, mode)]), rtol), (name, mode, W)
+            for i, ref in zip(g[name + "__pidx"], g["%s__%s_pe" % (name, mode)]):
+                e, w = er.particle_energy_virial(arr, int(i), L, L, pot)
+                assert _close(e, ref[0], rtol) and _close(w, ref[1], rtol), (name, mode, i)
+    assert float(g["kat3__f64_E"]) == pytest.approx(-21.123261258907107, rel=1e-6)   # float32 input rounding
+    assert np.isinf(g["kat3_overlap__f64_E"]) and np.isinf(g["overlap_n32__f32_E"])
+
+
+@pytest.mark.parametrize("mode", ["f64", "f32"])
+def test_local_traces(golden_dir, mode):
+    g = np.load(os.path.join(golden_dir, "mc_local.npz"))
+    for key in g["names"]:
+        if ("_%s_" % mode) not in key:
+            continue
+        p32 = g[key + "__pos0"]
+        arr = p32.astype(np.float64) if mode == "f64" else p32.copy()
+        L = float(g[key + "__L"])
+        steps = int(g[key + "__steps"])
+        # same PCG64 stream as the reference (monte_carlo.py:92-95)
+        ch = mr.ChainRef(arr, L, 1.0, POT, max_displacement=float(g[key + "__md0"]),
+                         rng=np.random.default_rng(int(g[key + "__seed"])))
+        rtol = 1e-12 if mode == "f64" else 5e-6
+        assert _close(ch.E, float(g[key + "__E0"]), rtol)
+        for s in range(steps):
+            p, eno, enn, acc, u = ch.local_step()
+            assert p == int(g[key + "__idx"][s])
+            assert _close(eno, g[key + "__eno"][s], rtol) and _close(enn, g[key + "__enn"][s], rtol), (key, s)
+            assert int(acc) == int(g[key + "__acc"][s]), (key, s)
+            if s + 1 == steps // 2:
+                ch.adjust_displacement()
+                assert ch.max_displacement == pytest.approx(float(g[key + "__md_mid"]), rel=1e-14)
+        ch.adjust_displacement()
+        assert ch.attempts == int(g[key + "__attempts"]) and ch.accepted == int(g[key + "__accepted"])
+        assert ch.max_displacement == pytest.approx(float(g[key + "__mdF"]), rel=1e-14)
+        np.testing.assert_allclose(np.asarray(ch.particles, np.float64), g[key + "__posF"],
+                                   rtol=0, atol=1e-12 if mode == "f64" else 0)
+        assert _close(ch.E, float(g[key + "__EF"]), 1e-11 if mode == "f64" else 5e-6)
+        assert _close(ch.W, float(g[key + "__WF"]), 1e-11 if mode == "f64" else 5e-6)
+
+
+def _load_sd(g, prefix="sd__"):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("tag", ["n3_k3", "n4_k4", "n32_k2", "n4_k23"])
+def test_flow(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "flow_%s.npz" % tag))
+    sd = _load_sd(g)
+    spec = fr.FlowSpec(sd, float(g["bound"]))
+    assert spec.K == int(g["K"]) and spec.H == int(g["H"]) and spec.nb == int(g["nb"])
+    assert spec.n_blocks == int(g["blocks"]) and spec.D == 2 * int(g["n"])
+    x = torch.from_numpy(g["x"])
+    z0 = torch.from_numpy(g["z0"])
+    with torch.no_grad():
+        y, ld = fr.layer_inverse(sd, spec.K - 1, spec, x)
+        np.testing.assert_allclose(y.numpy(), g["lastlayer_inv"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(ld.numpy(), g["lastlayer_ld"], rtol=1e-4, atol=1e-5)
+        z, ldi = fr.inverse_and_log_det(sd, spec, x)
+        np.testing.assert_allclose(z.numpy(), g["inv_z"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(ldi.numpy(), g["inv_ld"], rtol=1e-4, atol=1e-4)
+        lp = fr.log_prob(sd, spec, x).numpy()
+        ref = g["log_prob"]
+        assert np.array_equal(np.isinf(lp), np.isinf(ref)) and np.isinf(ref).sum() == 1
+        fin = ~np.isinf(ref)
+        np.testing.assert_allclose(lp[fin], ref[fin], rtol=1e-5)
+        xf, ldf = fr.forward_and_log_det(sd, spec, z0)
+        np.testing.assert_allclose(xf.numpy(), g["fwd_x"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(ldf.numpy(), g["fwd_ld"], rtol=1e-4, atol=1e-4)
+        # the reference's own round-trip property (flows/flow_test.py:40-48)
+        xr, ldr = fr.forward_and_log_det(sd, spec, z)
+        ok = (x.abs() <= spec.bound).all(dim=1)
+        np.testing.assert_allclose(xr[ok].numpy(), x[ok].numpy(), atol=2e-3 * spec.bound)
+        np.testing.assert_allclose((ldr + ldi)[ok].numpy(), 0, atol=5e-3)
+
+
+def test_global_traces(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mc_global.npz"))
+    for key in g["names"]:
+        tag = key.split("_")[0]
+        sd = _load_sd(g, tag + "__sd__")
+        bound = float(g[tag + "__bound"])
+        L = float(g[tag + "__L"])
+        spec = fr.FlowSpec(sd, bound)
+        ch = mr.ChainRef(g[key + "__pos0"].astype(np.float64), L, 1.0, POT, 0.65,
+                         rng=np.random.default_rng(int(g[key + "__seed"])))
+        for r in range(int(g[key + "__rounds"])):
+            for _ in range(int(g[key + "__local"])):
+                ch.local_step()
+            cfg = g[key + "__props"][r]
+            np.testing.assert_allclose(np.asarray(ch.particles, np.float64), g[key + "__pos_before"][r], atol=1e-12)
+            assert ch.E == pytest.approx(float(g[key + "__eno"][r]), rel=1e-10, abs=1e-10)
+            with torch.no_grad():
+                old = torch.tensor((np.asarray(ch.particles) - L / 2).reshape(1, -1), dtype=torch.float)
+                new = torch.tensor((cfg - np.array([L / 2, L / 2])).reshape(1, -1), dtype=torch.float)
+                nll_old = -fr.log_prob(sd, spec, old).item()
+                nll_new = -fr.log_prob(sd, spec, new).item()
+            acc, _, _ = ch.global_move(cfg, nll_old, nll_new)
+            assert int(acc) == int(g[key + "__acc"][r]), (key, r)
+            e_after = float(g[key + "__E_after"][r])
+            assert _close(ch.E, e_after, 1e-6), (key, r, ch.E, e_after)
+        assert ch.attempts == int(g[key + "__attempts"]) and ch.accepted == int(g[key + "__accepted"])
+        np.testing.assert_allclose(np.asarray(ch.particles, np.float64), g[key + "__posF"], atol=1e-6)
