@@ -1,0 +1,24 @@
+// Error plumbing of the C ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace fs {
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return FS_OK;
+    set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return FS_ERR_CUDA;
+}
+}  // namespace fs
+
+extern "C" const char* fs_last_error(void) { return fs::g_err; }
+extern "C" int fs_version(void) { return 100; }

@@ -1,0 +1,223 @@
+// Shared device helpers: pair potential, wells, RNG, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/flowstate_b200.h"
+
+namespace fs {
+
+void set_error(const char* fmt, ...);
+int cuda_check(cudaError_t e, const char* what);
+#define FS_CUDA(x)                                       \
+    do {                                                 \
+        int _r = fs::cuda_check((x), #x);                \
+        if (_r) return _r;                               \
+    } while (0)
+
+// Potential constants handed to kernels by value.
+struct PotDev {
+    int num_wells;
+    float V0[2];
+    float r0, k;
+    float rc2, rcore2, e_cut;
+    float Lx, Ly, inv_Lx, inv_Ly;
+    float cx[2], cy;      // well centres (L/4, L/2), (3L/4, L/2): potential.py:89-93
+};
+
+inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
+    PotDev d;
+    d.num_wells = p->num_wells;
+    d.V0[0] = p->V0[0];
+    d.V0[1] = p->V0[1];
+    d.r0 = p->r0;
+    d.k = p->k;
+    d.rc2 = p->r_cut * p->r_cut;
+    d.rcore2 = p->r_core * p->r_core;
+    double s6 = pow(1.0 / (double)p->r_cut, 6.0);
+    d.e_cut = (float)(4.0 * (s6 * s6 - s6));          // potential.py:21-26
+    d.Lx = Lx;
+    d.Ly = Ly;
+    d.inv_Lx = 1.0f / Lx;
+    d.inv_Ly = 1.0f / Ly;
+    d.cx[0] = Lx / 4;
+    d.cx[1] = 3 * Lx / 4;
+    d.cy = Ly / 2;
+    return d;
+}
+
+// round-half-even of |t| < 2^22 with two full-rate adds (np.round, simulation_box.py:38-39)
+__device__ __forceinline__ float rint_fast(float t) {
+    const float magic = 12582912.0f;   // 1.5 * 2^23
+    return __fsub_rn(__fadd_rn(t, magic), magic);
+}
+
+__device__ __forceinline__ float min_image(float d, float L, float invL) {
+    return __fmaf_rn(-L, rint_fast(d * invL), d);
+}
+
+// One pair: accumulates shifted LJ energy and virial when r <= r_cut and tracks the
+// smallest r^2 seen (hard-core test is done once on the minimum).
+// potential.py:11-27, energy_calculator.py:73-81.
+__device__ __forceinline__ void pair_accum(float dx, float dy, const PotDev& P,
+                                           float& e, float& w, float& r2min) {
+    dx = min_image(dx, P.Lx, P.inv_Lx);
+    dy = min_image(dy, P.Ly, P.inv_Ly);
+    float r2 = __fmaf_rn(dy, dy, dx * dx);
+    r2min = fminf(r2min, r2);
+    float inv = __frcp_rn(r2);
+    float s6 = inv * inv * inv;
+    if (r2 <= P.rc2) {
+        e += __fmaf_rn(4.0f * s6, s6 - 1.0f, -P.e_cut);
+        w += 48.0f * s6 * (s6 - 0.5f);
+    }
+}
+
+// External double well of one particle (potential.py:95-112).
+// V0 (1 - 0.5 (1 + tanh a)) == V0 / (1 + exp(2a)), evaluated in the stable form.
+__device__ __forceinline__ float well_term(float x, float y, int wi, const PotDev& P) {
+    float dx = min_image(x - P.cx[wi], P.Lx, P.inv_Lx);
+    float dy = min_image(y - P.cy, P.Ly, P.inv_Ly);
+    float r = sqrtf(__fmaf_rn(dy, dy, dx * dx));
+    float a2 = 2.0f * P.k * (r - P.r0);
+    return P.V0[wi] / (1.0f + expf(a2));
+}
+
+__device__ __forceinline__ float wells(float x, float y, const PotDev& P) {
+    float v = 0.f;
+    if (P.num_wells >= 1) v += well_term(x, y, 0, P);
+    if (P.num_wells == 2) v += well_term(x, y, 1, P);
+    return v;
+}
+
+// numpy float32 floor-mod (npy_divmodf), simulation_box.py:23-26 on a float32 state.
+__device__ __forceinline__ float np_mod(float a, float b) {
+    float m = fmodf(a, b);
+    if (m != 0.0f) {
+        if ((b < 0) != (m < 0)) m += b;
+    } else {
+        m = copysignf(0.0f, b);
+    }
+    return m;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// RNG
+// ---------------------------------------------------------------------------
+struct RngDev {
+    int kind;
+    unsigned long long* pcg_state;
+    unsigned long long philox_seed;
+    long long chain_id0;
+    const int* replay_idx;
+    const double* replay_u;
+    int idx_stride, u_stride;
+    int* replay_cursor;
+};
+
+inline RngDev make_rng(const fs_rng* r) {
+    RngDev d;
+    d.kind = r->kind;
+    d.pcg_state = r->pcg_state;
+    d.philox_seed = r->philox_seed;
+    d.chain_id0 = r->chain_id0;
+    d.replay_idx = r->replay_idx;
+    d.replay_u = r->replay_u;
+    d.idx_stride = r->idx_stride;
+    d.u_stride = r->u_stride;
+    d.replay_cursor = r->replay_cursor;
+    return d;
+}
+
+// PCG64 (XSL-RR 128/64) exactly as numpy drives it: step, then output.
+struct Pcg64 {
+    uint64_t hi, lo, inc_hi, inc_lo;
+    uint32_t has32, buf32;
+
+    __device__ __forceinline__ uint64_t next64() {
+        const uint64_t MH = 0x2360ED051FC65DA4ull, ML = 0x4385DF649FCCF645ull;
+        uint64_t nlo = lo * ML;
+        uint64_t nhi = __umul64hi(lo, ML) + hi * ML + lo * MH;
+        uint64_t slo = nlo + inc_lo;
+        nhi += inc_hi + (slo < nlo ? 1ull : 0ull);
+        lo = slo;
+        hi = nhi;
+        uint64_t x = hi ^ lo;
+        unsigned rot = (unsigned)(hi >> 58);
+        return (x >> rot) | (x << ((64u - rot) & 63u));
+    }
+    __device__ __forceinline__ uint32_t next32() {   // pcg64_next32: low half first, high half buffered
+        if (has32) {
+            has32 = 0;
+            return buf32;
+        }
+        uint64_t n = next64();
+        has32 = 1;
+        buf32 = (uint32_t)(n >> 32);
+        return (uint32_t)n;
+    }
+    __device__ __forceinline__ double next_double() {
+        return (double)(next64() >> 11) * (1.0 / 9007199254740992.0);
+    }
+    // Generator.integers(n), n < 2^32: buffered_bounded_lemire_uint32
+    __device__ __forceinline__ uint32_t bounded(uint32_t n) {
+        if (n <= 1) return 0;
+        uint32_t rng = n - 1;
+        uint64_t m = (uint64_t)next32() * (uint64_t)n;
+        uint32_t left = (uint32_t)m;
+        if (left < n) {
+            uint32_t thr = (0xFFFFFFFFu - rng) % n;
+            while (left < thr) {
+                m = (uint64_t)next32() * (uint64_t)n;
+                left = (uint32_t)m;
+            }
+        }
+        return (uint32_t)(m >> 32);
+    }
+    __device__ __forceinline__ void load(const unsigned long long* s) {
+        hi = s[0]; lo = s[1]; inc_hi = s[2]; inc_lo = s[3];
+        has32 = (uint32_t)s[4]; buf32 = (uint32_t)s[5];
+    }
+    __device__ __forceinline__ void store(unsigned long long* s) const {
+        s[0] = hi; s[1] = lo; s[4] = has32; s[5] = buf32;
+    }
+};
+
+// Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t h0 = __umulhi(M0, ctr.x), l0 = M0 * ctr.x;
+        uint32_t h1 = __umulhi(M1, ctr.z), l1 = M1 * ctr.z;
+        ctr = make_uint4(h1 ^ ctr.y ^ key.x, l1, h0 ^ ctr.w ^ key.y, l0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ double u32x2_to_double(uint32_t a, uint32_t b) {
+    uint64_t v = ((uint64_t)a << 32) | b;
+    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace fs

@@ -1,0 +1,664 @@
+// Circular coupled rational-quadratic-spline flow, inference (eval-mode) path.
+//
+// Reference (paths relative to <ref>/NF/normflows):
+//   flows/neural_spline/wrapper.py:98-275   layer wrapper (forward = prqct.inverse, inverse = prqct.forward)
+//   flows/neural_spline/coupling.py:71-134  split / conditioner / splines / scatter / roll by D/2
+//   flows/neural_spline/coupling.py:156-170,335-368  (B,N,3nb+1) parameters, widths/heights / sqrt(H)
+//   flows/neural_spline/coupling.py:176-265 unconditional spline of the identity half
+//   utils/splines.py:16-222                 unconstrained / rational-quadratic spline
+//   utils/nn.py:120-137                     cat[cos(s x), sin(s x)]
+//   nets/resnet.py:7-104                    residual conditioner (BatchNorm eps 1e-3, eval mode)
+//   Energy/Uniform.py:50-74                 base log-probability
+//   core.py:28-86,178-214                   layer loops
+//
+// This file holds the pack (BatchNorm folding, unconditional knot tables), the
+// CUDA-core FP32 conditioner (FS_PREC_FP32: reference arithmetic, used as the
+// precision yardstick for the tensor path) and the spline kernels, where one
+// warp owns one row and the nb <= 32 bins of a coordinate sit one per lane.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "flow.cuh"
+
+namespace fs {
+
+static const float kMinW = 1e-3f, kMinH = 1e-3f, kMinD = 1e-3f;   // utils/splines.py:6-8
+
+// ---------------------------------------------------------------------------
+// spline device code
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_t(float x) {   // F.softplus, threshold 20
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+
+// Rational-quadratic bin evaluation (utils/splines.py:163-222) given the selected bin.
+__device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, float hk, float dk, float dk1,
+                                        bool inverse, float& y, float& ld) {
+    const float sk = hk / wk;
+    const float t = dk + dk1 - 2.0f * sk;
+    if (inverse) {
+        const float dy = x - yk;
+        const float a = dy * t + hk * (sk - dk);
+        const float b = hk * dk - dy * t;
+        const float c = -sk * dy;
+        const float disc = fabsf(b * b - 4.0f * a * c);
+        const float root = (2.0f * c) / (-b - sqrtf(disc));
+        y = root * wk + xk;
+        const float tt = root * (1.0f - root);
+        const float den = sk + t * tt;
+        const float omr = 1.0f - root;
+        const float num = (sk * sk) * (dk1 * (root * root) + 2.0f * sk * tt + dk * (omr * omr));
+        ld = -(logf(num) - 2.0f * logf(den));
+    } else {
+        const float th = (x - xk) / wk;
+        const float tt = th * (1.0f - th);
+        const float num = hk * (sk * (th * th) + dk * tt);
+        const float den = sk + t * tt;
+        y = yk + num / den;
+        const float omt = 1.0f - th;
+        const float dnum = (sk * sk) * (dk1 * (th * th) + 2.0f * sk * tt + dk * (omt * omt));
+        ld = logf(dnum) - 2.0f * logf(den);
+    }
+}
+
+// softmax -> floor -> cumulative knots, one bin per lane (utils/splines.py:117-127).
+// Returns this lane's left knot and bin size.
+__device__ __forceinline__ void knots_warp(float un, bool active, int lane, int nb, float bound, float minsz,
+                                           float& left, float& size) {
+    const float ninf = -__int_as_float(0x7f800000);
+    const float m = warp_max(active ? un : ninf);
+    const float ex = active ? expf(un - m) : 0.0f;
+    const float sum = warp_sum(ex);
+    float w = minsz + (1.0f - minsz * (float)nb) * (ex / sum);
+    if (!active) w = 0.0f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+    }
+    float right = __fadd_rn(__fmul_rn(2.0f * bound, w), -bound);
+    if (lane == nb - 1) right = bound;
+    left = __shfl_up_sync(0xffffffffu, right, 1);
+    if (lane == 0) left = -bound;
+    size = right - left;
+}
+
+// bin = #(x >= knot_j, j = 0..nb) - 1 with the last knot + 1e-6 (utils/splines.py:11-13); clamped.
+__device__ __forceinline__ int bin_search(float x, float left, bool active, int nb, float bound) {
+    const unsigned m = __ballot_sync(0xffffffffu, active && x >= left);
+    int c = __popc(m) + (x >= __fadd_rn(bound, 1e-6f) ? 1 : 0) - 1;
+    return min(max(c, 0), nb - 1);
+}
+
+// Conditional spline of one coordinate; lanes k < nb hold (uw, uh, ud_k, ud_k+1) of bin k.
+__device__ __forceinline__ void rqs_cond_warp(float x, float uw, float uh, float ud, float ud1, int lane, int nb,
+                                              float bound, bool inverse, float& y, float& ld) {
+    if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39 (warp-uniform)
+        y = x;
+        ld = 0.0f;
+        return;
+    }
+    const bool active = lane < nb;
+    float xl, w, yl, h;
+    knots_warp(uw, active, lane, nb, bound, kMinW, xl, w);
+    knots_warp(uh, active, lane, nb, bound, kMinH, yl, h);
+    const float dk = kMinD + softplus_t(ud);
+    const float dk1 = kMinD + softplus_t(ud1);
+    const int bin = bin_search(x, inverse ? yl : xl, active, nb, bound);
+    rq_eval(x, __shfl_sync(0xffffffffu, xl, bin), __shfl_sync(0xffffffffu, w, bin),
+            __shfl_sync(0xffffffffu, yl, bin), __shfl_sync(0xffffffffu, h, bin),
+            __shfl_sync(0xffffffffu, dk, bin), __shfl_sync(0xffffffffu, dk1, bin), inverse, y, ld);
+}
+
+// Unconditional spline from the packed knot tables: lane k < nb holds the left knot of
+// bin k; knot nb is +bound by construction (utils/splines.py:125-126).
+__device__ __forceinline__ void rqs_table_warp(float x, const float* __restrict__ ux, const float* __restrict__ uy,
+                                               const float* __restrict__ ud, int lane, int nb, float bound,
+                                               bool inverse, float& y, float& ld) {
+    if (!(x >= -bound && x <= bound)) {
+        y = x;
+        ld = 0.0f;
+        return;
+    }
+    const bool has = lane < nb;
+    const float kx = has ? __ldg(ux + lane) : bound;
+    const float ky = has ? __ldg(uy + lane) : bound;
+    const int bin = bin_search(x, inverse ? ky : kx, has, nb, bound);
+    const float xk = __shfl_sync(0xffffffffu, kx, bin);
+    const float yk = __shfl_sync(0xffffffffu, ky, bin);
+    const float xk1 = (bin + 1 < nb) ? __shfl_sync(0xffffffffu, kx, (bin + 1) & 31) : bound;
+    const float yk1 = (bin + 1 < nb) ? __shfl_sync(0xffffffffu, ky, (bin + 1) & 31) : bound;
+    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + bin), __ldg(ud + bin + 1), inverse, y, ld);
+}
+
+struct FlowDev {
+    int N, D, H, nb, P;
+    float bound, pf_scale, inv_sqrt_h;
+    const int* idf;
+    const int* trf;
+};
+
+// v <- x - shift (float64 subtraction stored float32, MCMC/monte_carlo.py:251-258) or x + shift
+__global__ void shift_kernel(const float* __restrict__ x, float* __restrict__ v, size_t n, double shift) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (float)((double)x[i] + shift);
+}
+
+// density direction, step 1: periodic features of the identity half (utils/nn.py:125-127)
+__global__ void prep_inverse_kernel(const float* __restrict__ v, float* __restrict__ A0, int rows, FlowDev F) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * F.N) return;
+    const int b = (int)(i / F.N), j = (int)(i % F.N);
+    const float x = v[(size_t)b * F.D + F.idf[j]];
+    float s, c;
+    sincosf(F.pf_scale * x, &s, &c);
+    A0[(size_t)b * 2 * F.N + j] = c;
+    A0[(size_t)b * 2 * F.N + F.N + j] = s;
+}
+
+// density direction, step 3: conditional spline on the transformed half, unconditional
+// spline on the identity half, scatter + roll by D/2 (coupling.py:86-102)
+__global__ void __launch_bounds__(256) spline_inverse_kernel(const float* __restrict__ v,
+                                                             const float* __restrict__ theta,
+                                                             float* __restrict__ out, float* __restrict__ logdet,
+                                                             int rows, FlowDev F, const float* __restrict__ ux,
+                                                             const float* __restrict__ uy,
+                                                             const float* __restrict__ ud, int* nan_flag) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= rows) return;
+    const float* vr = v + (size_t)b * F.D;
+    float* orow = out + (size_t)b * F.D;
+    const float* th = theta + (size_t)b * F.N * F.P;
+    const int h = F.D / 2, nb = F.nb;
+    float acc = 0.f;
+    for (int j = 0; j < F.N; ++j) {
+        const float* tj = th + (size_t)j * F.P;
+        const bool a = lane < nb;
+        const float uw = a ? tj[lane] * F.inv_sqrt_h : 0.f;
+        const float uh = a ? tj[nb + lane] * F.inv_sqrt_h : 0.f;
+        const float d0 = a ? tj[2 * nb + lane] : 0.f;
+        const float d1 = a ? tj[2 * nb + lane + 1] : 0.f;
+        const int ft = F.trf[j], fi = F.idf[j];
+        float y, ld, y2, ld2;
+        rqs_cond_warp(vr[ft], uw, uh, d0, d1, lane, nb, F.bound, false, y, ld);
+        rqs_table_warp(vr[fi], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1), ud + (size_t)j * (nb + 1),
+                       lane, nb, F.bound, false, y2, ld2);
+        if (lane == 0) {
+            orow[(ft + h) % F.D] = y;
+            orow[(fi + h) % F.D] = y2;
+        }
+        acc += ld + ld2;
+        if (y != y || ld != ld || y2 != y2 || ld2 != ld2) {
+            if (lane == 0 && nan_flag) atomicOr(nan_flag, 1);
+        }
+    }
+    if (lane == 0) logdet[b] += acc;
+}
+
+// sampling direction, step 1: roll, inverse unconditional spline on the identity half,
+// periodic features of the NEW identity values (coupling.py:113-124)
+__global__ void __launch_bounds__(256) prep_forward_kernel(const float* __restrict__ v, float* __restrict__ out,
+                                                           float* __restrict__ A0, float* __restrict__ logdet,
+                                                           int rows, FlowDev F, const float* __restrict__ ux,
+                                                           const float* __restrict__ uy,
+                                                           const float* __restrict__ ud, int* nan_flag) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= rows) return;
+    const float* vr = v + (size_t)b * F.D;
+    const int h = F.D / 2, nb = F.nb;
+    float acc = 0.f;
+    for (int j = 0; j < F.N; ++j) {
+        const int fi = F.idf[j];
+        float y, ld;
+        rqs_table_warp(vr[(fi + h) % F.D], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1),
+                       ud + (size_t)j * (nb + 1), lane, nb, F.bound, true, y, ld);
+        if (lane == 0) {
+            out[(size_t)b * F.D + fi] = y;
+            float s, c;
+            sincosf(F.pf_scale * y, &s, &c);
+            A0[(size_t)b * 2 * F.N + j] = c;
+            A0[(size_t)b * 2 * F.N + F.N + j] = s;
+            if ((y != y || ld != ld) && nan_flag) atomicOr(nan_flag, 1);
+        }
+        acc += ld;
+    }
+    if (lane == 0 && logdet) logdet[b] += acc;
+}
+
+// sampling direction, step 3: inverse conditional spline on the transformed half (coupling.py:125-132)
+__global__ void __launch_bounds__(256) spline_forward_kernel(const float* __restrict__ v,
+                                                             const float* __restrict__ theta,
+                                                             float* __restrict__ out, float* __restrict__ logdet,
+                                                             int rows, FlowDev F, int* nan_flag) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= rows) return;
+    const float* vr = v + (size_t)b * F.D;
+    const float* th = theta + (size_t)b * F.N * F.P;
+    const int h = F.D / 2, nb = F.nb;
+    float acc = 0.f;
+    for (int j = 0; j < F.N; ++j) {
+        const float* tj = th + (size_t)j * F.P;
+        const bool a = lane < nb;
+        const float uw = a ? tj[lane] * F.inv_sqrt_h : 0.f;
+        const float uh = a ? tj[nb + lane] * F.inv_sqrt_h : 0.f;
+        const float d0 = a ? tj[2 * nb + lane] : 0.f;
+        const float d1 = a ? tj[2 * nb + lane + 1] : 0.f;
+        const int ft = F.trf[j];
+        float y, ld;
+        rqs_cond_warp(vr[(ft + h) % F.D], uw, uh, d0, d1, lane, nb, F.bound, true, y, ld);
+        if (lane == 0) {
+            out[(size_t)b * F.D + ft] = y;
+            if ((y != y || ld != ld) && nan_flag) atomicOr(nan_flag, 1);
+        }
+        acc += ld;
+    }
+    if (lane == 0 && logdet) logdet[b] += acc;
+}
+
+// out <- z (+ shift); logq <- logdet + UniformParticle.log_prob(z)  (Energy/Uniform.py:50-74)
+__global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ v, float* __restrict__ out,
+                                                     const float* __restrict__ logdet,
+                                                     float* __restrict__ logdet_out, float* __restrict__ logq,
+                                                     int rows, int D, float bound, float base_logc,
+                                                     double shift) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= rows) return;
+    bool inb = true;
+    for (int i = lane; i < D; i += 32) {
+        const float z = v[(size_t)b * D + i];
+        inb = inb && (z >= -bound) && (z <= bound);
+        if (out) out[(size_t)b * D + i] = (shift != 0.0) ? (float)((double)z + shift) : z;
+    }
+    inb = __all_sync(0xffffffffu, inb);
+    if (lane == 0) {
+        const float ld = logdet[b];
+        if (logdet_out) logdet_out[b] = ld;
+        if (logq) logq[b] = inb ? ld + base_logc : -__int_as_float(0x7f800000);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// FP32 conditioner GEMM: C[M,Nout] = pro(A)[M,K] . W[Nout,K]^T + bias (+ relu | + residual)
+// 64x64x16 tiles, 256 threads, 4x4 micro-tiles.
+// ---------------------------------------------------------------------------
+enum { PRO_NONE = 0, PRO_BNRELU = 1 };
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_RESIDUAL = 2 };
+
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
+                                                     const float* __restrict__ bias,
+                                                     const float* __restrict__ ps, const float* __restrict__ po,
+                                                     float* C, int M, int Nout, int K) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Ws[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid % 16, ty = tid / 16;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lr = tid / 4;          // 0..63 row inside the tile
+    const int lk = (tid % 4) * 4;    // 0,4,8,12
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lk + q;
+            float a = 0.f, w = 0.f;
+            if (k < K) {
+                if (m0 + lr < M) {
+                    a = A[(size_t)(m0 + lr) * K + k];
+                    if (PRO == PRO_BNRELU) a = fmaxf(__fmaf_rn(a, ps[k], po[k]), 0.f);
+                }
+                if (n0 + lr < Nout) w = __ldg(Wt + (size_t)(n0 + lr) * K + k);
+            }
+            As[lk + q][lr] = a;
+            Ws[lk + q][lr] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float av[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __fmaf_rn(av[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= Nout) continue;
+            float v = acc[i][j] + bias[n];
+            if (EPI == EPI_RELU) v = fmaxf(v, 0.f);
+            if (EPI == EPI_RESIDUAL) v += C[(size_t)m * Nout + n];
+            C[(size_t)m * Nout + n] = v;
+        }
+    }
+}
+
+template <int PRO, int EPI>
+static int linear(const float* A, const float* W, const float* bias, const float* ps, const float* po, float* C,
+                  int M, int Nout, int K, cudaStream_t s) {
+    dim3 grid((Nout + 63) / 64, (M + 63) / 64);
+    linear_kernel<PRO, EPI><<<grid, 256, 0, s>>>(A, W, bias, ps, po, C, M, Nout, K);
+    return cuda_check(cudaGetLastError(), "linear_kernel");
+}
+
+// resnet.py:92-104 in eval mode with BatchNorm folded at pack time
+static int conditioner_fp32(const fs_flow* f, int li, const float* A0, int rows, float* hbuf, float* tbuf,
+                            float* theta, cudaStream_t s) {
+    const fs_flow::Layer& L = f->layers[li];
+    const int H = f->H;
+    int r = linear<PRO_NONE, EPI_NONE>(A0, L.init_w, L.init_b, nullptr, nullptr, hbuf, rows, H, 2 * f->N, s);
+    if (r) return r;
+    for (int b = 0; b < f->n_blocks; ++b) {
+        r = linear<PRO_BNRELU, EPI_RELU>(hbuf, L.w0 + (size_t)b * H * H, L.b0 + (size_t)b * H,
+                                         L.bn0_s + (size_t)b * H, L.bn0_o + (size_t)b * H, tbuf, rows, H, H, s);
+        if (r) return r;
+        r = linear<PRO_NONE, EPI_RESIDUAL>(tbuf, L.w1 + (size_t)b * H * H, L.b1 + (size_t)b * H, nullptr, nullptr,
+                                           hbuf, rows, H, H, s);
+        if (r) return r;
+    }
+    return linear<PRO_NONE, EPI_NONE>(hbuf, L.final_w, L.final_b, nullptr, nullptr, theta, rows, f->N * f->P, H, s);
+}
+
+// ---------------------------------------------------------------------------
+// pack
+// ---------------------------------------------------------------------------
+template <typename T>
+static int upload(fs_flow* f, const std::vector<T>& h, T** out) {
+    void* d = nullptr;
+    FS_CUDA(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+    f->allocs.push_back(d);
+    FS_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (T*)d;
+    return FS_OK;
+}
+
+static void host_knots(const float* un, int nb, double bound, double minsz, std::vector<double>& k) {
+    // utils/splines.py:117-127 in float64
+    double m = un[0];
+    for (int i = 1; i < nb; ++i) m = un[i] > m ? un[i] : m;
+    double sum = 0;
+    std::vector<double> e(nb);
+    for (int i = 0; i < nb; ++i) { e[i] = exp((double)un[i] - m); sum += e[i]; }
+    k.assign(nb + 1, 0.0);
+    double c = 0;
+    for (int i = 0; i < nb; ++i) {
+        c += minsz + (1 - minsz * nb) * (e[i] / sum);
+        k[i + 1] = 2 * bound * c - bound;
+    }
+    k[0] = -bound;
+    k[nb] = bound;
+}
+
+static int pack_layer(fs_flow* f, const fs_flow_desc* d, const fs_layer_params* p, fs_flow::Layer* L) {
+    const int H = f->H, N = f->N, nb = f->nb, nB = f->n_blocks, P = f->P;
+    std::vector<float> v;
+    v.assign(p->init_w, p->init_w + (size_t)H * 2 * N);
+    if (int r = upload(f, v, &L->init_w)) return r;
+    v.assign(p->init_b, p->init_b + H);
+    if (int r = upload(f, v, &L->init_b)) return r;
+    std::vector<float> s0((size_t)nB * H), o0((size_t)nB * H), w0((size_t)nB * H * H), b0((size_t)nB * H);
+    for (int b = 0; b < nB; ++b) {
+        for (int j = 0; j < 2; ++j) {
+            const size_t o = ((size_t)b * 2 + j) * H;
+            for (int c = 0; c < H; ++c) {
+                // nn.BatchNorm1d(eps=1e-3) in eval mode: y = (x - mean) / sqrt(var + eps) * w + b
+                const double sc = (double)p->bn_w[o + c] / sqrt((double)p->bn_var[o + c] + (double)d->bn_eps);
+                const double of = (double)p->bn_b[o + c] - (double)p->bn_mean[o + c] * sc;
+                if (j == 0) {
+                    s0[(size_t)b * H + c] = (float)sc;
+                    o0[(size_t)b * H + c] = (float)of;
+                } else {
+                    // second BN follows linear 0 directly: fold into its rows
+                    const float* wr = p->lin_w + (((size_t)b * 2 + 0) * H + c) * H;
+                    for (int k = 0; k < H; ++k) w0[((size_t)b * H + c) * H + k] = (float)(sc * (double)wr[k]);
+                    b0[(size_t)b * H + c] = (float)(sc * (double)p->lin_b[((size_t)b * 2 + 0) * H + c] + of);
+                }
+            }
+        }
+    }
+    if (int r = upload(f, s0, &L->bn0_s)) return r;
+    if (int r = upload(f, o0, &L->bn0_o)) return r;
+    if (int r = upload(f, w0, &L->w0)) return r;
+    if (int r = upload(f, b0, &L->b0)) return r;
+    std::vector<float> w1((size_t)nB * H * H), b1((size_t)nB * H);
+    for (int b = 0; b < nB; ++b) {
+        memcpy(&w1[(size_t)b * H * H], p->lin_w + ((size_t)b * 2 + 1) * H * H, sizeof(float) * H * H);
+        memcpy(&b1[(size_t)b * H], p->lin_b + ((size_t)b * 2 + 1) * H, sizeof(float) * H);
+    }
+    if (int r = upload(f, w1, &L->w1)) return r;
+    if (int r = upload(f, b1, &L->b1)) return r;
+    v.assign(p->final_w, p->final_w + (size_t)N * P * H);
+    if (int r = upload(f, v, &L->final_w)) return r;
+    v.assign(p->final_b, p->final_b + (size_t)N * P);
+    if (int r = upload(f, v, &L->final_b)) return r;
+    std::vector<float> ux((size_t)N * (nb + 1)), uy((size_t)N * (nb + 1)), ud((size_t)N * (nb + 1));
+    std::vector<double> k;
+    for (int j = 0; j < N; ++j) {
+        host_knots(p->un_w + (size_t)j * nb, nb, f->bound, 1e-3, k);
+        for (int i = 0; i <= nb; ++i) ux[(size_t)j * (nb + 1) + i] = (float)k[i];
+        host_knots(p->un_h + (size_t)j * nb, nb, f->bound, 1e-3, k);
+        for (int i = 0; i <= nb; ++i) uy[(size_t)j * (nb + 1) + i] = (float)k[i];
+        for (int i = 0; i <= nb; ++i) {
+            const double x = p->un_d[(size_t)j * (nb + 1) + i];
+            ud[(size_t)j * (nb + 1) + i] = (float)(1e-3 + (x > 20 ? x : log1p(exp(x))));
+        }
+    }
+    if (int r = upload(f, ux, &L->u_x)) return r;
+    if (int r = upload(f, uy, &L->u_y)) return r;
+    return upload(f, ud, &L->u_d);
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// rows processed per pass so that the parameter buffer theta stays below 512 MiB
+static int chunk_rows(const fs_flow* f, int B) {
+    size_t per_row = (size_t)f->N * f->P * sizeof(float);
+    size_t rows = (512ull << 20) / per_row;
+    if (rows < 128) rows = 128;
+    rows = rows / 128 * 128;
+    return (int)(rows < (size_t)B ? rows : (size_t)B);
+}
+
+struct Workspace {
+    float *v0, *v1, *A0, *h, *t, *theta, *ld;
+    void* tc;
+    size_t tc_bytes;
+};
+
+static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspace* w) {
+    const int Bc = chunk_rows(f, B);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return base ? (void*)((char*)base + o) : nullptr;
+    };
+    float* v0 = (float*)take((size_t)Bc * f->D * 4);
+    float* v1 = (float*)take((size_t)Bc * f->D * 4);
+    float* A0 = (float*)take((size_t)Bc * 2 * f->N * 4);
+    float* h = (float*)take((size_t)Bc * f->H * 4);
+    float* t = (float*)take((size_t)Bc * f->H * 4);
+    float* th = (float*)take((size_t)Bc * f->N * f->P * 4);
+    float* ld = (float*)take((size_t)Bc * 4);
+    size_t tcb = precision == FS_PREC_TF32 ? tc_workspace_bytes(f, Bc) : 0;
+    void* tc = take(tcb);
+    if (w) *w = Workspace{v0, v1, A0, h, t, th, ld, tc, tcb};
+    return off;
+}
+
+static FlowDev flow_dev(const fs_flow* f) {
+    FlowDev F;
+    F.N = f->N; F.D = f->D; F.H = f->H; F.nb = f->nb; F.P = f->P;
+    F.bound = f->bound_f; F.pf_scale = f->pf_scale; F.inv_sqrt_h = f->inv_sqrt_h;
+    F.idf = f->idf; F.trf = f->trf;
+    return F;
+}
+
+static int run_conditioner(fs_flow* f, int li, const Workspace& w, int rows, int precision, cudaStream_t s) {
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, li, w.A0, rows, w.theta, w.tc, w.tc_bytes, s);
+    return conditioner_fp32(f, li, w.A0, rows, w.h, w.t, w.theta, s);
+}
+
+}  // namespace fs
+
+using namespace fs;
+
+extern "C" int fs_flow_create(const fs_flow_desc* d, fs_flow** out) {
+    if (!d || !out || d->K < 1 || d->N < 1 || d->H < 1 || d->n_blocks < 0 || d->nb < 1 || !d->layers ||
+        !d->identity_features || !d->transform_features || !(d->bound > 0)) {
+        set_error("fs_flow_create: invalid descriptor");
+        return FS_ERR_INVALID;
+    }
+    if (d->nb > 32) {   // one spline bin per lane
+        set_error("fs_flow_create: num_bins=%d > 32 is not supported", d->nb);
+        return FS_ERR_UNSUPPORTED;
+    }
+    fs_flow* f = new fs_flow();
+    f->K = d->K; f->N = d->N; f->D = 2 * d->N; f->H = d->H; f->n_blocks = d->n_blocks; f->nb = d->nb;
+    f->P = 3 * d->nb + 1;
+    f->bound = d->bound;
+    f->bound_f = (float)d->bound;
+    f->pf_scale = (float)(M_PI / d->bound);                       // wrapper.py:151-154
+    f->base_logc = (float)(-f->D) * logf((float)(2.0 * d->bound));  // Energy/Uniform.py:67-68
+    f->inv_sqrt_h = (float)(1.0 / sqrt((double)d->H));             // coupling.py:340-342
+    f->tc = nullptr;
+    std::vector<int> idf(d->identity_features, d->identity_features + d->N);
+    std::vector<int> trf(d->transform_features, d->transform_features + d->N);
+    for (int j = 0; j < d->N; ++j) {
+        if (idf[j] < 0 || idf[j] >= f->D || trf[j] < 0 || trf[j] >= f->D) {
+            delete f;
+            set_error("fs_flow_create: feature index out of range");
+            return FS_ERR_INVALID;
+        }
+    }
+    int r = upload(f, idf, &f->idf);
+    if (!r) r = upload(f, trf, &f->trf);
+    f->layers.resize(d->K);
+    for (int i = 0; i < d->K && !r; ++i) r = pack_layer(f, d, &d->layers[i], &f->layers[i]);
+    if (!r) r = tc_pack(f, d);
+    if (r) {
+        fs_flow_destroy(f);
+        return r;
+    }
+    *out = f;
+    return FS_OK;
+}
+
+extern "C" void fs_flow_destroy(fs_flow* f) {
+    if (!f) return;
+    tc_free(f);
+    for (void* p : f->allocs) cudaFree(p);
+    delete f;
+}
+
+extern "C" size_t fs_flow_workspace_bytes(const fs_flow* f, int B, int precision) {
+    if (!f || B < 1) return 0;
+    return carve(f, B, precision, nullptr, nullptr);
+}
+
+static int check_ws(const fs_flow* f, int B, int precision, void* ws, size_t bytes, const char* who) {
+    if (precision != FS_PREC_FP32 && precision != FS_PREC_TF32) {
+        set_error("%s: unknown precision %d", who, precision);
+        return FS_ERR_INVALID;
+    }
+    if (precision == FS_PREC_TF32 && !f->tc) {
+        set_error("%s: the tensor-core path does not support this shape (H=%d); use FS_PREC_FP32", who, f->H);
+        return FS_ERR_UNSUPPORTED;
+    }
+    size_t need = carve(f, B, precision, nullptr, nullptr);
+    if (!ws || bytes < need) {
+        set_error("%s: workspace too small (%zu < %zu)", who, bytes, need);
+        return FS_ERR_INVALID;
+    }
+    return FS_OK;
+}
+
+extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shift, float* z, float* logdet,
+                               float* logq, int* nan_flag, void* workspace, size_t workspace_bytes, int precision,
+                               void* stream) {
+    if (!f || !x || B < 0) { set_error("fs_flow_inverse: invalid argument"); return FS_ERR_INVALID; }
+    if (B == 0) return FS_OK;
+    if (int r = check_ws(f, B, precision, workspace, workspace_bytes, "fs_flow_inverse")) return r;
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    carve(f, B, precision, workspace, &w);
+    const int Bc = chunk_rows(f, B);
+    const FlowDev F = flow_dev(f);
+    for (int r0 = 0; r0 < B; r0 += Bc) {
+        const int rows = (B - r0 < Bc) ? B - r0 : Bc;
+        const size_t n = (size_t)rows * f->D;
+        shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x + (size_t)r0 * f->D, w.v0, n, -in_shift);
+        FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
+        float* cur = w.v0;
+        float* nxt = w.v1;
+        for (int li = f->K - 1; li >= 0; --li) {                        // core.py:82-85
+            const fs_flow::Layer& L = f->layers[li];
+            const size_t ne = (size_t)rows * f->N;
+            prep_inverse_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(cur, w.A0, rows, F);
+            if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+            spline_inverse_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, L.u_x, L.u_y,
+                                                                 L.u_d, nan_flag);
+            float* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, z ? z + (size_t)r0 * f->D : nullptr, w.ld,
+                                                     logdet ? logdet + r0 : nullptr, logq ? logq + r0 : nullptr,
+                                                     rows, f->D, f->bound_f, f->base_logc, 0.0);
+        FS_CUDA(cudaGetLastError());
+    }
+    return FS_OK;
+}
+
+extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_shift, float* x, float* logdet,
+                               int* nan_flag, void* workspace, size_t workspace_bytes, int precision,
+                               void* stream) {
+    if (!f || !zin || !x || B < 0) { set_error("fs_flow_forward: invalid argument"); return FS_ERR_INVALID; }
+    if (B == 0) return FS_OK;
+    if (int r = check_ws(f, B, precision, workspace, workspace_bytes, "fs_flow_forward")) return r;
+    cudaStream_t s = (cudaStream_t)stream;
+    Workspace w;
+    carve(f, B, precision, workspace, &w);
+    const int Bc = chunk_rows(f, B);
+    const FlowDev F = flow_dev(f);
+    for (int r0 = 0; r0 < B; r0 += Bc) {
+        const int rows = (B - r0 < Bc) ? B - r0 : Bc;
+        const size_t n = (size_t)rows * f->D;
+        FS_CUDA(cudaMemcpyAsync(w.v0, zin + (size_t)r0 * f->D, n * 4, cudaMemcpyDeviceToDevice, s));
+        FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
+        float* cur = w.v0;
+        float* nxt = w.v1;
+        for (int li = 0; li < f->K; ++li) {                              // core.py:52-55
+            const fs_flow::Layer& L = f->layers[li];
+            prep_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d,
+                                                               nan_flag);
+            if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+            spline_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+            float* tmp = cur; cur = nxt; nxt = tmp;
+        }
+        finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, x + (size_t)r0 * f->D, w.ld,
+                                                     logdet ? logdet + r0 : nullptr, nullptr, rows, f->D,
+                                                     f->bound_f, f->base_logc, out_shift);
+        FS_CUDA(cudaGetLastError());
+    }
+    return FS_OK;
+}

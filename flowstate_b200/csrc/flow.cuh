@@ -1,0 +1,42 @@
+// Packed flow (device-resident, inference form) shared by the FP32 and the
+// tensor-core conditioner paths.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct fs_flow {
+    int K, N, D, H, n_blocks, nb, P;   // P = 3 nb + 1 parameters per transformed coordinate
+    double bound;
+    float bound_f, pf_scale, base_logc, inv_sqrt_h;
+    int* idf;   // [N] identity feature indices
+    int* trf;   // [N] transformed feature indices
+    // per layer, FP32 row-major, BatchNorm folded (see flow.cu: pack_layer)
+    struct Layer {
+        float* init_w;   // [H, 2N]
+        float* init_b;   // [H]
+        float* bn0_s;    // [n_blocks, H]   scale  of the first BN of each block
+        float* bn0_o;    // [n_blocks, H]   offset
+        float* w0;       // [n_blocks, H, H]  first linear with the second BN folded in
+        float* b0;       // [n_blocks, H]
+        float* w1;       // [n_blocks, H, H]
+        float* b1;       // [n_blocks, H]
+        float* final_w;  // [N P, H]
+        float* final_b;  // [N P]
+        float* u_x;      // [N, nb+1] knots of the unconditional spline (x)
+        float* u_y;      // [N, nb+1] knots (y)
+        float* u_d;      // [N, nb+1] derivatives (already 1e-3 + softplus)
+    };
+    std::vector<Layer> layers;
+    std::vector<void*> allocs;
+    void* tc;   // tensor-core pack (flow_tc.cu), or nullptr
+};
+
+namespace fs {
+// tensor-core path (flow_tc.cu)
+int tc_pack(fs_flow* f, const fs_flow_desc* d);
+void tc_free(fs_flow* f);
+size_t tc_workspace_bytes(const fs_flow* f, int B);
+int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void* ws, size_t ws_bytes,
+                   cudaStream_t s);
+}  // namespace fs

@@ -1,0 +1,269 @@
+// Local-displacement Metropolis sweep: `steps` single-particle moves on each of B
+// independent chains in one launch.
+//
+// fs_local_sweep <- MonteCarlo.particle_displacement + metropolis_acceptance_particle_move
+//                   (MCMC/monte_carlo.py:146-223) with the two
+//                   calculate_particle_energy_virial calls (MCMC/energy_calculator.py:48-108)
+// fs_adjust_displacement <- MonteCarlo.adjust_displacement (MCMC/monte_carlo.py:375-403)
+//
+// One warp owns one chain for the whole launch: the chain's positions live in
+// shared memory, each lane evaluates the old and the new pair energy of the
+// moved particle against its slice of the other particles from a single load,
+// and six warp-shuffle reductions finish the step.  Draw order per step follows
+// the reference: particle index, two displacement uniforms, and a third uniform
+// only for finite uphill moves.
+#include "common.cuh"
+
+namespace fs {
+
+struct StepDraw {
+    int p;
+    double u1, u2;
+};
+
+template <int KIND>
+struct ChainRng {
+    Pcg64 pcg;
+    uint2 key;
+    uint4 ctr;
+    uint4 blk;
+    const int* ridx;
+    const double* ru;
+    int ci, cu;
+
+    __device__ __forceinline__ void init(const RngDev& R, int b, long long attempts) {
+        if (KIND == FS_RNG_PCG64) {
+            pcg.load(R.pcg_state + (size_t)b * 6);
+        } else if (KIND == FS_RNG_PHILOX) {
+            key = make_uint2((uint32_t)R.philox_seed, (uint32_t)(R.philox_seed >> 32));
+            long long cid = R.chain_id0 + b;
+            ctr = make_uint4(0u, 0u, (uint32_t)cid, (uint32_t)((unsigned long long)cid >> 32));
+        } else {
+            ridx = R.replay_idx + (size_t)b * R.idx_stride;
+            ru = R.replay_u + (size_t)b * R.u_stride;
+            ci = R.replay_cursor[2 * b];
+            cu = R.replay_cursor[2 * b + 1];
+        }
+    }
+    // step_id = value of the attempts counter before this step
+    __device__ __forceinline__ StepDraw draw(int N, long long step_id) {
+        StepDraw d;
+        if (KIND == FS_RNG_PCG64) {
+            d.p = (int)pcg.bounded((uint32_t)N);
+            d.u1 = pcg.next_double();
+            d.u2 = pcg.next_double();
+        } else if (KIND == FS_RNG_PHILOX) {
+            // two Philox blocks per step: {idx, -, u1} and {u2, u3}
+            ctr.x = (uint32_t)step_id;
+            ctr.y = (uint32_t)((unsigned long long)step_id >> 32) << 1;
+            uint4 a = philox4x32(ctr, key);
+            ctr.y |= 1u;
+            blk = philox4x32(ctr, key);
+            d.p = (int)(((uint64_t)a.x * (uint64_t)N) >> 32);
+            d.u1 = u32x2_to_double(a.z, a.w);
+            d.u2 = u32x2_to_double(blk.x, blk.y);
+        } else {
+            d.p = ridx[ci++];
+            d.u1 = ru[cu++];
+            d.u2 = ru[cu++];
+        }
+        return d;
+    }
+    __device__ __forceinline__ double accept_uniform() {
+        if (KIND == FS_RNG_PCG64) return pcg.next_double();
+        if (KIND == FS_RNG_PHILOX) return u32x2_to_double(blk.z, blk.w);
+        return ru[cu++];
+    }
+    __device__ __forceinline__ void finish(const RngDev& R, int b) {
+        if (KIND == FS_RNG_PCG64) {
+            pcg.store(R.pcg_state + (size_t)b * 6);
+        } else if (KIND == FS_RNG_REPLAY) {
+            R.replay_cursor[2 * b] = ci;
+            R.replay_cursor[2 * b + 1] = cu;
+        }
+    }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ pos, double* __restrict__ E,
+                                                          double* __restrict__ W,
+                                                          const double* __restrict__ max_disp,
+                                                          long long* __restrict__ attempts,
+                                                          long long* __restrict__ accepted, int B, int N,
+                                                          int steps, PotDev P, double beta, RngDev R,
+                                                          unsigned char* __restrict__ trace_accept,
+                                                          int* __restrict__ trace_idx,
+                                                          float* __restrict__ trace_e) {
+    extern __shared__ float2 smem[];
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= B) return;
+    float2* sp = smem + (size_t)wib * N;
+    float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
+    for (int i = lane; i < N; i += 32) sp[i] = gp[i];
+    __syncwarp();
+
+    const double md = max_disp[b];
+    long long att = attempts[b];
+    long long acc = accepted[b];
+    double Eb = E[b], Wb = W[b];
+    ChainRng<KIND> rng;
+    rng.init(R, b, att);
+    const float inf = __int_as_float(0x7f800000);
+
+    for (int s = 0; s < steps; ++s) {
+        StepDraw d = rng.draw(N, att);
+        att += 1;
+        const int p = d.p;
+        const float2 old = sp[p];
+        // new_positions[p] += displacement (float64 add, stored float32), then % L
+        // (monte_carlo.py:161-166 on a float32 state)
+        float nx = (float)((double)old.x + (d.u1 - 0.5) * md);
+        float ny = (float)((double)old.y + (d.u2 - 0.5) * md);
+        nx = np_mod(nx, P.Lx);
+        ny = np_mod(ny, P.Ly);
+
+        float eo = 0.f, wo = 0.f, en = 0.f, wn = 0.f, mo = 3.0e38f, mn = 3.0e38f;
+        for (int j = lane; j < N; j += 32) {
+            if (j == p) continue;
+            const float2 q = sp[j];
+            pair_accum(old.x - q.x, old.y - q.y, P, eo, wo, mo);
+            pair_accum(nx - q.x, ny - q.y, P, en, wn, mn);
+        }
+        // wells of the old / new position: lanes 0..3 take one tanh each
+        if (P.num_wells == 2) {
+            if (lane < 2) eo += well_term(old.x, old.y, lane, P);
+            else if (lane < 4) en += well_term(nx, ny, lane - 2, P);
+        } else if (P.num_wells == 1) {
+            if (lane == 0) eo += well_term(old.x, old.y, 0, P);
+            else if (lane == 1) en += well_term(nx, ny, 0, P);
+        }
+        eo = warp_sum(eo);
+        en = warp_sum(en);
+        wo = warp_sum(wo);
+        wn = warp_sum(wn);
+        mo = warp_min(mo);
+        mn = warp_min(mn);
+        if (mo < P.rcore2) { eo = inf; wo = inf; }
+        if (mn < P.rcore2) { en = inf; wn = inf; }
+
+        bool ok;
+        if (en <= eo) {
+            ok = true;
+        } else if (en == inf) {
+            ok = false;
+        } else {
+            const double factor = exp(-beta * ((double)en - (double)eo));
+            const double u = rng.accept_uniform();
+            ok = u < factor;
+        }
+        if (ok) {
+            if (lane == 0) sp[p] = make_float2(nx, ny);
+            acc += 1;
+            Eb += (double)en - (double)eo;
+            Wb += (double)wn - (double)wo;
+        }
+        if (lane == 0) {
+            const size_t o = (size_t)b * steps + s;
+            if (trace_accept) trace_accept[o] = ok ? 1 : 0;
+            if (trace_idx) trace_idx[o] = p;
+            if (trace_e) {
+                trace_e[2 * o] = eo;
+                trace_e[2 * o + 1] = en;
+            }
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < N; i += 32) gp[i] = sp[i];
+    if (lane == 0) {
+        attempts[b] = att;
+        accepted[b] = acc;
+        E[b] = Eb;
+        W[b] = Wb;
+        rng.finish(R, b);
+    }
+}
+
+__global__ void adjust_displacement_kernel(double* max_disp, const long long* att, const long long* acc,
+                                           long long* patt, long long* pacc, double target, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (att[b] > patt[b]) {
+        const long long da = att[b] - patt[b];
+        const long long dc = acc[b] - pacc[b];
+        const double frac = da > 0 ? (double)dc / (double)da : 0.0;
+        const double md = max_disp[b];
+        double nm = md * (frac / target);
+        const double ratio = nm / md;
+        if (ratio > 1.5) nm = md * 1.5;
+        else if (ratio < 0.5) nm = md * 0.5;
+        max_disp[b] = nm;
+        patt[b] = att[b];
+        pacc[b] = acc[b];
+    }
+}
+
+template <int KIND>
+static int launch_sweep(float* pos, double* E, double* W, const double* md, long long* att, long long* acc,
+                        int B, int N, int steps, const PotDev& P, double beta, const RngDev& R,
+                        unsigned char* ta, int* ti, float* te, cudaStream_t s) {
+    // warps per CTA: 4 unless the chain state is large
+    int wpc = 4;
+    while (wpc > 1 && (size_t)wpc * N * sizeof(float2) > 200 * 1024) wpc >>= 1;
+    size_t smem = (size_t)wpc * N * sizeof(float2);
+    if (smem > 227 * 1024) {
+        set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
+        return FS_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+        FS_CUDA(cudaFuncSetAttribute(local_sweep_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (B + wpc - 1) / wpc;
+    local_sweep_kernel<KIND><<<grid, wpc * 32, smem, s>>>(pos, E, W, md, att, acc, B, N, steps, P, beta, R, ta, ti, te);
+    return cuda_check(cudaGetLastError(), "local_sweep_kernel");
+}
+
+}  // namespace fs
+
+extern "C" int fs_local_sweep(float* pos, double* E, double* W, const double* max_disp, long long* attempts,
+                              long long* accepted, int B, int N, int steps, float Lx, float Ly, double beta,
+                              const fs_pot* pot, const fs_rng* rng, unsigned char* trace_accept,
+                              int* trace_idx, float* trace_e, void* stream) {
+    if (!pos || !E || !W || !max_disp || !attempts || !accepted || !pot || !rng || B < 0 || N < 1 || steps < 0 ||
+        !(Lx > 0) || !(Ly > 0)) {
+        fs::set_error("fs_local_sweep: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (B == 0 || steps == 0) return FS_OK;
+    fs::PotDev P = fs::make_pot(pot, Lx, Ly);
+    fs::RngDev R = fs::make_rng(rng);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (rng->kind) {
+        case FS_RNG_PCG64:
+            if (!rng->pcg_state) break;
+            return fs::launch_sweep<FS_RNG_PCG64>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
+                                                  trace_accept, trace_idx, trace_e, s);
+        case FS_RNG_PHILOX:
+            return fs::launch_sweep<FS_RNG_PHILOX>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
+                                                   trace_accept, trace_idx, trace_e, s);
+        case FS_RNG_REPLAY:
+            if (!rng->replay_idx || !rng->replay_u || !rng->replay_cursor) break;
+            return fs::launch_sweep<FS_RNG_REPLAY>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
+                                                   trace_accept, trace_idx, trace_e, s);
+    }
+    fs::set_error("fs_local_sweep: bad rng descriptor (kind=%d)", rng->kind);
+    return FS_ERR_INVALID;
+}
+
+extern "C" int fs_adjust_displacement(double* max_disp, const long long* attempts, const long long* accepted,
+                                      long long* prev_attempts, long long* prev_accepted, double target, int B,
+                                      void* stream) {
+    if (!max_disp || !attempts || !accepted || !prev_attempts || !prev_accepted || B < 0 || !(target > 0)) {
+        fs::set_error("fs_adjust_displacement: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (B == 0) return FS_OK;
+    fs::adjust_displacement_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        max_disp, attempts, accepted, prev_attempts, prev_accepted, target, B);
+    return fs::cuda_check(cudaGetLastError(), "adjust_displacement_kernel");
+}

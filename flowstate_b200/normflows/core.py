@@ -1,0 +1,122 @@
+"""NormalizingFlow container.  Mirrors NF/normflows/core.py:10-230 including the
+fork's edits: sample() returns z only, forward_kld omits the
+base log-probability, reverse_kld returns (loss, z) and calls p._energy.
+
+In eval mode the layer loops collapse into ONE C-ABI call per pass
+(fs_flow_inverse / fs_flow_forward over all K layers); train mode loops over
+the layers' autograd paths like the reference.
+"""
+import torch
+import torch.nn as nn
+
+from .flows import CircularCoupledRationalQuadraticSpline
+
+
+class NormalizingFlow(nn.Module):
+    def __init__(self, q0, flows, p=None):
+        super().__init__()
+        self.q0 = q0
+        self.flows = nn.ModuleList(flows)
+        self.p = p
+        self._pack = None
+        self.precision = "fp32"      # "fp32" (CUDA cores) | "tf32" (tcgen05 tensor cores)
+
+    # -- packing ----------------------------------------------------------
+    def _fusable(self):
+        return (not self.training and len(self.flows) > 0
+                and all(isinstance(f, CircularCoupledRationalQuadraticSpline) for f in self.flows))
+
+    def _cuda_pack(self):
+        from ._pack import FlowPack
+        layers = list(self.flows)
+        if self._pack is None or not self._pack.matches(layers):
+            self._pack = FlowPack(layers)
+        self._pack.precision = self.precision
+        return self._pack
+
+    def repack(self):
+        """Drop the packed inference weights (call after editing parameters in place in eval mode)."""
+        self._pack = None
+        for f in self.flows:
+            if hasattr(f, "_pack"):
+                f._pack = None
+
+    def train(self, mode=True):
+        if mode:
+            self._pack = None
+        return super().train(mode)
+
+    def load_state_dict(self, *a, **k):
+        self.repack()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.repack()
+        return super()._apply(fn, *a, **k)
+
+    # -- reference API ----------------------------------------------------
+    def forward(self, z):
+        if self._fusable():
+            return self._cuda_pack().forward(z, want_logdet=False)[0]
+        for flow in self.flows:
+            z, _ = flow(z)
+        return z
+
+    def forward_and_log_det(self, z):
+        if self._fusable():
+            return self._cuda_pack().forward(z, want_logdet=True)
+        log_det = torch.zeros(len(z), device=z.device)
+        for flow in self.flows:
+            z, ld = flow(z)
+            log_det = log_det + ld
+        return z, log_det
+
+    def inverse(self, x):
+        if self._fusable():
+            return self._cuda_pack().inverse(x)[0]
+        for i in range(len(self.flows) - 1, -1, -1):
+            x, _ = self.flows[i].inverse(x)
+        return x
+
+    def inverse_and_log_det(self, x):
+        if self._fusable():
+            z, ld, _ = self._cuda_pack().inverse(x)
+            return z, ld
+        log_det = torch.zeros(len(x), device=x.device)
+        for i in range(len(self.flows) - 1, -1, -1):
+            x, ld = self.flows[i].inverse(x)
+            log_det = log_det + ld
+        return x, log_det
+
+    def forward_kld(self, x):
+        log_q = torch.zeros(len(x), device=x.device)
+        z = x
+        for i in range(len(self.flows) - 1, -1, -1):
+            z, log_det = self.flows[i].inverse(z)
+            log_q = log_q + log_det
+        return -torch.mean(log_q)
+
+    def reverse_kld(self, num_samples=1, beta=1.0, score_fn=True):
+        z = self.q0(num_samples).to(next(self.parameters()).device)
+        log_q = torch.zeros(len(z), device=z.device)
+        for flow in self.flows:
+            z, log_det = flow(z)
+            log_q = log_q - log_det
+        energy = self.p._energy(z)
+        return torch.mean(energy) + torch.mean(log_q), z
+
+    def sample(self, num_samples=1):
+        z = self.q0(num_samples)
+        return self.forward(z)
+
+    def log_prob(self, x):
+        if self._fusable() and hasattr(self.q0, "bound"):
+            return self._cuda_pack().inverse(x, want_logq=True)[2]
+        z, log_q = self.inverse_and_log_det(x)
+        return log_q + self.q0.log_prob(z)
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))

@@ -1,0 +1,193 @@
+/*
+ * flowstate_b200 - C ABI of the B200-native NF-MCMC sampling hot path.
+ *
+ * The reference (Inesalmansa/flow-state) is pure Python and has no FFI of its
+ * own: its boundary is the Python class API that the experiment
+ * drivers call.  Each entry point below is what a ctypes/cffi binding placed
+ * under that class API binds; the comment on each names the reference
+ * function(s) it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the comment
+ *     says "host"; no allocation happens inside the hot calls;
+ *   - `stream` is the caller's cudaStream_t passed as void* (NULL = default);
+ *   - return value 0 = ok, non-zero = error (fs_last_error() has the text);
+ *   - positions are float32 [B, N, 2] in MC-box coordinates [0, L];
+ *   - running per-chain energies/virials, max displacement and counters keep
+ *     the reference's float64 / int64 types.
+ */
+#ifndef FLOWSTATE_B200_H
+#define FLOWSTATE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_OK 0
+#define FS_ERR_INVALID 1
+#define FS_ERR_CUDA 2
+#define FS_ERR_UNSUPPORTED 3
+
+/* External potential + pair cut-offs.  Reference: MCMC/energy_calculator.py:10-21
+ * (num_wells, V0_list, r0, k), MCMC/potential.py:3 (cutoff 2.5, shifted),
+ * MCMC/energy_calculator.py:73,150 (hard core r < 0.5 -> inf). */
+typedef struct fs_pot {
+    int   num_wells;   /* 0, 1 or 2 */
+    float V0[2];
+    float r0;
+    float k;
+    float r_cut;       /* 2.5 */
+    float r_core;      /* 0.5 */
+} fs_pot;
+
+/* Random source of the Metropolis kernels.
+ *   FS_RNG_PCG64  : bit-exact emulation of numpy.random.Generator(PCG64) as the
+ *                   reference uses it (MCMC/monte_carlo.py:92-95,153,161,215,287):
+ *                   integers(N) = buffered 32-bit Lemire, random() = 53-bit double.
+ *                   state: uint64 [B, 6] = {state_hi, state_lo, inc_hi, inc_lo,
+ *                   has_uint32, uinteger}, updated in place.
+ *   FS_RNG_PHILOX : Philox4x32-10 keyed by (seed, global chain id, per-chain step
+ *                   counter = attempts), so results do not depend on how chains
+ *                   are sharded over GPUs or split over launches.
+ *   FS_RNG_REPLAY : recorded draws; idx [B, idx_stride] consumed one per local
+ *                   step, u [B, u_stride] consumed through cursor [B, 2] =
+ *                   {idx cursor, u cursor} (third uniform only on finite uphill
+ *                   moves, like the reference). */
+#define FS_RNG_PCG64 0
+#define FS_RNG_PHILOX 1
+#define FS_RNG_REPLAY 2
+typedef struct fs_rng {
+    int                 kind;
+    unsigned long long* pcg_state;
+    unsigned long long  philox_seed;
+    long long           chain_id0;       /* global id of chain 0 of this call */
+    const int*          replay_idx;
+    const double*       replay_u;
+    int                 idx_stride;
+    int                 u_stride;
+    int*                replay_cursor;
+} fs_rng;
+
+const char* fs_last_error(void);
+int fs_version(void);
+
+/* Element-wise helpers behind the reference's small public functions:
+ *   SimulationBox.apply_pbc (MCMC/simulation_box.py:19-29): pos [n,2] wrapped in place (numpy floor-mod);
+ *   SimulationBox.compute_distances (:31-65): r[i] = |min_image(p1 - p2[i])|, p1 one point or [n,2];
+ *   lennard_jones_energy_virial (MCMC/potential.py:3-29): shifted, cut pair energy / virial of r[i];
+ *   double_well_potential (MCMC/potential.py:55-116): V_ext of each position. */
+int fs_apply_pbc(float* pos, long long n, float Lx, float Ly, void* stream);
+int fs_distances(const float* p1, int p1_is_single, const float* p2, long long n, float Lx, float Ly,
+                 float* r, void* stream);
+int fs_lj_pair(const float* r, long long n, const fs_pot* pot /*host*/, float* e, float* w, void* stream);
+int fs_double_well(const float* pos, long long n, float Lx, float Ly, const fs_pot* pot /*host*/, float* v,
+                   void* stream);
+
+/* EnergyCalculator.calculate_total_energy_virial  (MCMC/energy_calculator.py:121-203)
+ * for B configurations at once: E[b] = sum_{i<j} LJ + sum_i V_ext, W[b] = sum virial,
+ * overlap[b] = 1 and E = W = +inf when any pair is closer than r_core. */
+int fs_energy_total(const float* pos, int B, int N, float Lx, float Ly, const fs_pot* pot /*host*/,
+                    float* E, float* W, unsigned char* overlap, void* stream);
+
+/* EnergyCalculator.calculate_particle_energy_virial  (MCMC/energy_calculator.py:48-108)
+ * for particle idx[b] of each configuration, at its stored position (new_xy == NULL)
+ * or moved to new_xy[b] = (x, y). */
+int fs_energy_particle(const float* pos, const int* idx, const float* new_xy, int B, int N,
+                       float Lx, float Ly, const fs_pot* pot /*host*/,
+                       float* e, float* w, unsigned char* overlap, void* stream);
+
+/* `steps` calls of MonteCarlo.particle_displacement  (MCMC/monte_carlo.py:146-223)
+ * on each of B independent chains; chain state stays in shared memory for the
+ * whole launch.  Optional traces (NULL to skip): trace_accept/trace_idx [B, steps],
+ * trace_e [B, steps, 2] = (e_old, e_new) of the moved particle. */
+int fs_local_sweep(float* pos, double* E, double* W, const double* max_disp,
+                   long long* attempts, long long* accepted,
+                   int B, int N, int steps, float Lx, float Ly, double beta,
+                   const fs_pot* pot /*host*/, const fs_rng* rng /*host*/,
+                   unsigned char* trace_accept, int* trace_idx, float* trace_e, void* stream);
+
+/* MonteCarlo.adjust_displacement  (MCMC/monte_carlo.py:375-403), per chain. */
+int fs_adjust_displacement(double* max_disp, const long long* attempts, const long long* accepted,
+                           long long* prev_attempts, long long* prev_accepted,
+                           double target, int B, void* stream);
+
+/* Steps 3-5 of MonteCarlo.nf_big_move  (MCMC/monte_carlo.py:264-303):
+ * ratio = exp(-beta (E_new - E) - (nll_new - nll_old)), accept if >= 1 or u < ratio
+ * (uniform drawn only when ratio < 1), masked in-place copy prop -> pos, E/W and
+ * counter updates.  u == NULL draws from rng. */
+int fs_accept_global(float* pos, const float* prop, double* E, double* W,
+                     const float* E_new, const float* W_new,
+                     const float* logq_old, const float* logq_new,
+                     const double* u, const fs_rng* rng /*host, may be NULL if u*/,
+                     double beta, long long* attempts, long long* accepted,
+                     unsigned char* accept_mask, int B, int N, void* stream);
+
+/* ---- flow (NF/normflows) -------------------------------------------------- */
+
+/* Parameters of one CircularCoupledRationalQuadraticSpline layer in the
+ * reference's state_dict layout, HOST pointers, float32:
+ * prefix flows.<i>.prqct.  */
+typedef struct fs_layer_params {
+    const float* init_w;    /* transform_net.initial_layer.weight  [H, 2N] */
+    const float* init_b;    /* transform_net.initial_layer.bias    [H] */
+    const float* bn_w;      /* blocks.<b>.batch_norm_layers.<j>.weight        [n_blocks, 2, H] */
+    const float* bn_b;      /* ... .bias */
+    const float* bn_mean;   /* ... .running_mean */
+    const float* bn_var;    /* ... .running_var */
+    const float* lin_w;     /* blocks.<b>.linear_layers.<j>.weight  [n_blocks, 2, H, H] */
+    const float* lin_b;     /* blocks.<b>.linear_layers.<j>.bias    [n_blocks, 2, H] */
+    const float* final_w;   /* transform_net.final_layer.weight  [N (3 nb + 1), H] */
+    const float* final_b;   /* transform_net.final_layer.bias    [N (3 nb + 1)] */
+    const float* un_w;      /* unconditional_transform.unnormalized_widths      [N, nb] */
+    const float* un_h;      /* unconditional_transform.unnormalized_heights     [N, nb] */
+    const float* un_d;      /* unconditional_transform.unnormalized_derivatives [N, nb + 1] */
+} fs_layer_params;
+
+#define FS_PREC_FP32 0   /* CUDA-core FP32 conditioner (reference arithmetic) */
+#define FS_PREC_TF32 1   /* tcgen05 kind::tf32 conditioner, FP32 accumulate in TMEM */
+
+typedef struct fs_flow_desc {
+    int K;            /* number of coupling layers */
+    int N;            /* particles; D = 2 N features, N identity + N transformed */
+    int H;            /* hidden width of the residual conditioner */
+    int n_blocks;     /* residual blocks */
+    int nb;           /* spline bins (<= 32) */
+    double bound;     /* tail_bound = half box (the reference keeps it as a Python float) */
+    float bn_eps;     /* 1e-3 (nets/resnet.py:25) */
+    const int* identity_features;    /* host [N]  (prqct.identity_features) */
+    const int* transform_features;   /* host [N]  (prqct.transform_features) */
+    const fs_layer_params* layers;   /* host [K] */
+} fs_flow_desc;
+
+typedef struct fs_flow fs_flow;
+
+/* Packs a flow for inference: folds eval-mode BatchNorm, precomputes the
+ * unconditional spline knots, uploads weights (and, for the tensor path, lays
+ * them out as TMA-ready swizzled tiles).  Replaces nothing in the reference -
+ * it is the analogue of model.eval().to(device)
+ * (hybrid_NF_MCMC/main_algorithm_1.py:284,331). */
+int fs_flow_create(const fs_flow_desc* desc /*host*/, fs_flow** out);
+void fs_flow_destroy(fs_flow* flow);
+size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
+
+/* NormalizingFlow.inverse_and_log_det / log_prob  (NF/normflows/core.py:71-86,198-214):
+ * x [B, D] -> z [B, D], logdet [B]; x_in = x - in_shift (MC-box -> centred coords,
+ * MCMC/monte_carlo.py:251-258).  logq (nullable) = logdet + UniformParticle.log_prob(z)
+ * (NF/normflows/Energy/Uniform.py:50-74).  nan_flag (nullable) is set non-zero if a
+ * NaN was produced (the reference raises ValueError, utils/splines.py:176-183). */
+int fs_flow_inverse(fs_flow* flow, const float* x, int B, double in_shift,
+                    float* z, float* logdet, float* logq, int* nan_flag,
+                    void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* NormalizingFlow.forward_and_log_det / sample  (NF/normflows/core.py:28-56,178-196):
+ * z [B, D] -> x [B, D] (+ out_shift: centred -> MC-box coords), logdet [B] (nullable). */
+int fs_flow_forward(fs_flow* flow, const float* z, int B, double out_shift,
+                    float* x, float* logdet, int* nan_flag,
+                    void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWSTATE_B200_H */

@@ -302,6 +302,21 @@ def gen_global(ref):
     print("mc_global: %d traces" % len(names))
 
 
+def gen_init(ref):
+    """Fresh (unperturbed) reference flow for a fixed torch seed: pins parameter names,
+    shapes and the construction order of the random initialisation."""
+    NF = ref["normflows"]
+    torch.manual_seed(123)
+    with ref["quiet"]():
+        base = NF.Energy.UniformParticle(3, 2, 5.0, device="cpu")
+        layers = [NF.flows.CircularCoupledRationalQuadraticSpline(6, 2, 16, range(6), num_bins=8, tail_bound=5.0)
+                  for _ in range(2)]
+        model = NF.NormalizingFlow(base, layers)
+    out = {"sd__" + k: v.numpy() for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(GOLD, "flow_init_seed123.npz"), **out)
+    print("flow_init: %d tensors" % len(out))
+
+
 def main():
     ref = _refimport.load()
     os.makedirs(GOLD, exist_ok=True)
@@ -309,6 +324,7 @@ def main():
     gen_mc(ref)
     gen_flow(ref)
     gen_global(ref)
+    gen_init(ref)
 
 
 if __name__ == "__main__":

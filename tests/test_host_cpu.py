@@ -1,0 +1,184 @@
+"""CPU tests of the host side: C-ABI surface, module tree / state_dict parity with the
+reference, the train-mode autograd path against the golden vectors, fail-loud
+behaviour without a GPU, RNG state mirroring, and the world_size-2 sharding logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import flowstate_b200
+from flowstate_b200 import _lib
+import flowstate_b200.normflows as NF
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "flowstate_b200.h")).read()
+    declared = set(re.findall(r"\b(fs_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib().fs_version() >= 100
+
+
+def test_cabi_rejects_bad_arguments_without_gpu():
+    l = _lib.lib()
+    pot = _lib.make_pot(2, [-10, -10.5], 1.2, 15)
+    assert l.fs_energy_total(None, 1, 3, 10.0, 10.0, pot, None, None, None, None) == 1
+    assert b"fs_energy_total" in l.fs_last_error()
+    assert l.fs_local_sweep(None, None, None, None, None, None, 1, 3, 1, 10.0, 10.0, 1.0, pot, None, None, None,
+                            None, None) == 1
+    assert l.fs_flow_create(None, None) == 1
+
+
+def _sd(g, prefix="sd__"):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _build(n, K, blocks, H, nb, bound):
+    base = NF.Energy.UniformParticle(n, 2, bound)
+    layers = [NF.flows.CircularCoupledRationalQuadraticSpline(2 * n, blocks, H, range(2 * n), num_bins=nb,
+                                                              tail_bound=bound) for _ in range(K)]
+    return NF.NormalizingFlow(base, layers)
+
+
+def test_state_dict_matches_reference_names_and_seeded_init(golden_dir):
+    g = np.load(os.path.join(golden_dir, "flow_init_seed123.npz"))
+    ref = _sd(g)
+    torch.manual_seed(123)
+    model = _build(3, 2, 2, 16, 8, 5.0)
+    mine = model.state_dict()
+    assert list(mine.keys()) == list(ref.keys())
+    for k in ref:
+        assert mine[k].shape == ref[k].shape and mine[k].dtype == ref[k].dtype, k
+        assert torch.equal(mine[k], ref[k]), "seeded initialisation differs at %s" % k
+
+
+@pytest.mark.parametrize("tag", ["n3_k3", "n4_k4", "n32_k2"])
+def test_autograd_path_matches_reference(golden_dir, tag):
+    """Train-mode arithmetic (with BatchNorm modules left in eval so statistics match)."""
+    g = np.load(os.path.join(golden_dir, "flow_%s.npz" % tag))
+    model = _build(int(g["n"]), int(g["K"]), int(g["blocks"]), int(g["H"]), int(g["nb"]), float(g["bound"]))
+    model.load_state_dict(_sd(g))
+    model.eval()
+    for f in model.flows:
+        f.training = True            # coupling takes the autograd path, BN keeps running stats
+    model.training = True
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        z, ld = model.inverse_and_log_det(x)
+        xf, ldf = model.forward_and_log_det(torch.from_numpy(g["z0"]))
+    np.testing.assert_allclose(z.numpy(), g["inv_z"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ld.numpy(), g["inv_ld"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(xf.numpy(), g["fwd_x"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ldf.numpy(), g["fwd_ld"], rtol=1e-4, atol=1e-4)
+    # gradients flow to every learnable tensor that the reference trains
+    model.zero_grad()
+    loss = model.forward_kld(x[3:])
+    loss.backward()
+    missing = [n for n, p in model.named_parameters() if p.grad is None and "preprocessing.weights" not in n]
+    assert not missing, missing
+
+
+def test_eval_mode_fails_loudly_without_cuda():
+    model = _build(3, 2, 2, 16, 8, 5.0).eval()
+    x = torch.zeros(4, 6)
+    with pytest.raises(flowstate_b200.FlowStateError):
+        model.log_prob(x)
+    with pytest.raises(flowstate_b200.FlowStateError):
+        model.sample(2)
+    if not torch.cuda.is_available():
+        import flowstate_b200.MCMC as MC
+        with pytest.raises(flowstate_b200.FlowStateError):
+            MC.BatchedMonteCarlo(np.zeros((2, 3, 2), np.float32), MC.SimulationBox(10.0), 1.0, 3)
+        with pytest.raises(flowstate_b200.FlowStateError):
+            MC.SimulationBox(10.0).apply_pbc(np.array([1.0, 2.0]))
+
+
+def test_value_errors_match_reference_conventions():
+    layer = NF.flows.CircularCoupledRationalQuadraticSpline(6, 2, 16, range(6), num_bins=8, tail_bound=5.0)
+    with pytest.raises(ValueError):
+        layer.inverse(torch.zeros(6))
+    with pytest.raises(ValueError):
+        layer.forward(torch.zeros(2, 5))
+
+
+def test_pcg64_state_roundtrip():
+    from flowstate_b200.MCMC.batched import pcg64_set_state, pcg64_state_words
+    a = np.random.default_rng(42)
+    a.integers(7)                      # leaves a buffered 32-bit half behind
+    w = pcg64_state_words(a)
+    assert w[4] == 1
+    b = np.random.default_rng(0)
+    pcg64_set_state(b, w)
+    assert [a.integers(7), a.random(), a.integers(1000)] == [b.integers(7), b.random(), b.integers(1000)]
+
+
+def test_shard_range_covers_all_chains():
+    from flowstate_b200.parallel import shard_range
+    for total in (1, 7, 4096, 65536):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from flowstate_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)              # different weights per rank before the broadcast
+        model = _build(3, 2, 2, 16, 8, 5.0)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.01 * torch.randn_like(p))
+        parallel.broadcast_flow(model, src=0)
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same_weights = all(torch.equal(gathered[0], t) for t in gathered)
+        # data-parallel step: each rank a different half of one batch; averaged gradients must
+        # equal the single-process gradient of the mean loss over the whole batch (BN in eval)
+        model.eval()
+        for f in model.flows:
+            f.training = True
+        model.training = True
+        g = torch.Generator().manual_seed(7)
+        x = (torch.rand(8, 6, generator=g) * 2 - 1) * 5
+        model.zero_grad()
+        model.forward_kld(x).backward()
+        full = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+        model.zero_grad()
+        s, c = parallel.shard_range(8, rank, world)
+        model.forward_kld(x[s:s + c]).backward()
+        parallel.allreduce_gradients(model)
+        mine = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        att, acc = parallel.allreduce_counters(torch.tensor([3 + rank]), torch.tensor([1 + rank]))
+        ret[rank] = (same_weights, float((mine - full).abs().max()), float(full.abs().max()), att, acc)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_broadcast_and_gradient_allreduce():
+    import torch.multiprocessing as mp
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_gloo_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    for r in range(world):
+        same, err, scale, att, acc = res[r]
+        assert same
+        assert err <= 1e-5 * max(1.0, scale), (err, scale)
+        assert att == 7 and acc == 3
