@@ -42,6 +42,7 @@ _P = C.c_void_p
 _PROTOS = {
     "fs_last_error": (C.c_char_p, []),
     "fs_version": (C.c_int, []),
+    "fs_launch_count": (C.c_ulonglong, []),
     "fs_apply_pbc": (C.c_int, [_P, C.c_longlong, C.c_float, C.c_float, _P]),
     "fs_distances": (C.c_int, [_P, C.c_int, _P, C.c_longlong, C.c_float, C.c_float, _P, _P]),
     "fs_lj_pair": (C.c_int, [_P, C.c_longlong, C.POINTER(FsPot), _P, _P, _P]),

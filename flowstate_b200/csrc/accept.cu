@@ -106,5 +106,6 @@ extern "C" int fs_accept_global(float* pos, const float* prop, double* E, double
     else if (kind == FS_RNG_PHILOX) FS_LAUNCH(FS_RNG_PHILOX);
     else FS_LAUNCH(FS_RNG_REPLAY);
 #undef FS_LAUNCH
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "accept_global_kernel");
 }

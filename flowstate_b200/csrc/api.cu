@@ -20,5 +20,11 @@ int cuda_check(cudaError_t e, const char* what) {
 }
 }  // namespace fs
 
+namespace fs {
+static unsigned long long g_launches = 0;   // single host thread per process
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+}  // namespace fs
+
+extern "C" unsigned long long fs_launch_count(void) { return fs::g_launches; }
 extern "C" const char* fs_last_error(void) { return fs::g_err; }
 extern "C" int fs_version(void) { return 100; }

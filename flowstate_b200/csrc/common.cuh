@@ -11,6 +11,7 @@ namespace fs {
 
 void set_error(const char* fmt, ...);
 int cuda_check(cudaError_t e, const char* what);
+void count_launch(int n = 1);
 #define FS_CUDA(x)                                       \
     do {                                                 \
         int _r = fs::cuda_check((x), #x);                \

@@ -153,6 +153,7 @@ static int launch_total(const float* pos, int B, int N, const PotDev& P, float* 
         FS_CUDA(cudaFuncSetAttribute(energy_total_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (B + GROUPS - 1) / GROUPS;
     energy_total_kernel<G><<<grid, 256, smem, s>>>(pos, B, N, P, E, W, ov);
+    fs::count_launch();
     return cuda_check(cudaGetLastError(), "energy_total_kernel");
 }
 
@@ -189,5 +190,6 @@ extern "C" int fs_energy_particle(const float* pos, const int* idx, const float*
     fs::PotDev P = fs::make_pot(pot, Lx, Ly);
     int grid = (B + 7) / 8;
     fs::energy_particle_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pos, idx, new_xy, B, N, P, e, w, overlap);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "energy_particle_kernel");
 }

@@ -359,6 +359,7 @@ static int linear(const float* A, const float* W, const float* bias, const float
                   int M, int Nout, int K, cudaStream_t s) {
     dim3 grid((Nout + 63) / 64, (M + 63) / 64);
     linear_kernel<PRO, EPI><<<grid, 256, 0, s>>>(A, W, bias, ps, po, C, M, Nout, K);
+    fs::count_launch();
     return cuda_check(cudaGetLastError(), "linear_kernel");
 }
 
@@ -609,6 +610,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         const int rows = (B - r0 < Bc) ? B - r0 : Bc;
         const size_t n = (size_t)rows * f->D;
         shift_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x + (size_t)r0 * f->D, w.v0, n, -in_shift);
+    fs::count_launch();
         FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
         float* cur = w.v0;
         float* nxt = w.v1;
@@ -616,14 +618,17 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             const fs_flow::Layer& L = f->layers[li];
             const size_t ne = (size_t)rows * f->N;
             prep_inverse_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(cur, w.A0, rows, F);
+    fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
             spline_inverse_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, L.u_x, L.u_y,
                                                                  L.u_d, nan_flag);
+    fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, z ? z + (size_t)r0 * f->D : nullptr, w.ld,
                                                      logdet ? logdet + r0 : nullptr, logq ? logq + r0 : nullptr,
                                                      rows, f->D, f->bound_f, f->base_logc, 0.0);
+    fs::count_launch();
         FS_CUDA(cudaGetLastError());
     }
     return FS_OK;
@@ -651,13 +656,16 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
             const fs_flow::Layer& L = f->layers[li];
             prep_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d,
                                                                nan_flag);
+    fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
             spline_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+    fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, x + (size_t)r0 * f->D, w.ld,
                                                      logdet ? logdet + r0 : nullptr, nullptr, rows, f->D,
                                                      f->bound_f, f->base_logc, out_shift);
+    fs::count_launch();
         FS_CUDA(cudaGetLastError());
     }
     return FS_OK;

@@ -54,6 +54,7 @@ extern "C" int fs_apply_pbc(float* pos, long long n, float Lx, float Ly, void* s
     if (!pos || n < 0 || !(Lx > 0) || !(Ly > 0)) { fs::set_error("fs_apply_pbc: invalid argument"); return FS_ERR_INVALID; }
     if (n == 0) return FS_OK;
     fs::apply_pbc_kernel<<<FS_GRID(n)>>>(pos, (size_t)n, Lx, Ly);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "apply_pbc_kernel");
 }
 
@@ -64,6 +65,7 @@ extern "C" int fs_distances(const float* p1, int p1_is_single, const float* p2, 
     fs_pot pot = {0, {0, 0}, 1, 1, 2.5f, 0.5f};
     fs::PotDev P = fs::make_pot(&pot, Lx, Ly);
     fs::distances_kernel<<<FS_GRID(n)>>>(p1, p1_is_single ? 0 : 2, p2, (size_t)n, P, r);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "distances_kernel");
 }
 
@@ -72,6 +74,7 @@ extern "C" int fs_lj_pair(const float* r, long long n, const fs_pot* pot, float*
     if (n == 0) return FS_OK;
     fs::PotDev P = fs::make_pot(pot, 1.f, 1.f);
     fs::lj_pair_kernel<<<FS_GRID(n)>>>(r, (size_t)n, P, e, w);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "lj_pair_kernel");
 }
 
@@ -81,5 +84,6 @@ extern "C" int fs_double_well(const float* pos, long long n, float Lx, float Ly,
     if (n == 0) return FS_OK;
     fs::PotDev P = fs::make_pot(pot, Lx, Ly);
     fs::double_well_kernel<<<FS_GRID(n)>>>(pos, (size_t)n, P, v);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "double_well_kernel");
 }

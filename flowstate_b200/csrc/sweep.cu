@@ -220,6 +220,7 @@ static int launch_sweep(float* pos, double* E, double* W, const double* md, long
         FS_CUDA(cudaFuncSetAttribute(local_sweep_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (B + wpc - 1) / wpc;
     local_sweep_kernel<KIND><<<grid, wpc * 32, smem, s>>>(pos, E, W, md, att, acc, B, N, steps, P, beta, R, ta, ti, te);
+    fs::count_launch();
     return cuda_check(cudaGetLastError(), "local_sweep_kernel");
 }
 
@@ -265,5 +266,6 @@ extern "C" int fs_adjust_displacement(double* max_disp, const long long* attempt
     if (B == 0) return FS_OK;
     fs::adjust_displacement_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         max_disp, attempts, accepted, prev_attempts, prev_accepted, target, B);
+    fs::count_launch();
     return fs::cuda_check(cudaGetLastError(), "adjust_displacement_kernel");
 }

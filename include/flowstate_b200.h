@@ -72,6 +72,8 @@ typedef struct fs_rng {
 
 const char* fs_last_error(void);
 int fs_version(void);
+/* kernels launched by this library in this process so far (bench bookkeeping) */
+unsigned long long fs_launch_count(void);
 
 /* Element-wise helpers behind the reference's small public functions:
  *   SimulationBox.apply_pbc (MCMC/simulation_box.py:19-29): pos [n,2] wrapped in place (numpy floor-mod);

@@ -1,0 +1,156 @@
+"""GPU parity: spline-coupling flow kernels against reference-generated golden vectors
+and the oracle.  Tolerance: log-probabilities within 1e-4 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flow_ref as fr
+
+TAGS = ["n3_k3", "n4_k4", "n32_k2", "n4_k23"]
+
+
+def _sd(g, prefix="sd__"):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _build(n, K, blocks, H, nb, bound, device="cuda"):
+    import flowstate_b200.normflows as NF
+    base = NF.Energy.UniformParticle(n, 2, bound, device=device)
+    layers = [NF.flows.CircularCoupledRationalQuadraticSpline(2 * n, blocks, H, range(2 * n), num_bins=nb,
+                                                              tail_bound=bound) for _ in range(K)]
+    return NF.NormalizingFlow(base, layers)
+
+
+def _load(g):
+    m = _build(int(g["n"]), int(g["K"]), int(g["blocks"]), int(g["H"]), int(g["nb"]), float(g["bound"]))
+    m.load_state_dict(_sd(g))
+    return m.cuda().eval()
+
+
+def _precisions(model):
+    out = ["fp32"]
+    try:
+        model.precision = "tf32"
+        model.log_prob(torch.zeros(1, 2 * model.q0.n_particles, device="cuda"))
+        out.append("tf32")
+    except Exception:
+        pass
+    model.precision = "fp32"
+    return out
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_golden_flow(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "flow_%s.npz" % tag))
+    model = _load(g)
+    x = torch.from_numpy(g["x"]).cuda()
+    z0 = torch.from_numpy(g["z0"]).cuda()
+    bound = float(g["bound"])
+    for prec in _precisions(model):
+        model.precision = prec
+        tol = 1e-4
+        lp = model.log_prob(x).cpu().numpy()
+        ref = g["log_prob"]
+        assert np.array_equal(np.isinf(lp), np.isinf(ref)), prec
+        fin = np.isfinite(ref)
+        rel = np.abs(lp[fin] - ref[fin]) / np.abs(ref[fin])
+        assert rel.max() < tol, (tag, prec, rel.max())
+        z, ld = model.inverse_and_log_det(x)
+        np.testing.assert_allclose(z.cpu().numpy(), g["inv_z"], rtol=0, atol=2e-4 * bound)
+        np.testing.assert_allclose(ld.cpu().numpy(), g["inv_ld"], rtol=1e-4, atol=2e-3)
+        xf, ldf = model.forward_and_log_det(z0)
+        np.testing.assert_allclose(xf.cpu().numpy(), g["fwd_x"], rtol=0, atol=2e-4 * bound)
+        np.testing.assert_allclose(ldf.cpu().numpy(), g["fwd_ld"], rtol=1e-4, atol=2e-3)
+        assert torch.equal(model.forward(z0), xf) and torch.equal(model.inverse(x), z)
+        # round trip (the reference's own test property, flows/flow_test.py:40-48)
+        ok = (x.abs() <= bound).all(dim=1)
+        xr, ldr = model.forward_and_log_det(z)
+        assert (xr[ok] - x[ok]).abs().max().item() < 2e-3 * bound
+        assert (ldr + ld)[ok].abs().max().item() < 5e-3
+    model.precision = "fp32"
+    # single layer through the nn.Module interface of the layer itself
+    y, ldl = model.flows[int(g["K"]) - 1].inverse(x)
+    np.testing.assert_allclose(y.cpu().numpy(), g["lastlayer_inv"], rtol=0, atol=2e-5 * bound)
+    np.testing.assert_allclose(ldl.cpu().numpy(), g["lastlayer_ld"], rtol=1e-4, atol=1e-4)
+    yb, ldb = model.flows[int(g["K"]) - 1].forward(y)
+    assert (yb[ok] - x[ok]).abs().max().item() < 1e-3 * bound
+
+
+def test_against_oracle_alg_shapes():
+    """Wider random flows (Alg-1 style bins, Alg-2 style width) against the float64 oracle,
+    with the FP32-vs-FP64 self error of the reference arithmetic reported beside it."""
+    torch.manual_seed(0)
+    for (n, K, blocks, H, nb, sigma, B) in [(32, 3, 4, 128, 32, 0.02, 96), (16, 5, 2, 128, 15, 0.05, 64),
+                                            (5, 4, 2, 64, 8, 0.05, 33)]:
+        bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+        model = _build(n, K, blocks, H, nb, bound, device="cuda")
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(sigma * torch.randn(p.shape, generator=g))
+            for name, buf in model.named_buffers():
+                if name.endswith("running_mean"):
+                    buf.copy_(0.1 * torch.randn(buf.shape, generator=g))
+                elif name.endswith("running_var"):
+                    buf.copy_(0.5 + torch.rand(buf.shape, generator=g))
+        model = model.cuda().eval()
+        sd = {k: v.cpu() for k, v in model.state_dict().items()}
+        spec = fr.FlowSpec(sd, bound)
+        x = (torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound
+        with torch.no_grad():
+            truth = fr.log_prob(sd, spec, x.double(), dtype=torch.float64).numpy()
+            ref32 = fr.log_prob(sd, spec, x, dtype=torch.float32).numpy()
+        self_err = np.max(np.abs(ref32 - truth) / np.abs(truth))
+        for prec in _precisions(model):
+            model.precision = prec
+            got = model.log_prob(x.cuda()).cpu().numpy()
+            err = np.max(np.abs(got - truth) / np.abs(truth))
+            print("N=%d K=%d H=%d %s: kernel err %.2e, reference-fp32 self err %.2e" % (n, K, H, prec, err, self_err))
+            assert err < 1e-4, (n, prec, err, self_err)
+        model.precision = "fp32"
+        z = model.q0(B)
+        xs = model.forward(z)
+        with torch.no_grad():
+            xo, _ = fr.forward_and_log_det(sd, spec, z.cpu().double(), dtype=torch.float64)
+        assert (xs.cpu().double() - xo).abs().max().item() < 2e-4 * bound
+
+
+def test_sample_and_base_distribution():
+    g = torch.Generator().manual_seed(0)
+    model = _build(4, 2, 2, 32, 8, 5.0, device="cuda").cuda().eval()
+    torch.manual_seed(3)
+    s = model.sample(1000)
+    assert s.shape == (1000, 8) and s.is_cuda and s.dtype == torch.float32
+    # identity-initialised flow = identity map with log-det 0 (wrapper.py:181-185)
+    torch.manual_seed(3)
+    assert torch.allclose(s, model.q0(1000), atol=1e-5)
+    lp = model.log_prob(s)
+    assert torch.allclose(lp, torch.full_like(lp, -8 * np.log(10.0)), atol=1e-4)
+    out = s.clone()
+    out[0, 0] = 5.5
+    assert model.log_prob(out)[0].item() == -float("inf")
+    del g
+
+
+def test_pack_follows_parameter_updates():
+    model = _build(3, 2, 2, 16, 8, 5.0, device="cuda").cuda().eval()
+    x = (torch.rand(8, 6, device="cuda") * 2 - 1) * 5
+    a = model.log_prob(x)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    b = model.log_prob(x)
+    assert not torch.allclose(a, b)
+    model.train()
+    with torch.no_grad():
+        ref = model.log_prob(x[:8])           # autograd path, BN batch statistics
+    assert ref.shape == (8,)
+    model.eval()
+    c = model.log_prob(x)
+    assert torch.isfinite(c).all()
+    with pytest.raises(ValueError):
+        model.log_prob(torch.zeros(4, 5, device="cuda"))

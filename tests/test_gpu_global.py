@@ -1,0 +1,163 @@
+"""GPU parity: NF-proposed global moves (flow log-densities + total energy + fused accept)
+against reference nf_big_move traces, and the accept kernel against its formula."""
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import energy_ref as er
+from oracle import flow_ref as fr
+
+POT = er.Potential(2, [-10.0, -10.5], 1.2, 15.0)
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _model(sd, n, bound):
+    import flowstate_b200.normflows as NF
+    spec = fr.FlowSpec(sd, bound)
+    base = NF.Energy.UniformParticle(n, 2, bound, device="cuda")
+    layers = [NF.flows.CircularCoupledRationalQuadraticSpline(2 * n, spec.n_blocks, spec.H, range(2 * n),
+                                                              num_bins=spec.nb, tail_bound=bound)
+              for _ in range(spec.K)]
+    m = NF.NormalizingFlow(base, layers)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), spec
+
+
+def test_golden_global_traces(golden_dir):
+    """Replays hybrid runs (25 local steps + 1 global move, 12 rounds) through the drop-in
+    MonteCarlo with the reference's seeds.  The reference state is float64 until its first
+    NF acceptance, the device state float32, so decisions are required to match only while
+    the two trajectories have consumed identical random numbers and sit outside the
+    epsilon band; each compared round checks the old total energy and the decision."""
+    import flowstate_b200.MCMC as MC
+    g = np.load(os.path.join(golden_dir, "mc_global.npz"))
+    lg = logging.getLogger("fs_quiet")
+    lg.setLevel(logging.CRITICAL)
+    compared = 0
+    for key in g["names"]:
+        tag = key.split("_")[0]
+        sd = _sd(g, tag + "__sd__")
+        bound, L = float(g[tag + "__bound"]), float(g[tag + "__L"])
+        n = g[key + "__pos0"].shape[0]
+        model, spec = _model(sd, n, bound)
+        mc = MC.MonteCarlo(g[key + "__pos0"], MC.SimulationBox(L), 1.0, n, num_wells=2, V0_list=[-10.0, -10.5],
+                           r0=1.2, k=15, initial_max_displacement=0.65, logger=lg, seed=int(g[key + "__seed"]))
+        mc.set_nf_model(model)
+        for r in range(int(g[key + "__rounds"])):
+            for _ in range(int(g[key + "__local"])):
+                mc.particle_displacement()
+            ref_pos = g[key + "__pos_before"][r]
+            if np.abs(mc.particles.astype(np.float64) - ref_pos).max() > 1e-4:
+                break                      # an in-band local decision diverged; stop comparing this chain
+            eno = mc.energy_calculator.total_energy
+            assert abs(eno - float(g[key + "__eno"][r])) <= 2e-5 * max(1.0, abs(float(g[key + "__eno"][r])))
+            cfg = g[key + "__props"][r]
+            # decision margin from the oracle, to know whether this round is inside the band
+            with torch.no_grad():
+                lo = fr.log_prob(sd, spec, torch.tensor((ref_pos - L / 2).reshape(1, -1), dtype=torch.float)).item()
+                ln = fr.log_prob(sd, spec, torch.tensor((cfg.astype(np.float64) - L / 2).reshape(1, -1),
+                                                        dtype=torch.float)).item()
+            enn, _ = er.total_energy_virial(cfg, L, L, POT)
+            acc = mc.nf_big_move(cfg)
+            ref_acc = bool(g[key + "__acc"][r])
+            if acc != ref_acc:
+                delta = -(enn - float(g[key + "__eno"][r])) - ((-ln) - (-lo))
+                eps = 1e-5 * (abs(enn) + abs(eno)) + 1e-4 * (abs(lo) + abs(ln))
+                assert np.isfinite(delta) and abs(delta) < 50 * eps + 1.0, (key, r, delta, eps)
+                break
+            compared += 1
+            assert mc.attempts_displacement == (r + 1) * (int(g[key + "__local"]) + 1)
+    assert compared >= 20
+
+
+def test_accept_kernel_formula():
+    import flowstate_b200._lib as lib
+    B, n = 512, 8
+    rs = np.random.default_rng(0)
+    pos = rs.random((B, n, 2)).astype(np.float32)
+    prop = rs.random((B, n, 2)).astype(np.float32) + 1
+    E = rs.normal(-20, 5, B)
+    W = rs.normal(0, 5, B)
+    E_new = (E + rs.normal(0, 2, B)).astype(np.float32)
+    W_new = rs.normal(0, 5, B).astype(np.float32)
+    lq_old = rs.normal(-30, 3, B).astype(np.float32)
+    lq_new = rs.normal(-30, 3, B).astype(np.float32)
+    E_new[:8] = np.inf                  # overlapping proposals: always rejected, uniform still consumed
+    lq_new[8:12] = -np.inf              # proposal outside the box
+    u = rs.random(B)
+    beta = 1.0 / 0.7
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tpos, tprop, tE, tW = d(pos), d(prop), d(E), d(W)
+    att = torch.full((B,), 10, dtype=torch.int64, device="cuda")
+    acc = torch.full((B,), 4, dtype=torch.int64, device="cuda")
+    mask = torch.empty(B, dtype=torch.uint8, device="cuda")
+    lib.check(lib.lib().fs_accept_global(lib.ptr(tpos), lib.ptr(tprop), lib.ptr(tE), lib.ptr(tW), lib.ptr(d(E_new)),
+                                         lib.ptr(d(W_new)), lib.ptr(d(lq_old)), lib.ptr(d(lq_new)), lib.ptr(d(u)),
+                                         None, beta, lib.ptr(att), lib.ptr(acc), lib.ptr(mask), B, n,
+                                         lib.stream_ptr()))
+    with np.errstate(all="ignore"):
+        ratio_log = -beta * (E_new.astype(np.float64) - E) - ((-lq_new.astype(np.float64)) - (-lq_old.astype(np.float64)))
+        ratio = np.exp(ratio_log)
+        ref = (ratio >= 1.0) | (u < ratio)
+    got = mask.cpu().numpy().astype(bool)
+    assert np.array_equal(got, ref)
+    assert not got[:12].any() and 0.2 < got.mean() < 0.8
+    assert torch.equal(att.cpu(), torch.full((B,), 11, dtype=torch.int64))
+    assert np.array_equal(acc.cpu().numpy(), 4 + ref.astype(np.int64))
+    out = tpos.cpu().numpy()
+    assert np.array_equal(out[ref], prop[ref]) and np.array_equal(out[~ref], pos[~ref])
+    assert np.array_equal(tE.cpu().numpy()[ref], E_new.astype(np.float64)[ref])
+    assert np.array_equal(tE.cpu().numpy()[~ref], E[~ref])
+    assert np.array_equal(tW.cpu().numpy()[ref], W_new.astype(np.float64)[ref])
+
+
+def test_batched_global_move_equals_single_chain_facade(golden_dir):
+    import flowstate_b200.MCMC as MC
+    g = np.load(os.path.join(golden_dir, "mc_global.npz"))
+    tag = "n8"
+    sd = _sd(g, tag + "__sd__")
+    bound, L = float(g[tag + "__bound"]), float(g[tag + "__L"])
+    model, spec = _model(sd, 8, bound)
+    B = 16
+    pos, _ = er.batch_lattices(B, 8, 0.03, seed0=50)
+    seeds = list(range(100, 100 + B))
+    kw = dict(num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15, initial_max_displacement=0.65)
+    eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, 8, seeds=seeds, **kw)
+    eng.set_nf_model(model)
+    torch.manual_seed(9)
+    masks = []
+    props = []
+    for r in range(4):
+        eng.particle_displacement(20)
+        z = model.sample(B)
+        cfg = (z.reshape(B, 8, 2) + np.float32(L / 2)).contiguous()
+        if r % 2:
+            cfg = ((eng.pos + 0.003 * (r + 1)) % np.float32(L)).contiguous()     # near-identity proposals get accepted
+        props.append(cfg.cpu().numpy())
+        masks.append(eng.nf_big_move(cfg).cpu().numpy())
+    masks = np.stack(masks)
+    assert masks.sum() > 0
+    lg = logging.getLogger("fs_quiet")
+    lg.setLevel(logging.CRITICAL)
+    for b in (0, 5, 15):
+        mc = MC.MonteCarlo(pos[b], MC.SimulationBox(L), 1.0, 8, logger=lg, seed=seeds[b], **kw)
+        mc.set_nf_model(model)
+        for r in range(4):
+            for _ in range(20):
+                mc.particle_displacement()
+            assert mc.nf_big_move(props[r][b]) == bool(masks[r, b])
+        np.testing.assert_array_equal(mc.particles, eng.pos[b].cpu().numpy())
+        assert mc.accepted_displacement == int(eng.accepted[b].item())
+        assert mc.energy_calculator.total_energy == eng.E[b].item()
+    # sample() observables follow monte_carlo.py:416-444
+    cyc, e_per_n, rho, P, lx, ly, parts = eng.sample(7)
+    assert cyc == 7 and rho == pytest.approx(8 / (L * L)) and parts.shape == (B, 8, 2)
+    torch.testing.assert_close(P, rho / 1.0 + eng.W / (2 * L * L))

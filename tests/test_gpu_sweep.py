@@ -1,0 +1,191 @@
+"""GPU parity: local-displacement Metropolis sweep against reference traces.
+
+Decisions must match exactly except inside the stated epsilon-band of the
+acceptance threshold: |log u - Delta_ref| <= beta * tol_E * (|e_old| + |e_new|)
+with tol_E = 1e-5.  Counters and the adapted max displacement are
+compared only when every decision of the run was outside the band."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import energy_ref as er
+from oracle import mc_ref as mr
+
+POT = er.Potential(2, [-10.0, -10.5], 1.2, 15.0)
+TOL_E = 1e-5
+
+
+def _engine(pos, L, md, seeds=None, rng="pcg64", **kw):
+    import flowstate_b200.MCMC as MC
+    return MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, pos.shape[1], num_wells=2, V0_list=[-10.0, -10.5],
+                                r0=1.2, k=15, initial_max_displacement=md, seeds=seeds, rng=rng, **kw)
+
+
+def _band_mask(g, key, steps):
+    """True where the reference decision sits inside the epsilon band (may legitimately differ)."""
+    eno, enn = g[key + "__eno"], g[key + "__enn"]
+    u_all = g[key + "__u"]
+    inband = np.zeros(steps, bool)
+    cu = 0
+    for s in range(steps):
+        cu += 2
+        if enn[s] > eno[s] and np.isfinite(enn[s]):
+            u = u_all[cu]
+            cu += 1
+            delta = -(enn[s] - eno[s])
+            eps = TOL_E * (abs(eno[s]) + abs(enn[s]))
+            if abs(np.log(u) - delta) <= eps:
+                inband[s] = True
+        elif abs(enn[s] - eno[s]) <= TOL_E * (abs(eno[s]) + abs(enn[s])):
+            inband[s] = True          # downhill/uphill classification itself is within tolerance
+    return inband
+
+
+@pytest.mark.parametrize("tag", ["n3", "n32", "n64", "n256"])
+def test_golden_traces_pcg64(golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "mc_local.npz"))
+    keys = [k for k in g["names"] if k.startswith(tag + "_f32_")]
+    assert keys
+    pos0 = np.stack([g[k + "__pos0"] for k in keys])
+    L = float(g[keys[0] + "__L"])
+    steps = int(g[keys[0] + "__steps"])
+    md = float(g[keys[0] + "__md0"])
+    seeds = [int(g[k + "__seed"]) for k in keys]
+    eng = _engine(pos0, L, md, seeds=seeds)
+    half = steps // 2
+    t1 = eng.particle_displacement(half, trace=True)
+    eng.adjust_displacement()
+    md_mid = eng.max_disp.cpu().numpy().copy()
+    t2 = eng.particle_displacement(steps - half, trace=True)
+    eng.adjust_displacement()
+    acc = torch.cat([t1["accept"], t2["accept"]], 1).cpu().numpy()
+    idx = torch.cat([t1["idx"], t2["idx"]], 1).cpu().numpy()
+    e = torch.cat([t1["e"], t2["e"]], 1).cpu().numpy().astype(np.float64)
+    for c, key in enumerate(keys):
+        ref_acc = g[key + "__acc"]
+        band = _band_mask(g, key, steps)
+        diff = np.nonzero(acc[c] != ref_acc)[0]
+        first_div = diff[0] if len(diff) else steps
+        # up to the first differing decision the two runs consumed identical random numbers
+        np.testing.assert_array_equal(idx[c, :first_div + 1], g[key + "__idx"][:first_div + 1])
+        for name, col in (("eno", 0), ("enn", 1)):
+            ref = g[key + "__" + name][:first_div + 1]
+            got = e[c, :first_div + 1, col]
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isinf(got), ~fin), (key, name)
+            rel = np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))
+            assert rel.max() < TOL_E, (key, name, rel.max())
+        if len(diff):
+            assert band[first_div], "decision %d of %s differs outside the epsilon band" % (first_div, key)
+            continue
+        # every decision matched: state, counters and adaptation must agree
+        np.testing.assert_array_equal(eng.pos[c].cpu().numpy(), g[key + "__posF"].astype(np.float32))
+        assert int(eng.attempts[c].item()) == int(g[key + "__attempts"])
+        assert int(eng.accepted[c].item()) == int(g[key + "__accepted"])
+        assert md_mid[c] == pytest.approx(float(g[key + "__md_mid"]), rel=1e-15)
+        assert float(eng.max_disp[c].item()) == pytest.approx(float(g[key + "__mdF"]), rel=1e-15)
+        assert abs(eng.E[c].item() - float(g[key + "__EF"])) <= 2e-5 * max(1.0, abs(float(g[key + "__EF"])))
+        assert abs(eng.W[c].item() - float(g[key + "__WF"])) <= 2e-5 * max(1.0, abs(float(g[key + "__WF"])))
+
+
+def test_replay_equals_pcg64(golden_dir):
+    g = np.load(os.path.join(golden_dir, "mc_local.npz"))
+    key = "n32_f32_s42"
+    pos0 = g[key + "__pos0"][None]
+    L, steps, md = float(g[key + "__L"]), int(g[key + "__steps"]), float(g[key + "__md0"])
+    a = _engine(pos0, L, md, seeds=[42])
+    ta = a.particle_displacement(steps, trace=True)
+    b = _engine(pos0, L, md, seeds=[0])
+    idx = torch.from_numpy(g[key + "__idx"].astype(np.int32))[None].cuda().contiguous()
+    u = torch.from_numpy(np.concatenate([g[key + "__u"], np.zeros(8)]))[None].cuda().contiguous()
+    cursor = torch.zeros(1, 2, dtype=torch.int32, device="cuda")
+    tb = b.particle_displacement(steps, trace=True, replay=(idx, u, cursor))
+    if torch.equal(ta["accept"], torch.from_numpy(g[key + "__acc"])[None].cuda()):
+        assert torch.equal(ta["accept"], tb["accept"]) and torch.equal(a.pos, b.pos)
+        assert int(cursor[0, 0].item()) == steps and int(cursor[0, 1].item()) == len(g[key + "__u"])
+    # single-chain facade: same stream through the numpy Generator mirror
+    import flowstate_b200.MCMC as MC
+    mc = MC.MonteCarlo(g[key + "__pos0"], MC.SimulationBox(L), 1.0, 32, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2,
+                       k=15, initial_max_displacement=md, logger=_quiet(), seed=42)
+    for _ in range(40):
+        mc.particle_displacement()
+    assert mc.attempts_displacement == 40
+    assert mc.accepted_displacement == int(ta["accept"][0, :40].sum().item())
+    ref = np.random.default_rng(42)
+    chk = _engine(pos0, L, md, seeds=[42])
+    chk.particle_displacement(40)
+    np.testing.assert_array_equal(mc.particles, chk.pos[0].cpu().numpy())
+    # host generator continues exactly where the device left off
+    from flowstate_b200.MCMC.batched import pcg64_state_words
+    assert pcg64_state_words(mc.rng) == [int(x) for x in chk.pcg_state.cpu().numpy().view(np.uint64)[0]]
+    del ref
+
+
+def _quiet():
+    import logging
+    lg = logging.getLogger("fs_quiet")
+    lg.setLevel(logging.CRITICAL)
+    return lg
+
+
+def test_philox_is_invariant_to_launch_split_and_sharding():
+    n, B = 32, 64
+    pos, L = er.batch_lattices(B, n, 0.5, seed0=3)
+    a = _engine(pos, L, 0.5, rng="philox", philox_seed=1234)
+    a.particle_displacement(200)
+    b = _engine(pos, L, 0.5, rng="philox", philox_seed=1234)
+    b.particle_displacement(77)
+    b.particle_displacement(123)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.accepted, b.accepted) and torch.equal(a.E, b.E)
+    lo = _engine(pos[:40], L, 0.5, rng="philox", philox_seed=1234, chain_id0=0)
+    hi = _engine(pos[40:], L, 0.5, rng="philox", philox_seed=1234, chain_id0=40)
+    lo.particle_displacement(200)
+    hi.particle_displacement(200)
+    assert torch.equal(torch.cat([lo.pos, hi.pos]), a.pos)
+    c = _engine(pos, L, 0.5, rng="philox", philox_seed=99)
+    c.particle_displacement(200)
+    assert not torch.equal(c.pos, a.pos)
+    frac = a.accepted.double().mean().item() / 200
+    assert 0.05 < frac < 0.95
+
+
+@pytest.mark.parametrize("n,rho,steps", [(32, 0.5, 2000), (256, 0.5, 500), (1000, 0.5, 100)])
+def test_incremental_energy_tracks_recomputed_total(n, rho, steps):
+    B = 32
+    pos, L = er.batch_lattices(B, n, rho, seed0=11)
+    eng = _engine(pos, L, 0.3, rng="philox", philox_seed=5)
+    eng.particle_displacement(steps)
+    E_inc, W_inc = eng.E.clone(), eng.W.clone()
+    eng.refresh_energy()
+    assert ((E_inc - eng.E).abs() / eng.E.abs().clamp(min=1)).max().item() < 1e-5
+    assert ((W_inc - eng.W).abs() / eng.W.abs().clamp(min=1)).max().item() < 1e-5
+    # positions stay inside the box and no pair sits inside the hard core
+    p = eng.pos
+    assert (p >= 0).all() and (p <= L).all()
+    _, _, ov = eng.total_energy_virial()
+    assert int(ov.sum().item()) == 0
+    # oracle check of one chain's final state
+    Er, Wr = er.total_energy_virial(p[0].cpu().numpy().astype(np.float64), L, L, POT)
+    assert abs(eng.E[0].item() - Er) / max(1, abs(Er)) < 1e-5
+
+
+def test_adjust_displacement_matches_oracle_rule():
+    B = 5
+    pos, L = er.batch_lattices(B, 32, 0.5, seed0=2)
+    eng = _engine(pos, L, 0.65, rng="philox")
+    att = torch.tensor([100, 100, 100, 0, 10], dtype=torch.int64, device="cuda")
+    acc = torch.tensor([50, 5, 99, 0, 6], dtype=torch.int64, device="cuda")
+    eng.attempts.copy_(att)
+    eng.accepted.copy_(acc)
+    eng.adjust_displacement()
+    got = eng.max_disp.cpu().numpy()
+    for b in range(B):
+        ch = mr.ChainRef(pos[b].astype(np.float64), L, 1.0, POT, 0.65)
+        ch.attempts, ch.accepted = int(att[b]), int(acc[b])
+        ch.adjust_displacement()
+        assert got[b] == ch.max_displacement
+    assert torch.equal(eng.prev_attempts.cpu(), torch.tensor([100, 100, 100, 0, 10]))
