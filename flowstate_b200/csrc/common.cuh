@@ -25,7 +25,9 @@ struct PotDev {
     float r0, k;
     float rc2, rcore2, e_cut;
     float Lx, Ly, inv_Lx, inv_Ly;
-    float cx[2], cy;      // well centres (L/4, L/2), (3L/4, L/2): potential.py:89-93
+    // wells: geometry in float64 (the wall k (r - r0) is steep: k = 15 turns a float32 rounding of
+    // r, r0 or the centre into > 1e-5 of energy), potential.py:89-112
+    double cxd[2], cyd, Lxd, Lyd, r0d, k2d;
 };
 
 inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
@@ -43,9 +45,13 @@ inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
     d.Ly = Ly;
     d.inv_Lx = 1.0f / Lx;
     d.inv_Ly = 1.0f / Ly;
-    d.cx[0] = Lx / 4;
-    d.cx[1] = 3 * Lx / 4;
-    d.cy = Ly / 2;
+    d.Lxd = (double)Lx;
+    d.Lyd = (double)Ly;
+    d.cxd[0] = d.Lxd / 4;
+    d.cxd[1] = 3 * d.Lxd / 4;
+    d.cyd = d.Lyd / 2;
+    d.r0d = (double)p->r0;
+    d.k2d = 2.0 * (double)p->k;
     return d;
 }
 
@@ -77,12 +83,18 @@ __device__ __forceinline__ void pair_accum(float dx, float dy, const PotDev& P,
 }
 
 // External double well of one particle (potential.py:95-112).
-// V0 (1 - 0.5 (1 + tanh a)) == V0 / (1 + exp(2a)), evaluated in the stable form.
+// V0 (1 - 0.5 (1 + tanh a)) == V0 / (1 + exp(2a)), evaluated in the stable form; the distance
+// to the well centre is formed in float64 (float32 seed + one Newton step for the root).
 __device__ __forceinline__ float well_term(float x, float y, int wi, const PotDev& P) {
-    float dx = min_image(x - P.cx[wi], P.Lx, P.inv_Lx);
-    float dy = min_image(y - P.cy, P.Ly, P.inv_Ly);
-    float r = sqrtf(__fmaf_rn(dy, dy, dx * dx));
-    float a2 = 2.0f * P.k * (r - P.r0);
+    double dx = (double)x - P.cxd[wi];
+    double dy = (double)y - P.cyd;
+    dx -= P.Lxd * rint(dx / P.Lxd);
+    dy -= P.Lyd * rint(dy / P.Lyd);
+    const double r2 = dx * dx + dy * dy;
+    const float rf = sqrtf((float)r2);
+    double r = 0.0;
+    if (rf > 0.0f) r = (double)rf + (r2 - (double)rf * (double)rf) * (double)(0.5f / rf);
+    const float a2 = (float)(P.k2d * (r - P.r0d));
     return P.V0[wi] / (1.0f + expf(a2));
 }
 

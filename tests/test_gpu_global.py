@@ -96,11 +96,12 @@ def test_accept_kernel_formula():
     beta = 1.0 / 0.7
     d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     tpos, tprop, tE, tW = d(pos), d(prop), d(E), d(W)
+    tEn, tWn, tlo, tln, tu = d(E_new), d(W_new), d(lq_old), d(lq_new), d(u)     # keep the device buffers alive
     att = torch.full((B,), 10, dtype=torch.int64, device="cuda")
     acc = torch.full((B,), 4, dtype=torch.int64, device="cuda")
     mask = torch.empty(B, dtype=torch.uint8, device="cuda")
-    lib.check(lib.lib().fs_accept_global(lib.ptr(tpos), lib.ptr(tprop), lib.ptr(tE), lib.ptr(tW), lib.ptr(d(E_new)),
-                                         lib.ptr(d(W_new)), lib.ptr(d(lq_old)), lib.ptr(d(lq_new)), lib.ptr(d(u)),
+    lib.check(lib.lib().fs_accept_global(lib.ptr(tpos), lib.ptr(tprop), lib.ptr(tE), lib.ptr(tW), lib.ptr(tEn),
+                                         lib.ptr(tWn), lib.ptr(tlo), lib.ptr(tln), lib.ptr(tu),
                                          None, beta, lib.ptr(att), lib.ptr(acc), lib.ptr(mask), B, n,
                                          lib.stream_ptr()))
     with np.errstate(all="ignore"):

