@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 from .simulation_box import SimulationBox, _dev
 
 

@@ -6,7 +6,7 @@ import time
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 from .simulation_box import _dev
 
 

@@ -11,7 +11,7 @@ seeded like the reference draws the same numbers in the same order.
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 from .batched import BatchedMonteCarlo, pcg64_set_state, pcg64_state_words
 
 

@@ -4,7 +4,7 @@ MCMC/potential.py (lennard_jones_energy_virial :3-29, double_well_potential
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 from .simulation_box import _dev
 
 

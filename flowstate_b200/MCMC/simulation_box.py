@@ -4,7 +4,7 @@ CUDA helpers fs_apply_pbc / fs_distances."""
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 
 
 def _dev():

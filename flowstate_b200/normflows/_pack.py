@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _lib
+from ._bridge import _lib
 
 _PREC = {"fp32": _lib.FS_PREC_FP32, "tf32": _lib.FS_PREC_TF32}
 

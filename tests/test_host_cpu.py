@@ -182,3 +182,19 @@ def test_world_size_2_broadcast_and_gradient_allreduce():
         assert same
         assert err <= 1e-5 * max(1.0, scale), (err, scale)
         assert att == 7 and acc == 3
+
+
+def test_drop_in_top_level_import_names():
+    """The reference drivers do `import normflows as NF; import MCMC as MC`
+    (hybrid_NF_MCMC/main_algorithm_1.py:29-30): both names must resolve to this package when its
+    directory is placed on sys.path."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import normflows as NF, MCMC as MC;"
+            "assert 'flowstate_b200' in NF.__file__ and 'flowstate_b200' in MC.__file__;"
+            "NF.flows.CircularCoupledRationalQuadraticSpline; NF.Energy.UniformParticle; NF.NormalizingFlow;"
+            "MC.MonteCarlo; MC.EnergyCalculator; MC.SimulationBox; MC.initialise_low_left; print('ok')"
+            % (ROOT, os.path.join(ROOT, "flowstate_b200")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
