@@ -544,6 +544,7 @@ extern "C" int fs_flow_create(const fs_flow_desc* d, fs_flow** out) {
     f->base_logc = (float)(-f->D) * logf((float)(2.0 * d->bound));  // Energy/Uniform.py:67-68
     f->inv_sqrt_h = (float)(1.0 / sqrt((double)d->H));             // coupling.py:340-342
     f->tc = nullptr;
+    f->tc_err = nullptr;
     std::vector<int> idf(d->identity_features, d->identity_features + d->N);
     std::vector<int> trf(d->transform_features, d->transform_features + d->N);
     for (int j = 0; j < d->N; ++j) {
