@@ -11,12 +11,14 @@
 //                  R1 = [H, 2H)  : features / linear-0 accumulator -> after the epilogue: A operand relu(t)
 //   each region is split in two halves of NH = H/2 columns = one MMA (M=128, N=NH, K=8) per k-step,
 //   so the epilogue of one half overlaps the MMAs of the other.
-//   shared memory  h[H][128] FP32 (residual stream, column-major so a warp reads 32 consecutive rows),
-//                  NSTAGE weight tiles of NH x 32 tf32 (NH*128 bytes), mbarriers.
-//   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4-11: epilogue
-//                  (warp w touches TMEM lanes 32*(w%4).., warps 4-7 / 8-11 split the columns of a half)
+//   shared memory  u[H/4][128] float4 (residual stream with the biases folded out; a warp reads 32
+//                  consecutive rows), NSTAGE weight tiles of NH x 32 tf32 (NH*128 bytes), two
+//                  parameter sets (BatchNorm scale/offset, folded bias) prefetched by TMA, mbarriers.
+//   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4..: epilogue, one 32-column
+//                  chunk of a region half per thread (warp w touches TMEM lanes 32*(w%4)..)
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -26,17 +28,17 @@
 
 namespace fs {
 
-static constexpr int TC_KB = 32;          // K elements per weight tile (128 bytes of tf32)
-static constexpr int TC_THREADS = 384;
+static constexpr int TC_KB = 32;          // K elements per weight tile (one 128-byte swizzle atom per row)
 
 struct TcLayer {
     float* wstream;    // all weight tiles of the layer in consumption order
-    float* b_init;     // [H]
+    float* b_init;     // unused (folded)
     float* bn0_s;      // [n_blocks, H]
-    float* bn0_o;      // [n_blocks, H]
+    float* bn0_o;      // [n_blocks, H]  BatchNorm offset with the running bias folded in
     float* b0;         // [n_blocks, H]
-    float* b1;         // [n_blocks, H]
-    float* b_final;    // [n_chunks * NH]
+    float* b1;         // unused (folded)
+    float* b_final;    // [n_chunks * NH]  b_f + W_f c
+    float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
 };
 
 struct TcPack {
@@ -54,6 +56,8 @@ struct TcArgs {
     unsigned long long n_tiles;
     TcLayer L;
     int* err;
+    long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 8 per CTA
+    int dbg_mode;     // FS_TC_MODE (timing experiments only): 1 = epilogue skips data work, 4 = no weight copies
 };
 
 // ---------------------------------------------------------------------------
@@ -82,7 +86,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code,
+                                          long long* waited = nullptr) {
+    const long long t0 = waited ? clock64() : 0;
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
         if (++spins > 40000000u) {
@@ -90,6 +96,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
             __trap();
         }
     }
+    if (waited) *waited += clock64() - t0;
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -136,6 +143,15 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// One lane of a CONVERGED warp.  tcgen05.mma / commit / TMA must be issued from warp-uniform control
+// flow: from a divergent `if (lane == 0)` branch the compiler wraps every UTCHMMA in an R2UR waterfall
+// loop and the issue rate drops to ~92 clk per MMA (measured, scripts/mma_bench3.cu) - slower than the
+// 64 clk the tensor pipe needs for a 128x128x8 tf32 MMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -155,33 +171,43 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 
 // region ids: 0 = R0 half 0, 1 = R0 half 1, 2 = R1 half 0, 3 = R1 half 1
 template <int H>
-struct TcSmem {
+struct TcCfg {
     static constexpr int NH = H / 2;
+    static constexpr int EPI_WARPS = NH / 8;                 // 32 columns of a region half per warp-quad: 16 (H=256) / 8 (H=128)
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int STAGE_BYTES = NH * 128;
     static constexpr int H_BYTES = H * 128 * 4;
-    static constexpr int NSTAGE = (H == 256) ? 6 : 8;
-    static constexpr int BAR_OFF = H_BYTES + NSTAGE * STAGE_BYTES;
+    static constexpr int NSTAGE = (H == 256) ? 5 : 8;
+    static constexpr int PSET_FLOATS = 3 * H;                // per parameter set: b0' | s | o'
+    static constexpr int W_OFF = H_BYTES;
+    static constexpr int P_OFF = W_OFF + NSTAGE * STAGE_BYTES;
+    static constexpr int BAR_OFF = P_OFF + 2 * PSET_FLOATS * 4;
     static constexpr int TOTAL = BAR_OFF + 256;
 };
 
 template <int H>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g) {
-    using S = TcSmem<H>;
+__global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(TcArgs g) {
+    using S = TcCfg<H>;
     constexpr int NH = S::NH;
     constexpr int NSTAGE = S::NSTAGE;
+    constexpr int EPI_WARPS = S::EPI_WARPS;
     constexpr int KT = H / TC_KB;              // weight tiles along K for an H-wide GEMM
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float* hs = (float*)smem;                                   // h[c][r]
-    const uint32_t w_base = smem_u32(smem + S::H_BYTES);        // weight stages (1024-aligned)
+    float4* hs4 = reinterpret_cast<float4*>(smem);              // u[col/4][row] as float4
+    const uint32_t w_base = smem_u32(smem + S::W_OFF);          // weight stages (1024-aligned)
+    const float* pbuf = reinterpret_cast<const float*>(smem + S::P_OFF);
+    const uint32_t p_base = smem_u32(smem + S::P_OFF);
     const uint32_t bar_base = smem_u32(smem + S::BAR_OFF);
     // barrier map (8 bytes each)
-    const uint32_t bar_wfull = bar_base;                        // [NSTAGE]
-    const uint32_t bar_wempty = bar_base + 8 * NSTAGE;          // [NSTAGE]
+    const uint32_t bar_wfull = bar_base;                        // [NSTAGE] TMA -> MMA
+    const uint32_t bar_wempty = bar_base + 8 * NSTAGE;          // [NSTAGE] MMA -> TMA
     const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [4]  MMA -> epilogue (accumulator half ready)
     const uint32_t bar_ready = bar_full + 32;                   // [4]  epilogue -> MMA (operand half written / drained)
     const uint32_t bar_free1 = bar_ready + 32;                  // [1]  MMA -> epilogue (feature piece consumed)
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 72);
+    const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
+    const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 112);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,9 +220,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g)
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_ready + 8 * i, 8);
+            mbar_init(bar_ready + 8 * i, EPI_WARPS);
         }
         mbar_init(bar_free1, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_pfull + 8 * i, 1);
+            mbar_init(bar_pempty + 8 * i, EPI_WARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -210,51 +240,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g)
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer: stream the layer's weight tiles in order =====================
-        if (lane == 0) {
+        // ===================== TMA producer: parameter sets + the layer's weight tiles, in order =====================
+        {
             const uint8_t* src = (const uint8_t*)g.L.wstream;
             uint32_t stage = 0, phase = 0;
-            for (unsigned long long t = 0; t < g.n_tiles; ++t) {
-                mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1);
-                mbar_expect_tx(bar_wfull + 8 * stage, S::STAGE_BYTES);
-                tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, S::STAGE_BYTES,
-                             bar_wfull + 8 * stage);
-                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            long long w_empty = 0;
+            unsigned long long t = 0;
+            uint32_t pph = 0;                  // per-buffer parity of bar_pempty
+            auto load_pset = [&](int j) {      // set j: 0 = {-, s_0, o'_0}; b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
+                const int bsel = j & 1;
+                mbar_wait(bar_pempty + 8 * bsel, ((pph >> bsel) & 1) ^ 1, g.err, 6);
+                pph ^= 1u << bsel;
+                if (elect_one()) {
+                    mbar_expect_tx(bar_pfull + 8 * bsel, S::PSET_FLOATS * 4);
+                    tma_bulk_g2s(p_base + bsel * S::PSET_FLOATS * 4, g.L.psets + (size_t)j * S::PSET_FLOATS,
+                                 S::PSET_FLOATS * 4, bar_pfull + 8 * bsel);
+                }
+                __syncwarp();
+            };
+            auto stream = [&](unsigned long long n) {
+                for (unsigned long long e = t + n; t < e; ++t) {
+                    mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1, g.dbg ? &w_empty : nullptr);
+                    // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
+                    // scripts/tma_bw2.cu, 20 B/clk for 16 KB copies whatever the depth); copies issued by
+                    // different lanes overlap.  Rotate the issuing lane so 8 tiles can be in flight.
+                    if (lane == (int)(t & 7)) {
+                        if (g.dbg_mode & 4) {
+                            mbar_arrive(bar_wfull + 8 * stage);      // timing experiment: no weight traffic
+                        } else {
+                            mbar_expect_tx(bar_wfull + 8 * stage, S::STAGE_BYTES);
+                            tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, S::STAGE_BYTES,
+                                         bar_wfull + 8 * stage);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            };
+            load_pset(0);
+            load_pset(1);
+            stream(2ull * (g.Kp0 / TC_KB));                       // GEMM0
+            for (int b = 0; b < g.n_blocks; ++b) {
+                if (b >= 1) load_pset(b + 1);
+                stream(4ull * KT);
             }
+            stream((unsigned long long)g.n_chunks * KT);         // final layer
+            if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 0] = w_empty;
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        {
             // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NH, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | (8u << 24);
             uint32_t stage = 0, wphase = 0;
             uint32_t ph_ready = 0;     // parity to wait for, per region
+            long long w_ready = 0, w_weights = 0, t_issue = 0;
+            const long long t_start = g.dbg ? clock64() : 0;
             auto wait_ready = [&](int region) {
-                mbar_wait(bar_ready + 8 * region, (ph_ready >> region) & 1, g.err, 2);
+                mbar_wait(bar_ready + 8 * region, (ph_ready >> region) & 1, g.err, 2, g.dbg ? &w_ready : nullptr);
                 ph_ready ^= 1u << region;
                 tc_fence_after();
             };
-            // one weight tile = 4 k-steps of 8
-            auto mma_tile = [&](uint32_t dcol, uint32_t acol, bool first) {
-                mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3);
-                tc_fence_after();
-                const uint32_t sb = w_base + stage * S::STAGE_BYTES;
+            auto commit = [&](uint32_t bar) {
+                if (elect_one()) tc_commit(bar);
+                __syncwarp();
+            };
+            // Weight tiles are consumed in groups of up to TC_GROUP: the group's full-barriers are waited
+            // for back to back, then all 4*n MMAs are queued at once, so the issuing warp's bookkeeping
+            // (barrier probes, descriptor set-up) between two groups is shorter than the time the tensor
+            // pipe needs for a group.  The first barrier of the NEXT group is probed right after the
+            // MMAs are queued.
+            constexpr int TC_GROUP = 2;
+            bool peeked = false;
+            auto mma_group = [&](uint32_t dcol, uint32_t acol, int n, bool first) {
+                uint32_t st[TC_GROUP];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    tc_mma_ts(tmem + dcol, tmem + acol + 8 * j, make_b_desc(sb + 32 * j), idesc,
-                              (first && j == 0) ? 0u : 1u);
-                tc_commit(bar_wempty + 8 * stage);
-                if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+                for (int i = 0; i < TC_GROUP; ++i) {
+                    if (i < n) {
+                        if (!(i == 0 && peeked))
+                            mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3, g.dbg ? &w_weights : nullptr);
+                        st[i] = stage;
+                        if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+                    }
+                }
+                tc_fence_after();
+                const long long ti = g.dbg ? clock64() : 0;
+                if (elect_one()) {
+#pragma unroll
+                    for (int i = 0; i < TC_GROUP; ++i) {
+                        if (i < n) {
+                            const uint32_t sb = w_base + st[i] * S::STAGE_BYTES;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, make_b_desc(sb + 32 * j), idesc,
+                                          (first && i == 0 && j == 0) ? 0u : 1u);
+                            tc_commit(bar_wempty + 8 * st[i]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (g.dbg) t_issue += clock64() - ti;
+                peeked = mbar_try(bar_wfull + 8 * stage, wphase);
             };
             // GEMM over K = ktiles*32 columns of operand region `abase` (TMEM column), K-ordered waits on
             // the two halves of that region (region ids ra0, ra0 + 1)
             auto gemm_half = [&](uint32_t dcol, uint32_t abase, int ra0, int ktiles, bool fresh, bool waitA) {
-                for (int kt = 0; kt < ktiles; ++kt) {
+                for (int kt = 0; kt < ktiles; kt += TC_GROUP) {
                     if (waitA) {
                         if (kt == 0) wait_ready(ra0);
                         if (kt * TC_KB == NH) wait_ready(ra0 + 1);
                     }
-                    mma_tile(dcol, abase + kt * TC_KB, fresh && kt == 0);
+                    mma_group(dcol, abase + kt * TC_KB, min(TC_GROUP, ktiles - kt), fresh && kt == 0);
                 }
             };
             // ---- GEMM0: features (R1) -> R0 ----
@@ -262,44 +358,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g)
                 const int kcols = min(H, g.Kp0 - p * H);
                 const int ktiles = kcols / TC_KB;
                 for (int nh = 0; nh < 2; ++nh) {
-                    // both feature halves are signalled for every piece; wait for them once per piece
                     if (nh == 0) { wait_ready(2); wait_ready(3); }
                     gemm_half(nh * NH, H, 2, ktiles, p == 0, false);
-                    if (p == g.n_pieces - 1) tc_commit(bar_full + 8 * nh);
+                    if (p == g.n_pieces - 1) commit(bar_full + 8 * nh);
                 }
-                if (p < g.n_pieces - 1) tc_commit(bar_free1);
+                if (p < g.n_pieces - 1) commit(bar_free1);
             }
             // ---- residual blocks ----
             for (int b = 0; b < g.n_blocks; ++b) {
                 for (int nh = 0; nh < 2; ++nh) {           // linear 0: A = R0 (a), D = R1 half nh
                     gemm_half(H + nh * NH, 0, 0, KT, true, nh == 0);
-                    tc_commit(bar_full + 8 * (2 + nh));
+                    commit(bar_full + 8 * (2 + nh));
                 }
                 for (int nh = 0; nh < 2; ++nh) {           // linear 1: A = R1 (relu t), D = R0 half nh
                     gemm_half(nh * NH, H, 2, KT, true, nh == 0);
-                    tc_commit(bar_full + 8 * nh);
+                    commit(bar_full + 8 * nh);
                 }
             }
-            // ---- final layer: A = R0 (h), D = R1 half (c & 1), chunk after chunk ----
+            // ---- final layer: A = R0 (u), D = R1 half (c & 1), chunk after chunk ----
             for (int c = 0; c < g.n_chunks; ++c) {
                 if (c >= 2) wait_ready(2 + (c & 1));       // epilogue drained chunk c-2
                 gemm_half(H + (c & 1) * NH, 0, 0, KT, true, c == 0);
-                tc_commit(bar_full + 8 * (2 + (c & 1)));
+                commit(bar_full + 8 * (2 + (c & 1)));
+            }
+            if (g.dbg && lane == 0) {
+                g.dbg[8 * blockIdx.x + 1] = w_ready;
+                g.dbg[8 * blockIdx.x + 2] = w_weights;
+                g.dbg[8 * blockIdx.x + 3] = clock64() - t_start;
+                g.dbg[8 * blockIdx.x + 6] = t_issue;
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue warps =====================
+        // ===================== epilogue warps: one 32-column chunk of a region half per thread =====================
         const int ew = warp - 4;
         const int q = ew & 3;                    // TMEM lane quadrant (== warp % 4)
-        const int cg = ew >> 2;                  // which half of the columns of a region half
+        const int cgp = ew >> 2;                 // 32-column group inside a region half
         const int r = 32 * q + lane;             // row inside the tile
         const int grow = row0 + r;
         const bool row_ok = grow < g.rows;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
-        constexpr int CW = NH / 2;               // columns per thread per region half
-        uint32_t ph_full = 0, ph_free1 = 0;
+        uint32_t ph_full = 0, ph_free1 = 0, ph_pfull = 0;
+        long long w_full = 0;
+        const long long e_start = g.dbg ? clock64() : 0;
         auto wait_full = [&](int region) {
-            mbar_wait(bar_full + 8 * region, (ph_full >> region) & 1, g.err, 4);
+            mbar_wait(bar_full + 8 * region, (ph_full >> region) & 1, g.err, 4,
+                      (g.dbg && ew == 0 && lane == 0) ? &w_full : nullptr);
             ph_full ^= 1u << region;
             tc_fence_after();
         };
@@ -307,6 +410,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ready + 8 * region);
+        };
+        auto wait_pset = [&](int j) {
+            mbar_wait(bar_pfull + 8 * (j & 1), (ph_pfull >> (j & 1)) & 1, g.err, 7);
+            ph_pfull ^= 1u << (j & 1);
+        };
+        auto release_pset = [&](int j) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pempty + 8 * (j & 1));
         };
         uint32_t v[32];
 
@@ -319,91 +430,118 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conditioner_kernel(TcArgs g)
             }
             const int kcols = min(H, g.Kp0 - p * H);
             for (int nh = 0; nh < 2; ++nh) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < CW; c0 += 32) {
-                    const int col = nh * NH + cg * CW + c0;          // column inside R1
-                    if (col < kcols) {
-                        const int k0 = p * H + col;
-                        const float* src = g.A0 + (size_t)grow * g.K0 + k0;
+                const int col = nh * NH + cgp * 32;              // column inside R1
+                if (col < kcols) {
+                    const int k0 = p * H + col;
+                    const float* src = g.A0 + (size_t)grow * g.K0 + k0;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float x = 0.f;
-                            if (row_ok && k0 + i < g.K0) x = __ldg(src + i);
-                            v[i] = to_tf32(x);
-                        }
-                        tc_st32(lane_addr + H + col, v);
+                    for (int i = 0; i < 32; ++i) {
+                        float x = 0.f;
+                        if (row_ok && k0 + i < g.K0) x = __ldg(src + i);
+                        v[i] = to_tf32(x);
                     }
-                }
-                tc_wait_st();
-                signal_ready(2 + nh);
-            }
-        }
-        // ---- GEMM0 epilogue: h = D + b_init ; a = relu(bn0_0(h)) (or raw h when there are no blocks) ----
-        auto epi_residual = [&](int nh, const float* bias, const float* s_next, const float* o_next, bool init) {
-            wait_full(nh);
-#pragma unroll 1
-            for (int c0 = 0; c0 < CW; c0 += 32) {
-                const int col = nh * NH + cg * CW + c0;
-                tc_ld32(lane_addr + col, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float hval = __uint_as_float(v[i]) + __ldg(bias + col + i);
-                    float* hp = hs + (size_t)(col + i) * 128 + r;
-                    if (!init) hval += *hp;
-                    *hp = hval;
-                    float a = hval;
-                    if (s_next) a = fmaxf(__fmaf_rn(hval, __ldg(s_next + col + i), __ldg(o_next + col + i)), 0.f);
-                    v[i] = to_tf32(a);
-                }
-                tc_st32(lane_addr + col, v);
-            }
-            tc_wait_st();
-            signal_ready(nh);
-        };
-        for (int nh = 0; nh < 2; ++nh)
-            epi_residual(nh, g.L.b_init, g.n_blocks ? g.L.bn0_s : nullptr, g.L.bn0_o, true);
-        // ---- residual blocks ----
-        for (int b = 0; b < g.n_blocks; ++b) {
-            const float* b0 = g.L.b0 + (size_t)b * H;
-            for (int nh = 0; nh < 2; ++nh) {                 // relu(t + b0') in place in R1
-                wait_full(2 + nh);
-#pragma unroll 1
-                for (int c0 = 0; c0 < CW; c0 += 32) {
-                    const int col = nh * NH + cg * CW + c0;
-                    tc_ld32(lane_addr + H + col, v);
-                    tc_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        v[i] = to_tf32(fmaxf(__uint_as_float(v[i]) + __ldg(b0 + col + i), 0.f));
                     tc_st32(lane_addr + H + col, v);
                 }
                 tc_wait_st();
                 signal_ready(2 + nh);
             }
-            const bool last = (b == g.n_blocks - 1);
-            for (int nh = 0; nh < 2; ++nh)
-                epi_residual(nh, g.L.b1 + (size_t)b * H, last ? nullptr : g.L.bn0_s + (size_t)(b + 1) * H,
-                             g.L.bn0_o + (size_t)(b + 1) * H, false);
         }
-        // ---- final layer: theta chunk = D + b_final -> global ----
+        // ---- residual-stream epilogue.  The stream is kept as u = h - c, c = all biases added so far
+        //      (folded into the BatchNorm offsets and the final bias at pack time), so a block boundary
+        //      costs: u (+)= D ; operand = relu(s u + o')  (or u itself in front of the final layer) ----
+        auto epi_residual = [&](int nh, const float* prm, bool has_next, bool init) {
+            const int col = nh * NH + cgp * 32;
+            wait_full(nh);
+            if (g.dbg_mode & 1) { signal_ready(nh); return; }
+            tc_ld32(lane_addr + col, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+                float4* hp = hs4 + (size_t)((col >> 2) + i4) * 128 + r;
+                float4 u = make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),
+                                       __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
+                if (!init) {
+                    const float4 h0 = *hp;
+                    u.x += h0.x; u.y += h0.y; u.z += h0.z; u.w += h0.w;
+                }
+                *hp = u;
+                if (has_next) {
+                    const float4 sc = *reinterpret_cast<const float4*>(prm + H + col + 4 * i4);
+                    const float4 of = *reinterpret_cast<const float4*>(prm + 2 * H + col + 4 * i4);
+                    u.x = fmaxf(__fmaf_rn(u.x, sc.x, of.x), 0.f);
+                    u.y = fmaxf(__fmaf_rn(u.y, sc.y, of.y), 0.f);
+                    u.z = fmaxf(__fmaf_rn(u.z, sc.z, of.z), 0.f);
+                    u.w = fmaxf(__fmaf_rn(u.w, sc.w, of.w), 0.f);
+                }
+                v[4 * i4] = to_tf32(u.x);
+                v[4 * i4 + 1] = to_tf32(u.y);
+                v[4 * i4 + 2] = to_tf32(u.z);
+                v[4 * i4 + 3] = to_tf32(u.w);
+            }
+            tc_st32(lane_addr + col, v);
+            tc_wait_st();
+            signal_ready(nh);
+        };
+        wait_pset(0);
+        for (int nh = 0; nh < 2; ++nh) epi_residual(nh, pbuf, true, true);
+        release_pset(0);
+        // ---- residual blocks ----
+        for (int b = 0; b < g.n_blocks; ++b) {
+            const float* prm = pbuf + (size_t)((b + 1) & 1) * S::PSET_FLOATS;
+            wait_pset(b + 1);
+            for (int nh = 0; nh < 2; ++nh) {                 // relu(t + b0') in place in R1
+                const int col = nh * NH + cgp * 32;
+                wait_full(2 + nh);
+                if (g.dbg_mode & 1) { signal_ready(2 + nh); continue; }
+                tc_ld32(lane_addr + H + col, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(prm + col + 4 * i4);
+                    v[4 * i4] = to_tf32(fmaxf(__uint_as_float(v[4 * i4]) + bb.x, 0.f));
+                    v[4 * i4 + 1] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 1]) + bb.y, 0.f));
+                    v[4 * i4 + 2] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 2]) + bb.z, 0.f));
+                    v[4 * i4 + 3] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 3]) + bb.w, 0.f));
+                }
+                tc_st32(lane_addr + H + col, v);
+                tc_wait_st();
+                signal_ready(2 + nh);
+            }
+            const bool last = (b == g.n_blocks - 1);
+            for (int nh = 0; nh < 2; ++nh) epi_residual(nh, prm, !last, false);
+            release_pset(b + 1);
+        }
+        // ---- final layer: theta chunk = D + b_final' -> global ----
+        const bool vec_ok = (g.NP & 3) == 0;
         for (int c = 0; c < g.n_chunks; ++c) {
             const int region = 2 + (c & 1);
+            const int col = cgp * 32;                         // column inside the chunk
             wait_full(region);
-#pragma unroll 1
-            for (int c0 = 0; c0 < CW; c0 += 32) {
-                const int col = cg * CW + c0;                 // column inside the chunk
-                tc_ld32(lane_addr + H + (c & 1) * NH + col, v);
-                tc_wait_ld();
-                const int ocol = c * NH + col;
-                if (row_ok) {
-                    float* dst = g.theta + (size_t)grow * g.NP + ocol;
+            tc_ld32(lane_addr + H + (c & 1) * NH + col, v);
+            tc_wait_ld();
+            signal_ready(region);                             // accumulator half is in registers: MMA may reuse it
+            const int ocol = c * NH + col;
+            if (row_ok) {
+                float* dst = g.theta + (size_t)grow * g.NP + ocol;
+                const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_final + ocol);
+                if (vec_ok && ocol + 32 <= g.NP) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        const float4 bb = __ldg(bf4 + i4);
+                        reinterpret_cast<float4*>(dst)[i4] =
+                            make_float4(__uint_as_float(v[4 * i4]) + bb.x, __uint_as_float(v[4 * i4 + 1]) + bb.y,
+                                        __uint_as_float(v[4 * i4 + 2]) + bb.z, __uint_as_float(v[4 * i4 + 3]) + bb.w);
+                    }
+                } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (ocol + i < g.NP) dst[i] = __uint_as_float(v[i]) + __ldg(g.L.b_final + ocol + i);
                 }
             }
-            signal_ready(region);
+        }
+        if (g.dbg && ew == 0 && lane == 0) {
+            g.dbg[8 * blockIdx.x + 4] = w_full;
+            g.dbg[8 * blockIdx.x + 5] = clock64() - e_start;
         }
     }
     tc_fence_before();
@@ -473,7 +611,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     P->n_pieces = (P->Kp0 + H - 1) / H;
     const int NP = f->N * f->P;
     P->n_chunks = (NP + P->NH - 1) / P->NH;
-    P->smem_bytes = (H == 256 ? TcSmem<256>::TOTAL : TcSmem<128>::TOTAL) + 1024;
+    P->smem_bytes = (H == 256 ? TcCfg<256>::TOTAL : TcCfg<128>::TOTAL) + 1024;
     if ((int)P->smem_bytes > smem_max) { delete P; return FS_OK; }
     const int NH = P->NH, KT = H / TC_KB;
     P->layers.resize(f->K);
@@ -515,21 +653,42 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         }
         for (int c = 0; c < P->n_chunks; ++c)                            // final layer
             for (int kt = 0; kt < KT; ++kt) append_tile(stream, p->final_w, NP, H, c * NH, kt * TC_KB, NH);
-        P->tiles_per_layer = stream.size() / ((size_t)NH * 32);
+        P->tiles_per_layer = stream.size() / ((size_t)NH * TC_KB);
         TcLayer& L = P->layers[li];
-        std::vector<float> v;
+        // Bias folding: the kernel carries u = h - c (c = b_init + sum of linear-1 biases so far):
+        //   relu(s h + o) = relu(s u + (o + s c)),   W_f h + b_f = W_f u + (b_f + W_f c)
+        std::vector<double> c(p->init_b, p->init_b + H);
+        std::vector<float> o0f((size_t)nB * H);
+        for (int b = 0; b < nB; ++b) {
+            for (int k = 0; k < H; ++k) {
+                o0f[(size_t)b * H + k] = (float)((double)o0[(size_t)b * H + k] + (double)s0[(size_t)b * H + k] * c[k]);
+                c[k] += (double)p->lin_b[((size_t)b * 2 + 1) * H + k];
+            }
+        }
+        std::vector<float> bfin((size_t)P->n_chunks * NH, 0.f);
+        for (int n = 0; n < NP; ++n) {
+            double acc = (double)p->final_b[n];
+            const float* wr = p->final_w + (size_t)n * H;
+            for (int k = 0; k < H; ++k) acc += (double)tf32_round(wr[k]) * c[k];
+            bfin[n] = (float)acc;
+        }
+        std::vector<float> psets((size_t)(nB + 1) * 3 * H, 0.f);
+        for (int j = 0; j <= nB; ++j) {
+            float* ps = &psets[(size_t)j * 3 * H];
+            if (j >= 1) memcpy(ps, &b0[(size_t)(j - 1) * H], sizeof(float) * H);
+            if (j < nB) {
+                memcpy(ps + H, &s0[(size_t)j * H], sizeof(float) * H);
+                memcpy(ps + 2 * H, &o0f[(size_t)j * H], sizeof(float) * H);
+            }
+        }
         int r = tc_upload(f, stream, &L.wstream);
-        v.assign(p->init_b, p->init_b + H);
-        if (!r) r = tc_upload(f, v, &L.b_init);
+        if (!r) r = tc_upload(f, psets, &L.psets);
         if (!r) r = tc_upload(f, s0, &L.bn0_s);
-        if (!r) r = tc_upload(f, o0, &L.bn0_o);
+        if (!r) r = tc_upload(f, o0f, &L.bn0_o);
         if (!r) r = tc_upload(f, b0, &L.b0);
-        std::vector<float> b1((size_t)nB * H);
-        for (int b = 0; b < nB; ++b) memcpy(&b1[(size_t)b * H], p->lin_b + ((size_t)b * 2 + 1) * H, sizeof(float) * H);
-        if (!r) r = tc_upload(f, b1, &L.b1);
-        v.assign((size_t)P->n_chunks * NH, 0.f);
-        memcpy(v.data(), p->final_b, sizeof(float) * NP);
-        if (!r) r = tc_upload(f, v, &L.b_final);
+        if (!r) r = tc_upload(f, bfin, &L.b_final);
+        L.b_init = nullptr;
+        L.b1 = nullptr;
         if (r) { delete P; return r; }
     }
     int* err = nullptr;
@@ -552,6 +711,22 @@ void tc_free(fs_flow* f) {
 
 size_t tc_workspace_bytes(const fs_flow*, int) { return 0; }
 
+// FS_TC_DEBUG=1: per-CTA wait-cycle counters of the last launch, readable through fs_tc_debug_read()
+static long long* g_dbg = nullptr;
+static int g_dbg_ctas = 0;
+static long long* tc_debug_buffer(int ctas) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("FS_TC_DEBUG"); enabled = (e && e[0] == '1') ? 1 : 0; }
+    if (!enabled) return nullptr;
+    if (ctas > g_dbg_ctas) {
+        if (g_dbg) cudaFree(g_dbg);
+        cudaMalloc(&g_dbg, sizeof(long long) * 8 * ctas);
+        g_dbg_ctas = ctas;
+    }
+    cudaMemset(g_dbg, 0, sizeof(long long) * 8 * ctas);
+    return g_dbg;
+}
+
 int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, cudaStream_t s) {
     TcPack* P = (TcPack*)f->tc;
     if (!P) {
@@ -571,13 +746,30 @@ int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* thet
     g.n_tiles = P->tiles_per_layer;
     g.L = P->layers[layer];
     g.err = f->tc_err;
+    g.dbg = tc_debug_buffer((rows + 127) / 128);
+    {
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("FS_TC_MODE"); mode = e ? atoi(e) : 0; }
+        g.dbg_mode = mode;
+    }
     const int grid = (rows + 127) / 128;
     if (P->H == 256)
-        tc_conditioner_kernel<256><<<grid, TC_THREADS, P->smem_bytes, s>>>(g);
+        tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
     else
-        tc_conditioner_kernel<128><<<grid, TC_THREADS, P->smem_bytes, s>>>(g);
+        tc_conditioner_kernel<128><<<grid, TcCfg<128>::THREADS, P->smem_bytes, s>>>(g);
     fs::count_launch();
     return cuda_check(cudaGetLastError(), "tc_conditioner_kernel");
 }
 
 }  // namespace fs
+
+// development aid: copies the wait-cycle counters of the last tensor-kernel launch (8 int64 per CTA:
+// producer wait-empty, MMA wait-operand, MMA wait-weights, MMA total, epilogue wait-accumulator,
+// epilogue total, 0, 0).  Returns the number of CTAs copied.
+extern "C" int fs_tc_debug_read(long long* host, int max_ctas) {
+    int n = fs::g_dbg_ctas < max_ctas ? fs::g_dbg_ctas : max_ctas;
+    if (!fs::g_dbg || n <= 0) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, fs::g_dbg, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+    return n;
+}

@@ -189,6 +189,10 @@ int fs_flow_forward(fs_flow* flow, const float* z, int B, double out_shift,
                     float* x, float* logdet, int* nan_flag,
                     void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* Development aid (FS_TC_DEBUG=1): wait-cycle counters of the last tensor-core conditioner launch,
+ * 8 int64 per CTA; returns the number of CTAs copied to `host`. */
+int fs_tc_debug_read(long long* host, int max_ctas);
+
 #ifdef __cplusplus
 }
 #endif
