@@ -273,10 +273,34 @@ def main():
     half32 = np.float32(bound)
     torch.manual_seed(1234 + rank)
 
-    def one_round():
+    # Proposals do not depend on the chains (Alg 1 even pre-generates its whole pool,
+    # main_algorithm_1.py:340-343), so the sampling pass of round r+1 runs on a side stream in the shadow
+    # of round r's sweep + log-density pass; every round still does one sample pass, two log-densities,
+    # one proposal energy and `local` local moves per chain.
+    side = torch.cuda.Stream(device=dev)
+    pending = {}
+
+    def launch_proposals(z_host=None):
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(side):
+            if z_host is None:
+                z = model.q0(B)
+            else:
+                z = torch.empty(B, 2 * n, dtype=torch.float32, device=dev)
+                z.copy_(z_host, non_blocking=True)
+            cfg = (model.forward(z).reshape(B, n, 2) + half32).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        cfg.record_stream(main)
+        pending["cfg"], pending["ev"] = cfg, ev
+
+    def one_round(z_host=None):
+        if "cfg" not in pending:
+            launch_proposals(z_host)
+        cfg, ev = pending.pop("cfg"), pending.pop("ev")
+        launch_proposals(z_host)                       # next round's proposals, off the critical path
         eng.particle_displacement(w["local"])
-        z = model.q0(B)
-        cfg = (model.forward(z).reshape(B, n, 2) + half32).contiguous()
+        torch.cuda.current_stream(dev).wait_event(ev)
         return eng.nf_big_move(cfg)
 
     # ---- device-resident timing ------------------------------------------------
@@ -309,15 +333,11 @@ def main():
     h_out_pos = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
     h_out_E = torch.empty(B, dtype=torch.float64).pin_memory()
     h_out_mask = torch.empty(B, dtype=torch.uint8).pin_memory()
-    d_z = torch.empty(B, 2 * n, dtype=torch.float32, device=dev)
 
     def e2e_round():
         eng.pos.copy_(h_pos, non_blocking=True)
-        d_z.copy_(h_z, non_blocking=True)
         eng.refresh_energy()
-        eng.particle_displacement(w["local"])
-        cfg = (model.forward(d_z).reshape(B, n, 2) + half32).contiguous()
-        mask = eng.nf_big_move(cfg)
+        mask = one_round(h_z)                          # base noise comes from the host buffer
         h_out_pos.copy_(eng.pos, non_blocking=True)
         h_out_E.copy_(eng.E, non_blocking=True)
         h_out_mask.copy_(mask, non_blocking=True)
@@ -393,6 +413,7 @@ def main():
                    "local_steps_per_round": w["local"],
                    "flow": {"K": w["K"], "blocks": w["blocks"], "H": w["H"], "bins": w["nb"], "sigma": w["sigma"]},
                    "rho": w["rho"], "rng": "philox", "conditioner": prec,
+                   "pipelining": "proposals of round r+1 sampled on a side stream during round r",
                    "l2": "inputs larger than L2: %.0f MB of flow weights streamed per pass"
                          % (sum(p.numel() for p in model.parameters()) * 4 / 1e6),
                    "weight_broadcast_bytes": bcast_bytes},

@@ -260,6 +260,209 @@ __global__ void __launch_bounds__(256) spline_forward_kernel(const float* __rest
     if (lane == 0 && logdet) logdet[b] += acc;
 }
 
+// ---------------------------------------------------------------------------
+// Lane-per-coordinate spline kernels (the ones the flow passes launch).
+// One warp owns one row; a chunk of 32 coordinates sits one per lane.  The 32 x (3nb+1)
+// parameters of the chunk are staged in shared memory with coalesced loads (odd row stride, so the
+// per-lane walks over a coordinate's bins are bank-conflict free) and each lane runs softmax ->
+// cumulative knots -> bin search -> rational-quadratic evaluation sequentially over its bins in
+// registers: no shuffles, exps only for the two softmaxes, softplus only for the two derivatives
+// of the selected bin.
+// ---------------------------------------------------------------------------
+#define FS_SPLINE_WARPS 4
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Conditional spline of ONE coordinate: the 2nb softmax logits p[0..2nb) of this lane sit in shared memory
+// (the numerators are written back in place), the two derivatives of the selected bin are fetched from
+// the coordinate's parameter row `gp` in global memory.
+__device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __restrict__ gp, int nb, float bound,
+                                              float inv_sqrt_h, bool inverse, float& y, float& ld) {
+    if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39
+        y = x;
+        ld = 0.0f;
+        return;
+    }
+    const float c2 = inv_sqrt_h * 1.4426950408889634f;      // softmax(u / sqrt(H)) via exp2
+    float mw = -3.0e38f, mh = -3.0e38f;
+#pragma unroll 8
+    for (int k = 0; k < nb; ++k) {
+        mw = fmaxf(mw, p[k]);
+        mh = fmaxf(mh, p[nb + k]);
+    }
+    float sw = 0.f, sh = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < nb; ++k) {
+        const float ew = exp2f((p[k] - mw) * c2);
+        const float eh = exp2f((p[nb + k] - mh) * c2);
+        p[k] = ew;
+        p[nb + k] = eh;
+        sw += ew;
+        sh += eh;
+    }
+    const float gw = (1.0f - kMinW * (float)nb) / sw, gh = (1.0f - kMinH * (float)nb) / sh;
+    const float two_b = 2.0f * bound;
+    float cw = 0.f, ch = 0.f, xl = -bound, yl = -bound;
+    float xk = -bound, wk = 1.f, yk = -bound, hk = 1.f;
+    int sel = 0;
+#pragma unroll 4
+    for (int k = 0; k < nb; ++k) {
+        cw += __fmaf_rn(gw, p[k], kMinW);
+        ch += __fmaf_rn(gh, p[nb + k], kMinH);
+        const float xr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, cw), -bound);
+        const float yr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, ch), -bound);
+        if (x >= (inverse ? yl : xl)) {      // last knot <= x wins == #(x >= knots) - 1 (utils/splines.py:11-13)
+            sel = k;
+            xk = xl; wk = xr - xl; yk = yl; hk = yr - yl;
+        }
+        xl = xr;
+        yl = yr;
+    }
+    const float dk = kMinD + softplus_t(__ldg(gp + 2 * nb + sel));
+    const float dk1 = kMinD + softplus_t(__ldg(gp + 2 * nb + sel + 1));
+    rq_eval(x, xk, wk, yk, hk, dk, dk1, inverse, y, ld);
+}
+
+// Unconditional spline of one coordinate from the packed knot tables (global memory, L1/L2-resident).
+__device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict__ ux, const float* __restrict__ uy,
+                                               const float* __restrict__ ud, int nb, float bound, bool inverse,
+                                               float& y, float& ld) {
+    if (!(x >= -bound && x <= bound)) {
+        y = x;
+        ld = 0.0f;
+        return;
+    }
+    const float* ks = inverse ? uy : ux;
+    int sel = 0;
+    for (int k = 1; k < nb; ++k)
+        if (x >= __ldg(ks + k)) sel = k;
+    const float xk = __ldg(ux + sel), xk1 = __ldg(ux + sel + 1);
+    const float yk = __ldg(uy + sel), yk1 = __ldg(uy + sel + 1);
+    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + sel), __ldg(ud + sel + 1), inverse, y, ld);
+}
+
+// stage the 2nb softmax logits of coordinates [j0, j0+ncoord) of one row: theta row segment -> smem, row stride Ps (odd)
+__device__ __forceinline__ void stage_params(const float* __restrict__ th, float* sm, int j0, int ncoord, int P, int nb2,
+                                             int Ps, int lane) {
+    for (int c = 0; c < ncoord; ++c) {
+        const float* src = th + (size_t)(j0 + c) * P;
+        float* dst = sm + c * Ps;
+        for (int k = lane; k < nb2; k += 32) dst[k] = __ldg(src + k);
+    }
+    __syncwarp();
+}
+
+// density direction: conditional spline on the transformed half, unconditional spline on the identity
+// half, scatter + roll by D/2 (coupling.py:86-102)
+__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_inverse_v2(
+    const float* __restrict__ v, const float* __restrict__ theta, float* __restrict__ out,
+    float* __restrict__ logdet, int rows, FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy,
+    const float* __restrict__ ud, int* nan_flag) {
+    extern __shared__ float sp_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
+    if (b >= rows) return;
+    const int Ps = (2 * F.nb) | 1, nb = F.nb, h = F.D / 2;
+    float* sm = sp_smem + (size_t)wib * 32 * Ps;
+    const float* vr = v + (size_t)b * F.D;
+    float* orow = out + (size_t)b * F.D;
+    const float* th = theta + (size_t)b * F.N * F.P;
+    float acc = 0.f;
+    bool bad = false;
+    for (int j0 = 0; j0 < F.N; j0 += 32) {
+        const int nc = min(32, F.N - j0);
+        stage_params(th, sm, j0, nc, F.P, 2 * nb, Ps, lane);
+        if (lane < nc) {
+            const int j = j0 + lane;
+            const int ft = F.trf[j], fi = F.idf[j];
+            float y, ld, y2, ld2;
+            rqs_cond_lane(vr[ft], sm + lane * Ps, th + (size_t)j * F.P, nb, F.bound, F.inv_sqrt_h, false, y, ld);
+            rqs_table_lane(vr[fi], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1), ud + (size_t)j * (nb + 1), nb,
+                           F.bound, false, y2, ld2);
+            orow[(ft + h) % F.D] = y;
+            orow[(fi + h) % F.D] = y2;
+            acc += ld + ld2;
+            bad = bad || (y != y) || (ld != ld) || (y2 != y2) || (ld2 != ld2);
+        }
+        __syncwarp();
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0) logdet[b] += acc;
+    if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+
+// sampling direction, step 1: roll, inverse unconditional spline on the identity half, periodic
+// features of the NEW identity values (coupling.py:113-124)
+__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
+    const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
+    FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
+    int* nan_flag) {
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
+    if (b >= rows) return;
+    const float* vr = v + (size_t)b * F.D;
+    const int h = F.D / 2, nb = F.nb;
+    float acc = 0.f;
+    bool bad = false;
+    for (int j = lane; j < F.N; j += 32) {
+        const int fi = F.idf[j];
+        float y, ld;
+        rqs_table_lane(vr[(fi + h) % F.D], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1),
+                       ud + (size_t)j * (nb + 1), nb, F.bound, true, y, ld);
+        out[(size_t)b * F.D + fi] = y;
+        float sn, cs;
+        sincosf(F.pf_scale * y, &sn, &cs);
+        A0[(size_t)b * 2 * F.N + j] = cs;
+        A0[(size_t)b * 2 * F.N + F.N + j] = sn;
+        acc += ld;
+        bad = bad || (y != y) || (ld != ld);
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0 && logdet) logdet[b] += acc;
+    if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+
+// sampling direction, step 3: inverse conditional spline on the transformed half (coupling.py:125-132)
+__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_forward_v2(
+    const float* __restrict__ v, const float* __restrict__ theta, float* __restrict__ out,
+    float* __restrict__ logdet, int rows, FlowDev F, int* nan_flag) {
+    extern __shared__ float sp_smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
+    if (b >= rows) return;
+    const int Ps = (2 * F.nb) | 1, nb = F.nb, h = F.D / 2;
+    float* sm = sp_smem + (size_t)wib * 32 * Ps;
+    const float* vr = v + (size_t)b * F.D;
+    const float* th = theta + (size_t)b * F.N * F.P;
+    float acc = 0.f;
+    bool bad = false;
+    for (int j0 = 0; j0 < F.N; j0 += 32) {
+        const int nc = min(32, F.N - j0);
+        stage_params(th, sm, j0, nc, F.P, 2 * nb, Ps, lane);
+        if (lane < nc) {
+            const int ft = F.trf[j0 + lane];
+            float y, ld;
+            rqs_cond_lane(vr[(ft + h) % F.D], sm + lane * Ps, th + (size_t)(j0 + lane) * F.P, nb, F.bound, F.inv_sqrt_h,
+                          true, y, ld);
+            out[(size_t)b * F.D + ft] = y;
+            acc += ld;
+            bad = bad || (y != y) || (ld != ld);
+        }
+        __syncwarp();
+    }
+    acc = warp_sum_f(acc);
+    if (lane == 0 && logdet) logdet[b] += acc;
+    if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+
+static size_t spline_smem_bytes(const fs_flow* f) {
+    return (size_t)FS_SPLINE_WARPS * 32 * ((2 * f->nb) | 1) * sizeof(float);
+}
+
 // out <- z (+ shift); logq <- logdet + UniformParticle.log_prob(z)  (Energy/Uniform.py:50-74)
 __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ v, float* __restrict__ out,
                                                      const float* __restrict__ logdet,
@@ -472,10 +675,10 @@ static int pack_layer(fs_flow* f, const fs_flow_desc* d, const fs_layer_params* 
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// rows processed per pass so that the parameter buffer theta stays below 512 MiB
+// rows processed per pass so that the parameter buffer theta stays below 4 GiB (180 GB of HBM)
 static int chunk_rows(const fs_flow* f, int B) {
     size_t per_row = (size_t)f->N * f->P * sizeof(float);
-    size_t rows = (512ull << 20) / per_row;
+    size_t rows = (4096ull << 20) / per_row;
     if (rows < 128) rows = 128;
     rows = rows / 128 * 128;
     return (int)(rows < (size_t)B ? rows : (size_t)B);
@@ -558,6 +761,12 @@ extern "C" int fs_flow_create(const fs_flow_desc* d, fs_flow** out) {
     if (!r) r = upload(f, trf, &f->trf);
     f->layers.resize(d->K);
     for (int i = 0; i < d->K && !r; ++i) r = pack_layer(f, d, &d->layers[i], &f->layers[i]);
+    if (!r && spline_smem_bytes(f) > 48 * 1024) {
+        r = cuda_check(cudaFuncSetAttribute(spline_inverse_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)spline_smem_bytes(f)), "spline smem");
+        if (!r) r = cuda_check(cudaFuncSetAttribute(spline_forward_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)spline_smem_bytes(f)), "spline smem");
+    }
     if (!r) r = tc_pack(f, d);
     if (r) {
         fs_flow_destroy(f);
@@ -621,8 +830,9 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             prep_inverse_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(cur, w.A0, rows, F);
     fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_inverse_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, L.u_x, L.u_y,
-                                                                 L.u_d, nan_flag);
+            spline_inverse_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS,
+                                spline_smem_bytes(f), s>>>(cur, w.theta, nxt, w.ld, rows, F, L.u_x, L.u_y, L.u_d,
+                                                           nan_flag);
     fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
@@ -655,11 +865,12 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
         float* nxt = w.v1;
         for (int li = 0; li < f->K; ++li) {                              // core.py:52-55
             const fs_flow::Layer& L = f->layers[li];
-            prep_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d,
-                                                               nan_flag);
+            prep_forward_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_forward_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+            spline_forward_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS,
+                                spline_smem_bytes(f), s>>>(cur, w.theta, nxt, w.ld, rows, F, nan_flag);
     fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
