@@ -44,11 +44,10 @@ __global__ void __launch_bounds__(256) accept_global_kernel(
             } else if (KIND == FS_RNG_PHILOX) {
                 uint2 key = make_uint2((uint32_t)R.philox_seed, (uint32_t)(R.philox_seed >> 32));
                 long long cid = R.chain_id0 + b;
-                uint4 ctr = make_uint4((uint32_t)att, (uint32_t)((unsigned long long)att >> 32) << 1,
-                                       (uint32_t)cid, (uint32_t)((unsigned long long)cid >> 32));
-                ctr.y |= 1u;
+                uint4 ctr = make_uint4((uint32_t)att, (uint32_t)((unsigned long long)att >> 32), (uint32_t)cid,
+                                       (uint32_t)((unsigned long long)cid >> 32));
                 uint4 r = philox4x32(ctr, key);
-                u = u32x2_to_double(r.z, r.w);
+                u = (double)r.w * (1.0 / 4294967296.0);
             } else {
                 int cu = R.replay_cursor[2 * b + 1];
                 u = R.replay_u[(size_t)b * R.u_stride + cu];

@@ -28,6 +28,7 @@ struct PotDev {
     // wells: geometry in float64 (the wall k (r - r0) is steep: k = 15 turns a float32 rounding of
     // r, r0 or the centre into > 1e-5 of energy), potential.py:89-112
     double cxd[2], cyd, Lxd, Lyd, r0d, k2d;
+    float cxf[2], cyf, well_out2, well_in;   // float32 pre-test: outside -> 0, deep inside -> V0 (|2k(r-r0)| > 90)
 };
 
 inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
@@ -52,6 +53,15 @@ inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
     d.cyd = d.Lyd / 2;
     d.r0d = (double)p->r0;
     d.k2d = 2.0 * (double)p->k;
+    d.cxf[0] = (float)d.cxd[0];
+    d.cxf[1] = (float)d.cxd[1];
+    d.cyf = (float)d.cyd;
+    {
+        const double m = p->k > 0 ? 45.0 / (double)p->k : 1e30;     // 2k m = 90: exp(+-90) is 0 / inf in float32
+        const double ro = (double)p->r0 + m;
+        d.well_out2 = (float)(ro * ro);
+        d.well_in = (float)((double)p->r0 - m);                    // may be negative: shortcut never taken
+    }
     return d;
 }
 
@@ -86,6 +96,13 @@ __device__ __forceinline__ void pair_accum(float dx, float dy, const PotDev& P,
 // V0 (1 - 0.5 (1 + tanh a)) == V0 / (1 + exp(2a)), evaluated in the stable form; the distance
 // to the well centre is formed in float64 (float32 seed + one Newton step for the root).
 __device__ __forceinline__ float well_term(float x, float y, int wi, const PotDev& P) {
+    {   // float32 pre-test with a wide margin: far outside the wall the term is exactly 0, deep inside exactly V0
+        const float fx = min_image(x - P.cxf[wi], P.Lx, P.inv_Lx);
+        const float fy = min_image(y - P.cyf, P.Ly, P.inv_Ly);
+        const float r2f = __fmaf_rn(fy, fy, fx * fx);
+        if (r2f > P.well_out2) return 0.0f;
+        if (P.well_in > 0.0f && r2f < P.well_in * P.well_in) return P.V0[wi];
+    }
     double dx = (double)x - P.cxd[wi];
     double dy = (double)y - P.cyd;
     dx -= P.Lxd * rint(dx / P.Lxd);

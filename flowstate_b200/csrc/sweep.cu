@@ -53,15 +53,13 @@ struct ChainRng {
             d.u1 = pcg.next_double();
             d.u2 = pcg.next_double();
         } else if (KIND == FS_RNG_PHILOX) {
-            // two Philox blocks per step: {idx, -, u1} and {u2, u3}
+            // one Philox block per step id: {particle index, u1, u2, accept uniform}, 32-bit each
             ctr.x = (uint32_t)step_id;
-            ctr.y = (uint32_t)((unsigned long long)step_id >> 32) << 1;
-            uint4 a = philox4x32(ctr, key);
-            ctr.y |= 1u;
+            ctr.y = (uint32_t)((unsigned long long)step_id >> 32);
             blk = philox4x32(ctr, key);
-            d.p = (int)(((uint64_t)a.x * (uint64_t)N) >> 32);
-            d.u1 = u32x2_to_double(a.z, a.w);
-            d.u2 = u32x2_to_double(blk.x, blk.y);
+            d.p = (int)__umulhi(blk.x, (uint32_t)N);
+            d.u1 = (double)blk.y * (1.0 / 4294967296.0);
+            d.u2 = (double)blk.z * (1.0 / 4294967296.0);
         } else {
             d.p = ridx[ci++];
             d.u1 = ru[cu++];
@@ -71,7 +69,7 @@ struct ChainRng {
     }
     __device__ __forceinline__ double accept_uniform() {
         if (KIND == FS_RNG_PCG64) return pcg.next_double();
-        if (KIND == FS_RNG_PHILOX) return u32x2_to_double(blk.z, blk.w);
+        if (KIND == FS_RNG_PHILOX) return (double)blk.w * (1.0 / 4294967296.0);
         return ru[cu++];
     }
     __device__ __forceinline__ void finish(const RngDev& R, int b) {
@@ -185,6 +183,108 @@ __global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ po
     }
 }
 
+
+// Throughput variant (Philox streams, no traces): the same move, with the per-step overheads trimmed -
+// one Philox block per step generated 32 steps at a time (lane l prepares step base+l, the step reads it
+// with four shuffles), energy/virial DIFFERENCES reduced instead of four separate sums, the two
+// hard-core minima through single REDUX instructions, wells behind a float32 pre-test.
+__global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
+                                                               double* __restrict__ W,
+                                                               const double* __restrict__ max_disp,
+                                                               long long* __restrict__ attempts,
+                                                               long long* __restrict__ accepted, int B, int N,
+                                                               int steps, PotDev P, double beta,
+                                                               unsigned long long seed, long long chain_id0) {
+    extern __shared__ float2 smem[];
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= B) return;
+    float2* sp = smem + (size_t)wib * N;
+    float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
+    for (int i = lane; i < N; i += 32) sp[i] = gp[i];
+    __syncwarp();
+
+    const double md = max_disp[b];
+    long long att = attempts[b];
+    int acc = 0;
+    double Eb = E[b], Wb = W[b];
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const long long cid = chain_id0 + b;
+    const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
+    const float inf = __int_as_float(0x7f800000);
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    long long blk_base = -1;
+
+    for (int s = 0; s < steps; ++s, ++att) {
+        const long long base = att & ~31ll;
+        if (base != blk_base) {              // warp-uniform: refill the 32-step block of random numbers
+            const unsigned long long sid = (unsigned long long)(base + lane);
+            blk = philox4x32(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), cz, cw), key);
+            blk_base = base;
+        }
+        const int slot = (int)(att & 31);
+        const uint32_t r_idx = __shfl_sync(0xffffffffu, blk.x, slot);
+        const uint32_t r_u1 = __shfl_sync(0xffffffffu, blk.y, slot);
+        const uint32_t r_u2 = __shfl_sync(0xffffffffu, blk.z, slot);
+        const int p = (int)__umulhi(r_idx, (uint32_t)N);
+        const float2 old = sp[p];
+        float nx = (float)((double)old.x + ((double)r_u1 * (1.0 / 4294967296.0) - 0.5) * md);
+        float ny = (float)((double)old.y + ((double)r_u2 * (1.0 / 4294967296.0) - 0.5) * md);
+        nx = np_mod(nx, P.Lx);
+        ny = np_mod(ny, P.Ly);
+
+        float de = 0.f, dw = 0.f, mo = 3.0e38f, mn = 3.0e38f;
+        for (int j = lane; j < N; j += 32) {
+            if (j == p) continue;
+            const float2 q = sp[j];
+            float eo = 0.f, wo = 0.f, en = 0.f, wn = 0.f;
+            pair_accum(old.x - q.x, old.y - q.y, P, eo, wo, mo);
+            pair_accum(nx - q.x, ny - q.y, P, en, wn, mn);
+            de += en - eo;
+            dw += wn - wo;
+        }
+        if (P.num_wells == 2) {
+            if (lane < 2) de -= well_term(old.x, old.y, lane, P);
+            else if (lane < 4) de += well_term(nx, ny, lane - 2, P);
+        } else if (P.num_wells == 1) {
+            if (lane == 0) de -= well_term(old.x, old.y, 0, P);
+            else if (lane == 1) de += well_term(nx, ny, 0, P);
+        }
+        de = warp_sum(de);
+        dw = warp_sum(dw);
+        const bool ov_o = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mo))) < P.rcore2;
+        const bool ov_n = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mn))) < P.rcore2;
+
+        bool ok;
+        if (ov_o) {
+            ok = true;                         // e_old = inf: `enn <= eno` holds for any e_new (monte_carlo.py:198)
+        } else if (ov_n) {
+            ok = false;
+        } else if (de <= 0.f) {
+            ok = true;
+        } else {
+            const uint32_t r_u3 = __shfl_sync(0xffffffffu, blk.w, slot);
+            ok = (double)r_u3 * (1.0 / 4294967296.0) < exp(-beta * (double)de);
+        }
+        if (ok) {
+            if (lane == 0) sp[p] = make_float2(nx, ny);
+            acc += 1;
+            const float big_o = ov_o ? inf : 0.f, big_n = ov_n ? inf : 0.f;
+            Eb += (double)de + ((double)big_n - (double)big_o);
+            Wb += (double)dw + ((double)big_n - (double)big_o);
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < N; i += 32) gp[i] = sp[i];
+    if (lane == 0) {
+        attempts[b] = att;
+        accepted[b] += acc;
+        E[b] = Eb;
+        W[b] = Wb;
+    }
+}
+
 __global__ void adjust_displacement_kernel(double* max_disp, const long long* att, const long long* acc,
                                            long long* patt, long long* pacc, double target, int B) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -245,6 +345,21 @@ extern "C" int fs_local_sweep(float* pos, double* E, double* W, const double* ma
             return fs::launch_sweep<FS_RNG_PCG64>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
                                                   trace_accept, trace_idx, trace_e, s);
         case FS_RNG_PHILOX:
+            if (!trace_accept && !trace_idx && !trace_e) {
+                int wpc = 4;
+                while (wpc > 1 && (size_t)wpc * N * sizeof(float2) > 200 * 1024) wpc >>= 1;
+                const size_t smem = (size_t)wpc * N * sizeof(float2);
+                if (smem > 227 * 1024) {
+                    fs::set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
+                    return FS_ERR_UNSUPPORTED;
+                }
+                if (smem > 48 * 1024)
+                    FS_CUDA(cudaFuncSetAttribute(fs::local_sweep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                fs::local_sweep_fast_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, s>>>(
+                    pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, rng->philox_seed, rng->chain_id0);
+                fs::count_launch();
+                return fs::cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
+            }
             return fs::launch_sweep<FS_RNG_PHILOX>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
                                                    trace_accept, trace_idx, trace_e, s);
         case FS_RNG_REPLAY:
