@@ -9,13 +9,16 @@
 //
 //   TMEM columns   R0 = [0, H)   : GEMM0 / linear-1 accumulator  -> after the epilogue: A operand `a`
 //                  R1 = [H, 2H)  : features / linear-0 accumulator -> after the epilogue: A operand relu(t)
-//   each region is split in two halves of NH = H/2 columns = one MMA (M=128, N=NH, K=8) per k-step,
-//   so the epilogue of one half overlaps the MMAs of the other.
-//   shared memory  u[H/4][128] float4 (residual stream with the biases folded out; a warp reads 32
-//                  consecutive rows), NSTAGE weight tiles of NH x 32 tf32 (NH*128 bytes), two
-//                  parameter sets (BatchNorm scale/offset, folded bias) prefetched by TMA, mbarriers.
-//   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4..: epilogue, one 32-column
-//                  chunk of a region half per thread (warp w touches TMEM lanes 32*(w%4)..)
+//                  final layer   : 128-column accumulators ping-pong (halves of R1 for H = 256, R1 / R2 for H = 128)
+//   one MMA = M 128 x N H x K 8 (N = 128 for the final layer); a region is handed to the MMA warp in two
+//   column halves, so linear 1 starts on the first half of relu(t) while the epilogue still writes the second.
+//   residual       the stream u (biases folded out) belongs to the epilogue threads: thread (quadrant q, column
+//                  group c) owns u[row 32q+lane][half*NH + 32c .. +32): half 0 in registers, half 1 in shared memory.
+//   shared memory  NSTAGE weight stages of H x 32 tf32 (H*128 bytes, = 4 MMAs, 512 clk of tensor pipe at
+//                  H = 256), u half 1, two parameter sets (BatchNorm scale/offset, folded bias) prefetched
+//                  by TMA, mbarriers.
+//   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4..: epilogue (warp w touches TMEM
+//                  lanes 32*(w%4)..).
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -37,7 +40,7 @@ struct TcLayer {
     float* bn0_o;      // [n_blocks, H]  BatchNorm offset with the running bias folded in
     float* b0;         // [n_blocks, H]
     float* b1;         // unused (folded)
-    float* b_final;    // [n_chunks * NH]  b_f + W_f c
+    float* b_final;    // [n_chunks * 128]  b_f + W_f c
     float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
 };
 
@@ -152,6 +155,23 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -169,20 +189,29 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
     return d;
 }
 
-// region ids: 0 = R0 half 0, 1 = R0 half 1, 2 = R1 half 0, 3 = R1 half 1
+// barrier ids.  full: MMA -> epilogue (accumulator complete).  rdy: epilogue -> MMA (operand half written, or
+// final-layer accumulator drained).
+enum { FULL_R0 = 0, FULL_R1 = 1, FULL_F0 = 2, FULL_F1 = 3 };
+enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F1 = 5 };
+
 template <int H>
 struct TcCfg {
     static constexpr int NH = H / 2;
-    static constexpr int EPI_WARPS = NH / 8;                 // 32 columns of a region half per warp-quad: 16 (H=256) / 8 (H=128)
+    static constexpr int EPI_WARPS = 4 * (NH / 32);          // one 32-column chunk per region half per thread: 16 / 8
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
-    static constexpr int STAGE_BYTES = NH * 128;
-    static constexpr int H_BYTES = H * 128 * 4;
-    static constexpr int NSTAGE = (H == 256) ? 5 : 8;
+    static constexpr int STAGE_BYTES = H * 128;              // H rows x 32 tf32
+    static constexpr int NSTAGE = (H == 256) ? 4 : 8;
+    static constexpr int GROUP = (H == 256) ? 1 : 2;         // stages issued per barrier batch (>= 512 clk of MMAs)
+    static constexpr int FCH = 128;                          // final-layer chunk width (MMA N)
+    static constexpr int KPS = STAGE_BYTES / (FCH * 128);    // final-layer k-tiles per stage
+    static constexpr int FIN0 = H;                           // TMEM column of final accumulator 0
+    static constexpr int FIN1 = (H == 256) ? H + 128 : 2 * H;
+    static constexpr int TMEM_COLS = 512;
     static constexpr int PSET_FLOATS = 3 * H;                // per parameter set: b0' | s | o'
-    static constexpr int W_OFF = H_BYTES;
-    static constexpr int P_OFF = W_OFF + NSTAGE * STAGE_BYTES;
+    static constexpr int U_OFF = NSTAGE * STAGE_BYTES;       // second column half of the residual stream: [NH/4][128] float4
+    static constexpr int P_OFF = U_OFF + NH * 128 * 4;
     static constexpr int BAR_OFF = P_OFF + 2 * PSET_FLOATS * 4;
-    static constexpr int TOTAL = BAR_OFF + 256;
+    static constexpr int TOTAL = BAR_OFF + 512;
 };
 
 template <int H>
@@ -191,23 +220,23 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     constexpr int NH = S::NH;
     constexpr int NSTAGE = S::NSTAGE;
     constexpr int EPI_WARPS = S::EPI_WARPS;
-    constexpr int KT = H / TC_KB;              // weight tiles along K for an H-wide GEMM
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    float4* hs4 = reinterpret_cast<float4*>(smem);              // u[col/4][row] as float4
-    const uint32_t w_base = smem_u32(smem + S::W_OFF);          // weight stages (1024-aligned)
+    constexpr int KT = H / TC_KB;              // weight stages along K for an H-wide GEMM
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t w_base = smem_u32(smem);                     // weight stages (1024-aligned)
     const float* pbuf = reinterpret_cast<const float*>(smem + S::P_OFF);
     const uint32_t p_base = smem_u32(smem + S::P_OFF);
     const uint32_t bar_base = smem_u32(smem + S::BAR_OFF);
     // barrier map (8 bytes each)
     const uint32_t bar_wfull = bar_base;                        // [NSTAGE] TMA -> MMA
     const uint32_t bar_wempty = bar_base + 8 * NSTAGE;          // [NSTAGE] MMA -> TMA
-    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [4]  MMA -> epilogue (accumulator half ready)
-    const uint32_t bar_ready = bar_full + 32;                   // [4]  epilogue -> MMA (operand half written / drained)
-    const uint32_t bar_free1 = bar_ready + 32;                  // [1]  MMA -> epilogue (feature piece consumed)
+    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [4]
+    const uint32_t bar_rdy = bar_full + 32;                     // [6]
+    const uint32_t bar_free1 = bar_rdy + 48;                    // [1]  MMA -> epilogue (feature piece consumed)
     const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 112);
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 120);
+    static_assert(16 * NSTAGE + 124 <= 512, "barrier area overflow");
+    float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,10 +247,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_wfull + 8 * i, 1);
             mbar_init(bar_wempty + 8 * i, 1);
         }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_ready + 8 * i, EPI_WARPS);
-        }
+        for (int i = 0; i < 4; ++i) mbar_init(bar_full + 8 * i, 1);
+        for (int i = 0; i < 6; ++i) mbar_init(bar_rdy + 8 * i, EPI_WARPS);
         mbar_init(bar_free1, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "n"(2 * H));
+                     "n"(S::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -239,9 +266,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
-        // ===================== TMA producer: parameter sets + the layer's weight tiles, in order =====================
-        {
+    if (warp < 4) {
+        if (warp == 0) {
+            // ===================== TMA producer: parameter sets + the layer's weight stages, in order =====================
             const uint8_t* src = (const uint8_t*)g.L.wstream;
             uint32_t stage = 0, phase = 0;
             long long w_empty = 0;
@@ -262,16 +289,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 for (unsigned long long e = t + n; t < e; ++t) {
                     mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1, g.dbg ? &w_empty : nullptr);
                     // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
-                    // scripts/tma_bw2.cu, 20 B/clk for 16 KB copies whatever the depth); copies issued by
-                    // different lanes overlap.  Rotate the issuing lane so 8 tiles can be in flight.
+                    // scripts/tma_bw2.cu); copies issued by different lanes overlap -> rotate the issuing lane.
                     if (lane == (int)(t & 7)) {
-                        if (g.dbg_mode & 4) {
-                            mbar_arrive(bar_wfull + 8 * stage);      // timing experiment: no weight traffic
-                        } else {
-                            mbar_expect_tx(bar_wfull + 8 * stage, S::STAGE_BYTES);
-                            tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, S::STAGE_BYTES,
-                                         bar_wfull + 8 * stage);
-                        }
+                        mbar_expect_tx(bar_wfull + 8 * stage, S::STAGE_BYTES);
+                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, S::STAGE_BYTES,
+                                     bar_wfull + 8 * stage);
                     }
                     __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -279,46 +301,40 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             };
             load_pset(0);
             load_pset(1);
-            stream(2ull * (g.Kp0 / TC_KB));                       // GEMM0
+            stream((unsigned long long)(g.Kp0 / TC_KB));          // GEMM0
             for (int b = 0; b < g.n_blocks; ++b) {
                 if (b >= 1) load_pset(b + 1);
-                stream(4ull * KT);
+                stream(2ull * KT);
             }
-            stream((unsigned long long)g.n_chunks * KT);         // final layer
+            stream((unsigned long long)g.n_chunks * (KT / S::KPS));   // final layer
             if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 0] = w_empty;
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-        {
-            // instruction descriptor: D=F32, A=B=TF32, both K-major, N = NH, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | (8u << 24);
+        } else if (warp == 1) {
+            // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+            // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
+            const uint32_t idesc_blk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
+            const uint32_t idesc_fin = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
             uint32_t stage = 0, wphase = 0;
-            uint32_t ph_ready = 0;     // parity to wait for, per region
+            uint32_t ph_rdy = 0;       // parity to wait for, per rdy barrier
             long long w_ready = 0, w_weights = 0, t_issue = 0;
             const long long t_start = g.dbg ? clock64() : 0;
-            auto wait_ready = [&](int region) {
-                mbar_wait(bar_ready + 8 * region, (ph_ready >> region) & 1, g.err, 2, g.dbg ? &w_ready : nullptr);
-                ph_ready ^= 1u << region;
+            auto wait_rdy = [&](int id) {
+                mbar_wait(bar_rdy + 8 * id, (ph_rdy >> id) & 1, g.err, 2, g.dbg ? &w_ready : nullptr);
+                ph_rdy ^= 1u << id;
                 tc_fence_after();
             };
             auto commit = [&](uint32_t bar) {
                 if (elect_one()) tc_commit(bar);
                 __syncwarp();
             };
-            // Weight tiles are consumed in groups of up to TC_GROUP: the group's full-barriers are waited
-            // for back to back, then all 4*n MMAs are queued at once, so the issuing warp's bookkeeping
-            // (barrier probes, descriptor set-up) between two groups is shorter than the time the tensor
-            // pipe needs for a group.  The first barrier of the NEXT group is probed right after the
-            // MMAs are queued.
-            constexpr int TC_GROUP = 2;
-            bool peeked = false;
-            auto mma_group = [&](uint32_t dcol, uint32_t acol, int n, bool first) {
-                uint32_t st[TC_GROUP];
+            // Issues `n` weight stages (n <= GROUP): their full-barriers are waited for back to back, then all the
+            // MMAs are queued at once.  Block GEMMs: one stage = one 32-wide k-tile of all H output columns
+            // (4 MMAs of N = H).  Final layer: one stage = KPS consecutive k-tiles of a 128-column chunk.
+            auto issue = [&](uint32_t dcol, uint32_t acol, int n, bool first, bool fin) {
+                uint32_t st[S::GROUP];
 #pragma unroll
-                for (int i = 0; i < TC_GROUP; ++i) {
+                for (int i = 0; i < S::GROUP; ++i) {
                     if (i < n) {
-                        if (!(i == 0 && peeked))
-                            mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3, g.dbg ? &w_weights : nullptr);
+                        mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3, g.dbg ? &w_weights : nullptr);
                         st[i] = stage;
                         if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
                     }
@@ -327,59 +343,67 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const long long ti = g.dbg ? clock64() : 0;
                 if (elect_one()) {
 #pragma unroll
-                    for (int i = 0; i < TC_GROUP; ++i) {
+                    for (int i = 0; i < S::GROUP; ++i) {
                         if (i < n) {
                             const uint32_t sb = w_base + st[i] * S::STAGE_BYTES;
+                            if (!fin) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, make_b_desc(sb + 32 * j), idesc,
-                                          (first && i == 0 && j == 0) ? 0u : 1u);
+                                for (int j = 0; j < 4; ++j)
+                                    tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, make_b_desc(sb + 32 * j),
+                                              idesc_blk, (first && i == 0 && j == 0) ? 0u : 1u);
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < S::KPS; ++kk)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        tc_mma_ts(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
+                                                  make_b_desc(sb + kk * (S::FCH * 128) + 32 * j), idesc_fin,
+                                                  (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
+                            }
                             tc_commit(bar_wempty + 8 * st[i]);
                         }
                     }
                 }
                 __syncwarp();
                 if (g.dbg) t_issue += clock64() - ti;
-                peeked = mbar_try(bar_wfull + 8 * stage, wphase);
             };
-            // GEMM over K = ktiles*32 columns of operand region `abase` (TMEM column), K-ordered waits on
-            // the two halves of that region (region ids ra0, ra0 + 1)
-            auto gemm_half = [&](uint32_t dcol, uint32_t abase, int ra0, int ktiles, bool fresh, bool waitA) {
-                for (int kt = 0; kt < ktiles; kt += TC_GROUP) {
+            // block-type GEMM over `ktiles` k-tiles of operand region `abase`; K-ordered waits on its two halves
+            auto gemm_blk = [&](uint32_t dcol, uint32_t abase, int rdy0, int ktiles, bool fresh, bool waitA) {
+                for (int kt = 0; kt < ktiles; kt += S::GROUP) {
                     if (waitA) {
-                        if (kt == 0) wait_ready(ra0);
-                        if (kt * TC_KB == NH) wait_ready(ra0 + 1);
+                        if (kt == 0) wait_rdy(rdy0);
+                        if (kt * TC_KB == NH) wait_rdy(rdy0 + 1);
                     }
-                    mma_group(dcol, abase + kt * TC_KB, min(TC_GROUP, ktiles - kt), fresh && kt == 0);
+                    issue(dcol, abase + kt * TC_KB, min(S::GROUP, ktiles - kt), fresh && kt == 0, false);
                 }
             };
             // ---- GEMM0: features (R1) -> R0 ----
             for (int p = 0; p < g.n_pieces; ++p) {
                 const int kcols = min(H, g.Kp0 - p * H);
-                const int ktiles = kcols / TC_KB;
-                for (int nh = 0; nh < 2; ++nh) {
-                    if (nh == 0) { wait_ready(2); wait_ready(3); }
-                    gemm_half(nh * NH, H, 2, ktiles, p == 0, false);
-                    if (p == g.n_pieces - 1) commit(bar_full + 8 * nh);
-                }
+                wait_rdy(RDY_R1H0);
+                wait_rdy(RDY_R1H1);
+                gemm_blk(0, H, RDY_R1H0, kcols / TC_KB, p == 0, false);
                 if (p < g.n_pieces - 1) commit(bar_free1);
             }
+            commit(bar_full + 8 * FULL_R0);
             // ---- residual blocks ----
             for (int b = 0; b < g.n_blocks; ++b) {
-                for (int nh = 0; nh < 2; ++nh) {           // linear 0: A = R0 (a), D = R1 half nh
-                    gemm_half(H + nh * NH, 0, 0, KT, true, nh == 0);
-                    commit(bar_full + 8 * (2 + nh));
-                }
-                for (int nh = 0; nh < 2; ++nh) {           // linear 1: A = R1 (relu t), D = R0 half nh
-                    gemm_half(nh * NH, H, 2, KT, true, nh == 0);
-                    commit(bar_full + 8 * nh);
-                }
+                gemm_blk(H, 0, RDY_R0H0, KT, true, true);       // linear 0: A = R0 (a), D = R1
+                commit(bar_full + 8 * FULL_R1);
+                gemm_blk(0, H, RDY_R1H0, KT, true, true);       // linear 1: A = R1 (relu t), D = R0
+                commit(bar_full + 8 * FULL_R0);
             }
-            // ---- final layer: A = R0 (u), D = R1 half (c & 1), chunk after chunk ----
+            // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
+            wait_rdy(RDY_R0H0);
+            wait_rdy(RDY_R0H1);
             for (int c = 0; c < g.n_chunks; ++c) {
-                if (c >= 2) wait_ready(2 + (c & 1));       // epilogue drained chunk c-2
-                gemm_half(H + (c & 1) * NH, 0, 0, KT, true, c == 0);
-                commit(bar_full + 8 * (2 + (c & 1)));
+                const int f = c & 1;
+                if (c >= 2) wait_rdy(RDY_F0 + f);              // epilogue drained chunk c-2
+                const uint32_t dcol = f ? S::FIN1 : S::FIN0;
+                constexpr int SPC = KT / S::KPS;               // stages per chunk
+                for (int sg = 0; sg < SPC; sg += S::GROUP)
+                    issue(dcol, sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true);
+                commit(bar_full + 8 * (FULL_F0 + f));
             }
             if (g.dbg && lane == 0) {
                 g.dbg[8 * blockIdx.x + 1] = w_ready;
@@ -388,8 +412,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 g.dbg[8 * blockIdx.x + 6] = t_issue;
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue warps: one 32-column chunk of a region half per thread =====================
+    } else {
+        // ===================== epilogue warps =====================
         const int ew = warp - 4;
         const int q = ew & 3;                    // TMEM lane quadrant (== warp % 4)
         const int cgp = ew >> 2;                 // 32-column group inside a region half
@@ -400,16 +424,16 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         uint32_t ph_full = 0, ph_free1 = 0, ph_pfull = 0;
         long long w_full = 0;
         const long long e_start = g.dbg ? clock64() : 0;
-        auto wait_full = [&](int region) {
-            mbar_wait(bar_full + 8 * region, (ph_full >> region) & 1, g.err, 4,
+        auto wait_full = [&](int id) {
+            mbar_wait(bar_full + 8 * id, (ph_full >> id) & 1, g.err, 4,
                       (g.dbg && ew == 0 && lane == 0) ? &w_full : nullptr);
-            ph_full ^= 1u << region;
+            ph_full ^= 1u << id;
             tc_fence_after();
         };
-        auto signal_ready = [&](int region) {
+        auto signal_rdy = [&](int id) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_ready + 8 * region);
+            if (lane == 0) mbar_arrive(bar_rdy + 8 * id);
         };
         auto wait_pset = [&](int j) {
             mbar_wait(bar_pfull + 8 * (j & 1), (ph_pfull >> (j & 1)) & 1, g.err, 7);
@@ -419,7 +443,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_pempty + 8 * (j & 1));
         };
-        uint32_t v[32];
+        uint32_t v[16];
+        float u0[32];                            // residual stream, column half 0 (half 1 lives in shared memory)
 
         // ---- features -> R1 (A operand of GEMM0), piece by piece ----
         for (int p = 0; p < g.n_pieces; ++p) {
@@ -429,113 +454,144 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 tc_fence_after();
             }
             const int kcols = min(H, g.Kp0 - p * H);
-            for (int nh = 0; nh < 2; ++nh) {
-                const int col = nh * NH + cgp * 32;              // column inside R1
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                const int col = hf * NH + cgp * 32;              // column inside R1
                 if (col < kcols) {
                     const int k0 = p * H + col;
                     const float* src = g.A0 + (size_t)grow * g.K0 + k0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float x = 0.f;
-                        if (row_ok && k0 + i < g.K0) x = __ldg(src + i);
-                        v[i] = to_tf32(x);
+                    for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float x = 0.f;
+                            if (row_ok && k0 + 16 * sub + i < g.K0) x = __ldg(src + 16 * sub + i);
+                            v[i] = to_tf32(x);
+                        }
+                        tc_st16(lane_addr + H + col + 16 * sub, v);
                     }
-                    tc_st32(lane_addr + H + col, v);
                 }
                 tc_wait_st();
-                signal_ready(2 + nh);
+                signal_rdy(RDY_R1H0 + hf);
             }
         }
-        // ---- residual-stream epilogue.  The stream is kept as u = h - c, c = all biases added so far
-        //      (folded into the BatchNorm offsets and the final bias at pack time), so a block boundary
-        //      costs: u (+)= D ; operand = relu(s u + o')  (or u itself in front of the final layer) ----
-        auto epi_residual = [&](int nh, const float* prm, bool has_next, bool init) {
-            const int col = nh * NH + cgp * 32;
-            wait_full(nh);
-            if (g.dbg_mode & 1) { signal_ready(nh); return; }
-            tc_ld32(lane_addr + col, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-                float4* hp = hs4 + (size_t)((col >> 2) + i4) * 128 + r;
-                float4 u = make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),
-                                       __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
-                if (!init) {
-                    const float4 h0 = *hp;
-                    u.x += h0.x; u.y += h0.y; u.z += h0.z; u.w += h0.w;
-                }
-                *hp = u;
-                if (has_next) {
-                    const float4 sc = *reinterpret_cast<const float4*>(prm + H + col + 4 * i4);
-                    const float4 of = *reinterpret_cast<const float4*>(prm + 2 * H + col + 4 * i4);
-                    u.x = fmaxf(__fmaf_rn(u.x, sc.x, of.x), 0.f);
-                    u.y = fmaxf(__fmaf_rn(u.y, sc.y, of.y), 0.f);
-                    u.z = fmaxf(__fmaf_rn(u.z, sc.z, of.z), 0.f);
-                    u.w = fmaxf(__fmaf_rn(u.w, sc.w, of.w), 0.f);
-                }
-                v[4 * i4] = to_tf32(u.x);
-                v[4 * i4 + 1] = to_tf32(u.y);
-                v[4 * i4 + 2] = to_tf32(u.z);
-                v[4 * i4 + 3] = to_tf32(u.w);
-            }
-            tc_st32(lane_addr + col, v);
-            tc_wait_st();
-            signal_ready(nh);
-        };
+        // ---- residual-stream step on R0 (u = h - c, c = biases so far, folded at pack time):
+        //      u (+)= D ; operand = relu(s u + o')   (or u itself in front of the final layer) ----
+#define FS_EPI_RESIDUAL(HF, PRM, HAS_NEXT, INIT)                                                               \
+    {                                                                                                          \
+        const int col = (HF) * NH + cgp * 32;                                                                  \
+        _Pragma("unroll") for (int sub = 0; sub < 2; ++sub) {                                                  \
+            tc_ld16(lane_addr + col + 16 * sub, v);                                                            \
+            tc_wait_ld();                                                                                      \
+            _Pragma("unroll") for (int i4 = 0; i4 < 4; ++i4) {                                                 \
+                float4 uu = make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),            \
+                                        __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));       \
+                if ((HF) == 0) {                                                                               \
+                    if (!(INIT)) {                                                                             \
+                        uu.x += u0[16 * sub + 4 * i4]; uu.y += u0[16 * sub + 4 * i4 + 1];                      \
+                        uu.z += u0[16 * sub + 4 * i4 + 2]; uu.w += u0[16 * sub + 4 * i4 + 3];                  \
+                    }                                                                                          \
+                    u0[16 * sub + 4 * i4] = uu.x; u0[16 * sub + 4 * i4 + 1] = uu.y;                            \
+                    u0[16 * sub + 4 * i4 + 2] = uu.z; u0[16 * sub + 4 * i4 + 3] = uu.w;                        \
+                } else {                                                                                       \
+                    float4* hp = us4 + (size_t)(cgp * 8 + sub * 4 + i4) * 128 + r;                             \
+                    if (!(INIT)) {                                                                             \
+                        const float4 h0 = *hp;                                                                 \
+                        uu.x += h0.x; uu.y += h0.y; uu.z += h0.z; uu.w += h0.w;                                \
+                    }                                                                                          \
+                    *hp = uu;                                                                                  \
+                }                                                                                              \
+                if (HAS_NEXT) {                                                                                \
+                    const float4 sc = *reinterpret_cast<const float4*>((PRM) + H + col + 16 * sub + 4 * i4);   \
+                    const float4 of = *reinterpret_cast<const float4*>((PRM) + 2 * H + col + 16 * sub + 4 * i4); \
+                    uu.x = fmaxf(__fmaf_rn(uu.x, sc.x, of.x), 0.f);                                            \
+                    uu.y = fmaxf(__fmaf_rn(uu.y, sc.y, of.y), 0.f);                                            \
+                    uu.z = fmaxf(__fmaf_rn(uu.z, sc.z, of.z), 0.f);                                            \
+                    uu.w = fmaxf(__fmaf_rn(uu.w, sc.w, of.w), 0.f);                                            \
+                }                                                                                              \
+                v[4 * i4] = to_tf32(uu.x); v[4 * i4 + 1] = to_tf32(uu.y);                                      \
+                v[4 * i4 + 2] = to_tf32(uu.z); v[4 * i4 + 3] = to_tf32(uu.w);                                  \
+            }                                                                                                  \
+            tc_st16(lane_addr + col + 16 * sub, v);                                                            \
+        }                                                                                                      \
+        tc_wait_st();                                                                                          \
+        signal_rdy(RDY_R0H0 + (HF));                                                                           \
+    }
         wait_pset(0);
-        for (int nh = 0; nh < 2; ++nh) epi_residual(nh, pbuf, true, true);
+        wait_full(FULL_R0);
+        FS_EPI_RESIDUAL(0, pbuf, true, true)
+        FS_EPI_RESIDUAL(1, pbuf, true, true)
         release_pset(0);
         // ---- residual blocks ----
         for (int b = 0; b < g.n_blocks; ++b) {
             const float* prm = pbuf + (size_t)((b + 1) & 1) * S::PSET_FLOATS;
             wait_pset(b + 1);
-            for (int nh = 0; nh < 2; ++nh) {                 // relu(t + b0') in place in R1
-                const int col = nh * NH + cgp * 32;
-                wait_full(2 + nh);
-                if (g.dbg_mode & 1) { signal_ready(2 + nh); continue; }
-                tc_ld32(lane_addr + H + col, v);
-                tc_wait_ld();
+            wait_full(FULL_R1);
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(prm + col + 4 * i4);
-                    v[4 * i4] = to_tf32(fmaxf(__uint_as_float(v[4 * i4]) + bb.x, 0.f));
-                    v[4 * i4 + 1] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 1]) + bb.y, 0.f));
-                    v[4 * i4 + 2] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 2]) + bb.z, 0.f));
-                    v[4 * i4 + 3] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 3]) + bb.w, 0.f));
+            for (int hf = 0; hf < 2; ++hf) {                  // relu(t + b0') in place in R1
+                const int col = hf * NH + cgp * 32;
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    tc_ld16(lane_addr + H + col + 16 * sub, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(prm + col + 16 * sub + 4 * i4);
+                        v[4 * i4] = to_tf32(fmaxf(__uint_as_float(v[4 * i4]) + bb.x, 0.f));
+                        v[4 * i4 + 1] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 1]) + bb.y, 0.f));
+                        v[4 * i4 + 2] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 2]) + bb.z, 0.f));
+                        v[4 * i4 + 3] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 3]) + bb.w, 0.f));
+                    }
+                    tc_st16(lane_addr + H + col + 16 * sub, v);
                 }
-                tc_st32(lane_addr + H + col, v);
                 tc_wait_st();
-                signal_ready(2 + nh);
+                signal_rdy(RDY_R1H0 + hf);
             }
             const bool last = (b == g.n_blocks - 1);
-            for (int nh = 0; nh < 2; ++nh) epi_residual(nh, prm, !last, false);
+            wait_full(FULL_R0);
+            if (!last) {
+                FS_EPI_RESIDUAL(0, prm, true, false)
+                FS_EPI_RESIDUAL(1, prm, true, false)
+            } else {
+                FS_EPI_RESIDUAL(0, prm, false, false)
+                FS_EPI_RESIDUAL(1, prm, false, false)
+            }
             release_pset(b + 1);
         }
+#undef FS_EPI_RESIDUAL
         // ---- final layer: theta chunk = D + b_final' -> global ----
         const bool vec_ok = (g.NP & 3) == 0;
+        constexpr int CPT = (S::FCH / 32) * 4 / EPI_WARPS;     // 32-column chunks of a final accumulator per thread: 1 / 2
         for (int c = 0; c < g.n_chunks; ++c) {
-            const int region = 2 + (c & 1);
-            const int col = cgp * 32;                         // column inside the chunk
-            wait_full(region);
-            tc_ld32(lane_addr + H + (c & 1) * NH + col, v);
-            tc_wait_ld();
-            signal_ready(region);                             // accumulator half is in registers: MMA may reuse it
-            const int ocol = c * NH + col;
-            if (row_ok) {
-                float* dst = g.theta + (size_t)grow * g.NP + ocol;
-                const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_final + ocol);
-                if (vec_ok && ocol + 32 <= g.NP) {
+            const int f = c & 1;
+            wait_full(FULL_F0 + f);
+            const uint32_t fcol = f ? S::FIN1 : S::FIN0;
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        const float4 bb = __ldg(bf4 + i4);
-                        reinterpret_cast<float4*>(dst)[i4] =
-                            make_float4(__uint_as_float(v[4 * i4]) + bb.x, __uint_as_float(v[4 * i4 + 1]) + bb.y,
-                                        __uint_as_float(v[4 * i4 + 2]) + bb.z, __uint_as_float(v[4 * i4 + 3]) + bb.w);
+            for (int cc = 0; cc < CPT; ++cc) {
+                const int col = (cgp + cc * (EPI_WARPS / 4)) * 32;     // column inside the chunk
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    tc_ld16(lane_addr + fcol + col + 16 * sub, v);
+                    tc_wait_ld();
+                    if (cc == CPT - 1 && sub == 1) signal_rdy(RDY_F0 + f);   // all of this thread's reads are done
+                    const int ocol = c * S::FCH + col + 16 * sub;
+                    if (row_ok) {
+                        float* dst = g.theta + (size_t)grow * g.NP + ocol;
+                        if (vec_ok && ocol + 16 <= g.NP) {
+                            const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_final + ocol);
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 bb = __ldg(bf4 + i4);
+                                reinterpret_cast<float4*>(dst)[i4] =
+                                    make_float4(__uint_as_float(v[4 * i4]) + bb.x, __uint_as_float(v[4 * i4 + 1]) + bb.y,
+                                                __uint_as_float(v[4 * i4 + 2]) + bb.z, __uint_as_float(v[4 * i4 + 3]) + bb.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (ocol + i < g.NP) dst[i] = __uint_as_float(v[i]) + __ldg(g.L.b_final + ocol + i);
+                        }
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (ocol + i < g.NP) dst[i] = __uint_as_float(v[i]) + __ldg(g.L.b_final + ocol + i);
                 }
             }
         }
@@ -548,7 +604,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * H));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(S::TMEM_COLS));
     }
 }
 
@@ -566,12 +622,12 @@ static inline float tf32_round(float x) {
     return y;
 }
 
-// appends the tile rows [n0, n0+NH) x cols [k0, k0+32) of W [n_rows, n_cols] (row-major) in the
+// appends the tile rows [n0, n0+ROWS) x cols [k0, k0+32) of W [n_rows, n_cols] (row-major) in the
 // SWIZZLE_128B K-major shared-memory image: row i at i*128 bytes, its 16-byte chunk c at (c ^ (i & 7)).
-static void append_tile(std::vector<float>& out, const float* W, int n_rows, int n_cols, int n0, int k0, int NH) {
+static void append_tile(std::vector<float>& out, const float* W, int n_rows, int n_cols, int n0, int k0, int ROWS) {
     const size_t base = out.size();
-    out.resize(base + (size_t)NH * 32, 0.f);
-    for (int i = 0; i < NH; ++i) {
+    out.resize(base + (size_t)ROWS * 32, 0.f);
+    for (int i = 0; i < ROWS; ++i) {
         const int n = n0 + i;
         if (n >= n_rows) continue;
         for (int c = 0; c < 8; ++c) {
@@ -610,10 +666,11 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     P->Kp0 = (K0 + TC_KB - 1) / TC_KB * TC_KB;
     P->n_pieces = (P->Kp0 + H - 1) / H;
     const int NP = f->N * f->P;
-    P->n_chunks = (NP + P->NH - 1) / P->NH;
+    const int FCH = 128;                                   // final-layer chunk width (TcCfg::FCH)
+    P->n_chunks = (NP + FCH - 1) / FCH;
     P->smem_bytes = (H == 256 ? TcCfg<256>::TOTAL : TcCfg<128>::TOTAL) + 1024;
     if ((int)P->smem_bytes > smem_max) { delete P; return FS_OK; }
-    const int NH = P->NH, KT = H / TC_KB;
+    const int KT = H / TC_KB;
     P->layers.resize(f->K);
     for (int li = 0; li < f->K; ++li) {
         const fs_layer_params* p = &d->layers[li];
@@ -636,24 +693,25 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                     }
                 }
             }
+        // weight stream in consumption order, one stage = H*128 bytes:
+        //   block GEMMs: k-tile kt of all H output rows;  final layer: KPS consecutive k-tiles of a 128-row chunk
+        const int KPS = (H * 128) / (FCH * 128);
         std::vector<float> stream;
-        stream.reserve((size_t)NH * 32 * (2 * P->Kp0 / TC_KB + (size_t)nB * 4 * KT + (size_t)P->n_chunks * KT));
+        stream.reserve((size_t)H * 32 * (P->Kp0 / TC_KB + (size_t)nB * 2 * KT) + (size_t)P->n_chunks * FCH * H);
         for (int pc = 0; pc < P->n_pieces; ++pc) {                       // GEMM0
             const int kcols = std::min(H, P->Kp0 - pc * H);
-            for (int nh = 0; nh < 2; ++nh)
-                for (int kt = 0; kt < kcols / TC_KB; ++kt)
-                    append_tile(stream, p->init_w, H, K0, nh * NH, pc * H + kt * TC_KB, NH);
+            for (int kt = 0; kt < kcols / TC_KB; ++kt) append_tile(stream, p->init_w, H, K0, 0, pc * H + kt * TC_KB, H);
         }
         for (int b = 0; b < nB; ++b) {
-            for (int nh = 0; nh < 2; ++nh)                               // linear 0 (BN1 folded)
-                for (int kt = 0; kt < KT; ++kt) append_tile(stream, &w0[(size_t)b * H * H], H, H, nh * NH, kt * TC_KB, NH);
+            for (int kt = 0; kt < KT; ++kt) append_tile(stream, &w0[(size_t)b * H * H], H, H, 0, kt * TC_KB, H);   // linear 0 (BN1 folded)
             const float* w1 = p->lin_w + ((size_t)b * 2 + 1) * H * H;
-            for (int nh = 0; nh < 2; ++nh)                               // linear 1
-                for (int kt = 0; kt < KT; ++kt) append_tile(stream, w1, H, H, nh * NH, kt * TC_KB, NH);
+            for (int kt = 0; kt < KT; ++kt) append_tile(stream, w1, H, H, 0, kt * TC_KB, H);                      // linear 1
         }
         for (int c = 0; c < P->n_chunks; ++c)                            // final layer
-            for (int kt = 0; kt < KT; ++kt) append_tile(stream, p->final_w, NP, H, c * NH, kt * TC_KB, NH);
-        P->tiles_per_layer = stream.size() / ((size_t)NH * TC_KB);
+            for (int sg = 0; sg < KT / KPS; ++sg)
+                for (int kk = 0; kk < KPS; ++kk)
+                    append_tile(stream, p->final_w, NP, H, c * FCH, (sg * KPS + kk) * TC_KB, FCH);
+        P->tiles_per_layer = stream.size() / ((size_t)H * 32);
         TcLayer& L = P->layers[li];
         // Bias folding: the kernel carries u = h - c (c = b_init + sum of linear-1 biases so far):
         //   relu(s h + o) = relu(s u + (o + s c)),   W_f h + b_f = W_f u + (b_f + W_f c)
@@ -665,7 +723,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                 c[k] += (double)p->lin_b[((size_t)b * 2 + 1) * H + k];
             }
         }
-        std::vector<float> bfin((size_t)P->n_chunks * NH, 0.f);
+        std::vector<float> bfin((size_t)P->n_chunks * FCH, 0.f);
         for (int n = 0; n < NP; ++n) {
             double acc = (double)p->final_b[n];
             const float* wr = p->final_w + (size_t)n * H;
