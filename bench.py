@@ -77,7 +77,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -214,8 +214,8 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="alg1_n32", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="auto", choices=["auto", "tf32", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -359,19 +359,24 @@ def main():
     h2d = B * n * 2 * 4 + B * 2 * n * 4
     d2h = B * n * 2 * 4 + B * 8 + B
 
-    # ---- roofline of the dominant kernel: the conditioner GEMM chain inside one flow pass ----
+    # ---- roofline of the dominant kernel: the conditioner of one coupling layer (one launch per layer and pass),
+    #      timed alone with CUDA events on the launching stream, on the row count of the log-density pass ----
     xin = eng.centred(torch.cat([eng.pos, eng.pos]))
     model.log_prob(xin)
+    pack = model._cuda_pack()
+    feats = torch.cat([torch.cos(xin[:, 0::2] * (np.pi / bound)), torch.sin(xin[:, 0::2] * (np.pi / bound))], dim=1).contiguous()
+    for li in range(3):
+        pack.conditioner(li, feats)
     torch.cuda.synchronize()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
+    reps = 2 * w["K"]
     r0.record()
-    for _ in range(reps):
-        model.log_prob(xin)
+    for i in range(reps):
+        pack.conditioner(i % w["K"], feats)          # cycles through the layers: weights stream from HBM/L2 as in a pass
     r1.record()
     torch.cuda.synchronize()
     pass_ms = r0.elapsed_time(r1) / reps
-    flops_pass = flops_per_sample_layer(w) * w["K"] * xin.shape[0]
+    flops_pass = flops_per_sample_layer(w) * xin.shape[0]
     # phase split of one round (not part of the timed region above)
     phases = {}
 
@@ -421,7 +426,8 @@ def main():
         "gpu_launches": launches, "clocks": clk, "phases_ms": phases,
         "e2e": {"value": steps_total / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "roofline": {"bound": "tensor", "kernel": "flow conditioner GEMM chain (%s) inside fs_flow_inverse" % prec,
+        "roofline": {"bound": "tensor", "kernel": ("tc_conditioner_kernel (tcgen05 kind::tf32)" if prec == "tf32" else "linear_kernel chain (fp32)")
+                     + ", one coupling layer",
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                      "traffic": None, "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
                      "launch_ms": pass_ms, "rows": int(xin.shape[0])},

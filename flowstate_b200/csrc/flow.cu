@@ -805,6 +805,28 @@ static int check_ws(const fs_flow* f, int B, int precision, void* ws, size_t byt
     return FS_OK;
 }
 
+// ResidualNet.forward of one layer's conditioner (nets/resnet.py:92-104, eval mode) on ready-made
+// periodic features: features [rows, 2N] -> theta [rows, N (3nb+1)].  rows must not exceed the chunk
+// the workspace was sized for.
+extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features, int rows, float* theta,
+                                   void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    if (!f || !features || !theta || rows < 0 || layer < 0 || layer >= f->K) {
+        set_error("fs_flow_conditioner: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (rows == 0) return FS_OK;
+    if (int r = check_ws(f, rows, precision, workspace, workspace_bytes, "fs_flow_conditioner")) return r;
+    if (rows > chunk_rows(f, rows)) {
+        set_error("fs_flow_conditioner: rows=%d exceeds one workspace chunk (%d)", rows, chunk_rows(f, rows));
+        return FS_ERR_INVALID;
+    }
+    Workspace w;
+    carve(f, rows, precision, workspace, &w);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, layer, features, rows, theta, w.tc, w.tc_bytes, s);
+    return conditioner_fp32(f, layer, features, rows, w.h, w.t, theta, s);
+}
+
 extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shift, float* z, float* logdet,
                                float* logq, int* nan_flag, void* workspace, size_t workspace_bytes, int precision,
                                void* stream) {

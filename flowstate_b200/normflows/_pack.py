@@ -178,6 +178,17 @@ class FlowPack:
         self._nan = nan
         return x, ld
 
+    def conditioner(self, layer, features):
+        """Conditioner (ResidualNet, eval mode) of one layer on periodic features [rows, 2N] -> theta."""
+        features = _lib.require_cuda(features, "features")
+        rows = features.shape[0]
+        prec = _PREC[self.precision]
+        theta = torch.empty(rows, self.N * (3 * self.nb + 1), dtype=torch.float32, device=features.device)
+        ws = self._workspace(rows, prec)
+        _lib.check(_lib.lib().fs_flow_conditioner(self._h, int(layer), _lib.ptr(features), rows, _lib.ptr(theta),
+                                                  _lib.ptr(ws), ws.numel(), prec, _lib.stream_ptr(features.device)))
+        return theta
+
     def check_nan(self):
         """Surfaces the device-side NaN flag like the reference's ValueError (utils/splines.py:176-183)."""
         if int(self._nan.item()):

@@ -174,6 +174,11 @@ int fs_flow_create(const fs_flow_desc* desc /*host*/, fs_flow** out);
 void fs_flow_destroy(fs_flow* flow);
 size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
 
+/* ResidualNet.forward of the conditioner of layer `layer`  (NF/normflows/nets/resnet.py:92-104, eval mode)
+ * on ready-made periodic features [rows, 2N] (NF/normflows/utils/nn.py:120-137) -> theta [rows, N (3 nb + 1)]. */
+int fs_flow_conditioner(fs_flow* flow, int layer, const float* features, int rows, float* theta,
+                        void* workspace, size_t workspace_bytes, int precision, void* stream);
+
 /* NormalizingFlow.inverse_and_log_det / log_prob  (NF/normflows/core.py:71-86,198-214):
  * x [B, D] -> z [B, D], logdet [B]; x_in = x - in_shift (MC-box -> centred coords,
  * MCMC/monte_carlo.py:251-258).  logq (nullable) = logdet + UniformParticle.log_prob(z)
