@@ -43,6 +43,7 @@ _PROTOS = {
     "fs_last_error": (C.c_char_p, []),
     "fs_version": (C.c_int, []),
     "fs_launch_count": (C.c_ulonglong, []),
+    "fs_set_device": (C.c_int, [C.c_int]),
     "fs_apply_pbc": (C.c_int, [_P, C.c_longlong, C.c_float, C.c_float, _P]),
     "fs_distances": (C.c_int, [_P, C.c_int, _P, C.c_longlong, C.c_float, C.c_float, _P, _P]),
     "fs_lj_pair": (C.c_int, [_P, C.c_longlong, C.POINTER(FsPot), _P, _P, _P]),
@@ -106,7 +107,21 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_bound_device = None
+
+
+def bind_device(device=None):
+    """Points the library's CUDA runtime at `device` (default: torch's current device)."""
+    global _bound_device
+    idx = torch.cuda.current_device() if device is None or getattr(device, "index", device) is None \
+        else getattr(device, "index", device)
+    if idx != _bound_device:
+        check(lib().fs_set_device(int(idx)))
+        _bound_device = idx
+
+
 def stream_ptr(device=None):
+    bind_device(device)
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 

@@ -28,3 +28,9 @@ void count_launch(int n) { g_launches += (unsigned long long)n; }
 extern "C" unsigned long long fs_launch_count(void) { return fs::g_launches; }
 extern "C" const char* fs_last_error(void) { return fs::g_err; }
 extern "C" int fs_version(void) { return 100; }
+
+// The library links its own (static) CUDA runtime, whose "current device" is separate from the
+// caller's runtime: callers on a multi-GPU box bind it to the device that owns their buffers.
+extern "C" int fs_set_device(int device) {
+    return fs::cuda_check(cudaSetDevice(device), "cudaSetDevice");
+}

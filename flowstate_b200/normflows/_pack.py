@@ -99,6 +99,7 @@ class FlowPack:
         d.layers = C.cast(arr, C.POINTER(_lib.FsLayerParams))
         h = C.c_void_p()
         with torch.cuda.device(dev):
+            _lib.bind_device(dev)
             _lib.check(_lib.lib().fs_flow_create(C.byref(d), C.byref(h)))
         self._h = h
 

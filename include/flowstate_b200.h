@@ -72,6 +72,8 @@ typedef struct fs_rng {
 
 const char* fs_last_error(void);
 int fs_version(void);
+/* Binds the library's CUDA runtime to `device` (one process per GPU: the device that owns the caller's buffers). */
+int fs_set_device(int device);
 /* kernels launched by this library in this process so far (bench bookkeeping) */
 unsigned long long fs_launch_count(void);
 

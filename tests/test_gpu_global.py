@@ -162,3 +162,20 @@ def test_batched_global_move_equals_single_chain_facade(golden_dir):
     cyc, e_per_n, rho, P, lx, ly, parts = eng.sample(7)
     assert cyc == 7 and rho == pytest.approx(8 / (L * L)) and parts.shape == (B, 8, 2)
     torch.testing.assert_close(P, rho / 1.0 + eng.W / (2 * L * L))
+
+
+def test_second_device_binding():
+    """One process per GPU: the library's runtime must follow the device that owns the buffers."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import flowstate_b200.MCMC as MC
+    pos, L = er.batch_lattices(4, 16, 0.3, seed0=3)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev):
+            eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, 16, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2,
+                                       k=15, initial_max_displacement=0.4, rng="philox", philox_seed=7, device=dev)
+            eng.particle_displacement(50)
+            assert eng.pos.device == torch.device(dev)
+            outs.append(eng.pos.cpu())
+    assert torch.equal(outs[0], outs[1])
