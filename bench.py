@@ -407,6 +407,11 @@ def main():
     # TF32 tensor peak = half the measured BF16 figure (same pipe, K=8 instead of 16 per instruction)
     tensor_peak = bf16 / 2.0
     achieved = flops_pass / (pass_ms * 1e-3) / 1e12
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tj) and prec == "tf32":
+        # ncu dram bytes per launch of this kernel (captured at 4096 rows; weights dominate and do not scale with rows)
+        traffic = json.load(open(tj)).get("tc_conditioner_kernel<%d>@%s@4096" % (w["H"], args.workload))
     steps_total = world * B * (w["local"] + 1) * args.steps
     value = steps_total / (ms_total * 1e-3)
     line = {
@@ -429,7 +434,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": ("tc_conditioner_kernel (tcgen05 kind::tf32)" if prec == "tf32" else "linear_kernel chain (fp32)")
                      + ", one coupling layer",
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                     "traffic": None, "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
+                     "traffic": traffic, "peak_source": "%s bf16_tflops_sustained / 2 (tf32)" % peak_src,
                      "launch_ms": pass_ms, "rows": int(xin.shape[0])},
     }
     if not args.no_cpu_baseline and world == 1:
