@@ -13,6 +13,64 @@
 
 namespace fs {
 
+// Pair accumulation of the total-energy kernel.  Instead of the energy and the virial, the three sums
+//   A12 = sum r^-12,  A6 = sum r^-6,  cnt = #pairs   over pairs with r <= r_cut
+// are kept: E = 4 (A12 - A6) - cnt e_cut, W = 48 A12 - 24 A6 (potential.py:11-27) - three predicated
+// instructions per pair for both observables.  FASTWRAP: every coordinate of the configuration lies in
+// [0, L], so |d| <= L and the minimum image is one conditional shift by +-L (same result as
+// d - L rint(d / L), including the tie |d| = L/2 which both leave unshifted).
+template <bool FASTWRAP>
+__device__ __forceinline__ float wrap1(float d, float L, float halfL, float invL) {
+    if (FASTWRAP) return fabsf(d) > halfL ? d - copysignf(L, d) : d;
+    return min_image(d, L, invL);
+}
+
+template <bool FASTWRAP>
+__device__ __forceinline__ void pair_sums(float dx, float dy, const PotDev& P, float hx, float hy, float& a12,
+                                          float& a6, float& cnt, float& r2min) {
+    dx = wrap1<FASTWRAP>(dx, P.Lx, hx, P.inv_Lx);
+    dy = wrap1<FASTWRAP>(dy, P.Ly, hy, P.inv_Ly);
+    const float r2 = __fmaf_rn(dy, dy, dx * dx);
+    r2min = fminf(r2min, r2);
+    float inv;                                       // single MUFU.RCP (1 ulp; r^2 is never denormal here)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2));
+    const float s6 = inv * inv * inv;
+    if (r2 <= P.rc2) {
+        a12 = __fmaf_rn(s6, s6, a12);
+        a6 += s6;
+        cnt += 1.0f;
+    }
+}
+
+template <int G, bool FASTWRAP>
+__device__ __forceinline__ void total_pairs(const float2* sp, int N, int t, const PotDev& P, float& a12, float& a6,
+                                            float& cnt, float& r2min, float& ew) {
+    const float hx = 0.5f * P.Lx, hy = 0.5f * P.Ly;
+    const int half = (N - 1) / 2;
+    for (int i = t; i < N; i += G) {
+        const float2 pi = sp[i];
+        float b12 = 0.f, b6 = 0.f, bc = 0.f, c12 = 0.f, c6 = 0.f, cc = 0.f;
+        int k = 1;
+        for (; k + 1 <= half; k += 2) {
+            const float2 a = sp[i + k], c = sp[i + k + 1];
+            pair_sums<FASTWRAP>(pi.x - a.x, pi.y - a.y, P, hx, hy, b12, b6, bc, r2min);
+            pair_sums<FASTWRAP>(pi.x - c.x, pi.y - c.y, P, hx, hy, c12, c6, cc, r2min);
+        }
+        if (k <= half) {
+            const float2 a = sp[i + k];
+            pair_sums<FASTWRAP>(pi.x - a.x, pi.y - a.y, P, hx, hy, b12, b6, bc, r2min);
+        }
+        if ((N & 1) == 0 && i < N / 2) {
+            const float2 a = sp[i + N / 2];
+            pair_sums<FASTWRAP>(pi.x - a.x, pi.y - a.y, P, hx, hy, c12, c6, cc, r2min);
+        }
+        a12 += b12 + c12;
+        a6 += b6 + c6;
+        cnt += bc + cc;
+        ew += wells(pi.x, pi.y, P);
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(256) energy_total_kernel(const float* __restrict__ pos, int B, int N,
                                                            PotDev P, float* __restrict__ E,
@@ -28,53 +86,26 @@ __global__ void __launch_bounds__(256) energy_total_kernel(const float* __restri
     __shared__ float red_m[8];
 
     const bool live = b < B;
+    bool inbox = true;
     if (live) {
         const float2* src = reinterpret_cast<const float2*>(pos) + (size_t)b * N;
-        if ((N & 1) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-            for (int i = t; i < N / 2; i += G) {
-                float4 v = __ldg(s4 + i);
-                sp[2 * i] = make_float2(v.x, v.y);
-                sp[2 * i + 1] = make_float2(v.z, v.w);
-                sp[N + 2 * i] = make_float2(v.x, v.y);
-                sp[N + 2 * i + 1] = make_float2(v.z, v.w);
-            }
-        } else {
-            for (int i = t; i < N; i += G) {
-                float2 v = __ldg(src + i);
-                sp[i] = v;
-                sp[N + i] = v;
-            }
-        }
-    }
-    if (G > 32) __syncthreads(); else __syncwarp();
-
-    float e = 0.f, w = 0.f, r2min = 3.0e38f;
-    if (live) {
-        const int half = (N - 1) / 2;
         for (int i = t; i < N; i += G) {
-            const float2 pi = sp[i];
-            float e0 = 0.f, w0 = 0.f, e1 = 0.f, w1 = 0.f;
-            int k = 1;
-            for (; k + 1 <= half; k += 2) {
-                float2 a = sp[i + k], c = sp[i + k + 1];
-                pair_accum(pi.x - a.x, pi.y - a.y, P, e0, w0, r2min);
-                pair_accum(pi.x - c.x, pi.y - c.y, P, e1, w1, r2min);
-            }
-            if (k <= half) {
-                float2 a = sp[i + k];
-                pair_accum(pi.x - a.x, pi.y - a.y, P, e0, w0, r2min);
-            }
-            if ((N & 1) == 0 && i < N / 2) {
-                float2 a = sp[i + N / 2];
-                pair_accum(pi.x - a.x, pi.y - a.y, P, e1, w1, r2min);
-            }
-            e += e0 + e1 + wells(pi.x, pi.y, P);
-            w += w0 + w1;
+            const float2 v = __ldg(src + i);
+            sp[i] = v;
+            sp[N + i] = v;
+            inbox = inbox && v.x >= 0.f && v.x <= P.Lx && v.y >= 0.f && v.y <= P.Ly;
         }
     }
-    // reduce over the group: shuffles inside a warp, shared memory across warps
-    double de = e, dw = w;
+    const int all_in = __syncthreads_and(inbox ? 1 : 0);     // also orders the smem writes before the reads
+
+    float a12 = 0.f, a6 = 0.f, cnt = 0.f, ew = 0.f, r2min = 3.0e38f;
+    if (live) {
+        if (all_in) total_pairs<G, true>(sp, N, t, P, a12, a6, cnt, r2min, ew);
+        else total_pairs<G, false>(sp, N, t, P, a12, a6, cnt, r2min, ew);
+    }
+    // E = 4 (A12 - A6) - cnt e_cut + wells, W = 48 A12 - 24 A6; cross-thread sums in float64
+    double de = 4.0 * ((double)a12 - (double)a6) - (double)cnt * (double)P.e_cut + (double)ew;
+    double dw = 48.0 * (double)a12 - 24.0 * (double)a6;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         de += __shfl_xor_sync(0xffffffffu, de, o);
