@@ -1,0 +1,212 @@
+"""Hybrid NF-MCMC drivers on the batched GPU engine.
+
+The reference's drivers are module-level scripts with constants in the source
+(hybrid_NF_MCMC/main_algorithm_1.py:33-73, main_algorithm_2.py:33-76) that loop over
+MonteCarlo objects in Python.  These functions run the same algorithms with every chain
+resident on the GPU (BatchedMonteCarlo), take the constants as a config object / CLI
+flags, and carry the multi-GPU hooks (chains sharded by rank, weights broadcast after
+training, gradients all-reduced in Algorithm 2).  Defaults are the reference's constants.
+
+    python -m flowstate_b200.drivers.hybrid --algorithm 1 --particles 3 --chains 10
+    torchrun --nproc-per-node 8 -m flowstate_b200.drivers.hybrid --algorithm 2 --particles 64 --chains 4096
+
+Algorithm 1 (main_algorithm_1.py:203-395): equilibrate -> collect local samples -> train the
+flow by forward KL -> interleave `big_move_interval` local moves with one NF global move.
+Algorithm 2 (main_algorithm_2.py:393-577): per cycle `local_steps` local moves, a short
+forward-KL training pass on the newest samples, one NF global move per chain.  (The
+reference also evaluates a reverse-KL term whose weight 1-ALPHA is 0, main_algorithm_2.py:52;
+it is left out.)
+"""
+import argparse
+import dataclasses
+import json
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import MCMC as MC
+from .. import normflows as NF
+from .. import parallel
+
+
+@dataclasses.dataclass
+class HybridConfig:
+    particles: int = 3
+    chains: int = 10                 # total over all ranks
+    rho: float = 0.03
+    temperature: float = 1.0
+    V0_list: tuple = (-10.0, -10.5)
+    r0: float = 1.2
+    k: float = 15.0
+    max_displacement: float = 0.65
+    equilibration_steps: int = 5000
+    adjusting_frequency: int = 5000
+    sampling_frequency: int = 150
+    master_seed: int = 42
+    # flow (Alg-1 defaults: K=15, H=256, NUM_BINS passed as num_blocks -> 32 blocks, 32 bins)
+    K: int = 15
+    blocks: int = 32
+    hidden: int = 256
+    bins: int = 32
+    lr: float = 1e-4
+    weight_decay: float = 0.0
+    batch_size: int = 512
+    epochs: int = 100
+    training_samples: int = 102400
+    # hybrid phase
+    big_move_attempts: int = 1000
+    big_move_interval: int = 1000
+    # Alg 2
+    cycles: int = 1000
+    local_steps: int = 100
+    precision: str = "tf32"
+
+
+def _dist():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _init_chains(cfg, device):
+    rank, world = _dist()
+    start, count = parallel.shard_range(cfg.chains, rank, world)
+    L = float(np.float32(np.sqrt(cfg.particles / cfg.rho)))
+    box = MC.SimulationBox(L)
+    pos = np.empty((count, cfg.particles, 2), np.float32)
+    for i in range(count):                       # even chains start in the left well, odd in the right (main_algorithm_1.py:149-165)
+        init = MC.initialise_low_left if (start + i) % 2 == 0 else MC.initialise_low_right
+        p, _ = init(cfg.particles, cfg.rho)
+        pos[i] = p.astype(np.float32)
+    seeds = [cfg.master_seed + start + i for i in range(count)]
+    eng = MC.BatchedMonteCarlo(pos, box, cfg.temperature, cfg.particles, num_wells=2, V0_list=list(cfg.V0_list),
+                               r0=cfg.r0, k=cfg.k, initial_max_displacement=cfg.max_displacement, seeds=seeds,
+                               device=device)
+    return eng, L
+
+
+def _build_flow(cfg, L, device):
+    bound = L / 2
+    base = NF.Energy.UniformParticle(cfg.particles, 2, bound, device=device)
+    D = 2 * cfg.particles
+    layers = [NF.flows.CircularCoupledRationalQuadraticSpline(D, cfg.blocks, cfg.hidden, range(D), num_bins=cfg.bins,
+                                                              tail_bound=bound) for _ in range(cfg.K)]
+    model = NF.NormalizingFlow(base, layers).to(device)
+    model.precision = cfg.precision
+    return model
+
+
+def _local_phase(eng, steps, cfg, collect=None, step0=0):
+    """`steps` local moves per chain, adapting / sampling at the reference's frequencies."""
+    done = 0
+    while done < steps:
+        nxt = steps
+        for f in (cfg.adjusting_frequency, cfg.sampling_frequency if collect is not None else 0):
+            if f:
+                nxt = min(nxt, ((step0 + done) // f + 1) * f - step0)
+        n = max(1, min(nxt, steps) - done)
+        eng.particle_displacement(n)
+        done += n
+        g = step0 + done
+        if cfg.adjusting_frequency and g % cfg.adjusting_frequency == 0:
+            eng.adjust_displacement()
+        if collect is not None and g % cfg.sampling_frequency == 0:
+            collect.append(eng.centred(eng.pos).clone())
+    return step0 + done
+
+
+def _train(model, data, cfg, epochs, optimizer=None):
+    """Forward-KL training (main_algorithm_1.py:297-320); gradients are all-reduced over ranks."""
+    model.train()
+    opt = optimizer or torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay)
+    losses = []
+    for _ in range(epochs):
+        perm = torch.randperm(data.shape[0], device=data.device)
+        tot, nb = 0.0, 0
+        for i in range(0, data.shape[0] - 1, cfg.batch_size):
+            batch = data[perm[i:i + cfg.batch_size]]
+            if batch.shape[0] < 2:
+                continue
+            opt.zero_grad()
+            loss = model.forward_kld(batch)
+            if torch.isnan(loss) or torch.isinf(loss):        # main_algorithm_1.py:310-315
+                continue
+            loss.backward()
+            parallel.allreduce_gradients(model)
+            opt.step()
+            tot += float(loss.detach())
+            nb += 1
+        losses.append(tot / max(nb, 1))
+    model.eval()
+    parallel.broadcast_flow(model, src=0)
+    return losses
+
+
+def run_algorithm_1(cfg, device="cuda", log=print):
+    eng, L = _init_chains(cfg, device)
+    step = _local_phase(eng, cfg.equilibration_steps, cfg)
+    samples = []
+    per_chain = max(1, -(-cfg.training_samples // cfg.chains))
+    _local_phase(eng, per_chain * cfg.sampling_frequency, cfg, collect=samples, step0=step)
+    data = torch.cat(samples, dim=0)
+    model = _build_flow(cfg, L, device)
+    t0 = time.time()
+    losses = _train(model, data, cfg, cfg.epochs)
+    log("trained %d epochs on %d samples in %.1fs, loss %.4f -> %.4f" % (cfg.epochs, data.shape[0], time.time() - t0,
+                                                                         losses[0], losses[-1]))
+    eng.set_nf_model(model)
+    big_acc = 0
+    for _ in range(cfg.big_move_attempts):
+        eng.particle_displacement(cfg.big_move_interval)
+        big_acc += int(eng.nf_big_move().sum().item())
+    att, acc, big = parallel.allreduce_counters(eng.attempts, eng.accepted, torch.tensor([big_acc], device=eng.device))
+    return {"algorithm": 1, "attempts": att, "accepted": acc, "big_move_accepts": big,
+            "big_move_attempts": cfg.big_move_attempts * cfg.chains, "final_loss": losses[-1], "engine": eng,
+            "model": model}
+
+
+def run_algorithm_2(cfg, device="cuda", log=print):
+    eng, L = _init_chains(cfg, device)
+    _local_phase(eng, cfg.equilibration_steps, cfg)
+    model = _build_flow(cfg, L, device)
+    eng.set_nf_model(model)
+    big_acc, last = 0, float("nan")
+    for cycle in range(cfg.cycles):
+        samples = []
+        for s in range(0, cfg.local_steps, 10):               # SAMPLING_FREQUENCY = 10 in Alg 2 (main_algorithm_2.py:59)
+            eng.particle_displacement(min(10, cfg.local_steps - s))
+            samples.append(eng.centred(eng.pos).clone())
+        data = torch.cat(samples, dim=0)
+        last = _train(model, data, cfg, 1)[-1]                # new Adam every cycle (main_algorithm_2.py:440)
+        big_acc += int(eng.nf_big_move().sum().item())
+    att, acc, big = parallel.allreduce_counters(eng.attempts, eng.accepted, torch.tensor([big_acc], device=eng.device))
+    return {"algorithm": 2, "attempts": att, "accepted": acc, "big_move_accepts": big,
+            "big_move_attempts": cfg.cycles * cfg.chains, "final_loss": last, "engine": eng, "model": model}
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--algorithm", type=int, choices=(1, 2), default=1)
+    for f in dataclasses.fields(HybridConfig):
+        if f.type in (int, float, str):
+            ap.add_argument("--" + f.name.replace("_", "-"), type=f.type, default=f.default)
+    a = ap.parse_args(argv)
+    cfg = HybridConfig(**{f.name: getattr(a, f.name) for f in dataclasses.fields(HybridConfig)
+                          if f.type in (int, float, str)})
+    import os
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    out = (run_algorithm_1 if a.algorithm == 1 else run_algorithm_2)(cfg, device="cuda:%d" % local)
+    if _dist()[0] == 0:
+        print(json.dumps({k: v for k, v in out.items() if k not in ("engine", "model")}))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,8 +84,11 @@ def test_against_oracle_alg_shapes():
     """Wider random flows (Alg-1 style bins, Alg-2 style width) against the float64 oracle,
     with the FP32-vs-FP64 self error of the reference arithmetic reported beside it."""
     torch.manual_seed(0)
-    for (n, K, blocks, H, nb, sigma, B) in [(32, 3, 4, 128, 32, 0.02, 96), (16, 5, 2, 128, 15, 0.05, 64),
-                                            (5, 4, 2, 64, 8, 0.05, 33)]:
+    # (32, ...): Alg-1 bins; (64, ...): BASELINE config 4 shape (Alg 2: H=128, 2 blocks, 15 bins, N=64);
+    # (256, ...): BASELINE config 3 particle count (2N = 512 features > H: multi-piece GEMM0, 8 coordinate chunks);
+    # (5, ...): odd N, H outside the tensor path
+    for (n, K, blocks, H, nb, sigma, B) in [(32, 3, 4, 256, 32, 0.02, 200), (64, 4, 2, 128, 15, 0.05, 130),
+                                            (256, 2, 3, 256, 32, 0.02, 140), (5, 4, 2, 64, 8, 0.05, 33)]:
         bound = float(np.float32(np.sqrt(n / 0.03))) / 2
         model = _build(n, K, blocks, H, nb, bound, device="cuda")
         g = torch.Generator().manual_seed(1)
