@@ -63,76 +63,6 @@ __device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, f
     }
 }
 
-// softmax -> floor -> cumulative knots, one bin per lane (utils/splines.py:117-127).
-// Returns this lane's left knot and bin size.
-__device__ __forceinline__ void knots_warp(float un, bool active, int lane, int nb, float bound, float minsz,
-                                           float& left, float& size) {
-    const float ninf = -__int_as_float(0x7f800000);
-    const float m = warp_max(active ? un : ninf);
-    const float ex = active ? expf(un - m) : 0.0f;
-    const float sum = warp_sum(ex);
-    float w = minsz + (1.0f - minsz * (float)nb) * (ex / sum);
-    if (!active) w = 0.0f;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
-    }
-    float right = __fadd_rn(__fmul_rn(2.0f * bound, w), -bound);
-    if (lane == nb - 1) right = bound;
-    left = __shfl_up_sync(0xffffffffu, right, 1);
-    if (lane == 0) left = -bound;
-    size = right - left;
-}
-
-// bin = #(x >= knot_j, j = 0..nb) - 1 with the last knot + 1e-6 (utils/splines.py:11-13); clamped.
-__device__ __forceinline__ int bin_search(float x, float left, bool active, int nb, float bound) {
-    const unsigned m = __ballot_sync(0xffffffffu, active && x >= left);
-    int c = __popc(m) + (x >= __fadd_rn(bound, 1e-6f) ? 1 : 0) - 1;
-    return min(max(c, 0), nb - 1);
-}
-
-// Conditional spline of one coordinate; lanes k < nb hold (uw, uh, ud_k, ud_k+1) of bin k.
-__device__ __forceinline__ void rqs_cond_warp(float x, float uw, float uh, float ud, float ud1, int lane, int nb,
-                                              float bound, bool inverse, float& y, float& ld) {
-    if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39 (warp-uniform)
-        y = x;
-        ld = 0.0f;
-        return;
-    }
-    const bool active = lane < nb;
-    float xl, w, yl, h;
-    knots_warp(uw, active, lane, nb, bound, kMinW, xl, w);
-    knots_warp(uh, active, lane, nb, bound, kMinH, yl, h);
-    const float dk = kMinD + softplus_t(ud);
-    const float dk1 = kMinD + softplus_t(ud1);
-    const int bin = bin_search(x, inverse ? yl : xl, active, nb, bound);
-    rq_eval(x, __shfl_sync(0xffffffffu, xl, bin), __shfl_sync(0xffffffffu, w, bin),
-            __shfl_sync(0xffffffffu, yl, bin), __shfl_sync(0xffffffffu, h, bin),
-            __shfl_sync(0xffffffffu, dk, bin), __shfl_sync(0xffffffffu, dk1, bin), inverse, y, ld);
-}
-
-// Unconditional spline from the packed knot tables: lane k < nb holds the left knot of
-// bin k; knot nb is +bound by construction (utils/splines.py:125-126).
-__device__ __forceinline__ void rqs_table_warp(float x, const float* __restrict__ ux, const float* __restrict__ uy,
-                                               const float* __restrict__ ud, int lane, int nb, float bound,
-                                               bool inverse, float& y, float& ld) {
-    if (!(x >= -bound && x <= bound)) {
-        y = x;
-        ld = 0.0f;
-        return;
-    }
-    const bool has = lane < nb;
-    const float kx = has ? __ldg(ux + lane) : bound;
-    const float ky = has ? __ldg(uy + lane) : bound;
-    const int bin = bin_search(x, inverse ? ky : kx, has, nb, bound);
-    const float xk = __shfl_sync(0xffffffffu, kx, bin);
-    const float yk = __shfl_sync(0xffffffffu, ky, bin);
-    const float xk1 = (bin + 1 < nb) ? __shfl_sync(0xffffffffu, kx, (bin + 1) & 31) : bound;
-    const float yk1 = (bin + 1 < nb) ? __shfl_sync(0xffffffffu, ky, (bin + 1) & 31) : bound;
-    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + bin), __ldg(ud + bin + 1), inverse, y, ld);
-}
-
 struct FlowDev {
     int N, D, H, nb, P;
     float bound, pf_scale, inv_sqrt_h;
@@ -158,108 +88,6 @@ __global__ void prep_inverse_kernel(const float* __restrict__ v, float* __restri
     A0[(size_t)b * 2 * F.N + F.N + j] = s;
 }
 
-// density direction, step 3: conditional spline on the transformed half, unconditional
-// spline on the identity half, scatter + roll by D/2 (coupling.py:86-102)
-__global__ void __launch_bounds__(256) spline_inverse_kernel(const float* __restrict__ v,
-                                                             const float* __restrict__ theta,
-                                                             float* __restrict__ out, float* __restrict__ logdet,
-                                                             int rows, FlowDev F, const float* __restrict__ ux,
-                                                             const float* __restrict__ uy,
-                                                             const float* __restrict__ ud, int* nan_flag) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= rows) return;
-    const float* vr = v + (size_t)b * F.D;
-    float* orow = out + (size_t)b * F.D;
-    const float* th = theta + (size_t)b * F.N * F.P;
-    const int h = F.D / 2, nb = F.nb;
-    float acc = 0.f;
-    for (int j = 0; j < F.N; ++j) {
-        const float* tj = th + (size_t)j * F.P;
-        const bool a = lane < nb;
-        const float uw = a ? tj[lane] * F.inv_sqrt_h : 0.f;
-        const float uh = a ? tj[nb + lane] * F.inv_sqrt_h : 0.f;
-        const float d0 = a ? tj[2 * nb + lane] : 0.f;
-        const float d1 = a ? tj[2 * nb + lane + 1] : 0.f;
-        const int ft = F.trf[j], fi = F.idf[j];
-        float y, ld, y2, ld2;
-        rqs_cond_warp(vr[ft], uw, uh, d0, d1, lane, nb, F.bound, false, y, ld);
-        rqs_table_warp(vr[fi], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1), ud + (size_t)j * (nb + 1),
-                       lane, nb, F.bound, false, y2, ld2);
-        if (lane == 0) {
-            orow[(ft + h) % F.D] = y;
-            orow[(fi + h) % F.D] = y2;
-        }
-        acc += ld + ld2;
-        if (y != y || ld != ld || y2 != y2 || ld2 != ld2) {
-            if (lane == 0 && nan_flag) atomicOr(nan_flag, 1);
-        }
-    }
-    if (lane == 0) logdet[b] += acc;
-}
-
-// sampling direction, step 1: roll, inverse unconditional spline on the identity half,
-// periodic features of the NEW identity values (coupling.py:113-124)
-__global__ void __launch_bounds__(256) prep_forward_kernel(const float* __restrict__ v, float* __restrict__ out,
-                                                           float* __restrict__ A0, float* __restrict__ logdet,
-                                                           int rows, FlowDev F, const float* __restrict__ ux,
-                                                           const float* __restrict__ uy,
-                                                           const float* __restrict__ ud, int* nan_flag) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= rows) return;
-    const float* vr = v + (size_t)b * F.D;
-    const int h = F.D / 2, nb = F.nb;
-    float acc = 0.f;
-    for (int j = 0; j < F.N; ++j) {
-        const int fi = F.idf[j];
-        float y, ld;
-        rqs_table_warp(vr[(fi + h) % F.D], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1),
-                       ud + (size_t)j * (nb + 1), lane, nb, F.bound, true, y, ld);
-        if (lane == 0) {
-            out[(size_t)b * F.D + fi] = y;
-            float s, c;
-            sincosf(F.pf_scale * y, &s, &c);
-            A0[(size_t)b * 2 * F.N + j] = c;
-            A0[(size_t)b * 2 * F.N + F.N + j] = s;
-            if ((y != y || ld != ld) && nan_flag) atomicOr(nan_flag, 1);
-        }
-        acc += ld;
-    }
-    if (lane == 0 && logdet) logdet[b] += acc;
-}
-
-// sampling direction, step 3: inverse conditional spline on the transformed half (coupling.py:125-132)
-__global__ void __launch_bounds__(256) spline_forward_kernel(const float* __restrict__ v,
-                                                             const float* __restrict__ theta,
-                                                             float* __restrict__ out, float* __restrict__ logdet,
-                                                             int rows, FlowDev F, int* nan_flag) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= rows) return;
-    const float* vr = v + (size_t)b * F.D;
-    const float* th = theta + (size_t)b * F.N * F.P;
-    const int h = F.D / 2, nb = F.nb;
-    float acc = 0.f;
-    for (int j = 0; j < F.N; ++j) {
-        const float* tj = th + (size_t)j * F.P;
-        const bool a = lane < nb;
-        const float uw = a ? tj[lane] * F.inv_sqrt_h : 0.f;
-        const float uh = a ? tj[nb + lane] * F.inv_sqrt_h : 0.f;
-        const float d0 = a ? tj[2 * nb + lane] : 0.f;
-        const float d1 = a ? tj[2 * nb + lane + 1] : 0.f;
-        const int ft = F.trf[j];
-        float y, ld;
-        rqs_cond_warp(vr[(ft + h) % F.D], uw, uh, d0, d1, lane, nb, F.bound, true, y, ld);
-        if (lane == 0) {
-            out[(size_t)b * F.D + ft] = y;
-            if ((y != y || ld != ld) && nan_flag) atomicOr(nan_flag, 1);
-        }
-        acc += ld;
-    }
-    if (lane == 0 && logdet) logdet[b] += acc;
-}
-
 // ---------------------------------------------------------------------------
 // Lane-per-coordinate spline kernels (the ones the flow passes launch).
 // One warp owns one row; a chunk of 32 coordinates sits one per lane.  The 32 x (3nb+1)
@@ -277,11 +105,12 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// Conditional spline of ONE coordinate: the 2nb softmax logits p[0..2nb) of this lane sit in shared memory
-// (the numerators are written back in place), the two derivatives of the selected bin are fetched from
-// the coordinate's parameter row `gp` in global memory.
-__device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __restrict__ gp, int nb, float bound,
-                                              float inv_sqrt_h, bool inverse, float& y, float& ld) {
+// Conditional spline of ONE coordinate.  theta is parameter-major ([3nb+1][N] per row, see pack_layer), so the
+// 2nb softmax logits of this lane's coordinate sit at p[k * 32] in shared memory (staged with coalesced
+// copies; the numerators are written back in place) and the two derivatives of the selected bin are
+// fetched from global memory at gp[(2nb + sel) * N].
+__device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __restrict__ gp, int N, int nb,
+                                              float bound, float inv_sqrt_h, bool inverse, float& y, float& ld) {
     if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39
         y = x;
         ld = 0.0f;
@@ -291,16 +120,16 @@ __device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __
     float mw = -3.0e38f, mh = -3.0e38f;
 #pragma unroll 8
     for (int k = 0; k < nb; ++k) {
-        mw = fmaxf(mw, p[k]);
-        mh = fmaxf(mh, p[nb + k]);
+        mw = fmaxf(mw, p[k * 32]);
+        mh = fmaxf(mh, p[(nb + k) * 32]);
     }
     float sw = 0.f, sh = 0.f;
 #pragma unroll 8
     for (int k = 0; k < nb; ++k) {
-        const float ew = exp2f((p[k] - mw) * c2);
-        const float eh = exp2f((p[nb + k] - mh) * c2);
-        p[k] = ew;
-        p[nb + k] = eh;
+        const float ew = exp2f((p[k * 32] - mw) * c2);
+        const float eh = exp2f((p[(nb + k) * 32] - mh) * c2);
+        p[k * 32] = ew;
+        p[(nb + k) * 32] = eh;
         sw += ew;
         sh += eh;
     }
@@ -311,8 +140,8 @@ __device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __
     int sel = 0;
 #pragma unroll 4
     for (int k = 0; k < nb; ++k) {
-        cw += __fmaf_rn(gw, p[k], kMinW);
-        ch += __fmaf_rn(gh, p[nb + k], kMinH);
+        cw += __fmaf_rn(gw, p[k * 32], kMinW);
+        ch += __fmaf_rn(gh, p[(nb + k) * 32], kMinH);
         const float xr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, cw), -bound);
         const float yr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, ch), -bound);
         if (x >= (inverse ? yl : xl)) {      // last knot <= x wins == #(x >= knots) - 1 (utils/splines.py:11-13)
@@ -322,14 +151,15 @@ __device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __
         xl = xr;
         yl = yr;
     }
-    const float dk = kMinD + softplus_t(__ldg(gp + 2 * nb + sel));
-    const float dk1 = kMinD + softplus_t(__ldg(gp + 2 * nb + sel + 1));
+    const float dk = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel) * N));
+    const float dk1 = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel + 1) * N));
     rq_eval(x, xk, wk, yk, hk, dk, dk1, inverse, y, ld);
 }
 
-// Unconditional spline of one coordinate from the packed knot tables (global memory, L1/L2-resident).
+// Unconditional spline of one coordinate from the packed knot tables.  Tables are knot-major
+// ([nb+1][N]: entry k of coordinate j at k*N + j), so the 32 lanes of a warp read consecutive addresses.
 __device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict__ ux, const float* __restrict__ uy,
-                                               const float* __restrict__ ud, int nb, float bound, bool inverse,
+                                               const float* __restrict__ ud, int N, int nb, float bound, bool inverse,
                                                float& y, float& ld) {
     if (!(x >= -bound && x <= bound)) {
         y = x;
@@ -338,21 +168,27 @@ __device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict_
     }
     const float* ks = inverse ? uy : ux;
     int sel = 0;
+#pragma unroll 4
     for (int k = 1; k < nb; ++k)
-        if (x >= __ldg(ks + k)) sel = k;
-    const float xk = __ldg(ux + sel), xk1 = __ldg(ux + sel + 1);
-    const float yk = __ldg(uy + sel), yk1 = __ldg(uy + sel + 1);
-    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + sel), __ldg(ud + sel + 1), inverse, y, ld);
+        if (x >= __ldg(ks + (size_t)k * N)) sel = k;
+    const float xk = __ldg(ux + (size_t)sel * N), xk1 = __ldg(ux + (size_t)(sel + 1) * N);
+    const float yk = __ldg(uy + (size_t)sel * N), yk1 = __ldg(uy + (size_t)(sel + 1) * N);
+    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + (size_t)sel * N), __ldg(ud + (size_t)(sel + 1) * N), inverse, y,
+            ld);
 }
 
-// stage the 2nb softmax logits of coordinates [j0, j0+ncoord) of one row: theta row segment -> smem, row stride Ps (odd)
-__device__ __forceinline__ void stage_params(const float* __restrict__ th, float* sm, int j0, int ncoord, int P, int nb2,
-                                             int Ps, int lane) {
-    for (int c = 0; c < ncoord; ++c) {
-        const float* src = th + (size_t)(j0 + c) * P;
-        float* dst = sm + c * Ps;
-        for (int k = lane; k < nb2; k += 32) dst[k] = __ldg(src + k);
+// stage the 2nb softmax logits of coordinates [j0, j0+ncoord) of one row: theta[k][j0 + lane] -> sm[k*32 + lane],
+// all copies in flight at once (cp.async), one 128-byte row segment per k
+__device__ __forceinline__ void stage_params(const float* __restrict__ th, float* sm, int j0, int ncoord, int N, int nb2,
+                                             int lane) {
+    if (lane < ncoord) {
+        const float* src = th + j0 + lane;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + lane);
+        for (int k = 0; k < nb2; ++k)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + k * 128), "l"(src + (size_t)k * N) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
 }
 
@@ -366,8 +202,8 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_inverse_v2(
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
     if (b >= rows) return;
-    const int Ps = (2 * F.nb) | 1, nb = F.nb, h = F.D / 2;
-    float* sm = sp_smem + (size_t)wib * 32 * Ps;
+    const int nb = F.nb, h = F.D / 2;
+    float* sm = sp_smem + (size_t)wib * 32 * 2 * nb;
     const float* vr = v + (size_t)b * F.D;
     float* orow = out + (size_t)b * F.D;
     const float* th = theta + (size_t)b * F.N * F.P;
@@ -375,14 +211,13 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_inverse_v2(
     bool bad = false;
     for (int j0 = 0; j0 < F.N; j0 += 32) {
         const int nc = min(32, F.N - j0);
-        stage_params(th, sm, j0, nc, F.P, 2 * nb, Ps, lane);
+        stage_params(th, sm, j0, nc, F.N, 2 * nb, lane);
         if (lane < nc) {
             const int j = j0 + lane;
             const int ft = F.trf[j], fi = F.idf[j];
             float y, ld, y2, ld2;
-            rqs_cond_lane(vr[ft], sm + lane * Ps, th + (size_t)j * F.P, nb, F.bound, F.inv_sqrt_h, false, y, ld);
-            rqs_table_lane(vr[fi], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1), ud + (size_t)j * (nb + 1), nb,
-                           F.bound, false, y2, ld2);
+            rqs_cond_lane(vr[ft], sm + lane, th + j, F.N, nb, F.bound, F.inv_sqrt_h, false, y, ld);
+            rqs_table_lane(vr[fi], ux + j, uy + j, ud + j, F.N, nb, F.bound, false, y2, ld2);
             orow[(ft + h) % F.D] = y;
             orow[(fi + h) % F.D] = y2;
             acc += ld + ld2;
@@ -411,8 +246,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
     for (int j = lane; j < F.N; j += 32) {
         const int fi = F.idf[j];
         float y, ld;
-        rqs_table_lane(vr[(fi + h) % F.D], ux + (size_t)j * (nb + 1), uy + (size_t)j * (nb + 1),
-                       ud + (size_t)j * (nb + 1), nb, F.bound, true, y, ld);
+        rqs_table_lane(vr[(fi + h) % F.D], ux + j, uy + j, ud + j, F.N, nb, F.bound, true, y, ld);
         out[(size_t)b * F.D + fi] = y;
         float sn, cs;
         sincosf(F.pf_scale * y, &sn, &cs);
@@ -434,20 +268,19 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_forward_v2(
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
     if (b >= rows) return;
-    const int Ps = (2 * F.nb) | 1, nb = F.nb, h = F.D / 2;
-    float* sm = sp_smem + (size_t)wib * 32 * Ps;
+    const int nb = F.nb, h = F.D / 2;
+    float* sm = sp_smem + (size_t)wib * 32 * 2 * nb;
     const float* vr = v + (size_t)b * F.D;
     const float* th = theta + (size_t)b * F.N * F.P;
     float acc = 0.f;
     bool bad = false;
     for (int j0 = 0; j0 < F.N; j0 += 32) {
         const int nc = min(32, F.N - j0);
-        stage_params(th, sm, j0, nc, F.P, 2 * nb, Ps, lane);
+        stage_params(th, sm, j0, nc, F.N, 2 * nb, lane);
         if (lane < nc) {
             const int ft = F.trf[j0 + lane];
             float y, ld;
-            rqs_cond_lane(vr[(ft + h) % F.D], sm + lane * Ps, th + (size_t)(j0 + lane) * F.P, nb, F.bound, F.inv_sqrt_h,
-                          true, y, ld);
+            rqs_cond_lane(vr[(ft + h) % F.D], sm + lane, th + j0 + lane, F.N, nb, F.bound, F.inv_sqrt_h, true, y, ld);
             out[(size_t)b * F.D + ft] = y;
             acc += ld;
             bad = bad || (y != y) || (ld != ld);
@@ -460,7 +293,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_forward_v2(
 }
 
 static size_t spline_smem_bytes(const fs_flow* f) {
-    return (size_t)FS_SPLINE_WARPS * 32 * ((2 * f->nb) | 1) * sizeof(float);
+    return (size_t)FS_SPLINE_WARPS * 32 * 2 * f->nb * sizeof(float);
 }
 
 // out <- z (+ shift); logq <- logdet + UniformParticle.log_prob(z)  (Energy/Uniform.py:50-74)
@@ -614,6 +447,17 @@ static void host_knots(const float* un, int nb, double bound, double minsz, std:
     k[nb] = bound;
 }
 
+void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b) {
+    w.resize((size_t)N * P * H);
+    b.resize((size_t)N * P);
+    for (int j = 0; j < N; ++j)
+        for (int k = 0; k < P; ++k) {
+            const size_t src = (size_t)j * P + k, dst = (size_t)k * N + j;
+            memcpy(&w[dst * H], p->final_w + src * H, sizeof(float) * H);
+            b[dst] = p->final_b[src];
+        }
+}
+
 static int pack_layer(fs_flow* f, const fs_flow_desc* d, const fs_layer_params* p, fs_flow::Layer* L) {
     const int H = f->H, N = f->N, nb = f->nb, nB = f->n_blocks, P = f->P;
     std::vector<float> v;
@@ -652,20 +496,23 @@ static int pack_layer(fs_flow* f, const fs_flow_desc* d, const fs_layer_params* 
     }
     if (int r = upload(f, w1, &L->w1)) return r;
     if (int r = upload(f, b1, &L->b1)) return r;
-    v.assign(p->final_w, p->final_w + (size_t)N * P * H);
+    // The final layer's rows are permuted from the reference's coordinate-major order (row j*P + k,
+    // coupling.py:166) to parameter-major (row k*N + j): theta comes out as [P][N] per sample, and the 32
+    // coordinates a spline warp works on are contiguous for every parameter index.
+    std::vector<float> fb;
+    permute_final(p, N, P, H, v, fb);
     if (int r = upload(f, v, &L->final_w)) return r;
-    v.assign(p->final_b, p->final_b + (size_t)N * P);
-    if (int r = upload(f, v, &L->final_b)) return r;
+    if (int r = upload(f, fb, &L->final_b)) return r;
     std::vector<float> ux((size_t)N * (nb + 1)), uy((size_t)N * (nb + 1)), ud((size_t)N * (nb + 1));
     std::vector<double> k;
     for (int j = 0; j < N; ++j) {
         host_knots(p->un_w + (size_t)j * nb, nb, f->bound, 1e-3, k);
-        for (int i = 0; i <= nb; ++i) ux[(size_t)j * (nb + 1) + i] = (float)k[i];
+        for (int i = 0; i <= nb; ++i) ux[(size_t)i * N + j] = (float)k[i];
         host_knots(p->un_h + (size_t)j * nb, nb, f->bound, 1e-3, k);
-        for (int i = 0; i <= nb; ++i) uy[(size_t)j * (nb + 1) + i] = (float)k[i];
+        for (int i = 0; i <= nb; ++i) uy[(size_t)i * N + j] = (float)k[i];
         for (int i = 0; i <= nb; ++i) {
             const double x = p->un_d[(size_t)j * (nb + 1) + i];
-            ud[(size_t)j * (nb + 1) + i] = (float)(1e-3 + (x > 20 ? x : log1p(exp(x))));
+            ud[(size_t)i * N + j] = (float)(1e-3 + (x > 20 ? x : log1p(exp(x))));
         }
     }
     if (int r = upload(f, ux, &L->u_x)) return r;
@@ -806,7 +653,7 @@ static int check_ws(const fs_flow* f, int B, int precision, void* ws, size_t byt
 }
 
 // ResidualNet.forward of one layer's conditioner (nets/resnet.py:92-104, eval mode) on ready-made
-// periodic features: features [rows, 2N] -> theta [rows, N (3nb+1)].  rows must not exceed the chunk
+// periodic features: features [rows, 2N] -> theta [rows, 3nb+1, N] (the library's parameter-major order).  rows must not exceed the chunk
 // the workspace was sized for.
 extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features, int rows, float* theta,
                                    void* workspace, size_t workspace_bytes, int precision, void* stream) {

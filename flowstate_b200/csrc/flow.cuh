@@ -21,11 +21,11 @@ struct fs_flow {
         float* b0;       // [n_blocks, H]
         float* w1;       // [n_blocks, H, H]
         float* b1;       // [n_blocks, H]
-        float* final_w;  // [N P, H]
-        float* final_b;  // [N P]
-        float* u_x;      // [N, nb+1] knots of the unconditional spline (x)
-        float* u_y;      // [N, nb+1] knots (y)
-        float* u_d;      // [N, nb+1] derivatives (already 1e-3 + softplus)
+        float* final_w;  // [P N, H]  parameter-major rows (k*N + j)
+        float* final_b;  // [P N]
+        float* u_x;      // [nb+1, N] knots of the unconditional spline (x), knot-major
+        float* u_y;      // [nb+1, N] knots (y)
+        float* u_d;      // [nb+1, N] derivatives (already 1e-3 + softplus)
     };
     std::vector<Layer> layers;
     std::vector<void*> allocs;
@@ -34,6 +34,8 @@ struct fs_flow {
 };
 
 namespace fs {
+// final-layer rows/bias permuted to parameter-major order (row k*N + j), see flow.cu
+void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b);
 // tensor-core path (flow_tc.cu)
 int tc_pack(fs_flow* f, const fs_flow_desc* d);
 void tc_free(fs_flow* f);

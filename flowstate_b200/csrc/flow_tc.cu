@@ -693,6 +693,8 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                     }
                 }
             }
+        std::vector<float> fw, fbias;                       // final layer in parameter-major row order
+        permute_final(p, f->N, f->P, H, fw, fbias);
         // weight stream in consumption order, one stage = H*128 bytes:
         //   block GEMMs: k-tile kt of all H output rows;  final layer: KPS consecutive k-tiles of a 128-row chunk
         const int KPS = (H * 128) / (FCH * 128);
@@ -710,7 +712,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         for (int c = 0; c < P->n_chunks; ++c)                            // final layer
             for (int sg = 0; sg < KT / KPS; ++sg)
                 for (int kk = 0; kk < KPS; ++kk)
-                    append_tile(stream, p->final_w, NP, H, c * FCH, (sg * KPS + kk) * TC_KB, FCH);
+                    append_tile(stream, fw.data(), NP, H, c * FCH, (sg * KPS + kk) * TC_KB, FCH);
         P->tiles_per_layer = stream.size() / ((size_t)H * 32);
         TcLayer& L = P->layers[li];
         // Bias folding: the kernel carries u = h - c (c = b_init + sum of linear-1 biases so far):
@@ -725,8 +727,8 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         }
         std::vector<float> bfin((size_t)P->n_chunks * FCH, 0.f);
         for (int n = 0; n < NP; ++n) {
-            double acc = (double)p->final_b[n];
-            const float* wr = p->final_w + (size_t)n * H;
+            double acc = (double)fbias[n];
+            const float* wr = fw.data() + (size_t)n * H;
             for (int k = 0; k < H; ++k) acc += (double)tf32_round(wr[k]) * c[k];
             bfin[n] = (float)acc;
         }

@@ -177,7 +177,8 @@ void fs_flow_destroy(fs_flow* flow);
 size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
 
 /* ResidualNet.forward of the conditioner of layer `layer`  (NF/normflows/nets/resnet.py:92-104, eval mode)
- * on ready-made periodic features [rows, 2N] (NF/normflows/utils/nn.py:120-137) -> theta [rows, N (3 nb + 1)]. */
+ * on ready-made periodic features [rows, 2N] (NF/normflows/utils/nn.py:120-137) -> theta [rows, 3 nb + 1, N]:
+ * the library keeps the spline parameters parameter-major (the reference's column j (3nb+1) + k is k N + j here). */
 int fs_flow_conditioner(fs_flow* flow, int layer, const float* features, int rows, float* theta,
                         void* workspace, size_t workspace_bytes, int precision, void* stream);
 
