@@ -76,28 +76,19 @@ __global__ void shift_kernel(const float* __restrict__ x, float* __restrict__ v,
     if (i < n) v[i] = (float)((double)x[i] + shift);
 }
 
-// density direction, step 1: periodic features of the identity half (utils/nn.py:125-127)
-__global__ void prep_inverse_kernel(const float* __restrict__ v, float* __restrict__ A0, int rows, FlowDev F) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)rows * F.N) return;
-    const int b = (int)(i / F.N), j = (int)(i % F.N);
-    const float x = v[(size_t)b * F.D + F.idf[j]];
-    float s, c;
-    sincosf(F.pf_scale * x, &s, &c);
-    A0[(size_t)b * 2 * F.N + j] = c;
-    A0[(size_t)b * 2 * F.N + F.N + j] = s;
-}
-
 // ---------------------------------------------------------------------------
 // Lane-per-coordinate spline kernels (the ones the flow passes launch).
-// One warp owns one row; a chunk of 32 coordinates sits one per lane.  The 32 x (3nb+1)
-// parameters of the chunk are staged in shared memory with coalesced loads (odd row stride, so the
-// per-lane walks over a coordinate's bins are bank-conflict free) and each lane runs softmax ->
-// cumulative knots -> bin search -> rational-quadratic evaluation sequentially over its bins in
-// registers: no shuffles, exps only for the two softmaxes, softplus only for the two derivatives
-// of the selected bin.
+// A warp walks rows with a grid stride; a chunk of 32 coordinates sits one per lane.  theta is
+// parameter-major ([3nb+1][N] per row, see pack_layer), so the 2nb softmax logits of a chunk are 2nb
+// row segments of 128 bytes: they are copied to shared memory with cp.async (sm[k*32 + lane], bank-
+// conflict free for the per-lane walks), double buffered so the next chunk's copy is in flight while
+// this one is evaluated.  Each lane then runs softmax -> inclusive prefix sums (in place) -> binary
+// search for its bin -> rational-quadratic evaluation: no shuffles, exps only for the two softmaxes,
+// softplus only for the two derivatives of the selected bin (fetched from global memory; their rows
+// are prefetched into L2 together with the copy).
 // ---------------------------------------------------------------------------
-#define FS_SPLINE_WARPS 4
+#define FS_SPLINE_WARPS 4   // prep_forward_v2: rows per block
+#define FS_SPLINE_MAXW 4    // spline_kernel: warps (= chunks of a row in flight) per block
 
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -105,55 +96,10 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// Conditional spline of ONE coordinate.  theta is parameter-major ([3nb+1][N] per row, see pack_layer), so the
-// 2nb softmax logits of this lane's coordinate sit at p[k * 32] in shared memory (staged with coalesced
-// copies; the numerators are written back in place) and the two derivatives of the selected bin are
-// fetched from global memory at gp[(2nb + sel) * N].
-__device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __restrict__ gp, int N, int nb,
-                                              float bound, float inv_sqrt_h, bool inverse, float& y, float& ld) {
-    if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39
-        y = x;
-        ld = 0.0f;
-        return;
-    }
-    const float c2 = inv_sqrt_h * 1.4426950408889634f;      // softmax(u / sqrt(H)) via exp2
-    float mw = -3.0e38f, mh = -3.0e38f;
-#pragma unroll 8
-    for (int k = 0; k < nb; ++k) {
-        mw = fmaxf(mw, p[k * 32]);
-        mh = fmaxf(mh, p[(nb + k) * 32]);
-    }
-    float sw = 0.f, sh = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < nb; ++k) {
-        const float ew = exp2f((p[k * 32] - mw) * c2);
-        const float eh = exp2f((p[(nb + k) * 32] - mh) * c2);
-        p[k * 32] = ew;
-        p[(nb + k) * 32] = eh;
-        sw += ew;
-        sh += eh;
-    }
-    const float gw = (1.0f - kMinW * (float)nb) / sw, gh = (1.0f - kMinH * (float)nb) / sh;
-    const float two_b = 2.0f * bound;
-    float cw = 0.f, ch = 0.f, xl = -bound, yl = -bound;
-    float xk = -bound, wk = 1.f, yk = -bound, hk = 1.f;
-    int sel = 0;
-#pragma unroll 4
-    for (int k = 0; k < nb; ++k) {
-        cw += __fmaf_rn(gw, p[k * 32], kMinW);
-        ch += __fmaf_rn(gh, p[(nb + k) * 32], kMinH);
-        const float xr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, cw), -bound);
-        const float yr = (k == nb - 1) ? bound : __fadd_rn(__fmul_rn(two_b, ch), -bound);
-        if (x >= (inverse ? yl : xl)) {      // last knot <= x wins == #(x >= knots) - 1 (utils/splines.py:11-13)
-            sel = k;
-            xk = xl; wk = xr - xl; yk = yl; hk = yr - yl;
-        }
-        xl = xr;
-        yl = yr;
-    }
-    const float dk = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel) * N));
-    const float dk1 = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel + 1) * N));
-    rq_eval(x, xk, wk, yk, hk, dk, dk1, inverse, y, ld);
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // Unconditional spline of one coordinate from the packed knot tables.  Tables are knot-major
@@ -167,66 +113,167 @@ __device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict_
         return;
     }
     const float* ks = inverse ? uy : ux;
-    int sel = 0;
-#pragma unroll 4
-    for (int k = 1; k < nb; ++k)
-        if (x >= __ldg(ks + (size_t)k * N)) sel = k;
+    int lo = 0, hi = nb;                 // last knot <= x (utils/splines.py:11-13); knots increase strictly
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= __ldg(ks + (size_t)mid * N)) lo = mid; else hi = mid;
+    }
+    const int sel = lo;
     const float xk = __ldg(ux + (size_t)sel * N), xk1 = __ldg(ux + (size_t)(sel + 1) * N);
     const float yk = __ldg(uy + (size_t)sel * N), yk1 = __ldg(uy + (size_t)(sel + 1) * N);
     rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + (size_t)sel * N), __ldg(ud + (size_t)(sel + 1) * N), inverse, y,
             ld);
 }
 
-// stage the 2nb softmax logits of coordinates [j0, j0+ncoord) of one row: theta[k][j0 + lane] -> sm[k*32 + lane],
-// all copies in flight at once (cp.async), one 128-byte row segment per k
-__device__ __forceinline__ void stage_params(const float* __restrict__ th, float* sm, int j0, int ncoord, int N, int nb2,
-                                             int lane) {
-    if (lane < ncoord) {
+// Conditional spline of ONE coordinate.  p[k * 32], k < 2nb: the staged width and height logits of this
+// lane's coordinate (overwritten by the inclusive prefix sums of the softmax numerators); gp: this
+// coordinate's column of theta in global memory (stride N) for the two derivatives of the selected bin.
+// Knot k of an axis is 2b (g S[k-1] + min k) - b with g = (1 - min nb) / S[nb-1]  (utils/splines.py:84-100
+// restated on unnormalised sums); knot 0 = -b, knot nb = b.
+__device__ __forceinline__ void rqs_cond_lane(float x, float* p, const float* __restrict__ gp, int N, int nb,
+                                              float bound, float inv_sqrt_h, bool inverse, float& y, float& ld) {
+    if (!(x >= -bound && x <= bound)) {   // utils/splines.py:24,38-39
+        y = x;
+        ld = 0.0f;
+        return;
+    }
+    const float c2 = inv_sqrt_h * 1.4426950408889634f;      // softmax(u / sqrt(H)) via exp2
+    float* q = p + nb * 32;
+    float mw = -3.0e38f, mh = -3.0e38f;
+#pragma unroll 8
+    for (int k = 0; k < nb; ++k) {
+        mw = fmaxf(mw, p[k * 32]);
+        mh = fmaxf(mh, q[k * 32]);
+    }
+    const float ow = -mw * c2, oh = -mh * c2;
+    float sw = 0.f, sh = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < nb; ++k) {
+        sw += ex2_fast(__fmaf_rn(p[k * 32], c2, ow));
+        sh += ex2_fast(__fmaf_rn(q[k * 32], c2, oh));
+        p[k * 32] = sw;
+        q[k * 32] = sh;
+    }
+    const float gw = (1.0f - kMinW * (float)nb) / sw, gh = (1.0f - kMinH * (float)nb) / sh;
+    const float two_b = 2.0f * bound;
+    const float* srch = inverse ? q : p;
+    const float gs = inverse ? gh : gw, ms = inverse ? kMinH : kMinW;
+    int lo = 0, hi = nb;                 // last knot <= x == #(x >= knots) - 1 (utils/splines.py:11-13)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const float knot = __fmaf_rn(two_b, __fmaf_rn(gs, srch[(mid - 1) * 32], ms * (float)mid), -bound);
+        if (x >= knot) lo = mid; else hi = mid;
+    }
+    const int sel = lo;
+    const float w0 = sel ? p[(sel - 1) * 32] : 0.f, h0 = sel ? q[(sel - 1) * 32] : 0.f;
+    const float xl = __fmaf_rn(two_b, __fmaf_rn(gw, w0, kMinW * (float)sel), -bound);
+    const float yl = __fmaf_rn(two_b, __fmaf_rn(gh, h0, kMinH * (float)sel), -bound);
+    const float xr = (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gw, p[sel * 32], kMinW * (float)(sel + 1)), -bound);
+    const float yr = (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gh, q[sel * 32], kMinH * (float)(sel + 1)), -bound);
+    const float dk = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel) * N));
+    const float dk1 = kMinD + softplus_t(__ldg(gp + (size_t)(2 * nb + sel + 1) * N));
+    rq_eval(x, xl, xr - xl, yl, yr - yl, dk, dk1, inverse, y, ld);
+}
+
+// Start the copy of the 2nb logit rows of coordinates [j0, j0+nc) of one row of theta into sm[k*32 + lane]
+// (one cp.async group) and pull the nb+1 derivative rows of the same chunk into L2.
+__device__ __forceinline__ void stage_issue(const float* __restrict__ th, float* sm, int j0, int nc, int N, int nb,
+                                            int lane) {
+    const int nb2 = 2 * nb;
+    if (nc == 32 && (N & 3) == 0) {       // 16-byte copies: 8 lanes per 128-byte row segment, 4 rows per pass
+        const int seg = (lane & 7) * 4;
+        const float* src = th + j0 + seg;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + seg);
+        for (int k = lane >> 3; k < nb2; k += 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k * 128), "l"(src + (size_t)k * N) : "memory");
+    } else if (lane < nc) {
         const float* src = th + j0 + lane;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sm + lane);
         for (int k = 0; k < nb2; ++k)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + k * 128), "l"(src + (size_t)k * N) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    for (int k = nb2 + lane; k <= 3 * nb; k += 32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(th + (size_t)k * N + j0));
 }
 
-// density direction: conditional spline on the transformed half, unconditional spline on the identity
-// half, scatter + roll by D/2 (coupling.py:86-102)
-__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_inverse_v2(
+// DENSITY (step 2 of the density direction): conditional spline on the transformed half, scatter + roll by
+// D/2 (coupling.py:86-102).  !DENSITY (step 2 of sampling): inverse conditional spline on the transformed
+// half (coupling.py:126-135).  The identity half is written by prep_inverse_v2 / prep_forward_v2.
+// A block owns a row at a time (grid stride) and its warps take the row's 32-coordinate chunks, so the
+// block reads each parameter row of theta as one contiguous run; the per-row log-det is summed in a
+// fixed order (deterministic).  The operand of the next chunk is loaded together with its theta copy.
+template <bool DENSITY>
+__global__ void __launch_bounds__(32 * FS_SPLINE_MAXW) spline_kernel(
     const float* __restrict__ v, const float* __restrict__ theta, float* __restrict__ out,
-    float* __restrict__ logdet, int rows, FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy,
-    const float* __restrict__ ud, int* nan_flag) {
-    extern __shared__ float sp_smem[];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
-    if (b >= rows) return;
-    const int nb = F.nb, h = F.D / 2;
-    float* sm = sp_smem + (size_t)wib * 32 * 2 * nb;
-    const float* vr = v + (size_t)b * F.D;
-    float* orow = out + (size_t)b * F.D;
-    const float* th = theta + (size_t)b * F.N * F.P;
-    float acc = 0.f;
-    bool bad = false;
-    for (int j0 = 0; j0 < F.N; j0 += 32) {
-        const int nc = min(32, F.N - j0);
-        stage_params(th, sm, j0, nc, F.N, 2 * nb, lane);
-        if (lane < nc) {
-            const int j = j0 + lane;
-            const int ft = F.trf[j], fi = F.idf[j];
-            float y, ld, y2, ld2;
-            rqs_cond_lane(vr[ft], sm + lane, th + j, F.N, nb, F.bound, F.inv_sqrt_h, false, y, ld);
-            rqs_table_lane(vr[fi], ux + j, uy + j, ud + j, F.N, nb, F.bound, false, y2, ld2);
-            orow[(ft + h) % F.D] = y;
-            orow[(fi + h) % F.D] = y2;
-            acc += ld + ld2;
-            bad = bad || (y != y) || (ld != ld) || (y2 != y2) || (ld2 != ld2);
+    float* __restrict__ logdet, int rows, FlowDev F, int* nan_flag) {
+    extern __shared__ __align__(16) float sp_smem[];
+    __shared__ float red[FS_SPLINE_MAXW];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const int nb = F.nb, h = F.D / 2, nchunk = (F.N + 31) >> 5;
+    const int bufsz = 32 * 2 * nb;
+    float* sm = sp_smem + (size_t)wib * 2 * bufsz;
+    const size_t trow = (size_t)F.N * F.P;
+    int buf = 0;
+    int ft_n = 0;
+    float xt_n = 0.f;
+    if ((int)blockIdx.x < rows && wib < nchunk) {
+        stage_issue(theta + (size_t)blockIdx.x * trow, sm, wib * 32, min(32, F.N - wib * 32), F.N, nb, lane);
+        if (wib * 32 + lane < F.N) {
+            ft_n = F.trf[wib * 32 + lane];
+            xt_n = v[(size_t)blockIdx.x * F.D + (DENSITY ? ft_n : (ft_n + h) % F.D)];
         }
-        __syncwarp();
     }
-    acc = warp_sum_f(acc);
-    if (lane == 0) logdet[b] += acc;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    bool bad = false;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float* th = theta + (size_t)r * trow;
+        float acc = 0.f;
+        for (int c = wib; c < nchunk; c += W) {
+            const int ft = ft_n;
+            const float xt = xt_n;
+            int rn = r, cn = c + W;
+            if (cn >= nchunk) {
+                cn = wib;
+                rn = r + gridDim.x;
+            }
+            if (rn < rows) {
+                stage_issue(theta + (size_t)rn * trow, sm + (buf ^ 1) * bufsz, cn * 32, min(32, F.N - cn * 32), F.N, nb,
+                            lane);
+                if (cn * 32 + lane < F.N) {
+                    ft_n = F.trf[cn * 32 + lane];
+                    xt_n = v[(size_t)rn * F.D + (DENSITY ? ft_n : (ft_n + h) % F.D)];
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            const int j = c * 32 + lane;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            if (j < F.N) {
+                float y, ld;
+                rqs_cond_lane(xt, sm + buf * bufsz + lane, th + j, F.N, nb, F.bound, F.inv_sqrt_h, !DENSITY, y, ld);
+                bad = bad || (y != y) || (ld != ld);
+                acc += ld;
+                out[(size_t)r * F.D + (DENSITY ? (ft + h) % F.D : ft)] = y;
+            }
+            __syncwarp();
+            buf ^= 1;
+        }
+        if (logdet) {
+            acc = warp_sum_f(acc);
+            if (W == 1) {
+                if (lane == 0) logdet[r] += acc;
+            } else {
+                if (lane == 0) red[wib] = acc;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    float t = 0.f;
+                    for (int i = 0; i < W; ++i) t += red[i];
+                    logdet[r] += t;
+                }
+                __syncthreads();
+            }
+        }
+    }
     if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 
@@ -260,40 +307,60 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
     if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 
-// sampling direction, step 3: inverse conditional spline on the transformed half (coupling.py:125-132)
-__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) spline_forward_v2(
-    const float* __restrict__ v, const float* __restrict__ theta, float* __restrict__ out,
-    float* __restrict__ logdet, int rows, FlowDev F, int* nan_flag) {
-    extern __shared__ float sp_smem[];
+// density direction, step 1: periodic features of the identity half (utils/nn.py:125-127) and the
+// unconditional spline on the identity half, scattered + rolled by D/2 (coupling.py:86-102).  One warp per
+// row; the knot tables stay L1-resident here (no shared-memory carve-out).
+__global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
+    const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
+    FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
+    int* nan_flag) {
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * FS_SPLINE_WARPS + wib;
     if (b >= rows) return;
-    const int nb = F.nb, h = F.D / 2;
-    float* sm = sp_smem + (size_t)wib * 32 * 2 * nb;
     const float* vr = v + (size_t)b * F.D;
-    const float* th = theta + (size_t)b * F.N * F.P;
+    const int h = F.D / 2, nb = F.nb;
     float acc = 0.f;
     bool bad = false;
-    for (int j0 = 0; j0 < F.N; j0 += 32) {
-        const int nc = min(32, F.N - j0);
-        stage_params(th, sm, j0, nc, F.N, 2 * nb, lane);
-        if (lane < nc) {
-            const int ft = F.trf[j0 + lane];
-            float y, ld;
-            rqs_cond_lane(vr[(ft + h) % F.D], sm + lane, th + j0 + lane, F.N, nb, F.bound, F.inv_sqrt_h, true, y, ld);
-            out[(size_t)b * F.D + ft] = y;
-            acc += ld;
-            bad = bad || (y != y) || (ld != ld);
-        }
-        __syncwarp();
+    for (int j = lane; j < F.N; j += 32) {
+        const int fi = F.idf[j];
+        const float x = vr[fi];
+        float sn, cs;
+        sincosf(F.pf_scale * x, &sn, &cs);
+        A0[(size_t)b * 2 * F.N + j] = cs;
+        A0[(size_t)b * 2 * F.N + F.N + j] = sn;
+        float y, ld;
+        rqs_table_lane(x, ux + j, uy + j, ud + j, F.N, nb, F.bound, false, y, ld);
+        out[(size_t)b * F.D + (fi + h) % F.D] = y;
+        acc += ld;
+        bad = bad || (y != y) || (ld != ld);
     }
     acc = warp_sum_f(acc);
     if (lane == 0 && logdet) logdet[b] += acc;
     if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 
+
+// warps per block of spline_kernel: one per 32-coordinate chunk of a row, at most FS_SPLINE_MAXW
+static int spline_warps(const fs_flow* f) {
+    const int nchunk = (f->N + 31) / 32;
+    int maxw = FS_SPLINE_MAXW;
+    if (const char* e = getenv("FS_SPLINE_W")) maxw = atoi(e);
+    return nchunk < maxw ? nchunk : maxw;
+}
+
 static size_t spline_smem_bytes(const fs_flow* f) {
-    return (size_t)FS_SPLINE_WARPS * 32 * 2 * f->nb * sizeof(float);
+    return (size_t)spline_warps(f) * 2 * 32 * 2 * f->nb * sizeof(float);   // two buffers per warp
+}
+
+// one wave of resident blocks; blocks stride over rows
+static unsigned spline_grid(const fs_flow* f, int rows) {
+    const size_t per_block = spline_smem_bytes(f) + 1024;
+    int resident = (int)((227 * 1024) / per_block);
+    const int by_warps = 48 / spline_warps(f);
+    resident = resident > by_warps ? by_warps : resident;
+    resident = resident > 32 ? 32 : (resident < 1 ? 1 : resident);
+    const long long cap = (long long)f->sm_count * resident;
+    return (unsigned)(rows < cap ? rows : cap);
 }
 
 // out <- z (+ shift); logq <- logdet + UniformParticle.log_prob(z)  (Energy/Uniform.py:50-74)
@@ -608,11 +675,20 @@ extern "C" int fs_flow_create(const fs_flow_desc* d, fs_flow** out) {
     if (!r) r = upload(f, trf, &f->trf);
     f->layers.resize(d->K);
     for (int i = 0; i < d->K && !r; ++i) r = pack_layer(f, d, &d->layers[i], &f->layers[i]);
-    if (!r && spline_smem_bytes(f) > 48 * 1024) {
-        r = cuda_check(cudaFuncSetAttribute(spline_inverse_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)spline_smem_bytes(f)), "spline smem");
-        if (!r) r = cuda_check(cudaFuncSetAttribute(spline_forward_v2, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)spline_smem_bytes(f)), "spline smem");
+    if (!r && spline_smem_bytes(f) > 226 * 1024) {
+        set_error("fs_flow_create: num_bins too large for the spline kernel's shared-memory staging");
+        r = FS_ERR_INVALID;
+    }
+    if (!r) {   // opt in to the device maximum once per create: the attribute is per function, not per flow
+        r = cuda_check(cudaFuncSetAttribute(spline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            226 * 1024), "spline smem");
+        if (!r) r = cuda_check(cudaFuncSetAttribute(spline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    226 * 1024), "spline smem");
+    }
+    if (!r) {
+        int dev = 0;
+        r = cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+        if (!r) r = cuda_check(cudaDeviceGetAttribute(&f->sm_count, cudaDevAttrMultiProcessorCount, dev), "SM count");
     }
     if (!r) r = tc_pack(f, d);
     if (r) {
@@ -695,13 +771,12 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         float* nxt = w.v1;
         for (int li = f->K - 1; li >= 0; --li) {                        // core.py:82-85
             const fs_flow::Layer& L = f->layers[li];
-            const size_t ne = (size_t)rows * f->N;
-            prep_inverse_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(cur, w.A0, rows, F);
+            prep_inverse_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_inverse_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS,
-                                spline_smem_bytes(f), s>>>(cur, w.theta, nxt, w.ld, rows, F, L.u_x, L.u_y, L.u_d,
-                                                           nan_flag);
+            spline_kernel<true><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
+                cur, w.theta, nxt, w.ld, rows, F, nan_flag);
     fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
@@ -738,8 +813,8 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
                 cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
             if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_forward_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS,
-                                spline_smem_bytes(f), s>>>(cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+            spline_kernel<false><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
+                cur, w.theta, nxt, w.ld, rows, F, nan_flag);
     fs::count_launch();
             float* tmp = cur; cur = nxt; nxt = tmp;
         }

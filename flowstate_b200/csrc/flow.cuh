@@ -31,6 +31,7 @@ struct fs_flow {
     std::vector<void*> allocs;
     void* tc;   // tensor-core pack (flow_tc.cu), or nullptr
     int* tc_err;   // device error word written by the tensor kernel's watchdog
+    int sm_count;
 };
 
 namespace fs {
