@@ -59,7 +59,7 @@ struct TcArgs {
     unsigned long long n_tiles;
     TcLayer L;
     int* err;
-    long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 8 per CTA
+    long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 16 per CTA
     int dbg_mode;     // FS_TC_MODE (timing experiments only): 1 = epilogue skips data work, 4 = no weight copies
 };
 
@@ -177,6 +177,34 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
+// Epilogue arithmetic.  The epilogue warps are issue-bound, so they use Blackwell's packed FP32 pairs
+// (FADD2 / FFMA2) and fold ReLU and the TF32 rounding into one integer instruction: for finite x,
+// round-to-nearest (ties away) to 10 mantissa bits is bits(x) + 0x1000 with the low 13 bits ignored by the
+// tensor core, and relu on the bit pattern is a signed max with 0, so
+// tf32(relu(x)) = max(bits(x) + 0x1000, 0x1000)  (VIADDMNMX).  Same values as cvt.rna.tf32.f32 for finite
+// inputs; an infinity turns into a NaN, which the flow's nan_flag reports either way.
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t relu_tf32(float x) {
+    return (uint32_t)__viaddmax_s32(__float_as_int(x), 0x1000, 0x1000);
+}
+__device__ __forceinline__ uint32_t round_tf32(float x) { return __float_as_uint(x) + 0x1000u; }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row groups of 128-byte rows, 1024 B apart.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
@@ -191,7 +219,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 
 // barrier ids.  full: MMA -> epilogue (accumulator complete).  rdy: epilogue -> MMA (operand half written, or
 // final-layer accumulator drained).
-enum { FULL_R0 = 0, FULL_R1 = 1, FULL_F0 = 2, FULL_F1 = 3 };
+enum { FULL_R0H0 = 0, FULL_R0H1 = 1, FULL_R1H0 = 2, FULL_R1H1 = 3, FULL_F0 = 4, FULL_F1 = 5 };
 enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F1 = 5 };
 
 template <int H>
@@ -203,6 +231,7 @@ struct TcCfg {
     static constexpr int NSTAGE = (H == 256) ? 4 : 8;
     static constexpr int GROUP = (H == 256) ? 1 : 2;         // stages issued per barrier batch (>= 512 clk of MMAs)
     static constexpr int FCH = 128;                          // final-layer chunk width (MMA N)
+    static constexpr bool SPLIT = (H == 256);                // block GEMMs as N = 128 quarter-GEMMs (see gemm_split)
     static constexpr int KPS = STAGE_BYTES / (FCH * 128);    // final-layer k-tiles per stage
     static constexpr int FIN0 = H;                           // TMEM column of final accumulator 0
     static constexpr int FIN1 = (H == 256) ? H + 128 : 2 * H;
@@ -229,13 +258,13 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     // barrier map (8 bytes each)
     const uint32_t bar_wfull = bar_base;                        // [NSTAGE] TMA -> MMA
     const uint32_t bar_wempty = bar_base + 8 * NSTAGE;          // [NSTAGE] MMA -> TMA
-    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [4]
-    const uint32_t bar_rdy = bar_full + 32;                     // [6]
+    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [6]
+    const uint32_t bar_rdy = bar_full + 48;                     // [6]
     const uint32_t bar_free1 = bar_rdy + 48;                    // [1]  MMA -> epilogue (feature piece consumed)
     const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 120);
-    static_assert(16 * NSTAGE + 124 <= 512, "barrier area overflow");
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 144);
+    static_assert(16 * NSTAGE + 148 <= 512, "barrier area overflow");
     float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
     const int warp = threadIdx.x >> 5;
@@ -247,7 +276,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_wfull + 8 * i, 1);
             mbar_init(bar_wempty + 8 * i, 1);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar_full + 8 * i, 1);
+        for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
         for (int i = 0; i < 6; ++i) mbar_init(bar_rdy + 8 * i, EPI_WARPS);
         mbar_init(bar_free1, 1);
         for (int i = 0; i < 2; ++i) {
@@ -291,8 +320,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
                     // scripts/tma_bw2.cu); copies issued by different lanes overlap -> rotate the issuing lane.
                     if (lane == (int)(t & 7)) {
-                        mbar_expect_tx(bar_wfull + 8 * stage, S::STAGE_BYTES);
-                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, S::STAGE_BYTES,
+                        const uint32_t nbytes = (g.dbg_mode == 3) ? S::STAGE_BYTES / 2 : S::STAGE_BYTES;
+                        mbar_expect_tx(bar_wfull + 8 * stage, nbytes);
+                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, nbytes,
                                      bar_wfull + 8 * stage);
                     }
                     __syncwarp();
@@ -307,7 +337,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 stream(2ull * KT);
             }
             stream((unsigned long long)g.n_chunks * (KT / S::KPS));   // final layer
-            if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 0] = w_empty;
+            if (g.dbg && lane == 0) g.dbg[16 * blockIdx.x + 0] = w_empty;
         } else if (warp == 1) {
             // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
@@ -385,13 +415,40 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 gemm_blk(0, H, RDY_R1H0, kcols / TC_KB, p == 0, false);
                 if (p < g.n_pieces - 1) commit(bar_free1);
             }
-            commit(bar_full + 8 * FULL_R0);
+            commit(bar_full + 8 * FULL_R0H0);
+            commit(bar_full + 8 * FULL_R0H1);
+            // H = 256: split schedule.  Each H x H GEMM runs as
+            //   (all columns, K lo: 16 MMAs of N = 256) | (columns lo, K hi: 16 MMAs of N = 128) (columns hi, K hi: 16 of N = 128)
+            // The first part only needs the low half of the operand region, so it starts while the epilogue is still
+            // writing the high half; the accumulator's low column half completes a quarter-GEMM before the high one,
+            // so the epilogue starts on it while the tensor pipe finishes the other.  K-lo stages are k-tiles of all
+            // H weight rows; K-hi stages hold KPS k-tiles of a 128-row weight chunk (the final layer's stage format).
+            auto gemm_split = [&](uint32_t dcol, uint32_t abase, int rdy0, int full0) {
+                constexpr int SPQ = (KT / 2) / S::KPS;          // stages per quarter
+                wait_rdy(rdy0);
+#pragma unroll 1
+                for (int kt = 0; kt < KT / 2; ++kt) issue(dcol, abase + kt * TC_KB, 1, kt == 0, false);
+                wait_rdy(rdy0 + 1);
+#pragma unroll 1
+                for (int nh = 0; nh < 2; ++nh) {
+                    for (int sg = 0; sg < SPQ; ++sg)
+                        issue(dcol + nh * NH, abase + NH + sg * S::KPS * TC_KB, 1, false, true);
+                    commit(bar_full + 8 * (full0 + nh));
+                }
+            };
             // ---- residual blocks ----
             for (int b = 0; b < g.n_blocks; ++b) {
-                gemm_blk(H, 0, RDY_R0H0, KT, true, true);       // linear 0: A = R0 (a), D = R1
-                commit(bar_full + 8 * FULL_R1);
-                gemm_blk(0, H, RDY_R1H0, KT, true, true);       // linear 1: A = R1 (relu t), D = R0
-                commit(bar_full + 8 * FULL_R0);
+                if (S::SPLIT) {
+                    gemm_split(H, 0, RDY_R0H0, FULL_R1H0);          // linear 0: A = R0 (a), D = R1
+                    gemm_split(0, H, RDY_R1H0, FULL_R0H0);          // linear 1: A = R1 (relu t), D = R0
+                } else {
+                    gemm_blk(H, 0, RDY_R0H0, KT, true, true);
+                    commit(bar_full + 8 * FULL_R1H0);
+                    commit(bar_full + 8 * FULL_R1H1);
+                    gemm_blk(0, H, RDY_R1H0, KT, true, true);
+                    commit(bar_full + 8 * FULL_R0H0);
+                    commit(bar_full + 8 * FULL_R0H1);
+                }
             }
             // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
             wait_rdy(RDY_R0H0);
@@ -406,10 +463,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 commit(bar_full + 8 * (FULL_F0 + f));
             }
             if (g.dbg && lane == 0) {
-                g.dbg[8 * blockIdx.x + 1] = w_ready;
-                g.dbg[8 * blockIdx.x + 2] = w_weights;
-                g.dbg[8 * blockIdx.x + 3] = clock64() - t_start;
-                g.dbg[8 * blockIdx.x + 6] = t_issue;
+                g.dbg[16 * blockIdx.x + 1] = w_ready;
+                g.dbg[16 * blockIdx.x + 2] = w_weights;
+                g.dbg[16 * blockIdx.x + 3] = clock64() - t_start;
+                g.dbg[16 * blockIdx.x + 6] = t_issue;
             }
         }
     } else {
@@ -422,7 +479,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         const bool row_ok = grow < g.rows;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         uint32_t ph_full = 0, ph_free1 = 0, ph_pfull = 0;
-        long long w_full = 0;
+        long long w_full = 0, t_res0 = 0, t_res1 = 0, t_relu = 0, t_fin = 0, t_mark = 0;
+        const bool dbg_me = g.dbg && ew == 0 && lane == 0;
         const long long e_start = g.dbg ? clock64() : 0;
         auto wait_full = [&](int id) {
             mbar_wait(bar_full + 8 * id, (ph_full >> id) & 1, g.err, 4,
@@ -482,35 +540,44 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         const int col = (HF) * NH + cgp * 32;                                                                  \
         _Pragma("unroll") for (int sub = 0; sub < 2; ++sub) {                                                  \
             tc_ld16(lane_addr + col + 16 * sub, v);                                                            \
+            float4 hh[4];                                                                                      \
+            if ((HF) == 1 && !(INIT)) {                                                                        \
+                _Pragma("unroll") for (int i4 = 0; i4 < 4; ++i4)                                               \
+                    hh[i4] = us4[(size_t)(cgp * 8 + sub * 4 + i4) * 128 + r];                                  \
+            }                                                                                                  \
             tc_wait_ld();                                                                                      \
             _Pragma("unroll") for (int i4 = 0; i4 < 4; ++i4) {                                                 \
-                float4 uu = make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),            \
-                                        __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));       \
+                unsigned long long ua = pk2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]));       \
+                unsigned long long ub = pk2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));   \
+                float4 uu;                                                                                     \
                 if ((HF) == 0) {                                                                               \
                     if (!(INIT)) {                                                                             \
-                        uu.x += u0[16 * sub + 4 * i4]; uu.y += u0[16 * sub + 4 * i4 + 1];                      \
-                        uu.z += u0[16 * sub + 4 * i4 + 2]; uu.w += u0[16 * sub + 4 * i4 + 3];                  \
+                        ua = add2(ua, pk2(u0[16 * sub + 4 * i4], u0[16 * sub + 4 * i4 + 1]));                  \
+                        ub = add2(ub, pk2(u0[16 * sub + 4 * i4 + 2], u0[16 * sub + 4 * i4 + 3]));              \
                     }                                                                                          \
+                    upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
                     u0[16 * sub + 4 * i4] = uu.x; u0[16 * sub + 4 * i4 + 1] = uu.y;                            \
                     u0[16 * sub + 4 * i4 + 2] = uu.z; u0[16 * sub + 4 * i4 + 3] = uu.w;                        \
                 } else {                                                                                       \
                     float4* hp = us4 + (size_t)(cgp * 8 + sub * 4 + i4) * 128 + r;                             \
                     if (!(INIT)) {                                                                             \
-                        const float4 h0 = *hp;                                                                 \
-                        uu.x += h0.x; uu.y += h0.y; uu.z += h0.z; uu.w += h0.w;                                \
+                        ua = add2(ua, pk2(hh[i4].x, hh[i4].y)); ub = add2(ub, pk2(hh[i4].z, hh[i4].w));        \
                     }                                                                                          \
+                    upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
                     *hp = uu;                                                                                  \
                 }                                                                                              \
                 if (HAS_NEXT) {                                                                                \
                     const float4 sc = *reinterpret_cast<const float4*>((PRM) + H + col + 16 * sub + 4 * i4);   \
                     const float4 of = *reinterpret_cast<const float4*>((PRM) + 2 * H + col + 16 * sub + 4 * i4); \
-                    uu.x = fmaxf(__fmaf_rn(uu.x, sc.x, of.x), 0.f);                                            \
-                    uu.y = fmaxf(__fmaf_rn(uu.y, sc.y, of.y), 0.f);                                            \
-                    uu.z = fmaxf(__fmaf_rn(uu.z, sc.z, of.z), 0.f);                                            \
-                    uu.w = fmaxf(__fmaf_rn(uu.w, sc.w, of.w), 0.f);                                            \
+                    ua = fma2(ua, pk2(sc.x, sc.y), pk2(of.x, of.y));                                           \
+                    ub = fma2(ub, pk2(sc.z, sc.w), pk2(of.z, of.w));                                           \
+                    upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
+                    v[4 * i4] = relu_tf32(uu.x); v[4 * i4 + 1] = relu_tf32(uu.y);                              \
+                    v[4 * i4 + 2] = relu_tf32(uu.z); v[4 * i4 + 3] = relu_tf32(uu.w);                          \
+                } else {                                                                                       \
+                    v[4 * i4] = round_tf32(uu.x); v[4 * i4 + 1] = round_tf32(uu.y);                            \
+                    v[4 * i4 + 2] = round_tf32(uu.z); v[4 * i4 + 3] = round_tf32(uu.w);                        \
                 }                                                                                              \
-                v[4 * i4] = to_tf32(uu.x); v[4 * i4 + 1] = to_tf32(uu.y);                                      \
-                v[4 * i4 + 2] = to_tf32(uu.z); v[4 * i4 + 3] = to_tf32(uu.w);                                  \
             }                                                                                                  \
             tc_st16(lane_addr + col + 16 * sub, v);                                                            \
         }                                                                                                      \
@@ -518,17 +585,19 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         signal_rdy(RDY_R0H0 + (HF));                                                                           \
     }
         wait_pset(0);
-        wait_full(FULL_R0);
+        wait_full(FULL_R0H0);
         FS_EPI_RESIDUAL(0, pbuf, true, true)
+        wait_full(FULL_R0H1);
         FS_EPI_RESIDUAL(1, pbuf, true, true)
         release_pset(0);
         // ---- residual blocks ----
         for (int b = 0; b < g.n_blocks; ++b) {
             const float* prm = pbuf + (size_t)((b + 1) & 1) * S::PSET_FLOATS;
             wait_pset(b + 1);
-            wait_full(FULL_R1);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {                  // relu(t + b0') in place in R1
+                wait_full(FULL_R1H0 + hf);
+                if (dbg_me) t_mark = clock64();
                 const int col = hf * NH + cgp * 32;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
@@ -537,34 +606,55 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #pragma unroll
                     for (int i4 = 0; i4 < 4; ++i4) {
                         const float4 bb = *reinterpret_cast<const float4*>(prm + col + 16 * sub + 4 * i4);
-                        v[4 * i4] = to_tf32(fmaxf(__uint_as_float(v[4 * i4]) + bb.x, 0.f));
-                        v[4 * i4 + 1] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 1]) + bb.y, 0.f));
-                        v[4 * i4 + 2] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 2]) + bb.z, 0.f));
-                        v[4 * i4 + 3] = to_tf32(fmaxf(__uint_as_float(v[4 * i4 + 3]) + bb.w, 0.f));
+                        const unsigned long long ta =
+                            add2(pk2(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1])), pk2(bb.x, bb.y));
+                        const unsigned long long tb =
+                            add2(pk2(__uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3])), pk2(bb.z, bb.w));
+                        float t0, t1, t2, t3;
+                        upk2(ta, t0, t1);
+                        upk2(tb, t2, t3);
+                        v[4 * i4] = relu_tf32(t0);
+                        v[4 * i4 + 1] = relu_tf32(t1);
+                        v[4 * i4 + 2] = relu_tf32(t2);
+                        v[4 * i4 + 3] = relu_tf32(t3);
                     }
                     tc_st16(lane_addr + H + col + 16 * sub, v);
                 }
                 tc_wait_st();
                 signal_rdy(RDY_R1H0 + hf);
+                if (dbg_me) t_relu += clock64() - t_mark;
             }
             const bool last = (b == g.n_blocks - 1);
-            wait_full(FULL_R0);
+            wait_full(FULL_R0H0);
             if (!last) {
+                if (dbg_me) t_mark = clock64();
                 FS_EPI_RESIDUAL(0, prm, true, false)
+                if (dbg_me) t_res0 += clock64() - t_mark;
+                wait_full(FULL_R0H1);
+                if (dbg_me) t_mark = clock64();
                 FS_EPI_RESIDUAL(1, prm, true, false)
+                if (dbg_me) t_res1 += clock64() - t_mark;
             } else {
                 FS_EPI_RESIDUAL(0, prm, false, false)
+                wait_full(FULL_R0H1);
                 FS_EPI_RESIDUAL(1, prm, false, false)
             }
             release_pset(b + 1);
         }
 #undef FS_EPI_RESIDUAL
         // ---- final layer: theta chunk = D + b_final' -> global ----
+        // A thread holds 32 columns of ONE row, so storing straight from registers would touch 32 different lines
+        // per instruction.  Each warp transposes its 32 x 32 block through a private 4 KB patch of the (now dead)
+        // u buffer -- float4 slot c of row rr at rr*8 + (c ^ (rr & 7)), conflict-free both ways -- and stores
+        // 4 rows x 128 contiguous bytes per instruction.
         const bool vec_ok = (g.NP & 3) == 0;
         constexpr int CPT = (S::FCH / 32) * 4 / EPI_WARPS;     // 32-column chunks of a final accumulator per thread: 1 / 2
+        float4* patch = reinterpret_cast<float4*>(smem + S::U_OFF) + ew * 256;
+        const int slot = lane & 7, rsub = lane >> 3;
         for (int c = 0; c < g.n_chunks; ++c) {
             const int f = c & 1;
             wait_full(FULL_F0 + f);
+            if (dbg_me) t_mark = clock64();
             const uint32_t fcol = f ? S::FIN1 : S::FIN0;
 #pragma unroll
             for (int cc = 0; cc < CPT; ++cc) {
@@ -573,31 +663,49 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 for (int sub = 0; sub < 2; ++sub) {
                     tc_ld16(lane_addr + fcol + col + 16 * sub, v);
                     tc_wait_ld();
-                    if (cc == CPT - 1 && sub == 1) signal_rdy(RDY_F0 + f);   // all of this thread's reads are done
-                    const int ocol = c * S::FCH + col + 16 * sub;
-                    if (row_ok) {
-                        float* dst = g.theta + (size_t)grow * g.NP + ocol;
-                        if (vec_ok && ocol + 16 <= g.NP) {
-                            const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_final + ocol);
 #pragma unroll
-                            for (int i4 = 0; i4 < 4; ++i4) {
-                                const float4 bb = __ldg(bf4 + i4);
-                                reinterpret_cast<float4*>(dst)[i4] =
-                                    make_float4(__uint_as_float(v[4 * i4]) + bb.x, __uint_as_float(v[4 * i4 + 1]) + bb.y,
-                                                __uint_as_float(v[4 * i4 + 2]) + bb.z, __uint_as_float(v[4 * i4 + 3]) + bb.w);
-                            }
-                        } else {
+                    for (int i4 = 0; i4 < 4; ++i4)
+                        patch[lane * 8 + ((sub * 4 + i4) ^ (lane & 7))] =
+                            make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),
+                                        __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
+                }
+                if (cc == CPT - 1) signal_rdy(RDY_F0 + f);             // all of this thread's TMEM reads are done
+                __syncwarp();
+                const int ocol = c * S::FCH + col + 4 * slot;          // this lane's 4 columns
+                if (vec_ok && c * S::FCH + col + 32 <= g.NP) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(g.L.b_final + ocol));
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (ocol + i < g.NP) dst[i] = __uint_as_float(v[i]) + __ldg(g.L.b_final + ocol + i);
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + rsub;
+                        const int gr = row0 + 32 * q + rr;
+                        const float4 t = patch[rr * 8 + (slot ^ (rr & 7))];
+                        if (gr < g.rows)
+                            *reinterpret_cast<float4*>(g.theta + (size_t)gr * g.NP + ocol) =
+                                make_float4(t.x + bb.x, t.y + bb.y, t.z + bb.z, t.w + bb.w);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + rsub;
+                        const int gr = row0 + 32 * q + rr;
+                        const float4 t = patch[rr * 8 + (slot ^ (rr & 7))];
+                        const float tv[4] = {t.x, t.y, t.z, t.w};
+                        if (gr < g.rows)
+                            for (int e = 0; e < 4; ++e)
+                                if (ocol + e < g.NP) g.theta[(size_t)gr * g.NP + ocol + e] = tv[e] + __ldg(g.L.b_final + ocol + e);
                     }
                 }
+                __syncwarp();
             }
+            if (dbg_me) t_fin += clock64() - t_mark;
         }
-        if (g.dbg && ew == 0 && lane == 0) {
-            g.dbg[8 * blockIdx.x + 4] = w_full;
-            g.dbg[8 * blockIdx.x + 5] = clock64() - e_start;
+        if (dbg_me) {
+            g.dbg[16 * blockIdx.x + 4] = w_full;
+            g.dbg[16 * blockIdx.x + 5] = clock64() - e_start;
+            g.dbg[16 * blockIdx.x + 7] = t_res0;
+            g.dbg[16 * blockIdx.x + 8] = t_res1;
+            g.dbg[16 * blockIdx.x + 9] = t_relu;
+            g.dbg[16 * blockIdx.x + 10] = t_fin;
         }
     }
     tc_fence_before();
@@ -704,10 +812,20 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             const int kcols = std::min(H, P->Kp0 - pc * H);
             for (int kt = 0; kt < kcols / TC_KB; ++kt) append_tile(stream, p->init_w, H, K0, 0, pc * H + kt * TC_KB, H);
         }
+        // H = 256 (split schedule, see gemm_split): K-lo k-tiles of all H rows, then (rows lo, K hi) and (rows hi, K hi)
+        // as stages of KPS k-tiles of a 128-row chunk
+        auto append_gemm = [&](const float* W) {
+            if (H == 256) {
+                for (int kt = 0; kt < KT / 2; ++kt) append_tile(stream, W, H, H, 0, kt * TC_KB, H);
+                for (int nh = 0; nh < 2; ++nh)
+                    for (int kt = KT / 2; kt < KT; ++kt) append_tile(stream, W, H, H, nh * (H / 2), kt * TC_KB, H / 2);
+            } else {
+                for (int kt = 0; kt < KT; ++kt) append_tile(stream, W, H, H, 0, kt * TC_KB, H);
+            }
+        };
         for (int b = 0; b < nB; ++b) {
-            for (int kt = 0; kt < KT; ++kt) append_tile(stream, &w0[(size_t)b * H * H], H, H, 0, kt * TC_KB, H);   // linear 0 (BN1 folded)
-            const float* w1 = p->lin_w + ((size_t)b * 2 + 1) * H * H;
-            for (int kt = 0; kt < KT; ++kt) append_tile(stream, w1, H, H, 0, kt * TC_KB, H);                      // linear 1
+            append_gemm(&w0[(size_t)b * H * H]);                               // linear 0 (BN1 folded)
+            append_gemm(p->lin_w + ((size_t)b * 2 + 1) * H * H);               // linear 1
         }
         for (int c = 0; c < P->n_chunks; ++c)                            // final layer
             for (int sg = 0; sg < KT / KPS; ++sg)
@@ -780,10 +898,10 @@ static long long* tc_debug_buffer(int ctas) {
     if (!enabled) return nullptr;
     if (ctas > g_dbg_ctas) {
         if (g_dbg) cudaFree(g_dbg);
-        cudaMalloc(&g_dbg, sizeof(long long) * 8 * ctas);
+        cudaMalloc(&g_dbg, sizeof(long long) * 16 * ctas);
         g_dbg_ctas = ctas;
     }
-    cudaMemset(g_dbg, 0, sizeof(long long) * 8 * ctas);
+    cudaMemset(g_dbg, 0, sizeof(long long) * 16 * ctas);
     return g_dbg;
 }
 
@@ -823,13 +941,13 @@ int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* thet
 
 }  // namespace fs
 
-// development aid: copies the wait-cycle counters of the last tensor-kernel launch (8 int64 per CTA:
+// development aid: copies the wait-cycle counters of the last tensor-kernel launch (16 int64 per CTA:
 // producer wait-empty, MMA wait-operand, MMA wait-weights, MMA total, epilogue wait-accumulator,
 // epilogue total, 0, 0).  Returns the number of CTAs copied.
 extern "C" int fs_tc_debug_read(long long* host, int max_ctas) {
     int n = fs::g_dbg_ctas < max_ctas ? fs::g_dbg_ctas : max_ctas;
     if (!fs::g_dbg || n <= 0) return 0;
     cudaDeviceSynchronize();
-    cudaMemcpy(host, fs::g_dbg, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost);
+    cudaMemcpy(host, fs::g_dbg, sizeof(long long) * 16 * n, cudaMemcpyDeviceToHost);
     return n;
 }

@@ -198,7 +198,7 @@ int fs_flow_forward(fs_flow* flow, const float* z, int B, double out_shift,
                     void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* Development aid (FS_TC_DEBUG=1): wait-cycle counters of the last tensor-core conditioner launch,
- * 8 int64 per CTA; returns the number of CTAs copied to `host`. */
+ * 16 int64 per CTA; returns the number of CTAs copied to `host`. */
 int fs_tc_debug_read(long long* host, int max_ctas);
 
 #ifdef __cplusplus
