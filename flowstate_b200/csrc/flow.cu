@@ -24,45 +24,6 @@
 
 namespace fs {
 
-static const float kMinW = 1e-3f, kMinH = 1e-3f, kMinD = 1e-3f;   // utils/splines.py:6-8
-
-// ---------------------------------------------------------------------------
-// spline device code
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float softplus_t(float x) {   // F.softplus, threshold 20
-    return x > 20.0f ? x : log1pf(expf(x));
-}
-
-// Rational-quadratic bin evaluation (utils/splines.py:163-222) given the selected bin.
-__device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, float hk, float dk, float dk1,
-                                        bool inverse, float& y, float& ld) {
-    const float sk = hk / wk;
-    const float t = dk + dk1 - 2.0f * sk;
-    if (inverse) {
-        const float dy = x - yk;
-        const float a = dy * t + hk * (sk - dk);
-        const float b = hk * dk - dy * t;
-        const float c = -sk * dy;
-        const float disc = fabsf(b * b - 4.0f * a * c);
-        const float root = (2.0f * c) / (-b - sqrtf(disc));
-        y = root * wk + xk;
-        const float tt = root * (1.0f - root);
-        const float den = sk + t * tt;
-        const float omr = 1.0f - root;
-        const float num = (sk * sk) * (dk1 * (root * root) + 2.0f * sk * tt + dk * (omr * omr));
-        ld = -(logf(num) - 2.0f * logf(den));
-    } else {
-        const float th = (x - xk) / wk;
-        const float tt = th * (1.0f - th);
-        const float num = hk * (sk * (th * th) + dk * tt);
-        const float den = sk + t * tt;
-        y = yk + num / den;
-        const float omt = 1.0f - th;
-        const float dnum = (sk * sk) * (dk1 * (th * th) + 2.0f * sk * tt + dk * (omt * omt));
-        ld = logf(dnum) - 2.0f * logf(den);
-    }
-}
-
 struct FlowDev {
     int N, D, H, nb, P;
     float bound, pf_scale, inv_sqrt_h;
@@ -761,6 +722,8 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
     carve(f, B, precision, workspace, &w);
     const int Bc = chunk_rows(f, B);
     const FlowDev F = flow_dev(f);
+    // tensor path with the spline applied in the conditioner's epilogue (FS_NO_FUSE=1 keeps theta + spline kernel)
+    const bool fused = precision == FS_PREC_TF32 && tc_has_fused(f) && !getenv("FS_NO_FUSE");
     for (int r0 = 0; r0 < B; r0 += Bc) {
         const int rows = (B - r0 < Bc) ? B - r0 : Bc;
         const size_t n = (size_t)rows * f->D;
@@ -774,10 +737,14 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             prep_inverse_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
                 cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
-            if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_kernel<true><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
-                cur, w.theta, nxt, w.ld, rows, F, nan_flag);
-    fs::count_launch();
+            if (fused) {
+                if (int r = tc_conditioner_spline(f, li, w.A0, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
+            } else {
+                if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+                spline_kernel<true><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
+                    cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+                fs::count_launch();
+            }
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, z ? z + (size_t)r0 * f->D : nullptr, w.ld,
@@ -800,6 +767,8 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
     carve(f, B, precision, workspace, &w);
     const int Bc = chunk_rows(f, B);
     const FlowDev F = flow_dev(f);
+    // tensor path with the spline applied in the conditioner's epilogue (FS_NO_FUSE=1 keeps theta + spline kernel)
+    const bool fused = precision == FS_PREC_TF32 && tc_has_fused(f) && !getenv("FS_NO_FUSE");
     for (int r0 = 0; r0 < B; r0 += Bc) {
         const int rows = (B - r0 < Bc) ? B - r0 : Bc;
         const size_t n = (size_t)rows * f->D;
@@ -812,10 +781,14 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
             prep_forward_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
                 cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
-            if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
-            spline_kernel<false><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
-                cur, w.theta, nxt, w.ld, rows, F, nan_flag);
-    fs::count_launch();
+            if (fused) {
+                if (int r = tc_conditioner_spline(f, li, w.A0, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
+            } else {
+                if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+                spline_kernel<false><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
+                    cur, w.theta, nxt, w.ld, rows, F, nan_flag);
+                fs::count_launch();
+            }
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, x + (size_t)r0 * f->D, w.ld,

@@ -35,6 +35,45 @@ struct fs_flow {
 };
 
 namespace fs {
+static constexpr float kMinW = 1e-3f, kMinH = 1e-3f, kMinD = 1e-3f;   // utils/splines.py:6-8
+
+// ---------------------------------------------------------------------------
+// spline device code
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float softplus_t(float x) {   // F.softplus, threshold 20
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+
+// Rational-quadratic bin evaluation (utils/splines.py:163-222) given the selected bin.
+__device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, float hk, float dk, float dk1,
+                                        bool inverse, float& y, float& ld) {
+    const float sk = hk / wk;
+    const float t = dk + dk1 - 2.0f * sk;
+    if (inverse) {
+        const float dy = x - yk;
+        const float a = dy * t + hk * (sk - dk);
+        const float b = hk * dk - dy * t;
+        const float c = -sk * dy;
+        const float disc = fabsf(b * b - 4.0f * a * c);
+        const float root = (2.0f * c) / (-b - sqrtf(disc));
+        y = root * wk + xk;
+        const float tt = root * (1.0f - root);
+        const float den = sk + t * tt;
+        const float omr = 1.0f - root;
+        const float num = (sk * sk) * (dk1 * (root * root) + 2.0f * sk * tt + dk * (omr * omr));
+        ld = -(logf(num) - 2.0f * logf(den));
+    } else {
+        const float th = (x - xk) / wk;
+        const float tt = th * (1.0f - th);
+        const float num = hk * (sk * (th * th) + dk * tt);
+        const float den = sk + t * tt;
+        y = yk + num / den;
+        const float omt = 1.0f - th;
+        const float dnum = (sk * sk) * (dk1 * (th * th) + 2.0f * sk * tt + dk * (omt * omt));
+        ld = logf(dnum) - 2.0f * logf(den);
+    }
+}
+
 // final-layer rows/bias permuted to parameter-major order (row k*N + j), see flow.cu
 void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b);
 // tensor-core path (flow_tc.cu)
@@ -43,4 +82,7 @@ void tc_free(fs_flow* f);
 size_t tc_workspace_bytes(const fs_flow* f, int B);
 int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void* ws, size_t ws_bytes,
                    cudaStream_t s);
+bool tc_has_fused(const fs_flow* f);
+int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, int rows, int direction, const float* xin, float* xout,
+                          float* logdet, int* nan_flag, cudaStream_t s);
 }  // namespace fs

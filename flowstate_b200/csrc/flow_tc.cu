@@ -42,11 +42,14 @@ struct TcLayer {
     float* b1;         // unused (folded)
     float* b_final;    // [n_chunks * 128]  b_f + W_f c
     float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
+    float* wfused;     // fused-spline final layer: per coordinate, KT/KPS stages of KPS k-tiles of a chn-row chunk
+    float* b_fused;    // [N][chn] (+ 32 floats of padding)
 };
 
 struct TcPack {
     int H, NH, Kp0, n_pieces, n_chunks, nstage;
-    size_t tiles_per_layer;
+    int chn;           // columns of a fused final-layer chunk (0: fused path unavailable)
+    size_t tiles_per_layer, tiles_before_final;
     size_t smem_bytes;
     std::vector<TcLayer> layers;
 };
@@ -56,8 +59,17 @@ struct TcArgs {
     float* theta;          // [rows, NP]
     int rows, K0, NP;
     int Kp0, n_pieces, n_blocks, n_chunks;
-    unsigned long long n_tiles;
+    unsigned long long n_tiles, tiles_before_final;
     TcLayer L;
+    // fused spline epilogue (fused != 0): the final layer runs one chunk per transformed coordinate and the
+    // epilogue applies the spline in place of writing theta.  1 = density direction, 2 = sampling direction.
+    int fused, N, D, nb, chn;
+    float bound, inv_sqrt_h;
+    const float* xin;      // [rows, D] layer input
+    float* xout;           // [rows, D] layer output (transformed half written here)
+    float* logdet;         // [rows] accumulated, or nullptr
+    const int* trf;        // [N] transformed feature indices
+    int* nan_flag;
     int* err;
     long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 16 per CTA
     int dbg_mode;     // FS_TC_MODE (timing experiments only): 1 = epilogue skips data work, 4 = no weight copies
@@ -314,35 +326,42 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 }
                 __syncwarp();
             };
-            auto stream = [&](unsigned long long n) {
+            auto stream = [&](unsigned long long n, uint32_t nbytes) {   // n stages of nbytes each, contiguous at src
                 for (unsigned long long e = t + n; t < e; ++t) {
                     mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1, g.dbg ? &w_empty : nullptr);
                     // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
                     // scripts/tma_bw2.cu); copies issued by different lanes overlap -> rotate the issuing lane.
                     if (lane == (int)(t & 7)) {
-                        const uint32_t nbytes = (g.dbg_mode == 3) ? S::STAGE_BYTES / 2 : S::STAGE_BYTES;
                         mbar_expect_tx(bar_wfull + 8 * stage, nbytes);
-                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src + t * S::STAGE_BYTES, nbytes,
-                                     bar_wfull + 8 * stage);
+                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src, nbytes, bar_wfull + 8 * stage);
                     }
+                    src += nbytes;
                     __syncwarp();
                     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
                 }
             };
             load_pset(0);
             load_pset(1);
-            stream((unsigned long long)(g.Kp0 / TC_KB));          // GEMM0
+            stream((unsigned long long)(g.Kp0 / TC_KB), S::STAGE_BYTES);          // GEMM0
             for (int b = 0; b < g.n_blocks; ++b) {
                 if (b >= 1) load_pset(b + 1);
-                stream(2ull * KT);
+                stream(2ull * KT, S::STAGE_BYTES);
             }
-            stream((unsigned long long)g.n_chunks * (KT / S::KPS));   // final layer
+            if (g.fused) {                                                        // final layer
+                src = (const uint8_t*)g.L.wfused;
+                stream((unsigned long long)g.N * (KT / S::KPS), (uint32_t)(S::KPS * g.chn * 128));
+            } else {
+                stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
+            }
             if (g.dbg && lane == 0) g.dbg[16 * blockIdx.x + 0] = w_empty;
         } else if (warp == 1) {
             // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
             const uint32_t idesc_blk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
             const uint32_t idesc_fin = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
+            // fused final layer: chunk of g.chn weight rows (one coordinate's spline parameters)
+            const uint32_t idesc_fus = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.chn >> 3) << 17) | (8u << 24);
+            const uint32_t fus_tile = (uint32_t)g.chn * 128;
             uint32_t stage = 0, wphase = 0;
             uint32_t ph_rdy = 0;       // parity to wait for, per rdy barrier
             long long w_ready = 0, w_weights = 0, t_issue = 0;
@@ -359,7 +378,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // Issues `n` weight stages (n <= GROUP): their full-barriers are waited for back to back, then all the
             // MMAs are queued at once.  Block GEMMs: one stage = one 32-wide k-tile of all H output columns
             // (4 MMAs of N = H).  Final layer: one stage = KPS consecutive k-tiles of a 128-column chunk.
-            auto issue = [&](uint32_t dcol, uint32_t acol, int n, bool first, bool fin) {
+            auto issue = [&](uint32_t dcol, uint32_t acol, int n, bool first, bool fin, bool fus = false) {
                 uint32_t st[S::GROUP];
 #pragma unroll
                 for (int i = 0; i < S::GROUP; ++i) {
@@ -387,7 +406,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #pragma unroll
                                     for (int j = 0; j < 4; ++j)
                                         tc_mma_ts(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
-                                                  make_b_desc(sb + kk * (S::FCH * 128) + 32 * j), idesc_fin,
+                                                  make_b_desc(sb + kk * (fus ? fus_tile : (uint32_t)(S::FCH * 128)) + 32 * j),
+                                                  fus ? idesc_fus : idesc_fin,
                                                   (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
                             }
                             tc_commit(bar_wempty + 8 * st[i]);
@@ -453,13 +473,14 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
             wait_rdy(RDY_R0H0);
             wait_rdy(RDY_R0H1);
-            for (int c = 0; c < g.n_chunks; ++c) {
+            const int n_final = g.fused ? g.N : g.n_chunks;
+            for (int c = 0; c < n_final; ++c) {
                 const int f = c & 1;
                 if (c >= 2) wait_rdy(RDY_F0 + f);              // epilogue drained chunk c-2
                 const uint32_t dcol = f ? S::FIN1 : S::FIN0;
                 constexpr int SPC = KT / S::KPS;               // stages per chunk
                 for (int sg = 0; sg < SPC; sg += S::GROUP)
-                    issue(dcol, sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true);
+                    issue(dcol, sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true, g.fused != 0);
                 commit(bar_full + 8 * (FULL_F0 + f));
             }
             if (g.dbg && lane == 0) {
@@ -642,6 +663,153 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             release_pset(b + 1);
         }
 #undef FS_EPI_RESIDUAL
+        // ---- fused final layer: one chunk = the 3nb+1 spline parameters of ONE transformed coordinate for the 128
+        //      rows of the tile, laid out [widths | pad to 32 | heights | pad to 64 | derivatives]; theta never leaves
+        //      the SM.  The four warps of a TMEM lane quadrant (they share an SM sub-partition) split the chunk by
+        //      column group: 0 = widths, 1 = heights (softmax numerators and inclusive prefix sums in registers),
+        //      2 = derivatives 0..31, 3 = derivative 32 + rational-quadratic evaluation.  The warp on the search
+        //      axis finds the bin; bin edges and derivatives meet in a per-row mailbox (two named barriers per
+        //      chunk).  coupling.py:86-102 / 126-135, utils/splines.py:84-222. ----
+        if (g.fused) {
+            const int role = cgp, nb = g.nb;
+            const bool inv = (g.fused == 2);
+            const int srch = inv ? 1 : 0;
+            const float c2 = g.inv_sqrt_h * 1.4426950408889634f, bound = g.bound, two_b = 2.0f * g.bound;
+            const int hD = g.D / 2;
+            const float gnum = 1.0f - kMinW * (float)nb;       // kMinW == kMinH
+            const float rgnum = 1.0f / gnum, r2b = 1.0f / two_b;
+            // The u buffer is dead: thread-private 128-byte rows for values a later dynamic index picks from
+            // (float4 slot i4 at i4 ^ (lane & 7): conflict-free stores); the rows of the role-3 warp, which parks
+            // nothing, hold the quadrant's mailbox: [parity][field][lane], fields sel, x-left, width, y-left,
+            // height, d[sel], d[sel+1] (sel < 31), d[32].
+            float* myrow = reinterpret_cast<float*>(smem + S::U_OFF) + (size_t)(ew * 32 + lane) * 32;
+            float* mbq = reinterpret_cast<float*>(smem + S::U_OFF) + (size_t)((q + 12) * 32) * 32 + lane;
+            float acc_ld = 0.f;
+            bool bad = false;
+            // barrier A: roles 0-2 (bin index published); barrier B: all four roles (bin edges and derivatives
+            // published).  Role 3 evaluates chunk c while roles 0-2 already work on chunk c+1.
+            auto sync_a = [&]() { asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory"); };
+            auto sync_b = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(5 + q) : "memory"); };
+            for (int c = 0; c < g.N; ++c) {
+                const int f = c & 1;
+                float* mb = mbq + f * 256;
+                const int ft = __ldg(g.trf + c);
+                float x = 0.f;
+                if (row_ok && (role == srch || role == 3))
+                    x = __ldg(g.xin + (size_t)grow * g.D + (inv ? (ft + hD) % g.D : ft));
+                float4 bias[8];                                     // in flight while the accumulator completes
+                const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_fused + (size_t)c * g.chn + 32 * role);
+                if (role < 3) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) bias[i4] = __ldg(bf4 + i4);
+                } else {
+                    bias[0] = __ldg(bf4);
+                }
+                wait_full(FULL_F0 + f);
+                if (dbg_me) t_mark = clock64();
+                const uint32_t fcol = (f ? S::FIN1 : S::FIN0) + 32 * role;
+                float e[32];
+                tc_ld16(lane_addr + fcol, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) e[i] = __uint_as_float(v[i]);
+                if (role < 3) {
+                    tc_ld16(lane_addr + fcol + 16, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
+                }
+                signal_rdy(RDY_F0 + f);                             // accumulator drained
+                auto park = [&]() {
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4)
+                        reinterpret_cast<float4*>(myrow)[i4 ^ (lane & 7)] =
+                            make_float4(e[4 * i4], e[4 * i4 + 1], e[4 * i4 + 2], e[4 * i4 + 3]);
+                };
+                auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
+                if (role < 3) {
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        upk2(add2(pk2(e[4 * i4], e[4 * i4 + 1]), pk2(bias[i4].x, bias[i4].y)), e[4 * i4], e[4 * i4 + 1]);
+                        upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bias[i4].z, bias[i4].w)), e[4 * i4 + 2],
+                             e[4 * i4 + 3]);
+                    }
+                }
+                if (role < 2) {
+                    // softmax numerators and inclusive prefix sums; pad columns (>= nb) contribute exp(-inf) = 0
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i >= nb) e[i] = -3.0e38f;
+                    float m8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(e[i], e[i + 8]), fmaxf(e[i + 16], e[i + 24]));
+                    const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                          fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                    const float off = -m * c2;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float ex;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(__fmaf_rn(e[i], c2, off)));
+                        sum += ex;
+                        e[i] = sum;
+                    }
+                    const float gs = gnum * __frcp_rn(sum);
+                    float s0 = 0.f, s1 = e[0];                       // S[sel-1], S[sel]
+                    int sel;
+                    if (role == srch) {                              // last knot <= x (utils/splines.py:11-13)
+                        // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
+                        const float rg = sum * rgnum;
+                        const float t0 = (x + bound) * r2b * rg, dt = -kMinW * rg;
+                        sel = 0;
+#pragma unroll
+                        for (int i = 1; i < 32; ++i)
+                            if (i < nb && e[i - 1] <= __fmaf_rn((float)i, dt, t0)) {
+                                sel = i;
+                                s0 = e[i - 1];
+                                s1 = e[i];
+                            }
+                        mb[0] = __int_as_float(sel);
+                        sync_a();
+                    } else {
+                        park();
+                        sync_a();
+                        sel = __float_as_int(mb[0]);
+                        s1 = pick(sel);
+                        if (sel) s0 = pick(sel - 1);
+                    }
+                    const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
+                    const float right =
+                        (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gs, s1, kMinW * (float)(sel + 1)), -bound);
+                    mb[32 * (1 + 2 * role)] = left;
+                    mb[32 * (2 + 2 * role)] = right - left;
+                    sync_b();
+                } else if (role == 2) {
+                    park();
+                    sync_a();
+                    const int sel = __float_as_int(mb[0]);
+                    mb[32 * 5] = kMinD + softplus_t(pick(sel));
+                    if (sel < 31) mb[32 * 6] = kMinD + softplus_t(pick(sel + 1));
+                    sync_b();
+                } else {
+                    mb[32 * 7] = kMinD + softplus_t(e[0] + bias[0].x);     // derivative 32 sits in column 96
+                    sync_b();
+                    const int sel = __float_as_int(mb[0]);
+                    float y = x, ld = 0.f;
+                    if (x >= -bound && x <= bound)
+                        rq_eval(x, mb[32 * 1], mb[32 * 2], mb[32 * 3], mb[32 * 4], mb[32 * 5],
+                                sel == 31 ? mb[32 * 7] : mb[32 * 6], inv, y, ld);
+                    if (row_ok) {
+                        g.xout[(size_t)grow * g.D + (inv ? ft : (ft + hD) % g.D)] = y;
+                        acc_ld += ld;
+                        bad = bad || (y != y) || (ld != ld);
+                    }
+                }
+                if (dbg_me) t_fin += clock64() - t_mark;
+            }
+            if (role == 3 && row_ok && g.logdet) g.logdet[grow] += acc_ld;
+            if (bad && g.nan_flag) atomicOr(g.nan_flag, 1);
+        } else {
         // ---- final layer: theta chunk = D + b_final' -> global ----
         // A thread holds 32 columns of ONE row, so storing straight from registers would touch 32 different lines
         // per instruction.  Each warp transposes its 32 x 32 block through a private 4 KB patch of the (now dead)
@@ -699,6 +867,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             if (dbg_me) t_fin += clock64() - t_mark;
         }
+        }   // !fused
         if (dbg_me) {
             g.dbg[16 * blockIdx.x + 4] = w_full;
             g.dbg[16 * blockIdx.x + 5] = clock64() - e_start;
@@ -776,6 +945,8 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     const int NP = f->N * f->P;
     const int FCH = 128;                                   // final-layer chunk width (TcCfg::FCH)
     P->n_chunks = (NP + FCH - 1) / FCH;
+    // fused spline epilogue: split-schedule kernel only, derivatives 0..nb must fit columns 64..127
+    P->chn = (H == 256 && f->nb <= 32) ? (64 + f->nb + 1 + 15) / 16 * 16 : 0;
     P->smem_bytes = (H == 256 ? TcCfg<256>::TOTAL : TcCfg<128>::TOTAL) + 1024;
     if ((int)P->smem_bytes > smem_max) { delete P; return FS_OK; }
     const int KT = H / TC_KB;
@@ -832,6 +1003,26 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                 for (int kk = 0; kk < KPS; ++kk)
                     append_tile(stream, fw.data(), NP, H, c * FCH, (sg * KPS + kk) * TC_KB, FCH);
         P->tiles_per_layer = stream.size() / ((size_t)H * 32);
+        // Fused-spline final layer (H = 256, nb <= 32): chunk j = the parameters of transformed coordinate j in the
+        // order [widths | pad to 32 | heights | pad to 64 | derivatives | pad to chn]; rows come from the
+        // reference's coordinate-major final layer (row j*P + index, coupling.py:166).
+        std::vector<float> fstream, bfused;
+        std::vector<int> frow;                                  // chunk column -> parameter index (or -1)
+        if (P->chn) {
+            const int chn = P->chn, nb = f->nb, Pp = f->P;
+            frow.assign(chn, -1);
+            for (int k = 0; k < nb; ++k) { frow[k] = k; frow[32 + k] = nb + k; }
+            for (int k = 0; k <= nb; ++k) frow[64 + k] = 2 * nb + k;
+            std::vector<float> wc((size_t)chn * H);
+            fstream.reserve((size_t)f->N * chn * H);
+            for (int j = 0; j < f->N; ++j) {
+                std::fill(wc.begin(), wc.end(), 0.f);
+                for (int cidx = 0; cidx < chn; ++cidx)
+                    if (frow[cidx] >= 0)
+                        memcpy(&wc[(size_t)cidx * H], p->final_w + ((size_t)j * Pp + frow[cidx]) * H, sizeof(float) * H);
+                for (int kt = 0; kt < KT; ++kt) append_tile(fstream, wc.data(), chn, H, 0, kt * TC_KB, chn);
+            }
+        }
         TcLayer& L = P->layers[li];
         // Bias folding: the kernel carries u = h - c (c = b_init + sum of linear-1 biases so far):
         //   relu(s h + o) = relu(s u + (o + s c)),   W_f h + b_f = W_f u + (b_f + W_f c)
@@ -850,6 +1041,19 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             for (int k = 0; k < H; ++k) acc += (double)tf32_round(wr[k]) * c[k];
             bfin[n] = (float)acc;
         }
+        if (P->chn) {
+            const int chn = P->chn, Pp = f->P;
+            bfused.assign((size_t)f->N * chn + 32, 0.f);
+            for (int j = 0; j < f->N; ++j)
+                for (int cidx = 0; cidx < chn; ++cidx) {
+                    if (frow[cidx] < 0) continue;
+                    const size_t row = (size_t)j * Pp + frow[cidx];
+                    double acc = (double)p->final_b[row];
+                    const float* wr = p->final_w + row * H;
+                    for (int k = 0; k < H; ++k) acc += (double)tf32_round(wr[k]) * c[k];
+                    bfused[(size_t)j * chn + cidx] = (float)acc;
+                }
+        }
         std::vector<float> psets((size_t)(nB + 1) * 3 * H, 0.f);
         for (int j = 0; j <= nB; ++j) {
             float* ps = &psets[(size_t)j * 3 * H];
@@ -865,6 +1069,10 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         if (!r) r = tc_upload(f, o0f, &L.bn0_o);
         if (!r) r = tc_upload(f, b0, &L.b0);
         if (!r) r = tc_upload(f, bfin, &L.b_final);
+        L.wfused = nullptr;
+        L.b_fused = nullptr;
+        if (!r && P->chn) r = tc_upload(f, fstream, &L.wfused);
+        if (!r && P->chn) r = tc_upload(f, bfused, &L.b_fused);
         L.b_init = nullptr;
         L.b1 = nullptr;
         if (r) { delete P; return r; }
@@ -905,10 +1113,15 @@ static long long* tc_debug_buffer(int ctas) {
     return g_dbg;
 }
 
-int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, cudaStream_t s) {
+static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* theta, int fused, const float* xin,
+                     float* xout, float* logdet, int* nan_flag, cudaStream_t s) {
     TcPack* P = (TcPack*)f->tc;
     if (!P) {
         set_error("tensor-core conditioner not available for this flow shape (H=%d, blocks=%d)", f->H, f->n_blocks);
+        return FS_ERR_UNSUPPORTED;
+    }
+    if (fused && !P->chn) {
+        set_error("fused spline epilogue not available for this flow shape (H=%d, bins=%d)", f->H, f->nb);
         return FS_ERR_UNSUPPORTED;
     }
     TcArgs g;
@@ -924,6 +1137,18 @@ int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* thet
     g.n_tiles = P->tiles_per_layer;
     g.L = P->layers[layer];
     g.err = f->tc_err;
+    g.fused = fused;
+    g.N = f->N;
+    g.D = f->D;
+    g.nb = f->nb;
+    g.chn = P->chn;
+    g.bound = f->bound_f;
+    g.inv_sqrt_h = f->inv_sqrt_h;
+    g.xin = xin;
+    g.xout = xout;
+    g.logdet = logdet;
+    g.trf = f->trf;
+    g.nan_flag = nan_flag;
     g.dbg = tc_debug_buffer((rows + 127) / 128);
     {
         static int mode = -1;
@@ -937,6 +1162,20 @@ int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* thet
         tc_conditioner_kernel<128><<<grid, TcCfg<128>::THREADS, P->smem_bytes, s>>>(g);
     fs::count_launch();
     return cuda_check(cudaGetLastError(), "tc_conditioner_kernel");
+}
+
+int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, cudaStream_t s) {
+    return tc_launch(f, layer, A0, rows, theta, 0, nullptr, nullptr, nullptr, nullptr, s);
+}
+
+bool tc_has_fused(const fs_flow* f) { return f->tc && ((TcPack*)f->tc)->chn > 0; }
+
+// conditioner + conditional spline of the transformed half in one kernel: direction 1 = density (coupling.py:86-102),
+// 2 = sampling (coupling.py:126-135).  Reads the layer input xin, writes the transformed half of xout and
+// accumulates the log-determinant.
+int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, int rows, int direction, const float* xin, float* xout,
+                          float* logdet, int* nan_flag, cudaStream_t s) {
+    return tc_launch(f, layer, A0, rows, nullptr, direction, xin, xout, logdet, nan_flag, s);
 }
 
 }  // namespace fs
