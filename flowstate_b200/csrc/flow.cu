@@ -711,6 +711,16 @@ extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features,
     return conditioner_fp32(f, layer, features, rows, w.h, w.t, theta, s);
 }
 
+extern "C" int fs_flow_coupling(fs_flow* f, int layer, int direction, const float* features, const float* xin,
+                                float* xout, float* logdet, int rows, int* nan_flag, void* stream) {
+    if (!f || !features || !xin || !xout || rows < 0 || layer < 0 || layer >= f->K || (direction != 1 && direction != 2)) {
+        set_error("fs_flow_coupling: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (rows == 0) return FS_OK;
+    return tc_conditioner_spline(f, layer, features, rows, direction, xin, xout, logdet, nan_flag, (cudaStream_t)stream);
+}
+
 extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shift, float* z, float* logdet,
                                float* logq, int* nan_flag, void* workspace, size_t workspace_bytes, int precision,
                                void* stream) {

@@ -190,6 +190,22 @@ class FlowPack:
                                                   _lib.ptr(ws), ws.numel(), prec, _lib.stream_ptr(features.device)))
         return theta
 
+    def coupling(self, layer, direction, features, xin, xout=None, logdet=None):
+        """Conditioner + conditional spline of the transformed half of one layer in one kernel (fused
+        tensor-core path; coupling.py:86-102 density / 126-135 sampling).  Returns (xout, logdet)."""
+        features = _lib.require_cuda(features, "features")
+        xin = _lib.require_cuda(xin, "xin")
+        rows = features.shape[0]
+        if xout is None:
+            xout = torch.zeros_like(xin)
+        if logdet is None:
+            logdet = torch.zeros(rows, dtype=torch.float32, device=xin.device)
+        code = {"density": 1, "sampling": 2}[direction]
+        _lib.check(_lib.lib().fs_flow_coupling(self._h, int(layer), code, _lib.ptr(features), _lib.ptr(xin),
+                                               _lib.ptr(xout), _lib.ptr(logdet), rows, _lib.ptr(self._nan),
+                                               _lib.stream_ptr(xin.device)))
+        return xout, logdet
+
     def check_nan(self):
         """Surfaces the device-side NaN flag like the reference's ValueError (utils/splines.py:176-183)."""
         if int(self._nan.item()):

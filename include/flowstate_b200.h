@@ -182,6 +182,15 @@ size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
 int fs_flow_conditioner(fs_flow* flow, int layer, const float* features, int rows, float* theta,
                         void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* Conditioner + conditional spline of the transformed half of one coupling layer in ONE kernel (tensor-core path
+ * with the fused spline epilogue; FS_ERR_UNSUPPORTED for flow shapes without it: H != 256 or nb > 32):
+ * PiecewiseRationalQuadraticCoupling forward / inverse on the transformed features
+ * (NF/normflows/flows/neural_spline/coupling.py:86-102 / 126-135).  direction 1 = density direction, 2 = sampling.
+ * features [rows, 2N] as for fs_flow_conditioner; xin [rows, D] is the layer input, the transformed half of
+ * xout [rows, D] is written (rolled by D/2 in the density direction) and logdet [rows] (may be NULL) accumulated. */
+int fs_flow_coupling(fs_flow* flow, int layer, int direction, const float* features, const float* xin, float* xout,
+                     float* logdet, int rows, int* nan_flag, void* stream);
+
 /* NormalizingFlow.inverse_and_log_det / log_prob  (NF/normflows/core.py:71-86,198-214):
  * x [B, D] -> z [B, D], logdet [B]; x_in = x - in_shift (MC-box -> centred coords,
  * MCMC/monte_carlo.py:251-258).  logq (nullable) = logdet + UniformParticle.log_prob(z)

@@ -116,12 +116,60 @@ def test_against_oracle_alg_shapes():
             err = np.max(np.abs(got - truth) / np.abs(truth))
             print("N=%d K=%d H=%d %s: kernel err %.2e, reference-fp32 self err %.2e" % (n, K, H, prec, err, self_err))
             assert err < 1e-4, (n, prec, err, self_err)
-        model.precision = "fp32"
         z = model.q0(B)
-        xs = model.forward(z)
         with torch.no_grad():
-            xo, _ = fr.forward_and_log_det(sd, spec, z.cpu().double(), dtype=torch.float64)
-        assert (xs.cpu().double() - xo).abs().max().item() < 2e-4 * bound
+            xo, ldo = fr.forward_and_log_det(sd, spec, z.cpu().double(), dtype=torch.float64)
+        for prec in _precisions(model):                 # sampling direction, both conditioner paths
+            model.precision = prec
+            xs, lds = model.forward_and_log_det(z)
+            tol = 2e-4 if prec == "fp32" else 2e-3
+            assert (xs.cpu().double() - xo).abs().max().item() < tol * bound, (n, prec)
+            np.testing.assert_allclose(lds.cpu().numpy(), ldo.numpy(), rtol=1e-3, atol=2e-3 * n)
+        model.precision = "fp32"
+
+
+def test_fused_spline_epilogue_matches_unfused(monkeypatch):
+    """H = 256: the tensor path applies the spline in the conditioner's epilogue (fs_flow_coupling);
+    FS_NO_FUSE=1 keeps theta + the separate spline kernel.  Both directions must agree to rounding, and the
+    single-layer entry point must reproduce the unfused layer."""
+    torch.manual_seed(5)
+    n, K, blocks, H, nb = 40, 3, 2, 256, 32              # 2 coordinate chunks, ragged (40 = 32 + 8)
+    bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+    model = _build(n, K, blocks, H, nb, bound, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.03 * torch.randn(p.shape, generator=g))
+    model = model.cuda().eval()
+    if "tf32" not in _precisions(model):
+        pytest.skip("tensor path unavailable")
+    model.precision = "tf32"
+    B = 300                                              # 3 row tiles, last one partial
+    x = ((torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    x[0, 3] = bound * 1.5                                # outside the spline interval: identity, zero log-det
+    z = model.q0(B)
+    lq_f = model.log_prob(x)
+    xs_f, ld_f = model.forward_and_log_det(z)
+    monkeypatch.setenv("FS_NO_FUSE", "1")
+    lq_u = model.log_prob(x)
+    xs_u, ld_u = model.forward_and_log_det(z)
+    monkeypatch.delenv("FS_NO_FUSE")
+    np.testing.assert_allclose(lq_f.cpu().numpy(), lq_u.cpu().numpy(), rtol=2e-6, atol=2e-4)
+    np.testing.assert_allclose(ld_f.cpu().numpy(), ld_u.cpu().numpy(), rtol=2e-6, atol=2e-4)
+    assert (xs_f - xs_u).abs().max().item() < 2e-5 * bound
+    # single-layer entry point against theta + oracle-checked spline of the same layer
+    pack = model._cuda_pack()
+    idf = model.flows[1].prqct.identity_features.tolist()
+    trf = model.flows[1].prqct.transform_features.tolist()
+    xi = x[:, idf]
+    feats = torch.cat([torch.cos(xi * (np.pi / bound)), torch.sin(xi * (np.pi / bound))], 1).contiguous()
+    xo, ld = pack.coupling(1, "density", feats, x)
+    monkeypatch.setenv("FS_NO_FUSE", "1")
+    y_ref, ld_ref = model.flows[1].inverse(x)
+    monkeypatch.delenv("FS_NO_FUSE")
+    h = n                                                # roll by D/2
+    cols = [(t + h) % (2 * n) for t in trf]
+    assert (xo[:, cols] - y_ref[:, cols]).abs().max().item() < 2e-5 * bound
 
 
 def test_sample_and_base_distribution():
