@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         const bool row_ok = grow < g.rows;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         uint32_t ph_full = 0, ph_free1 = 0, ph_pfull = 0;
-        long long w_full = 0, t_res0 = 0, t_res1 = 0, t_relu = 0, t_fin = 0, t_mark = 0;
+        long long w_full = 0, t_res0 = 0, t_res1 = 0, t_relu = 0, t_fin = 0, t_mark = 0, t_fa = 0, t_fb = 0, t_fl = 0, t_m2 = 0;
         const bool dbg_me = g.dbg && ew == 0 && lane == 0;
         const long long e_start = g.dbg ? clock64() : 0;
         auto wait_full = [&](int id) {
@@ -720,6 +720,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
                 }
                 signal_rdy(RDY_F0 + f);                             // accumulator drained
+                if (dbg_me) { t_m2 = clock64(); t_fl += t_m2 - t_mark; }
                 auto park = [&]() {
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4)
@@ -770,7 +771,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                                 s1 = e[i];
                             }
                         mb[0] = __int_as_float(sel);
+                        if (dbg_me) t_fa += clock64() - t_m2;
                         sync_a();
+                        if (dbg_me) t_m2 = clock64();
                     } else {
                         park();
                         sync_a();
@@ -784,6 +787,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     mb[32 * (1 + 2 * role)] = left;
                     mb[32 * (2 + 2 * role)] = right - left;
                     sync_b();
+                    if (dbg_me) t_fb += clock64() - t_m2;
                 } else if (role == 2) {
                     park();
                     sync_a();
@@ -875,6 +879,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             g.dbg[16 * blockIdx.x + 8] = t_res1;
             g.dbg[16 * blockIdx.x + 9] = t_relu;
             g.dbg[16 * blockIdx.x + 10] = t_fin;
+            g.dbg[16 * blockIdx.x + 11] = t_fl;
+            g.dbg[16 * blockIdx.x + 12] = t_fa;
+            g.dbg[16 * blockIdx.x + 13] = t_fb;
         }
     }
     tc_fence_before();
