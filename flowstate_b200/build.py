@@ -50,6 +50,8 @@ def build(force=False, verbose=False):
                "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        if os.environ.get("FS_TC_TIMERS") == "1":       # in-kernel timers for scripts/tc_debug.py (development only)
+            cmd.insert(1, "-DFS_TC_TIMERS=1")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

@@ -101,9 +101,24 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code,
                                           long long* waited = nullptr) {
     const long long t0 = waited ? clock64() : 0;
+    if (mbar_test(bar, parity)) {
+        if (waited) *waited += clock64() - t0;
+        return;
+    }
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
         if (++spins > 40000000u) {
@@ -234,6 +249,12 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 enum { FULL_R0H0 = 0, FULL_R0H1 = 1, FULL_R1H0 = 2, FULL_R1H1 = 3, FULL_F0 = 4, FULL_F1 = 5 };
 enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F1 = 5 };
 
+// In-kernel wait/phase timers (scripts/tc_debug.py): compiled in only with -DFS_TC_TIMERS=1; the clock reads sit in
+// the issue loops and cost the single MMA-issuing warp real time.
+#ifndef FS_TC_TIMERS
+#define FS_TC_TIMERS 0
+#endif
+
 template <int H>
 struct TcCfg {
     static constexpr int NH = H / 2;
@@ -252,11 +273,13 @@ struct TcCfg {
     static constexpr int U_OFF = NSTAGE * STAGE_BYTES;       // second column half of the residual stream: [NH/4][128] float4
     static constexpr int P_OFF = U_OFF + NH * 128 * 4;
     static constexpr int BAR_OFF = P_OFF + 2 * PSET_FLOATS * 4;
-    static constexpr int TOTAL = BAR_OFF + 512;
+    static constexpr int MB_OFF = BAR_OFF + 512;             // fused epilogue mailboxes: 8 pair groups x 2 x 5 x 32 floats
+    static constexpr int TOTAL = MB_OFF + 8 * 320 * 4;
 };
 
 template <int H>
 __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(TcArgs g) {
+    long long* const dbg = FS_TC_TIMERS ? g.dbg : nullptr;
     using S = TcCfg<H>;
     constexpr int NH = S::NH;
     constexpr int NSTAGE = S::NSTAGE;
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_wempty + 8 * i, 1);
         }
         for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
-        for (int i = 0; i < 6; ++i) mbar_init(bar_rdy + 8 * i, EPI_WARPS);
+        for (int i = 0; i < 6; ++i) mbar_init(bar_rdy + 8 * i, (i >= RDY_F0 && g.fused) ? EPI_WARPS / 2 : EPI_WARPS);
         mbar_init(bar_free1, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
@@ -328,12 +351,13 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             };
             auto stream = [&](unsigned long long n, uint32_t nbytes) {   // n stages of nbytes each, contiguous at src
                 for (unsigned long long e = t + n; t < e; ++t) {
-                    mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1, g.dbg ? &w_empty : nullptr);
+                    mbar_wait(bar_wempty + 8 * stage, phase ^ 1, g.err, 1, dbg ? &w_empty : nullptr);
                     // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
                     // scripts/tma_bw2.cu); copies issued by different lanes overlap -> rotate the issuing lane.
                     if (lane == (int)(t & 7)) {
-                        mbar_expect_tx(bar_wfull + 8 * stage, nbytes);
-                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src, nbytes, bar_wfull + 8 * stage);
+                        const uint32_t nb_ = (g.dbg_mode == 3) ? nbytes / 2 : nbytes;   // timing experiment only
+                        mbar_expect_tx(bar_wfull + 8 * stage, nb_);
+                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src, nb_, bar_wfull + 8 * stage);
                     }
                     src += nbytes;
                     __syncwarp();
@@ -353,7 +377,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             } else {
                 stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
             }
-            if (g.dbg && lane == 0) g.dbg[16 * blockIdx.x + 0] = w_empty;
+            if (dbg && lane == 0) dbg[16 * blockIdx.x + 0] = w_empty;
         } else if (warp == 1) {
             // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
@@ -365,9 +389,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             uint32_t stage = 0, wphase = 0;
             uint32_t ph_rdy = 0;       // parity to wait for, per rdy barrier
             long long w_ready = 0, w_weights = 0, t_issue = 0;
-            const long long t_start = g.dbg ? clock64() : 0;
+            const long long t_start = dbg ? clock64() : 0;
             auto wait_rdy = [&](int id) {
-                mbar_wait(bar_rdy + 8 * id, (ph_rdy >> id) & 1, g.err, 2, g.dbg ? &w_ready : nullptr);
+                mbar_wait(bar_rdy + 8 * id, (ph_rdy >> id) & 1, g.err, 2, dbg ? &w_ready : nullptr);
                 ph_rdy ^= 1u << id;
                 tc_fence_after();
             };
@@ -383,31 +407,38 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #pragma unroll
                 for (int i = 0; i < S::GROUP; ++i) {
                     if (i < n) {
-                        mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3, g.dbg ? &w_weights : nullptr);
+                        mbar_wait(bar_wfull + 8 * stage, wphase, g.err, 3, dbg ? &w_weights : nullptr);
                         st[i] = stage;
                         if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
                     }
                 }
                 tc_fence_after();
-                const long long ti = g.dbg ? clock64() : 0;
+                const long long ti = dbg ? clock64() : 0;
                 if (elect_one()) {
 #pragma unroll
                     for (int i = 0; i < S::GROUP; ++i) {
                         if (i < n) {
-                            const uint32_t sb = w_base + st[i] * S::STAGE_BYTES;
+                            // one descriptor per stage; a tile / k-slice offset only moves the 14-bit start-address
+                            // field (units of 16 bytes, no carry out of it: shared memory is < 256 KB)
+                            const uint64_t d0 = make_b_desc(w_base + st[i] * S::STAGE_BYTES);
+                            const uint32_t d0_lo = (uint32_t)d0, d0_hi = (uint32_t)(d0 >> 32);
+                            auto desc = [&](uint32_t byte_off) {
+                                return ((uint64_t)d0_hi << 32) | (uint64_t)(d0_lo + (byte_off >> 4));
+                            };
                             if (!fin) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
-                                    tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, make_b_desc(sb + 32 * j),
+                                    tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, desc(32 * j),
                                               idesc_blk, (first && i == 0 && j == 0) ? 0u : 1u);
                             } else {
+                                const uint32_t tile = fus ? fus_tile : (uint32_t)(S::FCH * 128);
+                                const uint32_t idesc = fus ? idesc_fus : idesc_fin;
 #pragma unroll
                                 for (int kk = 0; kk < S::KPS; ++kk)
 #pragma unroll
                                     for (int j = 0; j < 4; ++j)
                                         tc_mma_ts(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
-                                                  make_b_desc(sb + kk * (fus ? fus_tile : (uint32_t)(S::FCH * 128)) + 32 * j),
-                                                  fus ? idesc_fus : idesc_fin,
+                                                  desc(kk * tile + 32 * j), idesc,
                                                   (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
                             }
                             tc_commit(bar_wempty + 8 * st[i]);
@@ -415,7 +446,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     }
                 }
                 __syncwarp();
-                if (g.dbg) t_issue += clock64() - ti;
+                if (dbg) t_issue += clock64() - ti;
             };
             // block-type GEMM over `ktiles` k-tiles of operand region `abase`; K-ordered waits on its two halves
             auto gemm_blk = [&](uint32_t dcol, uint32_t abase, int rdy0, int ktiles, bool fresh, bool waitA) {
@@ -483,11 +514,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     issue(dcol, sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true, g.fused != 0);
                 commit(bar_full + 8 * (FULL_F0 + f));
             }
-            if (g.dbg && lane == 0) {
-                g.dbg[16 * blockIdx.x + 1] = w_ready;
-                g.dbg[16 * blockIdx.x + 2] = w_weights;
-                g.dbg[16 * blockIdx.x + 3] = clock64() - t_start;
-                g.dbg[16 * blockIdx.x + 6] = t_issue;
+            if (dbg && lane == 0) {
+                dbg[16 * blockIdx.x + 1] = w_ready;
+                dbg[16 * blockIdx.x + 2] = w_weights;
+                dbg[16 * blockIdx.x + 3] = clock64() - t_start;
+                dbg[16 * blockIdx.x + 6] = t_issue;
             }
         }
     } else {
@@ -500,12 +531,12 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         const bool row_ok = grow < g.rows;
         const uint32_t lane_addr = tmem + ((uint32_t)(32 * q) << 16);
         uint32_t ph_full = 0, ph_free1 = 0, ph_pfull = 0;
-        long long w_full = 0, t_res0 = 0, t_res1 = 0, t_relu = 0, t_fin = 0, t_mark = 0, t_fa = 0, t_fb = 0, t_fl = 0, t_m2 = 0;
-        const bool dbg_me = g.dbg && ew == 0 && lane == 0;
-        const long long e_start = g.dbg ? clock64() : 0;
+        long long w_full = 0, t_res0 = 0, t_res1 = 0, t_relu = 0, t_fin = 0, t_mark = 0, t_f1 = 0, t_f2 = 0, t_f3 = 0, t_m2 = 0;
+        const bool dbg_me = dbg && ew == 0 && lane == 0;
+        const long long e_start = dbg ? clock64() : 0;
         auto wait_full = [&](int id) {
             mbar_wait(bar_full + 8 * id, (ph_full >> id) & 1, g.err, 4,
-                      (g.dbg && ew == 0 && lane == 0) ? &w_full : nullptr);
+                      (dbg && ew == 0 && lane == 0) ? &w_full : nullptr);
             ph_full ^= 1u << id;
             tc_fence_after();
         };
@@ -665,144 +696,144 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #undef FS_EPI_RESIDUAL
         // ---- fused final layer: one chunk = the 3nb+1 spline parameters of ONE transformed coordinate for the 128
         //      rows of the tile, laid out [widths | pad to 32 | heights | pad to 64 | derivatives]; theta never leaves
-        //      the SM.  The four warps of a TMEM lane quadrant (they share an SM sub-partition) split the chunk by
-        //      column group: 0 = widths, 1 = heights (softmax numerators and inclusive prefix sums in registers),
-        //      2 = derivatives 0..31, 3 = derivative 32 + rational-quadratic evaluation.  The warp on the search
-        //      axis finds the bin; bin edges and derivatives meet in a per-row mailbox (two named barriers per
-        //      chunk).  coupling.py:86-102 / 126-135, utils/splines.py:84-222. ----
+        //      the SM.  The epilogue warps of a TMEM lane quadrant (they share an SM sub-partition) form two pairs:
+        //      pair 0 (column groups 0,1) takes the even chunks / accumulator 0, pair 1 the odd chunks /
+        //      accumulator 1, so every warp has two chunk periods of the tensor pipe for its serial
+        //      softmax -> search -> evaluate chain.  In a pair, warp A owns the search axis (widths in the density
+        //      direction, heights when sampling): softmax numerators and inclusive prefix sums in registers, bin
+        //      search, the two derivatives of the bin; warp B owns the other axis, receives bin index, edge,
+        //      width and derivatives through a per-row mailbox (one named barrier per chunk), evaluates the
+        //      rational-quadratic formula, writes the output coordinate and accumulates the log-determinant.
+        //      coupling.py:86-102 / 126-135, utils/splines.py:84-222. ----
         if (g.fused) {
-            const int role = cgp, nb = g.nb;
+            const int nb = g.nb, pair = cgp >> 1;
+            const bool isA = (cgp & 1) == 0;
             const bool inv = (g.fused == 2);
-            const int srch = inv ? 1 : 0;
+            const int axis = isA ? (inv ? 1 : 0) : (inv ? 0 : 1);   // 0 = widths columns, 1 = heights columns
             const float c2 = g.inv_sqrt_h * 1.4426950408889634f, bound = g.bound, two_b = 2.0f * g.bound;
             const int hD = g.D / 2;
             const float gnum = 1.0f - kMinW * (float)nb;       // kMinW == kMinH
             const float rgnum = 1.0f / gnum, r2b = 1.0f / two_b;
             // The u buffer is dead: thread-private 128-byte rows for values a later dynamic index picks from
-            // (float4 slot i4 at i4 ^ (lane & 7): conflict-free stores); the rows of the role-3 warp, which parks
-            // nothing, hold the quadrant's mailbox: [parity][field][lane], fields sel, x-left, width, y-left,
-            // height, d[sel], d[sel+1] (sel < 31), d[32].
+            // (float4 slot i4 at i4 ^ (lane & 7): conflict-free stores).  Mailbox [pair group][parity][field][lane].
             float* myrow = reinterpret_cast<float*>(smem + S::U_OFF) + (size_t)(ew * 32 + lane) * 32;
-            float* mbq = reinterpret_cast<float*>(smem + S::U_OFF) + (size_t)((q + 12) * 32) * 32 + lane;
+            float* mbq = reinterpret_cast<float*>(smem + S::MB_OFF) + (size_t)(q * 2 + pair) * 320 + lane;
             float acc_ld = 0.f;
             bool bad = false;
-            // barrier A: roles 0-2 (bin index published); barrier B: all four roles (bin edges and derivatives
-            // published).  Role 3 evaluates chunk c while roles 0-2 already work on chunk c+1.
-            auto sync_a = [&]() { asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory"); };
-            auto sync_b = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(5 + q) : "memory"); };
-            for (int c = 0; c < g.N; ++c) {
-                const int f = c & 1;
-                float* mb = mbq + f * 256;
+            auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * pair) : "memory"); };
+            auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
+            const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
+            for (int c = pair; c < g.N; c += 2) {
+                float* mb = mbq + ((c >> 1) & 1) * 160;
                 const int ft = __ldg(g.trf + c);
                 float x = 0.f;
-                if (row_ok && (role == srch || role == 3))
-                    x = __ldg(g.xin + (size_t)grow * g.D + (inv ? (ft + hD) % g.D : ft));
+                if (row_ok) x = __ldg(g.xin + (size_t)grow * g.D + (inv ? (ft + hD) % g.D : ft));
+                const float* bch = g.L.b_fused + (size_t)c * g.chn;
                 float4 bias[8];                                     // in flight while the accumulator completes
-                const float4* bf4 = reinterpret_cast<const float4*>(g.L.b_fused + (size_t)c * g.chn + 32 * role);
-                if (role < 3) {
 #pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) bias[i4] = __ldg(bf4 + i4);
-                } else {
-                    bias[0] = __ldg(bf4);
-                }
-                wait_full(FULL_F0 + f);
+                for (int i4 = 0; i4 < 8; ++i4) bias[i4] = __ldg(reinterpret_cast<const float4*>(bch + 32 * axis) + i4);
+                wait_full(FULL_F0 + pair);
                 if (dbg_me) t_mark = clock64();
-                const uint32_t fcol = (f ? S::FIN1 : S::FIN0) + 32 * role;
                 float e[32];
-                tc_ld16(lane_addr + fcol, v);
+                float d32 = 0.f;
+                if (isA) {                                          // derivatives first, parked right away
+                    tc_ld16(lane_addr + fcol + 64, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4)
+                        reinterpret_cast<float4*>(myrow)[i4 ^ (lane & 7)] =
+                            make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),
+                                        __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
+                    tc_ld16(lane_addr + fcol + 80, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4)
+                        reinterpret_cast<float4*>(myrow)[(4 + i4) ^ (lane & 7)] =
+                            make_float4(__uint_as_float(v[4 * i4]), __uint_as_float(v[4 * i4 + 1]),
+                                        __uint_as_float(v[4 * i4 + 2]), __uint_as_float(v[4 * i4 + 3]));
+                    tc_ld16(lane_addr + fcol + 96, v);              // derivative 32 sits in column 96
+                    tc_wait_ld();
+                    d32 = __uint_as_float(v[0]);
+                }
+                tc_ld16(lane_addr + fcol + 32 * axis, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) e[i] = __uint_as_float(v[i]);
-                if (role < 3) {
-                    tc_ld16(lane_addr + fcol + 16, v);
-                    tc_wait_ld();
+                tc_ld16(lane_addr + fcol + 32 * axis + 16, v);
+                tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
+                for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
+                signal_rdy(RDY_F0 + pair);                          // accumulator drained
+                if (dbg_me) { t_m2 = clock64(); t_f1 += t_m2 - t_mark; }
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    upk2(add2(pk2(e[4 * i4], e[4 * i4 + 1]), pk2(bias[i4].x, bias[i4].y)), e[4 * i4], e[4 * i4 + 1]);
+                    upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bias[i4].z, bias[i4].w)), e[4 * i4 + 2],
+                         e[4 * i4 + 3]);
                 }
-                signal_rdy(RDY_F0 + f);                             // accumulator drained
-                if (dbg_me) { t_m2 = clock64(); t_fl += t_m2 - t_mark; }
-                auto park = [&]() {
+                // softmax numerators and inclusive prefix sums; pad columns (>= nb) contribute exp(-inf) = 0
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i >= nb) e[i] = -3.0e38f;
+                float m8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(e[i], e[i + 8]), fmaxf(e[i + 16], e[i + 24]));
+                const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
+                                      fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+                const float off = -m * c2;
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float ex;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(__fmaf_rn(e[i], c2, off)));
+                    sum += ex;
+                    e[i] = sum;
+                }
+                const float gs = gnum * __frcp_rn(sum);
+                if (dbg_me) { const long long tt = clock64(); t_f2 += tt - t_m2; t_m2 = tt; }
+                if (isA) {                                          // last knot <= x (utils/splines.py:11-13)
+                    // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
+                    const float rg = sum * rgnum;
+                    const float t0 = (x + bound) * r2b * rg, dt = -kMinW * rg;
+                    int sel = 0;
+                    float s0 = 0.f, s1 = e[0];                      // S[sel-1], S[sel]
+#pragma unroll
+                    for (int i = 1; i < 32; ++i)
+                        if (i < nb && e[i - 1] <= __fmaf_rn((float)i, dt, t0)) {
+                            sel = i;
+                            s0 = e[i - 1];
+                            s1 = e[i];
+                        }
+                    const float bd0 = __ldg(bch + 64 + sel), bd1 = __ldg(bch + 65 + sel);
+                    const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
+                    const float right =
+                        (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gs, s1, kMinW * (float)(sel + 1)), -bound);
+                    const float dk = pick(sel) + bd0;
+                    const float dk1 = (sel < 31 ? pick(sel + 1) : d32) + bd1;
+                    mb[0] = __int_as_float(sel);
+                    mb[32] = left;
+                    mb[64] = right - left;
+                    mb[96] = kMinD + softplus_t(dk);
+                    mb[128] = kMinD + softplus_t(dk1);
+                    if (dbg_me) t_f3 += clock64() - t_m2;
+                    pair_sync();
+                } else {
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4)
                         reinterpret_cast<float4*>(myrow)[i4 ^ (lane & 7)] =
                             make_float4(e[4 * i4], e[4 * i4 + 1], e[4 * i4 + 2], e[4 * i4 + 3]);
-                };
-                auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
-                if (role < 3) {
-#pragma unroll
-                    for (int i4 = 0; i4 < 8; ++i4) {
-                        upk2(add2(pk2(e[4 * i4], e[4 * i4 + 1]), pk2(bias[i4].x, bias[i4].y)), e[4 * i4], e[4 * i4 + 1]);
-                        upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bias[i4].z, bias[i4].w)), e[4 * i4 + 2],
-                             e[4 * i4 + 3]);
-                    }
-                }
-                if (role < 2) {
-                    // softmax numerators and inclusive prefix sums; pad columns (>= nb) contribute exp(-inf) = 0
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i >= nb) e[i] = -3.0e38f;
-                    float m8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(e[i], e[i + 8]), fmaxf(e[i + 16], e[i + 24]));
-                    const float m = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])),
-                                          fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-                    const float off = -m * c2;
-                    float sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float ex;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(__fmaf_rn(e[i], c2, off)));
-                        sum += ex;
-                        e[i] = sum;
-                    }
-                    const float gs = gnum * __frcp_rn(sum);
-                    float s0 = 0.f, s1 = e[0];                       // S[sel-1], S[sel]
-                    int sel;
-                    if (role == srch) {                              // last knot <= x (utils/splines.py:11-13)
-                        // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
-                        const float rg = sum * rgnum;
-                        const float t0 = (x + bound) * r2b * rg, dt = -kMinW * rg;
-                        sel = 0;
-#pragma unroll
-                        for (int i = 1; i < 32; ++i)
-                            if (i < nb && e[i - 1] <= __fmaf_rn((float)i, dt, t0)) {
-                                sel = i;
-                                s0 = e[i - 1];
-                                s1 = e[i];
-                            }
-                        mb[0] = __int_as_float(sel);
-                        if (dbg_me) t_fa += clock64() - t_m2;
-                        sync_a();
-                        if (dbg_me) t_m2 = clock64();
-                    } else {
-                        park();
-                        sync_a();
-                        sel = __float_as_int(mb[0]);
-                        s1 = pick(sel);
-                        if (sel) s0 = pick(sel - 1);
-                    }
+                    pair_sync();
+                    const int sel = __float_as_int(mb[0]);
+                    const float s1 = pick(sel), s0 = sel ? pick(sel - 1) : 0.f;
                     const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
                     const float right =
                         (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gs, s1, kMinW * (float)(sel + 1)), -bound);
-                    mb[32 * (1 + 2 * role)] = left;
-                    mb[32 * (2 + 2 * role)] = right - left;
-                    sync_b();
-                    if (dbg_me) t_fb += clock64() - t_m2;
-                } else if (role == 2) {
-                    park();
-                    sync_a();
-                    const int sel = __float_as_int(mb[0]);
-                    mb[32 * 5] = kMinD + softplus_t(pick(sel));
-                    if (sel < 31) mb[32 * 6] = kMinD + softplus_t(pick(sel + 1));
-                    sync_b();
-                } else {
-                    mb[32 * 7] = kMinD + softplus_t(e[0] + bias[0].x);     // derivative 32 sits in column 96
-                    sync_b();
-                    const int sel = __float_as_int(mb[0]);
+                    const float aL = mb[32], aW = mb[64];
                     float y = x, ld = 0.f;
-                    if (x >= -bound && x <= bound)
-                        rq_eval(x, mb[32 * 1], mb[32 * 2], mb[32 * 3], mb[32 * 4], mb[32 * 5],
-                                sel == 31 ? mb[32 * 7] : mb[32 * 6], inv, y, ld);
+                    if (x >= -bound && x <= bound) {
+                        if (inv) rq_eval(x, left, right - left, aL, aW, mb[96], mb[128], true, y, ld);
+                        else rq_eval(x, aL, aW, left, right - left, mb[96], mb[128], false, y, ld);
+                    }
                     if (row_ok) {
                         g.xout[(size_t)grow * g.D + (inv ? ft : (ft + hD) % g.D)] = y;
                         acc_ld += ld;
@@ -811,7 +842,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 }
                 if (dbg_me) t_fin += clock64() - t_mark;
             }
-            if (role == 3 && row_ok && g.logdet) g.logdet[grow] += acc_ld;
+            if (!isA) {                                             // the two B warps of a quadrant: fixed-order sum
+                if (pair == 1) mbq[0] = acc_ld;                     // pair 1's mailbox is idle now
+                asm volatile("bar.sync %0, 64;" ::"r"(9 + q) : "memory");
+                if (pair == 0 && row_ok && g.logdet) g.logdet[grow] += acc_ld + mbq[320];
+            }
             if (bad && g.nan_flag) atomicOr(g.nan_flag, 1);
         } else {
         // ---- final layer: theta chunk = D + b_final' -> global ----
@@ -873,15 +908,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         }
         }   // !fused
         if (dbg_me) {
-            g.dbg[16 * blockIdx.x + 4] = w_full;
-            g.dbg[16 * blockIdx.x + 5] = clock64() - e_start;
-            g.dbg[16 * blockIdx.x + 7] = t_res0;
-            g.dbg[16 * blockIdx.x + 8] = t_res1;
-            g.dbg[16 * blockIdx.x + 9] = t_relu;
-            g.dbg[16 * blockIdx.x + 10] = t_fin;
-            g.dbg[16 * blockIdx.x + 11] = t_fl;
-            g.dbg[16 * blockIdx.x + 12] = t_fa;
-            g.dbg[16 * blockIdx.x + 13] = t_fb;
+            dbg[16 * blockIdx.x + 4] = w_full;
+            dbg[16 * blockIdx.x + 5] = clock64() - e_start;
+            dbg[16 * blockIdx.x + 7] = t_res0;
+            dbg[16 * blockIdx.x + 8] = t_res1;
+            dbg[16 * blockIdx.x + 9] = t_relu;
+            dbg[16 * blockIdx.x + 10] = t_fin;
+            dbg[16 * blockIdx.x + 11] = t_f1;
+            dbg[16 * blockIdx.x + 12] = t_f2;
+            dbg[16 * blockIdx.x + 13] = t_f3;
         }
     }
     tc_fence_before();
