@@ -139,6 +139,181 @@ __global__ void __launch_bounds__(256) energy_total_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------
+// Packed variant (shared-memory tile <= 112 KB, i.e. N <= 3584 at one configuration per block): the same enumeration, two pairs per step in Blackwell's packed FP32 pairs
+// (add/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2).  Shared memory holds the configuration as separate x and y
+// arrays, each stored cyclically (2N entries) and once more shifted by one element, so the coordinates of two
+// consecutive partners (x[j], x[j+1]) are ONE aligned 64-bit load whatever the parity of j.  Minimum image for
+// both pairs and both axes with d - L rint(d / L) (rint by the 1.5 * 2^23 trick, round-half-even like np.round);
+// the cut-off mask is a 0/1 float multiplied into r^-6.  ~12 instructions per pair instead of ~19.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pk2f(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2f(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2f(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2f(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long sub2f(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2f(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+struct Pk2Consts {
+    unsigned long long invLx, invLy, nLx, nLy, magic, nmagic;
+};
+
+// two pairs: X = (dx_a, dx_c), Y = (dy_a, dy_c) before the minimum image
+__device__ __forceinline__ void pair_sums_x2(unsigned long long X, unsigned long long Y, const Pk2Consts& C, float rc2,
+                                             unsigned long long& a12, unsigned long long& a6,
+                                             unsigned long long& cnt, float& r2min) {
+    unsigned long long t = add2f(add2f(mul2f(X, C.invLx), C.magic), C.nmagic);
+    X = fma2f(t, C.nLx, X);
+    t = add2f(add2f(mul2f(Y, C.invLy), C.magic), C.nmagic);
+    Y = fma2f(t, C.nLy, Y);
+    const unsigned long long r2 = fma2f(Y, Y, mul2f(X, X));
+    float ra, rc;
+    upk2f(r2, ra, rc);
+    r2min = fminf(r2min, fminf(ra, rc));
+    float ia, ic;                                    // MUFU.RCP (1 ulp; r^2 is never denormal here)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(ra));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ic) : "f"(rc));
+    const unsigned long long inv = pk2f(ia, ic);
+    const unsigned long long s6 = mul2f(mul2f(inv, inv), inv);
+    const unsigned long long m = pk2f(ra <= rc2 ? 1.0f : 0.0f, rc <= rc2 ? 1.0f : 0.0f);
+    const unsigned long long s6m = mul2f(s6, m);
+    a12 = fma2f(s6m, s6, a12);
+    a6 = add2f(a6, s6m);
+    cnt = add2f(cnt, m);
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) energy_total_kernel_v2(const float* __restrict__ pos, int B, int N, PotDev P,
+                                                              float* __restrict__ E, float* __restrict__ W,
+                                                              unsigned char* __restrict__ overlap) {
+    extern __shared__ __align__(16) float smem_f[];
+    constexpr int GROUPS = 256 / G;
+    const int g = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    const int b = blockIdx.x * GROUPS + g;
+    // per configuration: X0[2N] Y0[2N] X1[2N] Y1[2N]; X1[m] = x[m + 1] (cyclic)
+    float* X0 = smem_f + (size_t)g * 8 * N;
+    float* Y0 = X0 + 2 * N;
+    float* X1 = Y0 + 2 * N;
+    float* Y1 = X1 + 2 * N;
+    __shared__ double red_e[8], red_w[8];
+    __shared__ float red_m[8];
+
+    const bool live = b < B;
+    if (live) {
+        const float2* src = reinterpret_cast<const float2*>(pos) + (size_t)b * N;
+        for (int i = t; i < N; i += G) {
+            const float2 v = __ldg(src + i);
+            X0[i] = v.x; X0[N + i] = v.x;
+            Y0[i] = v.y; Y0[N + i] = v.y;
+            const int m = (i == 0) ? N - 1 : i - 1;          // X1[m] = x[m + 1]
+            X1[m] = v.x; X1[N + m] = v.x;
+            Y1[m] = v.y; Y1[N + m] = v.y;
+        }
+    }
+    __syncthreads();
+
+    float a12 = 0.f, a6 = 0.f, cnt = 0.f, ew = 0.f, r2min = 3.0e38f;
+    if (live) {
+        Pk2Consts C;
+        C.invLx = pk2f(P.inv_Lx, P.inv_Lx); C.invLy = pk2f(P.inv_Ly, P.inv_Ly);
+        C.nLx = pk2f(-P.Lx, -P.Lx); C.nLy = pk2f(-P.Ly, -P.Ly);
+        C.magic = pk2f(12582912.0f, 12582912.0f); C.nmagic = pk2f(-12582912.0f, -12582912.0f);
+        const float hx = 0.5f * P.Lx, hy = 0.5f * P.Ly;
+        const int half = (N - 1) / 2;
+        for (int i = t; i < N; i += G) {
+            const float pix = X0[i], piy = Y0[i];
+            const unsigned long long PX = pk2f(pix, pix), PY = pk2f(piy, piy);
+            unsigned long long b12 = 0ull, b6 = 0ull, bc = 0ull, c12 = 0ull, c6 = 0ull, cc = 0ull;   // +0.0f pairs
+            // partners j = i+1 .. i+half; (x[j], x[j+1]) is an aligned pair in X0 for even j, in X1 - 1 for odd j
+            const bool odd = ((i + 1) & 1) != 0;
+            const float* bx = odd ? X1 - 1 : X0;
+            const float* by = odd ? Y1 - 1 : Y0;
+            int k = 1;
+            for (; k + 3 <= half; k += 4) {
+                const unsigned long long xa = *reinterpret_cast<const unsigned long long*>(bx + i + k);
+                const unsigned long long ya = *reinterpret_cast<const unsigned long long*>(by + i + k);
+                const unsigned long long xc = *reinterpret_cast<const unsigned long long*>(bx + i + k + 2);
+                const unsigned long long yc = *reinterpret_cast<const unsigned long long*>(by + i + k + 2);
+                pair_sums_x2(sub2f(PX, xa), sub2f(PY, ya), C, P.rc2, b12, b6, bc, r2min);
+                pair_sums_x2(sub2f(PX, xc), sub2f(PY, yc), C, P.rc2, c12, c6, cc, r2min);
+            }
+            for (; k + 1 <= half; k += 2) {
+                const unsigned long long xa = *reinterpret_cast<const unsigned long long*>(bx + i + k);
+                const unsigned long long ya = *reinterpret_cast<const unsigned long long*>(by + i + k);
+                pair_sums_x2(sub2f(PX, xa), sub2f(PY, ya), C, P.rc2, b12, b6, bc, r2min);
+            }
+            float s12, s6, sc, u, v;
+            upk2f(add2f(b12, c12), u, v); s12 = u + v;
+            upk2f(add2f(b6, c6), u, v); s6 = u + v;
+            upk2f(add2f(bc, cc), u, v); sc = u + v;
+            if (k <= half)
+                pair_sums<false>(pix - X0[i + k], piy - Y0[i + k], P, hx, hy, s12, s6, sc, r2min);
+            if ((N & 1) == 0 && i < N / 2)
+                pair_sums<false>(pix - X0[i + N / 2], piy - Y0[i + N / 2], P, hx, hy, s12, s6, sc, r2min);
+            a12 += s12;
+            a6 += s6;
+            cnt += sc;
+            ew += wells(pix, piy, P);
+        }
+    }
+    double de = 4.0 * ((double)a12 - (double)a6) - (double)cnt * (double)P.e_cut + (double)ew;
+    double dw = 48.0 * (double)a12 - 24.0 * (double)a6;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        de += __shfl_xor_sync(0xffffffffu, de, o);
+        dw += __shfl_xor_sync(0xffffffffu, dw, o);
+    }
+    r2min = warp_min(r2min);
+    if (G > 32) {
+        const int wid = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) {
+            red_e[wid] = de;
+            red_w[wid] = dw;
+            red_m[wid] = r2min;
+        }
+        __syncthreads();
+        if (t == 0) {
+            constexpr int WPG = G / 32;
+            de = 0; dw = 0; r2min = 3.0e38f;
+            for (int i = 0; i < WPG; ++i) {
+                de += red_e[g * WPG + i];
+                dw += red_w[g * WPG + i];
+                r2min = fminf(r2min, red_m[g * WPG + i]);
+            }
+        }
+    }
+    if (live && t == 0) {
+        const bool ov = r2min < P.rcore2;
+        const float inf = __int_as_float(0x7f800000);
+        E[b] = ov ? inf : (float)de;
+        W[b] = ov ? inf : (float)dw;
+        if (overlap) overlap[b] = ov ? 1 : 0;
+    }
+}
+
 // One warp per configuration: energy of particle idx[b] against all others.
 __global__ void __launch_bounds__(256) energy_particle_kernel(const float* __restrict__ pos,
                                                               const int* __restrict__ idx,
@@ -179,10 +354,18 @@ template <int G>
 static int launch_total(const float* pos, int B, int N, const PotDev& P, float* E, float* W,
                         unsigned char* ov, cudaStream_t s) {
     constexpr int GROUPS = 256 / G;
+    int grid = (B + GROUPS - 1) / GROUPS;
+    const size_t smem2 = (size_t)GROUPS * 8 * N * sizeof(float);
+    if (smem2 <= 112 * 1024) {                           // packed variant while two blocks per SM still fit
+        if (smem2 > 48 * 1024)
+            FS_CUDA(cudaFuncSetAttribute(energy_total_kernel_v2<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        energy_total_kernel_v2<G><<<grid, 256, smem2, s>>>(pos, B, N, P, E, W, ov);
+        fs::count_launch();
+        return cuda_check(cudaGetLastError(), "energy_total_kernel_v2");
+    }
     size_t smem = (size_t)GROUPS * 2 * N * sizeof(float2);
     if (smem > 48 * 1024)
         FS_CUDA(cudaFuncSetAttribute(energy_total_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (B + GROUPS - 1) / GROUPS;
     energy_total_kernel<G><<<grid, 256, smem, s>>>(pos, B, N, P, E, W, ov);
     fs::count_launch();
     return cuda_check(cudaGetLastError(), "energy_total_kernel");
