@@ -188,6 +188,14 @@ __global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ po
 // one Philox block per step generated 32 steps at a time (lane l prepares step base+l, the step reads it
 // with four shuffles), energy/virial DIFFERENCES reduced instead of four separate sums, the two
 // hard-core minima through single REDUX instructions, wells behind a float32 pre-test.
+// numpy float32 floor-mod for the common case -L <= a < 2L (one shift); anything else takes np_mod.
+__device__ __forceinline__ float np_mod_near(float a, float L) {
+    if (a >= 0.0f && a < L) return a + 0.0f;            // -0.0 -> +0.0 like copysignf(0, L)
+    if (a >= L && a < 2.0f * L) return a - L;           // exact (Sterbenz), what fmodf returns
+    if (a < 0.0f && a >= -L) return a + L;              // fmodf keeps a, numpy adds the divisor (may round to L)
+    return np_mod(a, L);
+}
+
 __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
                                                                double* __restrict__ W,
                                                                const double* __restrict__ max_disp,
@@ -208,11 +216,19 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const double md = max_disp[b];
     long long att = attempts[b];
     int acc = 0;
-    double Eb = E[b], Wb = W[b];
+    double Eb = E[b];
+    double Wl = 0.0;                         // this lane's share of the accepted virial differences (summed at the end)
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const long long cid = chain_id0 + b;
     const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
     const float inf = __int_as_float(0x7f800000);
+    const float Lx = P.Lx, Ly = P.Ly, iLx = P.inv_Lx, iLy = P.inv_Ly, rc2 = P.rc2, ecut = P.e_cut;
+    const float nbeta = -(float)beta;
+    // wells: lanes 0..3 evaluate (old, well 0), (old, well 1), (new, well 0), (new, well 1) with one code path
+    const int nw = P.num_wells;
+    const bool well_lane = (nw == 2) ? lane < 4 : (nw == 1 ? (lane == 0 || lane == 2) : false);
+    const int well_idx = lane & 1;
+    const float well_sign = (lane & 2) ? 1.0f : -1.0f;
     uint4 blk = make_uint4(0, 0, 0, 0);
     long long blk_base = -1;
 
@@ -227,61 +243,71 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         const uint32_t r_idx = __shfl_sync(0xffffffffu, blk.x, slot);
         const uint32_t r_u1 = __shfl_sync(0xffffffffu, blk.y, slot);
         const uint32_t r_u2 = __shfl_sync(0xffffffffu, blk.z, slot);
+        const uint32_t r_u3 = __shfl_sync(0xffffffffu, blk.w, slot);
         const int p = (int)__umulhi(r_idx, (uint32_t)N);
         const float2 old = sp[p];
         float nx = (float)((double)old.x + ((double)r_u1 * (1.0 / 4294967296.0) - 0.5) * md);
         float ny = (float)((double)old.y + ((double)r_u2 * (1.0 / 4294967296.0) - 0.5) * md);
-        nx = np_mod(nx, P.Lx);
-        ny = np_mod(ny, P.Ly);
+        nx = np_mod_near(nx, Lx);
+        ny = np_mod_near(ny, Ly);
 
+        // pair terms of the moved particle at its old and new position (energy_calculator.py:48-108); the
+        // particle itself is masked out by an "infinite" r^2 instead of a branch
         float de = 0.f, dw = 0.f, mo = 3.0e38f, mn = 3.0e38f;
         for (int j = lane; j < N; j += 32) {
-            if (j == p) continue;
             const float2 q = sp[j];
-            float eo = 0.f, wo = 0.f, en = 0.f, wn = 0.f;
-            pair_accum(old.x - q.x, old.y - q.y, P, eo, wo, mo);
-            pair_accum(nx - q.x, ny - q.y, P, en, wn, mn);
+            const bool self = (j == p);
+            float ox = min_image(old.x - q.x, Lx, iLx), oy = min_image(old.y - q.y, Ly, iLy);
+            float qx = min_image(nx - q.x, Lx, iLx), qy = min_image(ny - q.y, Ly, iLy);
+            float r2o = __fmaf_rn(oy, oy, ox * ox), r2n = __fmaf_rn(qy, qy, qx * qx);
+            r2o = self ? 3.0e38f : r2o;
+            r2n = self ? 3.0e38f : r2n;
+            mo = fminf(mo, r2o);
+            mn = fminf(mn, r2n);
+            float io, in_;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(io) : "f"(r2o));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(in_) : "f"(r2n));
+            io = (r2o <= rc2) ? io : 0.f;                 // outside the cut-off (and self): every term is 0
+            in_ = (r2n <= rc2) ? in_ : 0.f;
+            const float so = io * io * io, sn = in_ * in_ * in_;
+            // e = 4 s6 (s6 - 1) - e_cut, w = 48 s6 (s6 - 1/2)   (potential.py:11-27)
+            const float eo = __fmaf_rn(4.0f * so, so - 1.0f, (r2o <= rc2) ? -ecut : 0.f);
+            const float en = __fmaf_rn(4.0f * sn, sn - 1.0f, (r2n <= rc2) ? -ecut : 0.f);
             de += en - eo;
-            dw += wn - wo;
+            dw += 48.0f * (sn * (sn - 0.5f) - so * (so - 0.5f));
         }
-        if (P.num_wells == 2) {
-            if (lane < 2) de -= well_term(old.x, old.y, lane, P);
-            else if (lane < 4) de += well_term(nx, ny, lane - 2, P);
-        } else if (P.num_wells == 1) {
-            if (lane == 0) de -= well_term(old.x, old.y, 0, P);
-            else if (lane == 1) de += well_term(nx, ny, 0, P);
-        }
+        if (well_lane) de += well_sign * well_term((lane & 2) ? nx : old.x, (lane & 2) ? ny : old.y, well_idx, P);
         de = warp_sum(de);
-        dw = warp_sum(dw);
         const bool ov_o = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mo))) < P.rcore2;
         const bool ov_n = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mn))) < P.rcore2;
 
-        bool ok;
-        if (ov_o) {
-            ok = true;                         // e_old = inf: `enn <= eno` holds for any e_new (monte_carlo.py:198)
-        } else if (ov_n) {
-            ok = false;
-        } else if (de <= 0.f) {
-            ok = true;
-        } else {
-            const uint32_t r_u3 = __shfl_sync(0xffffffffu, blk.w, slot);
+        // metropolis_acceptance_particle_move (monte_carlo.py:191-223): e_old = inf makes `new <= old` true for any
+        // e_new; otherwise an overlapping new position is rejected; downhill is accepted; uphill draws
+        // u < exp(-beta dE).  A float exponential decides unless u falls within 1e-4 (relative) of the threshold;
+        // only then is the float64 expression evaluated, so the decision is always the float64 one.
+        const float uf = (float)r_u3 * (1.0f / 4294967296.0f);
+        const float pf = __expf(nbeta * de);
+        bool ok = ov_o || (!ov_n && (de <= 0.f || uf < pf * 0.9999f));
+        if (!ov_o && !ov_n && de > 0.f && uf >= pf * 0.9999f && uf <= pf * 1.0001f)
             ok = (double)r_u3 * (1.0 / 4294967296.0) < exp(-beta * (double)de);
-        }
         if (ok) {
             if (lane == 0) sp[p] = make_float2(nx, ny);
             acc += 1;
             const float big_o = ov_o ? inf : 0.f, big_n = ov_n ? inf : 0.f;
             Eb += (double)de + ((double)big_n - (double)big_o);
-            Wb += (double)dw + ((double)big_n - (double)big_o);
+            Wl += (double)dw;
+            if (lane == 0) Wl += (double)big_n - (double)big_o;
         }
         __syncwarp();
     }
     for (int i = lane; i < N; i += 32) gp[i] = sp[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Wl += __shfl_xor_sync(0xffffffffu, Wl, o);
     if (lane == 0) {
         attempts[b] = att;
         accepted[b] += acc;
         E[b] = Eb;
-        W[b] = Wb;
+        W[b] += Wl;
     }
 }
 
