@@ -188,6 +188,36 @@ __global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ po
 // one Philox block per step generated 32 steps at a time (lane l prepares step base+l, the step reads it
 // with four shuffles), energy/virial DIFFERENCES reduced instead of four separate sums, the two
 // hard-core minima through single REDUX instructions, wells behind a float32 pre-test.
+// packed FP32 pairs (add/sub/mul/fma.f32x2)
+__device__ __forceinline__ unsigned long long pk2s(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2s(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2s(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned long long add2s(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long sub2s(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long mul2s(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // numpy float32 floor-mod for the common case -L <= a < 2L (one shift); anything else takes np_mod.
 __device__ __forceinline__ float np_mod_near(float a, float L) {
     if (a >= 0.0f && a < L) return a + 0.0f;            // -0.0 -> +0.0 like copysignf(0, L)
@@ -231,6 +261,12 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const float well_sign = (lane & 2) ? 1.0f : -1.0f;
     uint4 blk = make_uint4(0, 0, 0, 0);
     long long blk_base = -1;
+    struct {
+        unsigned long long iLx, iLy, nLx, nLy, magic, nmagic, four, mone, mhalf;
+    } K;
+    K.iLx = pk2s(iLx, iLx); K.iLy = pk2s(iLy, iLy); K.nLx = pk2s(-Lx, -Lx); K.nLy = pk2s(-Ly, -Ly);
+    K.magic = pk2s(12582912.0f, 12582912.0f); K.nmagic = pk2s(-12582912.0f, -12582912.0f);
+    K.four = pk2s(4.0f, 4.0f); K.mone = pk2s(-1.0f, -1.0f); K.mhalf = pk2s(-0.5f, -0.5f);
 
     for (int s = 0; s < steps; ++s, ++att) {
         const long long base = att & ~31ll;
@@ -253,13 +289,18 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
 
         // pair terms of the moved particle at its old and new position (energy_calculator.py:48-108); the
         // particle itself is masked out by an "infinite" r^2 instead of a branch
-        float de = 0.f, dw = 0.f, mo = 3.0e38f, mn = 3.0e38f;
+        // (old, new) ride in the two halves of Blackwell's packed FP32 pairs (FADD2 / FMUL2 / FFMA2)
+        float mo = 3.0e38f, mn = 3.0e38f;
+        unsigned long long e2 = 0ull, w2 = 0ull;                     // (sum e_old, sum e_new), (sum w_old, sum w_new)
+        const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny);
         for (int j = lane; j < N; j += 32) {
             const float2 q = sp[j];
             const bool self = (j == p);
-            float ox = min_image(old.x - q.x, Lx, iLx), oy = min_image(old.y - q.y, Ly, iLy);
-            float qx = min_image(nx - q.x, Lx, iLx), qy = min_image(ny - q.y, Ly, iLy);
-            float r2o = __fmaf_rn(oy, oy, ox * ox), r2n = __fmaf_rn(qy, qy, qx * qx);
+            unsigned long long X = sub2s(PX, pk2s(q.x, q.x)), Y = sub2s(PY, pk2s(q.y, q.y));
+            X = fma2s(add2s(fma2s(X, K.iLx, K.magic), K.nmagic), K.nLx, X);      // d - L rint(d / L)
+            Y = fma2s(add2s(fma2s(Y, K.iLy, K.magic), K.nmagic), K.nLy, Y);
+            float r2o, r2n;
+            upk2s(fma2s(Y, Y, mul2s(X, X)), r2o, r2n);
             r2o = self ? 3.0e38f : r2o;
             r2n = self ? 3.0e38f : r2n;
             mo = fminf(mo, r2o);
@@ -267,15 +308,18 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
             float io, in_;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(io) : "f"(r2o));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(in_) : "f"(r2n));
-            io = (r2o <= rc2) ? io : 0.f;                 // outside the cut-off (and self): every term is 0
-            in_ = (r2n <= rc2) ? in_ : 0.f;
-            const float so = io * io * io, sn = in_ * in_ * in_;
+            const bool co = r2o <= rc2, cn = r2n <= rc2;          // outside the cut-off (and self): every term is 0
+            const unsigned long long inv = pk2s(co ? io : 0.f, cn ? in_ : 0.f);
+            const unsigned long long s6 = mul2s(mul2s(inv, inv), inv);
             // e = 4 s6 (s6 - 1) - e_cut, w = 48 s6 (s6 - 1/2)   (potential.py:11-27)
-            const float eo = __fmaf_rn(4.0f * so, so - 1.0f, (r2o <= rc2) ? -ecut : 0.f);
-            const float en = __fmaf_rn(4.0f * sn, sn - 1.0f, (r2n <= rc2) ? -ecut : 0.f);
-            de += en - eo;
-            dw += 48.0f * (sn * (sn - 0.5f) - so * (so - 0.5f));
+            e2 = add2s(e2, fma2s(mul2s(s6, K.four), add2s(s6, K.mone), pk2s(co ? -ecut : 0.f, cn ? -ecut : 0.f)));
+            w2 = fma2s(s6, add2s(s6, K.mhalf), w2);
         }
+        float eo_s, en_s, wo_s, wn_s;
+        upk2s(e2, eo_s, en_s);
+        upk2s(w2, wo_s, wn_s);
+        float de = en_s - eo_s;
+        const float dw = 48.0f * (wn_s - wo_s);
         if (well_lane) de += well_sign * well_term((lane & 2) ? nx : old.x, (lane & 2) ? ny : old.y, well_idx, P);
         de = warp_sum(de);
         const bool ov_o = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mo))) < P.rcore2;
