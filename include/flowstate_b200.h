@@ -210,6 +210,22 @@ int fs_flow_forward(fs_flow* flow, const float* z, int B, double out_shift,
  * 16 int64 per CTA; returns the number of CTAs copied to `host`. */
 int fs_tc_debug_read(long long* host, int max_ctas);
 
+/* ---- observables of sampled configurations ------------------------------------------- */
+
+/* classify_particles + the per-configuration part of calculate_well_statistics
+ * (hybrid_NF_MCMC/utils.py:61-141): pos [B, N, 2] MC-box coordinates ->
+ * cls [B, N] (0 outside, 1 well A around (Lx/4, Ly/2), 2 well B around (3Lx/4, Ly/2); radius 1.1 r0, minimum image),
+ * state [B] (1 all particles in A, 2 all in B, 0 otherwise), avg_x [B] mean x.  Any output may be NULL. */
+int fs_classify_wells(const float* pos, int B, int N, double Lx, double Ly, double r0, unsigned char* cls,
+                      unsigned char* state, double* avg_x, void* stream);
+
+/* Per-configuration pair-distance histogram of calculate_pair_correlation (hybrid_NF_MCMC/utils.py:530-556):
+ * cfg [B, N, 2] centred coordinates in [-bound, bound], float32 minimum-image distances as numpy computes them,
+ * bins [k dr, (k+1) dr), k < nbins, last bin closed, zero distances dropped, every unordered pair counted twice
+ * -> counts [B, nbins]. */
+int fs_pair_histogram(const float* cfg, int B, int N, double bound, double dr, int nbins, unsigned int* counts,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,3 +60,26 @@ def load():
         quiet=lambda: contextlib.redirect_stdout(io.StringIO()),
     )
     return _loaded
+
+
+def load_hybrid_utils():
+    """The reference's hybrid_NF_MCMC/utils.py (analysis helpers).  It imports matplotlib / cycler for its
+    plotting functions only; neither is installed here, so inert stand-ins are registered first."""
+    if "hybrid_utils" in _loaded:
+        return _loaded["hybrid_utils"]
+    import importlib.util
+    import types
+
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "cycler"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(cycler=lambda *a, **k: None, LinearSegmentedColormap=object, rcParams={})
+            sys.modules[name] = m
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].colors = sys.modules["matplotlib.colors"]
+    spec = importlib.util.spec_from_file_location("fs_ref_hybrid_utils",
+                                                  os.path.join(REF_ROOT, "hybrid_NF_MCMC", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _loaded["hybrid_utils"] = mod
+    return mod

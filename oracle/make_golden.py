@@ -317,6 +317,58 @@ def gen_init(ref):
     print("flow_init: %d tensors" % len(out))
 
 
+def gen_observables(ref):
+    """Outputs of the unmodified hybrid_NF_MCMC/utils.py analysis functions on seeded configurations."""
+    from oracle import _refimport
+    hu = _refimport.load_hybrid_utils()
+    rng = np.random.default_rng(77)
+    out = {}
+    # well statistics: N = 3 particles in an L = 10 box, a mix of all-in-A, all-in-B and scattered configurations
+    half_box, r0, n, M = 5.0, 1.2, 3, 60
+    L = 2 * half_box
+    cfgs = np.empty((M, n, 2), dtype=np.float32)
+    for m in range(M):
+        kind = m % 3
+        if kind == 2:
+            cfgs[m] = rng.uniform(0, L, size=(n, 2))
+        else:
+            cx = L / 4 if kind == 0 else 3 * L / 4
+            ang = rng.uniform(0, 2 * np.pi, n)
+            rad = rng.uniform(0, 1.3, n)                      # a few land just outside 1.1 r0 = 1.32
+            cfgs[m, :, 0] = cx + rad * np.cos(ang)
+            cfgs[m, :, 1] = L / 2 + rad * np.sin(ang)
+    cfgs[5, 0] = [L / 4 - L, L / 2 + L]                        # periodic images of the well centre
+    cls = hu.classify_particles(cfgs, half_box, r0)
+    code = np.zeros(cls.shape, dtype=np.uint8)
+    code[cls == "A"] = 1
+    code[cls == "B"] = 2
+    avg_x, p_a, p_b, dF, runs = hu.calculate_well_statistics(cfgs, 7, half_box, r0)
+    out.update(ws_cfgs=cfgs, ws_half_box=half_box, ws_r0=r0, ws_start=7, ws_class=code,
+               ws_avg_x=np.array(avg_x, dtype=np.float64), ws_p_a=np.array(p_a), ws_p_b=np.array(p_b),
+               ws_dF=np.array(dF), ws_runs=np.array(runs))
+    # pair correlation: float32 centred samples, as model.sample(...).cpu().numpy() delivers them
+    # (the reference's default dr = bound / 50 makes np.arange(0, bound + dr, dr) one bin too long for most
+    # bounds and the function then fails on a shape mismatch; dr = bound / 49.5 keeps both aranges at 50)
+    for tag, npart, nsamp, bound, dr in (("a", 8, 12, float(np.float32(np.sqrt(8 / 0.03))) / 2, None),
+                                         ("b", 32, 6, float(np.float32(np.sqrt(32 / 0.03))) / 2, None),
+                                         ("c", 3, 20, 5.0, "default")):
+        if dr is None:
+            dr = bound / 49.5
+        samples = rng.uniform(-bound, bound, size=(nsamp, npart, 2)).astype(np.float32)
+        samples[0, 1] = samples[0, 0]                          # coincident particles: zero distance is dropped
+        with ref["quiet"]():
+            if dr == "default":
+                r_vals, g_r = hu.calculate_pair_correlation(samples, npart, bound)
+                dr = bound / 50
+            else:
+                r_vals, g_r = hu.calculate_pair_correlation(samples, npart, bound, dr)
+        out.update({"pc_%s_samples" % tag: samples, "pc_%s_bound" % tag: bound, "pc_%s_n" % tag: npart,
+                    "pc_%s_dr" % tag: dr,
+                    "pc_%s_r" % tag: np.asarray(r_vals), "pc_%s_g" % tag: np.asarray(g_r, dtype=np.float64)})
+    np.savez_compressed(os.path.join(GOLD, "observables.npz"), **out)
+    print("observables.npz:", len(out), "arrays")
+
+
 def main():
     ref = _refimport.load()
     os.makedirs(GOLD, exist_ok=True)
@@ -325,6 +377,7 @@ def main():
     gen_flow(ref)
     gen_global(ref)
     gen_init(ref)
+    gen_observables(ref)
 
 
 if __name__ == "__main__":

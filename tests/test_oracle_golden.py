@@ -150,3 +150,20 @@ def test_global_traces(golden_dir):
             assert _close(ch.E, e_after, 1e-6), (key, r, ch.E, e_after)
         assert ch.attempts == int(g[key + "__attempts"]) and ch.accepted == int(g[key + "__accepted"])
         np.testing.assert_allclose(np.asarray(ch.particles, np.float64), g[key + "__posF"], atol=1e-6)
+
+
+def test_observables_oracle_matches_reference_golden(golden_dir):
+    """oracle/observables_ref.py against the outputs of the unmodified hybrid_NF_MCMC/utils.py functions."""
+    from oracle import observables_ref as obr
+    g = np.load(os.path.join(golden_dir, "observables.npz"))
+    half_box, r0, start = float(g["ws_half_box"]), float(g["ws_r0"]), int(g["ws_start"])
+    assert np.array_equal(obr.classify(g["ws_cfgs"], half_box, r0), g["ws_class"])
+    avg_x, p_a, p_b, dF, runs = obr.well_statistics(g["ws_cfgs"], start, half_box, r0)
+    assert np.array_equal(np.array(avg_x, dtype=np.float64), g["ws_avg_x"])
+    assert np.array_equal(p_a, g["ws_p_a"]) and np.array_equal(p_b, g["ws_p_b"])
+    np.testing.assert_allclose(dF, g["ws_dF"], rtol=0, atol=1e-15)
+    for tag in "abc":
+        r, gr = obr.pair_correlation(g["pc_%s_samples" % tag], int(g["pc_%s_n" % tag]), float(g["pc_%s_bound" % tag]),
+                                     float(g["pc_%s_dr" % tag]))
+        assert np.array_equal(r, g["pc_%s_r" % tag])
+        np.testing.assert_allclose(gr, g["pc_%s_g" % tag], rtol=1e-14, atol=0)
