@@ -86,11 +86,13 @@ def test_against_oracle_alg_shapes():
     torch.manual_seed(0)
     # (32, ...): Alg-1 bins; (64, ...): BASELINE config 4 shape (Alg 2: H=128, 2 blocks, 15 bins, N=64);
     # (256, ...): BASELINE config 3 particle count (2N = 512 features > H: multi-piece GEMM0, 8 coordinate chunks);
+    # (20, ...), (9, ...): fused spline epilogue with fewer than 32 bins (pad columns) and odd N;
     # (5, ...): odd N, H outside the tensor path; (150, ...): ragged last chunk, warps of a block with unequal
     # chunk counts, 4-byte staging path (N % 4 != 0); (148, ...): ragged chunk on the 16-byte staging path
     for (n, K, blocks, H, nb, sigma, B) in [(32, 3, 4, 256, 32, 0.02, 200), (64, 4, 2, 128, 15, 0.05, 130),
                                             (256, 2, 3, 256, 32, 0.02, 140), (5, 4, 2, 64, 8, 0.05, 33),
-                                            (150, 2, 1, 128, 7, 0.03, 37), (148, 2, 1, 64, 6, 0.03, 19)]:
+                                            (150, 2, 1, 128, 7, 0.03, 37), (148, 2, 1, 64, 6, 0.03, 19),
+                                            (20, 2, 1, 256, 12, 0.03, 150), (9, 2, 2, 256, 31, 0.03, 70)]:
         bound = float(np.float32(np.sqrt(n / 0.03))) / 2
         model = _build(n, K, blocks, H, nb, bound, device="cuda")
         g = torch.Generator().manual_seed(1)
