@@ -551,6 +551,12 @@ static int pack_layer(fs_flow* f, const fs_flow_desc* d, const fs_layer_params* 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // rows processed per pass so that the parameter buffer theta stays below 4 GiB (180 GB of HBM)
+// tensor path with the spline applied in the conditioner's epilogue: theta is never materialised
+// (FS_NO_FUSE=1 keeps theta + the spline kernel; read per call so tests can switch it)
+static bool fused_path(const fs_flow* f, int precision) {
+    return precision == FS_PREC_TF32 && tc_has_fused(f) && !getenv("FS_NO_FUSE");
+}
+
 static int chunk_rows(const fs_flow* f, int B) {
     size_t per_row = (size_t)f->N * f->P * sizeof(float);
     size_t rows = (4096ull << 20) / per_row;
@@ -576,9 +582,10 @@ static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspac
     float* v0 = (float*)take((size_t)Bc * f->D * 4);
     float* v1 = (float*)take((size_t)Bc * f->D * 4);
     float* A0 = (float*)take((size_t)Bc * 2 * f->N * 4);
-    float* h = (float*)take((size_t)Bc * f->H * 4);
-    float* t = (float*)take((size_t)Bc * f->H * 4);
-    float* th = (float*)take((size_t)Bc * f->N * f->P * 4);
+    const bool fp32 = precision != FS_PREC_TF32;                   // hidden activations live in TMEM on the tensor path
+    float* h = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
+    float* t = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
+    float* th = (float*)take(fused_path(f, precision) ? 0 : (size_t)Bc * f->N * f->P * 4);
     float* ld = (float*)take((size_t)Bc * 4);
     size_t tcb = precision == FS_PREC_TF32 ? tc_workspace_bytes(f, Bc) : 0;
     void* tc = take(tcb);
@@ -732,8 +739,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
     carve(f, B, precision, workspace, &w);
     const int Bc = chunk_rows(f, B);
     const FlowDev F = flow_dev(f);
-    // tensor path with the spline applied in the conditioner's epilogue (FS_NO_FUSE=1 keeps theta + spline kernel)
-    const bool fused = precision == FS_PREC_TF32 && tc_has_fused(f) && !getenv("FS_NO_FUSE");
+    const bool fused = fused_path(f, precision);
     for (int r0 = 0; r0 < B; r0 += Bc) {
         const int rows = (B - r0 < Bc) ? B - r0 : Bc;
         const size_t n = (size_t)rows * f->D;
@@ -777,8 +783,7 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
     carve(f, B, precision, workspace, &w);
     const int Bc = chunk_rows(f, B);
     const FlowDev F = flow_dev(f);
-    // tensor path with the spline applied in the conditioner's epilogue (FS_NO_FUSE=1 keeps theta + spline kernel)
-    const bool fused = precision == FS_PREC_TF32 && tc_has_fused(f) && !getenv("FS_NO_FUSE");
+    const bool fused = fused_path(f, precision);
     for (int r0 = 0; r0 < B; r0 += Bc) {
         const int rows = (B - r0 < Bc) ? B - r0 : Bc;
         const size_t n = (size_t)rows * f->D;

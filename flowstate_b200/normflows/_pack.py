@@ -10,6 +10,8 @@ on request.
 import ctypes as C
 
 import numpy as np
+import os
+
 import torch
 
 from ._bridge import _lib
@@ -130,7 +132,7 @@ class FlowPack:
 
     # -- calls ------------------------------------------------------------
     def _workspace(self, B, prec):
-        key = (B, prec)
+        key = (B, prec, bool(os.environ.get("FS_NO_FUSE")))      # the fused tensor path needs no theta buffer
         ws = self._ws.get(key)
         if ws is None:
             n = _lib.lib().fs_flow_workspace_bytes(self._h, B, prec)
