@@ -86,6 +86,43 @@ __device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict_
             ld);
 }
 
+// U coordinates of one lane at once: the binary searches (same trip count for every coordinate) and the
+// table loads of the U coordinates interleave, which hides the L1/L2 latency of the dependent knot loads.
+template <int U>
+__device__ __forceinline__ void rqs_table_multi(const float (&x)[U], const bool (&valid)[U], const int (&j)[U],
+                                                const float* __restrict__ ux, const float* __restrict__ uy,
+                                                const float* __restrict__ ud, int N, int nb, float bound, bool inverse,
+                                                float (&y)[U], float (&ld)[U]) {
+    const float* ks = inverse ? uy : ux;
+    int lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { lo[u] = 0; hi[u] = nb; }
+    for (int span = nb; span > 1; span = (span + 1) >> 1) {           // ceil-halving covers every hi - lo
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (valid[u] && hi[u] - lo[u] > 1) {
+                const int mid = (lo[u] + hi[u]) >> 1;
+                if (x[u] >= __ldg(ks + (size_t)mid * N + j[u])) lo[u] = mid; else hi[u] = mid;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        y[u] = x[u];
+        ld[u] = 0.f;
+        if (valid[u] && x[u] >= -bound && x[u] <= bound) {
+            const int sel = lo[u];
+            const float* cx = ux + j[u];
+            const float* cy = uy + j[u];
+            const float* cd = ud + j[u];
+            const float xk = __ldg(cx + (size_t)sel * N), xk1 = __ldg(cx + (size_t)(sel + 1) * N);
+            const float yk = __ldg(cy + (size_t)sel * N), yk1 = __ldg(cy + (size_t)(sel + 1) * N);
+            rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, __ldg(cd + (size_t)sel * N), __ldg(cd + (size_t)(sel + 1) * N),
+                    inverse, y[u], ld[u]);
+        }
+    }
+}
+
 // Conditional spline of ONE coordinate.  p[k * 32], k < 2nb: the staged width and height logits of this
 // lane's coordinate (overwritten by the inclusive prefix sums of the softmax numerators); gp: this
 // coordinate's column of theta in global memory (stride N) for the two derivatives of the selected bin.
@@ -240,6 +277,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_MAXW) spline_kernel(
 
 // sampling direction, step 1: roll, inverse unconditional spline on the identity half, periodic
 // features of the NEW identity values (coupling.py:113-124)
+template <int U>
 __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
     const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
     FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
@@ -251,17 +289,29 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
     const int h = F.D / 2, nb = F.nb;
     float acc = 0.f;
     bool bad = false;
-    for (int j = lane; j < F.N; j += 32) {
-        const int fi = F.idf[j];
-        float y, ld;
-        rqs_table_lane(vr[(fi + h) % F.D], ux + j, uy + j, ud + j, F.N, nb, F.bound, true, y, ld);
-        out[(size_t)b * F.D + fi] = y;
-        float sn, cs;
-        sincosf(F.pf_scale * y, &sn, &cs);
-        A0[(size_t)b * 2 * F.N + j] = cs;
-        A0[(size_t)b * 2 * F.N + F.N + j] = sn;
-        acc += ld;
-        bad = bad || (y != y) || (ld != ld);
+    for (int j0 = lane; j0 < F.N; j0 += 32 * U) {
+        float x[U], y[U], ld[U];
+        int j[U], fi[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            j[u] = j0 + 32 * u;
+            valid[u] = j[u] < F.N;
+            fi[u] = valid[u] ? F.idf[j[u]] : 0;
+            x[u] = valid[u] ? vr[(fi[u] + h) % F.D] : 0.f;
+        }
+        rqs_table_multi<U>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, true, y, ld);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            out[(size_t)b * F.D + fi[u]] = y[u];
+            float sn, cs;
+            sincosf(F.pf_scale * y[u], &sn, &cs);
+            A0[(size_t)b * 2 * F.N + j[u]] = cs;
+            A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            acc += ld[u];
+            bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
+        }
     }
     acc = warp_sum_f(acc);
     if (lane == 0 && logdet) logdet[b] += acc;
@@ -271,6 +321,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
 // density direction, step 1: periodic features of the identity half (utils/nn.py:125-127) and the
 // unconditional spline on the identity half, scattered + rolled by D/2 (coupling.py:86-102).  One warp per
 // row; the knot tables stay L1-resident here (no shared-memory carve-out).
+template <int U>
 __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
     const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
     FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
@@ -282,18 +333,29 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
     const int h = F.D / 2, nb = F.nb;
     float acc = 0.f;
     bool bad = false;
-    for (int j = lane; j < F.N; j += 32) {
-        const int fi = F.idf[j];
-        const float x = vr[fi];
-        float sn, cs;
-        sincosf(F.pf_scale * x, &sn, &cs);
-        A0[(size_t)b * 2 * F.N + j] = cs;
-        A0[(size_t)b * 2 * F.N + F.N + j] = sn;
-        float y, ld;
-        rqs_table_lane(x, ux + j, uy + j, ud + j, F.N, nb, F.bound, false, y, ld);
-        out[(size_t)b * F.D + (fi + h) % F.D] = y;
-        acc += ld;
-        bad = bad || (y != y) || (ld != ld);
+    for (int j0 = lane; j0 < F.N; j0 += 32 * U) {
+        float x[U], y[U], ld[U];
+        int j[U], fi[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            j[u] = j0 + 32 * u;
+            valid[u] = j[u] < F.N;
+            fi[u] = valid[u] ? F.idf[j[u]] : 0;
+            x[u] = valid[u] ? vr[fi[u]] : 0.f;
+        }
+        rqs_table_multi<U>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, false, y, ld);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            float sn, cs;
+            sincosf(F.pf_scale * x[u], &sn, &cs);
+            A0[(size_t)b * 2 * F.N + j[u]] = cs;
+            A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            out[(size_t)b * F.D + (fi[u] + h) % F.D] = y[u];
+            acc += ld[u];
+            bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
+        }
     }
     acc = warp_sum_f(acc);
     if (lane == 0 && logdet) logdet[b] += acc;
@@ -750,8 +812,12 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         float* nxt = w.v1;
         for (int li = f->K - 1; li >= 0; --li) {                        // core.py:82-85
             const fs_flow::Layer& L = f->layers[li];
-            prep_inverse_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            if (f->N > 32)
+                prep_inverse_v2<4><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            else
+                prep_inverse_v2<1><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
@@ -793,8 +859,12 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
         float* nxt = w.v1;
         for (int li = 0; li < f->K; ++li) {                              // core.py:52-55
             const fs_flow::Layer& L = f->layers[li];
-            prep_forward_v2<<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            if (f->N > 32)
+                prep_forward_v2<4><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            else
+                prep_forward_v2<1><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
+                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
     fs::count_launch();
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
