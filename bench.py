@@ -327,30 +327,41 @@ def main():
     clk = clocks.stop() if clocks else None
 
     # ---- end to end: host buffers in, host results out, copies inside the timed region ----
-    h_pos = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
-    h_pos.copy_(eng.pos.cpu())
+    # Every step uploads that step's chain positions and base noise from pinned host memory, runs the round and
+    # reads positions, energies and accept mask back.  Two host-resident chain batches alternate (batch k % 2 in
+    # step k, its output becoming its next input), so the host waits for the results of step k-1 while step k is
+    # already queued: the copies and the launch work of consecutive steps overlap as in a real pipeline.
     h_z = torch.empty(B, 2 * n, dtype=torch.float32).uniform_(-bound, bound).pin_memory()
-    h_out_pos = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
-    h_out_E = torch.empty(B, dtype=torch.float64).pin_memory()
-    h_out_mask = torch.empty(B, dtype=torch.uint8).pin_memory()
+    hb = []
+    for k in range(2):
+        hp = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
+        hp.copy_(eng.pos.cpu())
+        hb.append({"pos": hp, "out_pos": torch.empty(B, n, 2, dtype=torch.float32).pin_memory(),
+                   "out_E": torch.empty(B, dtype=torch.float64).pin_memory(),
+                   "out_mask": torch.empty(B, dtype=torch.uint8).pin_memory(), "ev": None})
 
-    def e2e_round():
-        eng.pos.copy_(h_pos, non_blocking=True)
+    def e2e_round(k):
+        buf = hb[k % 2]
+        if buf["ev"] is not None:                      # results of this batch's previous step have landed
+            buf["ev"].synchronize()
+            buf["pos"].copy_(buf["out_pos"])
+        eng.pos.copy_(buf["pos"], non_blocking=True)
         eng.refresh_energy()
         mask = one_round(h_z)                          # base noise comes from the host buffer
-        h_out_pos.copy_(eng.pos, non_blocking=True)
-        h_out_E.copy_(eng.E, non_blocking=True)
-        h_out_mask.copy_(mask, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        h_pos.copy_(h_out_pos)
+        buf["out_pos"].copy_(eng.pos, non_blocking=True)
+        buf["out_E"].copy_(eng.E, non_blocking=True)
+        buf["out_mask"].copy_(mask, non_blocking=True)
+        buf["ev"] = torch.cuda.Event()
+        buf["ev"].record()
 
-    e2e_round()
+    for k in range(2):
+        e2e_round(k)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_round()
+    for k in range(args.steps):
+        e2e_round(k)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
