@@ -63,29 +63,8 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-// Unconditional spline of one coordinate from the packed knot tables.  Tables are knot-major
-// ([nb+1][N]: entry k of coordinate j at k*N + j), so the 32 lanes of a warp read consecutive addresses.
-__device__ __forceinline__ void rqs_table_lane(float x, const float* __restrict__ ux, const float* __restrict__ uy,
-                                               const float* __restrict__ ud, int N, int nb, float bound, bool inverse,
-                                               float& y, float& ld) {
-    if (!(x >= -bound && x <= bound)) {
-        y = x;
-        ld = 0.0f;
-        return;
-    }
-    const float* ks = inverse ? uy : ux;
-    int lo = 0, hi = nb;                 // last knot <= x (utils/splines.py:11-13); knots increase strictly
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (x >= __ldg(ks + (size_t)mid * N)) lo = mid; else hi = mid;
-    }
-    const int sel = lo;
-    const float xk = __ldg(ux + (size_t)sel * N), xk1 = __ldg(ux + (size_t)(sel + 1) * N);
-    const float yk = __ldg(uy + (size_t)sel * N), yk1 = __ldg(uy + (size_t)(sel + 1) * N);
-    rq_eval(x, xk, xk1 - xk, yk, yk1 - yk, __ldg(ud + (size_t)sel * N), __ldg(ud + (size_t)(sel + 1) * N), inverse, y,
-            ld);
-}
-
+// Unconditional spline of the identity half from the packed knot tables.  Tables are knot-major ([nb+1][N]: entry k of
+// coordinate j at k*N + j), so the 32 lanes of a warp read consecutive addresses.
 // U coordinates of one lane at once: the binary searches (same trip count for every coordinate) and the
 // table loads of the U coordinates interleave, which hides the L1/L2 latency of the dependent knot loads.
 template <int U>
@@ -366,9 +345,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
 // warps per block of spline_kernel: one per 32-coordinate chunk of a row, at most FS_SPLINE_MAXW
 static int spline_warps(const fs_flow* f) {
     const int nchunk = (f->N + 31) / 32;
-    int maxw = FS_SPLINE_MAXW;
-    if (const char* e = getenv("FS_SPLINE_W")) maxw = atoi(e);
-    return nchunk < maxw ? nchunk : maxw;
+    return nchunk < FS_SPLINE_MAXW ? nchunk : FS_SPLINE_MAXW;
 }
 
 static size_t spline_smem_bytes(const fs_flow* f) {

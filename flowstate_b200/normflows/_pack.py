@@ -132,12 +132,13 @@ class FlowPack:
 
     # -- calls ------------------------------------------------------------
     def _workspace(self, B, prec):
-        key = (B, prec, bool(os.environ.get("FS_NO_FUSE")))      # the fused tensor path needs no theta buffer
+        # one buffer per (batch, precision, path, stream): passes issued on different streams may overlap
+        key = (B, prec, bool(os.environ.get("FS_NO_FUSE")), torch.cuda.current_stream(self.device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None:
             n = _lib.lib().fs_flow_workspace_bytes(self._h, B, prec)
             ws = torch.empty(max(int(n), 16), dtype=torch.uint8, device=self.device)
-            if len(self._ws) > 4:
+            if len(self._ws) > 6:
                 self._ws.clear()
             self._ws[key] = ws
         return ws

@@ -1,4 +1,6 @@
-"""Prints where the tensor-core conditioner's roles wait (FS_TC_DEBUG=1), alg1_n32 shapes."""
+"""Prints where the tensor-core conditioner's roles wait (FS_TC_DEBUG=1).  The in-kernel timers are compiled in only when
+the library is built with FS_TC_TIMERS=1:  FS_TC_TIMERS=1 python -c "from flowstate_b200 import build; build.build(force=True)"
+(rebuild without it afterwards: the clock reads slow the MMA-issuing warp down)."""
 import ctypes as C
 import os
 import sys
