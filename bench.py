@@ -377,8 +377,8 @@ def main():
     pack = model._cuda_pack()
     feats = torch.cat([torch.cos(xin[:, 0::2] * (np.pi / bound)), torch.sin(xin[:, 0::2] * (np.pi / bound))], dim=1).contiguous()
     # the kernel the passes launch: conditioner with the fused spline epilogue when the flow shape has it
-    # (H = 256), else the conditioner writing theta
-    fused = prec == "tf32" and w["H"] == 256 and w["nb"] <= 32 and not os.environ.get("FS_NO_FUSE")
+    # (H = 128 / 256, at most 32 bins), else the conditioner writing theta
+    fused = prec == "tf32" and w["H"] in (128, 256) and w["nb"] <= 32 and not os.environ.get("FS_NO_FUSE")
     xo, ldo = torch.zeros_like(xin), torch.zeros(xin.shape[0], device=dev)
 
     def dominant(li):

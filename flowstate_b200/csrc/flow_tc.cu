@@ -258,7 +258,10 @@ enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F
 template <int H>
 struct TcCfg {
     static constexpr int NH = H / 2;
-    static constexpr int EPI_WARPS = 4 * (NH / 32);          // one 32-column chunk per region half per thread: 16 / 8
+    static constexpr int EPI_WARPS = 16;                     // 4 TMEM lane quadrants x 4 column groups
+    static constexpr int BLK_WARPS = 4 * (NH / 32);          // of which take part in the H-wide stages (one 32-column
+                                                             // chunk per region half per thread): 16 (H = 256) / 8 (H = 128);
+                                                             // all 16 work on the final layer
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int STAGE_BYTES = H * 128;              // H rows x 32 tf32
     static constexpr int NSTAGE = (H == 256) ? 4 : 8;
@@ -270,8 +273,10 @@ struct TcCfg {
     static constexpr int FIN1 = (H == 256) ? H + 128 : 2 * H;
     static constexpr int TMEM_COLS = 512;
     static constexpr int PSET_FLOATS = 3 * H;                // per parameter set: b0' | s | o'
-    static constexpr int U_OFF = NSTAGE * STAGE_BYTES;       // second column half of the residual stream: [NH/4][128] float4
-    static constexpr int P_OFF = U_OFF + NH * 128 * 4;
+    static constexpr int U_OFF = NSTAGE * STAGE_BYTES;       // second column half of the residual stream: [NH/4][128] float4;
+                                                             // in the final layer 4 KB per epilogue warp (transpose patch / parked values)
+    static constexpr int U_BYTES = (NH * 128 * 4 > EPI_WARPS * 4096) ? NH * 128 * 4 : EPI_WARPS * 4096;
+    static constexpr int P_OFF = U_OFF + U_BYTES;
     static constexpr int BAR_OFF = P_OFF + 2 * PSET_FLOATS * 4;
     static constexpr int MB_OFF = BAR_OFF + 512;             // fused epilogue mailboxes: 8 pair groups x 2 x 5 x 32 floats
     static constexpr int TOTAL = MB_OFF + 8 * 320 * 4;
@@ -312,11 +317,12 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_wempty + 8 * i, 1);
         }
         for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
-        for (int i = 0; i < 6; ++i) mbar_init(bar_rdy + 8 * i, (i >= RDY_F0 && g.fused) ? EPI_WARPS / 2 : EPI_WARPS);
+        for (int i = 0; i < 6; ++i)
+            mbar_init(bar_rdy + 8 * i, i < RDY_F0 ? S::BLK_WARPS : (g.fused ? EPI_WARPS / 2 : EPI_WARPS));
         mbar_init(bar_free1, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
-            mbar_init(bar_pempty + 8 * i, EPI_WARPS);
+            mbar_init(bar_pempty + 8 * i, S::BLK_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -556,6 +562,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         uint32_t v[16];
         float u0[32];                            // residual stream, column half 0 (half 1 lives in shared memory)
 
+        if (cgp < NH / 32) {   // warps of the H-wide stages (all of them at H = 256)
         // ---- features -> R1 (A operand of GEMM0), piece by piece ----
         for (int p = 0; p < g.n_pieces; ++p) {
             if (p > 0) {
@@ -693,6 +700,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             release_pset(b + 1);
         }
+        }   // H-wide stages
 #undef FS_EPI_RESIDUAL
         // ---- fused final layer: one chunk = the 3nb+1 spline parameters of ONE transformed coordinate for the 128
         //      rows of the tile, laid out [widths | pad to 32 | heights | pad to 64 | derivatives]; theta never leaves
@@ -987,8 +995,8 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     const int NP = f->N * f->P;
     const int FCH = 128;                                   // final-layer chunk width (TcCfg::FCH)
     P->n_chunks = (NP + FCH - 1) / FCH;
-    // fused spline epilogue: split-schedule kernel only, derivatives 0..nb must fit columns 64..127
-    P->chn = (H == 256 && f->nb <= 32) ? (64 + f->nb + 1 + 15) / 16 * 16 : 0;
+    // fused spline epilogue: derivatives 0..nb must fit columns 64..127
+    P->chn = (f->nb <= 32) ? (64 + f->nb + 1 + 15) / 16 * 16 : 0;
     P->smem_bytes = (H == 256 ? TcCfg<256>::TOTAL : TcCfg<128>::TOTAL) + 1024;
     if ((int)P->smem_bytes > smem_max) { delete P; return FS_OK; }
     const int KT = H / TC_KB;

@@ -183,7 +183,7 @@ int fs_flow_conditioner(fs_flow* flow, int layer, const float* features, int row
                         void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* Conditioner + conditional spline of the transformed half of one coupling layer in ONE kernel (tensor-core path
- * with the fused spline epilogue; FS_ERR_UNSUPPORTED for flow shapes without it: H != 256 or nb > 32):
+ * with the fused spline epilogue; FS_ERR_UNSUPPORTED for flow shapes without it: H not 128 / 256 or nb > 32):
  * PiecewiseRationalQuadraticCoupling forward / inverse on the transformed features
  * (NF/normflows/flows/neural_spline/coupling.py:86-102 / 126-135).  direction 1 = density direction, 2 = sampling.
  * features [rows, 2N] as for fs_flow_conditioner; xin [rows, D] is the layer input, the transformed half of
