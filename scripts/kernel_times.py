@@ -1,4 +1,5 @@
-"""Per-kernel device time of one flow pass (torch.profiler / CUPTI), for a bench workload."""
+"""Per-kernel device time of one flow pass (torch.profiler / CUPTI), for a bench workload.
+usage: kernel_times.py [workload] [rows] [tf32|fp32] [density|sampling]"""
 import sys
 
 import numpy as np
@@ -16,10 +17,13 @@ bound = float(np.float32(np.sqrt(w["n"] / w["rho"]))) / 2
 m = bench.build_flow(NF, w, bound, "cuda").cuda().eval()
 m.precision = sys.argv[3] if len(sys.argv) > 3 else "tf32"
 x = (torch.rand(rows, 2 * w["n"], device="cuda") * 2 - 1) * bound
+direction = sys.argv[4] if len(sys.argv) > 4 else "density"      # or "sampling"
+z = m.q0(rows)
+run = (lambda: m.log_prob(x)) if direction == "density" else (lambda: m.forward(z))
 for _ in range(2):
-    m.log_prob(x)
+    run()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    m.log_prob(x)
+    run()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
