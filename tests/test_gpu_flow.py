@@ -209,3 +209,21 @@ def test_pack_follows_parameter_updates():
     assert torch.isfinite(c).all()
     with pytest.raises(ValueError):
         model.log_prob(torch.zeros(4, 5, device="cuda"))
+
+
+def test_empty_and_single_row_batches():
+    """Empty input (the reference's torch modules return empty tensors) and a single row (one partial tile)."""
+    torch.manual_seed(2)
+    n, bound = 16, 6.0
+    model = _build(n, 2, 1, 256, 32, bound, device="cuda").cuda().eval()
+    for prec in _precisions(model):
+        model.precision = prec
+        e = model.log_prob(torch.empty(0, 2 * n, device="cuda"))
+        assert e.shape == (0,)
+        z, ld = model.forward_and_log_det(torch.empty(0, 2 * n, device="cuda"))
+        assert z.shape == (0, 2 * n) and ld.shape == (0,)
+        x1 = (torch.rand(1, 2 * n, device="cuda") * 2 - 1) * bound
+        x5 = torch.cat([x1, (torch.rand(4, 2 * n, device="cuda") * 2 - 1) * bound])
+        a, b = model.log_prob(x1), model.log_prob(x5)
+        assert a.shape == (1,) and torch.isfinite(a).all()
+        assert abs(a[0].item() - b[0].item()) <= 1e-6 * abs(b[0].item())      # rows are independent
