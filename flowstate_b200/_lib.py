@@ -63,6 +63,7 @@ _PROTOS = {
     "fs_flow_conditioner": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, C.c_int, _P]),
     "fs_classify_wells": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     "fs_pair_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "fs_flow_has_tensor_path": (C.c_int, [_P]),
     "fs_flow_coupling": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_inverse": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),
     "fs_flow_forward": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),

@@ -757,6 +757,8 @@ extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features,
     return conditioner_fp32(f, layer, features, rows, w.h, w.t, theta, s);
 }
 
+extern "C" int fs_flow_has_tensor_path(const fs_flow* f) { return (f && f->tc) ? 1 : 0; }
+
 extern "C" int fs_flow_coupling(fs_flow* f, int layer, int direction, const float* features, const float* xin,
                                 float* xout, float* logdet, int rows, int* nan_flag, void* stream) {
     if (!f || !features || !xin || !xout || rows < 0 || layer < 0 || layer >= f->K || (direction != 1 && direction != 2)) {

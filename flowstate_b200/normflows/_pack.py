@@ -50,7 +50,7 @@ class FlowPack:
         self.nb = l0.num_bins
         self.n_blocks = len(l0.transform_net.blocks)
         self.bound = float(l0.tail_bound)
-        self.precision = "fp32"
+        self.precision = "auto"      # "auto": tensor cores when the flow shape has them | "fp32" | "tf32"
         self._sig = self._signature(layers)
         self._ws = {}
         self.launches = 0
@@ -130,6 +130,11 @@ class FlowPack:
     def matches(self, layers):
         return len(layers) == self.K and self._signature(layers) == self._sig
 
+    def resolved_precision(self):
+        if self.precision != "auto":
+            return self.precision
+        return "tf32" if _lib.lib().fs_flow_has_tensor_path(self._h) else "fp32"
+
     # -- calls ------------------------------------------------------------
     def _workspace(self, B, prec):
         # one buffer per (batch, precision, path, stream): passes issued on different streams may overlap
@@ -153,7 +158,7 @@ class FlowPack:
         """Density direction over all K layers: returns (z, logdet, logq or None)."""
         x = self._prep(x)
         B = x.shape[0]
-        prec = _PREC[self.precision]
+        prec = _PREC[self.resolved_precision()]
         z = torch.empty_like(x)
         ld = torch.empty(B, dtype=torch.float32, device=x.device)
         lq = torch.empty(B, dtype=torch.float32, device=x.device) if want_logq else None
@@ -170,7 +175,7 @@ class FlowPack:
         """Sampling direction over all K layers: returns (x, logdet or None)."""
         z = self._prep(z)
         B = z.shape[0]
-        prec = _PREC[self.precision]
+        prec = _PREC[self.resolved_precision()]
         x = torch.empty_like(z)
         ld = torch.empty(B, dtype=torch.float32, device=z.device) if want_logdet else None
         nan = torch.zeros(1, dtype=torch.int32, device=z.device)
@@ -186,7 +191,7 @@ class FlowPack:
         """Conditioner (ResidualNet, eval mode) of one layer on periodic features [rows, 2N] -> theta."""
         features = _lib.require_cuda(features, "features")
         rows = features.shape[0]
-        prec = _PREC[self.precision]
+        prec = _PREC[self.resolved_precision()]
         theta = torch.empty(rows, self.N * (3 * self.nb + 1), dtype=torch.float32, device=features.device)
         ws = self._workspace(rows, prec)
         _lib.check(_lib.lib().fs_flow_conditioner(self._h, int(layer), _lib.ptr(features), rows, _lib.ptr(theta),

@@ -19,7 +19,9 @@ class NormalizingFlow(nn.Module):
         self.flows = nn.ModuleList(flows)
         self.p = p
         self._pack = None
-        self.precision = "fp32"      # "fp32" (CUDA cores) | "tf32" (tcgen05 tensor cores)
+        # "auto": tcgen05 tensor cores (TF32 operands, FP32 accumulation; log-density within ~5e-6 of float64)
+        # when the flow shape has the tensor path, else the FP32 CUDA-core path | "fp32" | "tf32"
+        self.precision = "auto"
 
     # -- packing ----------------------------------------------------------
     def _fusable(self):

@@ -182,6 +182,10 @@ size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
 int fs_flow_conditioner(fs_flow* flow, int layer, const float* features, int rows, float* theta,
                         void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* 1 when the packed flow has the tensor-core conditioner (sm_100, H = 128 / 256, at least one residual block), so
+ * FS_PREC_TF32 can be passed to the calls below; 0 otherwise (FS_PREC_FP32 only). */
+int fs_flow_has_tensor_path(const fs_flow* flow);
+
 /* Conditioner + conditional spline of the transformed half of one coupling layer in ONE kernel (tensor-core path
  * with the fused spline epilogue; FS_ERR_UNSUPPORTED for flow shapes without it: H not 128 / 256 or nb > 32):
  * PiecewiseRationalQuadraticCoupling forward / inverse on the transformed features
