@@ -74,6 +74,41 @@ __device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, f
     }
 }
 
+// Fast-math variants for the tensor-core epilogue (MUFU-based exp / log / reciprocal: ~1e-6 relative, far inside
+// the TF32 path's error budget; the FP32 path keeps the accurate ones above).
+__device__ __forceinline__ float softplus_fast(float x) {
+    return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x)));
+}
+__device__ __forceinline__ void rq_eval_fast(float x, float xk, float wk, float yk, float hk, float dk, float dk1,
+                                             bool inverse, float& y, float& ld) {
+    const float sk = __fdividef(hk, wk);
+    const float t = dk + dk1 - 2.0f * sk;
+    if (inverse) {
+        const float dy = x - yk;
+        const float a = dy * t + hk * (sk - dk);
+        const float b = hk * dk - dy * t;
+        const float c = -sk * dy;
+        const float disc = fabsf(b * b - 4.0f * a * c);
+        const float root = __fdividef(2.0f * c, -b - sqrtf(disc));
+        y = root * wk + xk;
+        const float tt = root * (1.0f - root);
+        const float den = sk + t * tt;
+        const float omr = 1.0f - root;
+        const float num = (sk * sk) * (dk1 * (root * root) + 2.0f * sk * tt + dk * (omr * omr));
+        ld = -__logf(__fdividef(num, den * den));
+    } else {
+        const float th = __fdividef(x - xk, wk);
+        const float tt = th * (1.0f - th);
+        const float num = hk * (sk * (th * th) + dk * tt);
+        const float den = sk + t * tt;
+        const float rden = __frcp_rn(den);
+        y = yk + num * rden;
+        const float omt = 1.0f - th;
+        const float dnum = (sk * sk) * (dk1 * (th * th) + 2.0f * sk * tt + dk * (omt * omt));
+        ld = __logf(dnum * rden * rden);
+    }
+}
+
 // final-layer rows/bias permuted to parameter-major order (row k*N + j), see flow.cu
 void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b);
 // tensor-core path (flow_tc.cu)

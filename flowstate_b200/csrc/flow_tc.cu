@@ -19,6 +19,7 @@
 //                  by TMA, mbarriers.
 //   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4..: epilogue (warp w touches TMEM
 //                  lanes 32*(w%4)..).
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -42,8 +43,9 @@ struct TcLayer {
     float* b1;         // unused (folded)
     float* b_final;    // [n_chunks * 128]  b_f + W_f c
     float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
-    float* wfused;     // fused-spline final layer: per coordinate, KT/KPS stages of KPS k-tiles of a chn-row chunk
-    float* b_fused;    // [N][chn] (+ 32 floats of padding)
+    void* wfused;      // fused-spline final layer, FP16 operands: per coordinate (H/64)/KPS stages of KPS tiles of
+                       // [chn rows x 64 k] halves (half the bytes and twice the MMA rate of TF32, same 11-bit significand)
+    float* b_fused;    // [N][chn] (+ 32 floats of padding), folded with the FP16-rounded weights
 };
 
 struct TcPack {
@@ -191,6 +193,26 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// two consecutive K elements in one 32-bit TMEM column: the lower half holds the even one
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -335,6 +357,12 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // final-layer TMEM map.  theta path (TF32): A = u in R0, accumulators in R1.  Fused path (FP16 operands): u is handed
+    // over as packed halves in a16 (H/2 columns), the accumulators take the region the last residual epilogue has drained.
+    const bool f16mode = g.fused != 0;
+    const uint32_t fin0 = f16mode ? (H == 256 ? 0u : 128u) : (uint32_t)S::FIN0;
+    const uint32_t fin1 = f16mode ? (H == 256 ? 128u : 256u) : (uint32_t)S::FIN1;
+    const uint32_t a16 = (H == 256) ? 256u : 384u;
 
     if (warp < 4) {
         if (warp == 0) {
@@ -377,9 +405,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 if (b >= 1) load_pset(b + 1);
                 stream(2ull * KT, S::STAGE_BYTES);
             }
-            if (g.fused) {                                                        // final layer
+            if (g.fused) {                                                        // final layer, FP16 tiles of 64 k
                 src = (const uint8_t*)g.L.wfused;
-                stream((unsigned long long)g.N * (KT / S::KPS), (uint32_t)(S::KPS * g.chn * 128));
+                stream((unsigned long long)g.N * ((H / 64) / S::KPS), (uint32_t)(S::KPS * g.chn * 128));
             } else {
                 stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
             }
@@ -389,9 +417,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
             const uint32_t idesc_blk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
             const uint32_t idesc_fin = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
-            // fused final layer: chunk of g.chn weight rows (one coordinate's spline parameters)
-            const uint32_t idesc_fus = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.chn >> 3) << 17) | (8u << 24);
+            // fused final layer: chunk of g.chn weight rows (one coordinate's spline parameters), FP16 operands:
+            // D = F32, A = B = F16 (format 0), K = 16 per instruction
+            const uint32_t idesc_f16 = (1u << 4) | ((uint32_t)(g.chn >> 3) << 17) | (8u << 24);
             const uint32_t fus_tile = (uint32_t)g.chn * 128;
+            const bool fin16 = g.fused != 0;
             uint32_t stage = 0, wphase = 0;
             uint32_t ph_rdy = 0;       // parity to wait for, per rdy barrier
             long long w_ready = 0, w_weights = 0, t_issue = 0;
@@ -438,14 +468,24 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                                               idesc_blk, (first && i == 0 && j == 0) ? 0u : 1u);
                             } else {
                                 const uint32_t tile = fus ? fus_tile : (uint32_t)(S::FCH * 128);
-                                const uint32_t idesc = fus ? idesc_fus : idesc_fin;
+                                const uint32_t idesc = idesc_fin;
+                                if (fus) {                   // a 128-byte row is 64 halves: 4 MMAs of K = 16, 8 packed columns each
 #pragma unroll
-                                for (int kk = 0; kk < S::KPS; ++kk)
+                                    for (int kk = 0; kk < S::KPS; ++kk)
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-                                        tc_mma_ts(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
-                                                  desc(kk * tile + 32 * j), idesc,
-                                                  (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
+                                        for (int j = 0; j < 4; ++j)
+                                            tc_mma_ts_f16(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
+                                                          desc(kk * tile + 32 * j), idesc_f16,
+                                                          (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
+                                } else {
+#pragma unroll
+                                    for (int kk = 0; kk < S::KPS; ++kk)
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            tc_mma_ts(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
+                                                      desc(kk * tile + 32 * j), idesc,
+                                                      (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
+                                }
                             }
                             tc_commit(bar_wempty + 8 * st[i]);
                         }
@@ -514,10 +554,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             for (int c = 0; c < n_final; ++c) {
                 const int f = c & 1;
                 if (c >= 2) wait_rdy(RDY_F0 + f);              // epilogue drained chunk c-2
-                const uint32_t dcol = f ? S::FIN1 : S::FIN0;
-                constexpr int SPC = KT / S::KPS;               // stages per chunk
+                const uint32_t dcol = f ? fin1 : fin0;
+                const int SPC = (fin16 ? H / 64 : KT) / S::KPS;   // stages per chunk
                 for (int sg = 0; sg < SPC; sg += S::GROUP)
-                    issue(dcol, sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true, g.fused != 0);
+                    issue(dcol, (fin16 ? a16 : 0u) + sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true,
+                          g.fused != 0);
                 commit(bar_full + 8 * (FULL_F0 + f));
             }
             if (dbg && lane == 0) {
@@ -633,12 +674,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
                     v[4 * i4] = relu_tf32(uu.x); v[4 * i4 + 1] = relu_tf32(uu.y);                              \
                     v[4 * i4 + 2] = relu_tf32(uu.z); v[4 * i4 + 3] = relu_tf32(uu.w);                          \
+                } else if (f16mode) {                                                                          \
+                    v[2 * i4] = pack_f16x2(uu.x, uu.y); v[2 * i4 + 1] = pack_f16x2(uu.z, uu.w);                \
                 } else {                                                                                       \
                     v[4 * i4] = round_tf32(uu.x); v[4 * i4 + 1] = round_tf32(uu.y);                            \
                     v[4 * i4 + 2] = round_tf32(uu.z); v[4 * i4 + 3] = round_tf32(uu.w);                        \
                 }                                                                                              \
             }                                                                                                  \
-            tc_st16(lane_addr + col + 16 * sub, v);                                                            \
+            if (!(HAS_NEXT) && f16mode) tc_st8(lane_addr + a16 + ((col + 16 * sub) >> 1), v);                  \
+            else tc_st16(lane_addr + col + 16 * sub, v);                                                       \
         }                                                                                                      \
         tc_wait_st();                                                                                          \
         signal_rdy(RDY_R0H0 + (HF));                                                                           \
@@ -730,7 +774,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             bool bad = false;
             auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * pair) : "memory"); };
             auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
-            const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
+            const uint32_t fcol = pair ? fin1 : fin0;
             for (int c = pair; c < g.N; c += 2) {
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 const int ft = __ldg(g.trf + c);
@@ -803,14 +847,32 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
                     const float rg = sum * rgnum;
                     const float t0 = (x + bound) * r2b * rg, dt = -kMinW * rg;
-                    int sel = 0;
-                    float s0 = 0.f, s1 = e[0];                      // S[sel-1], S[sel]
+                    // Two-level search in registers (knot conditions are monotone: true up to the bin): pick the block of
+                    // 8 bins from the knots 8, 16, 24, copy that block's prefix sums (static indices only), scan it.
+                    auto hit = [&](int i, float s_prev) { return i < nb && s_prev <= __fmaf_rn((float)i, dt, t0); };
+                    int blk8 = 0;
+                    blk8 += hit(8, e[7]) ? 1 : 0;
+                    blk8 += hit(16, e[15]) ? 1 : 0;
+                    blk8 += hit(24, e[23]) ? 1 : 0;
+                    float w9[9];                                    // S[8 blk8 - 1 .. 8 blk8 + 7]
+                    w9[0] = 0.f;
 #pragma unroll
-                    for (int i = 1; i < 32; ++i)
-                        if (i < nb && e[i - 1] <= __fmaf_rn((float)i, dt, t0)) {
-                            sel = i;
-                            s0 = e[i - 1];
-                            s1 = e[i];
+                    for (int i = 0; i < 8; ++i) w9[i + 1] = e[i];
+#pragma unroll
+                    for (int bk = 1; bk < 4; ++bk)
+                        if (blk8 == bk) {
+#pragma unroll
+                            for (int i = 0; i < 9; ++i) w9[i] = e[8 * bk - 1 + i];
+                        }
+                    const int base8 = 8 * blk8;
+                    int sel = base8;
+                    float s0 = w9[0], s1 = w9[1];                   // S[sel-1], S[sel]
+#pragma unroll
+                    for (int i = 1; i < 8; ++i)
+                        if (base8 + i < nb && w9[i] <= __fmaf_rn((float)(base8 + i), dt, t0)) {
+                            sel = base8 + i;
+                            s0 = w9[i];
+                            s1 = w9[i + 1];
                         }
                     const float bd0 = __ldg(bch + 64 + sel), bd1 = __ldg(bch + 65 + sel);
                     const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
@@ -821,8 +883,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     mb[0] = __int_as_float(sel);
                     mb[32] = left;
                     mb[64] = right - left;
-                    mb[96] = kMinD + softplus_t(dk);
-                    mb[128] = kMinD + softplus_t(dk1);
+                    mb[96] = kMinD + softplus_fast(dk);
+                    mb[128] = kMinD + softplus_fast(dk1);
                     if (dbg_me) t_f3 += clock64() - t_m2;
                     pair_sync();
                 } else {
@@ -839,8 +901,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     const float aL = mb[32], aW = mb[64];
                     float y = x, ld = 0.f;
                     if (x >= -bound && x <= bound) {
-                        if (inv) rq_eval(x, left, right - left, aL, aW, mb[96], mb[128], true, y, ld);
-                        else rq_eval(x, aL, aW, left, right - left, mb[96], mb[128], false, y, ld);
+                        if (inv) rq_eval_fast(x, left, right - left, aL, aW, mb[96], mb[128], true, y, ld);
+                        else rq_eval_fast(x, aL, aW, left, right - left, mb[96], mb[128], false, y, ld);
                     }
                     if (row_ok) {
                         g.xout[(size_t)grow * g.D + (inv ? ft : (ft + hD) % g.D)] = y;
@@ -951,6 +1013,27 @@ static inline float tf32_round(float x) {
 
 // appends the tile rows [n0, n0+ROWS) x cols [k0, k0+32) of W [n_rows, n_cols] (row-major) in the
 // SWIZZLE_128B K-major shared-memory image: row i at i*128 bytes, its 16-byte chunk c at (c ^ (i & 7)).
+static float half_round(float x) { return __half2float(__float2half_rn(x)); }
+
+// [ROWS x 64] FP16 tile, K-major, 128-byte swizzle (16-byte chunk c of row i at chunk c ^ (i & 7))
+static void append_tile16(std::vector<uint16_t>& out, const float* W, int n_rows, int n_cols, int k0, int ROWS) {
+    const size_t base = out.size();
+    out.resize(base + (size_t)ROWS * 64, 0);
+    for (int i = 0; i < ROWS && i < n_rows; ++i)
+        for (int c = 0; c < 8; ++c) {
+            const int pc = c ^ (i & 7);
+            for (int e = 0; e < 8; ++e) {
+                const int k = k0 + 8 * c + e;
+                if (k < n_cols) {
+                    const __half h = __float2half_rn(W[(size_t)i * n_cols + k]);
+                    uint16_t bits;
+                    memcpy(&bits, &h, 2);
+                    out[base + (size_t)i * 64 + pc * 8 + e] = bits;
+                }
+            }
+        }
+}
+
 static void append_tile(std::vector<float>& out, const float* W, int n_rows, int n_cols, int n0, int k0, int ROWS) {
     const size_t base = out.size();
     out.resize(base + (size_t)ROWS * 32, 0.f);
@@ -1056,7 +1139,8 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         // Fused-spline final layer (H = 256, nb <= 32): chunk j = the parameters of transformed coordinate j in the
         // order [widths | pad to 32 | heights | pad to 64 | derivatives | pad to chn]; rows come from the
         // reference's coordinate-major final layer (row j*P + index, coupling.py:166).
-        std::vector<float> fstream, bfused;
+        std::vector<float> bfused;
+        std::vector<uint16_t> fstream16;
         std::vector<int> frow;                                  // chunk column -> parameter index (or -1)
         if (P->chn) {
             const int chn = P->chn, nb = f->nb, Pp = f->P;
@@ -1064,13 +1148,13 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             for (int k = 0; k < nb; ++k) { frow[k] = k; frow[32 + k] = nb + k; }
             for (int k = 0; k <= nb; ++k) frow[64 + k] = 2 * nb + k;
             std::vector<float> wc((size_t)chn * H);
-            fstream.reserve((size_t)f->N * chn * H);
+            fstream16.reserve((size_t)f->N * chn * H);
             for (int j = 0; j < f->N; ++j) {
                 std::fill(wc.begin(), wc.end(), 0.f);
                 for (int cidx = 0; cidx < chn; ++cidx)
                     if (frow[cidx] >= 0)
                         memcpy(&wc[(size_t)cidx * H], p->final_w + ((size_t)j * Pp + frow[cidx]) * H, sizeof(float) * H);
-                for (int kt = 0; kt < KT; ++kt) append_tile(fstream, wc.data(), chn, H, 0, kt * TC_KB, chn);
+                for (int kt = 0; kt < H / 64; ++kt) append_tile16(fstream16, wc.data(), chn, H, kt * 64, chn);
             }
         }
         TcLayer& L = P->layers[li];
@@ -1100,7 +1184,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                     const size_t row = (size_t)j * Pp + frow[cidx];
                     double acc = (double)p->final_b[row];
                     const float* wr = p->final_w + row * H;
-                    for (int k = 0; k < H; ++k) acc += (double)tf32_round(wr[k]) * c[k];
+                    for (int k = 0; k < H; ++k) acc += (double)half_round(wr[k]) * c[k];
                     bfused[(size_t)j * chn + cidx] = (float)acc;
                 }
         }
@@ -1121,8 +1205,16 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         if (!r) r = tc_upload(f, bfin, &L.b_final);
         L.wfused = nullptr;
         L.b_fused = nullptr;
-        if (!r && P->chn) r = tc_upload(f, fstream, &L.wfused);
         if (!r && P->chn) r = tc_upload(f, bfused, &L.b_fused);
+        if (!r && P->chn) {
+            void* d16 = nullptr;
+            r = cuda_check(cudaMalloc(&d16, fstream16.size() * 2), "cudaMalloc");
+            if (!r) {
+                f->allocs.push_back(d16);
+                r = cuda_check(cudaMemcpy(d16, fstream16.data(), fstream16.size() * 2, cudaMemcpyHostToDevice), "cudaMemcpy");
+                L.wfused = d16;
+            }
+        }
         L.b_init = nullptr;
         L.b1 = nullptr;
         if (r) { delete P; return r; }
