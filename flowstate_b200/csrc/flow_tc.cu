@@ -357,12 +357,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    // final-layer TMEM map.  theta path (TF32): A = u in R0, accumulators in R1.  Fused path (FP16 operands): u is handed
-    // over as packed halves in a16 (H/2 columns), the accumulators take the region the last residual epilogue has drained.
-    const bool f16mode = g.fused != 0;
-    const uint32_t fin0 = f16mode ? (H == 256 ? 0u : 128u) : (uint32_t)S::FIN0;
-    const uint32_t fin1 = f16mode ? (H == 256 ? 128u : 256u) : (uint32_t)S::FIN1;
-    const uint32_t a16 = (H == 256) ? 256u : 384u;
+    const bool f16mode = g.fused != 0;   // fused final layer: u is handed over as packed halves like every block operand
 
     if (warp < 4) {
         if (warp == 0) {
@@ -403,7 +398,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             stream((unsigned long long)(g.Kp0 / TC_KB), S::STAGE_BYTES);          // GEMM0
             for (int b = 0; b < g.n_blocks; ++b) {
                 if (b >= 1) load_pset(b + 1);
-                stream(2ull * KT, S::STAGE_BYTES);
+                stream(2ull * (H / 64), S::STAGE_BYTES);           // two GEMMs of H/64 FP16 stages
             }
             if (g.fused) {                                                        // final layer, FP16 tiles of 64 k
                 src = (const uint8_t*)g.L.wfused;
@@ -421,7 +416,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // D = F32, A = B = F16 (format 0), K = 16 per instruction
             const uint32_t idesc_f16 = (1u << 4) | ((uint32_t)(g.chn >> 3) << 17) | (8u << 24);
             const uint32_t fus_tile = (uint32_t)g.chn * 128;
-            const bool fin16 = g.fused != 0;
+            // residual blocks with FP16 operands: N = H and N = 128
+            const uint32_t idesc_blk16 = (1u << 4) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
+            const uint32_t idesc_q16 = (1u << 4) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
             uint32_t stage = 0, wphase = 0;
             uint32_t ph_rdy = 0;       // parity to wait for, per rdy barrier
             long long w_ready = 0, w_weights = 0, t_issue = 0;
@@ -438,7 +435,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // Issues `n` weight stages (n <= GROUP): their full-barriers are waited for back to back, then all the
             // MMAs are queued at once.  Block GEMMs: one stage = one 32-wide k-tile of all H output columns
             // (4 MMAs of N = H).  Final layer: one stage = KPS consecutive k-tiles of a 128-column chunk.
-            auto issue = [&](uint32_t dcol, uint32_t acol, int n, bool first, bool fin, bool fus = false) {
+            // FP16 operands: a weight tile row is 64 halves = 4 MMAs of K = 16.  The epilogue thread that owns 32 features
+            // packs them into the first 16 of its own 32 TMEM columns (no thread ever writes a column another thread
+            // still has to read), so K-block j of a 64-feature tile sits at column 32 (j / 2) + 8 (j % 2).
+            auto issue = [&](uint32_t dcol, uint32_t acol, int n, bool first, bool fin, bool fus = false, bool f16 = false) {
                 uint32_t st[S::GROUP];
 #pragma unroll
                 for (int i = 0; i < S::GROUP; ++i) {
@@ -462,20 +462,28 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                                 return ((uint64_t)d0_hi << 32) | (uint64_t)(d0_lo + (byte_off >> 4));
                             };
                             if (!fin) {
+                                if (f16) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, desc(32 * j),
-                                              idesc_blk, (first && i == 0 && j == 0) ? 0u : 1u);
+                                    for (int j = 0; j < 4; ++j)
+                                        tc_mma_ts_f16(tmem + dcol, tmem + acol + 64 * i + 32 * (j >> 1) + 8 * (j & 1),
+                                                      desc(32 * j), idesc_blk16, (first && i == 0 && j == 0) ? 0u : 1u);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        tc_mma_ts(tmem + dcol, tmem + acol + 32 * i + 8 * j, desc(32 * j),
+                                                  idesc_blk, (first && i == 0 && j == 0) ? 0u : 1u);
+                                }
                             } else {
                                 const uint32_t tile = fus ? fus_tile : (uint32_t)(S::FCH * 128);
                                 const uint32_t idesc = idesc_fin;
-                                if (fus) {                   // a 128-byte row is 64 halves: 4 MMAs of K = 16, 8 packed columns each
+                                if (f16) {
 #pragma unroll
                                     for (int kk = 0; kk < S::KPS; ++kk)
 #pragma unroll
                                         for (int j = 0; j < 4; ++j)
-                                            tc_mma_ts_f16(tmem + dcol, tmem + acol + 32 * (i * S::KPS + kk) + 8 * j,
-                                                          desc(kk * tile + 32 * j), idesc_f16,
+                                            tc_mma_ts_f16(tmem + dcol,
+                                                          tmem + acol + 64 * (i * S::KPS + kk) + 32 * (j >> 1) + 8 * (j & 1),
+                                                          desc(kk * tile + 32 * j), fus ? idesc_f16 : idesc_q16,
                                                           (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
                                 } else {
 #pragma unroll
@@ -504,6 +512,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     issue(dcol, abase + kt * TC_KB, min(S::GROUP, ktiles - kt), fresh && kt == 0, false);
                 }
             };
+            // the same with FP16 operands: k-tiles of 64 features (64 TMEM columns of the operand region each)
+            auto gemm_blk16 = [&](uint32_t dcol, uint32_t abase, int rdy0) {
+                constexpr int KT16 = H / 64;
+                for (int kt = 0; kt < KT16; ++kt) {             // one stage per call: the half boundary may fall on any tile
+                    if (kt == 0) wait_rdy(rdy0);
+                    if (kt * 64 == NH) wait_rdy(rdy0 + 1);
+                    issue(dcol, abase + kt * 64, 1, kt == 0, false, false, true);
+                }
+            };
             // ---- GEMM0: features (R1) -> R0 ----
             for (int p = 0; p < g.n_pieces; ++p) {
                 const int kcols = min(H, g.Kp0 - p * H);
@@ -521,15 +538,16 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // so the epilogue starts on it while the tensor pipe finishes the other.  K-lo stages are k-tiles of all
             // H weight rows; K-hi stages hold KPS k-tiles of a 128-row weight chunk (the final layer's stage format).
             auto gemm_split = [&](uint32_t dcol, uint32_t abase, int rdy0, int full0) {
-                constexpr int SPQ = (KT / 2) / S::KPS;          // stages per quarter
+                constexpr int KT16 = H / 64;                    // k-tiles of 64 features (FP16 operands)
+                constexpr int SPQ = (KT16 / 2) / S::KPS;        // stages per quarter
                 wait_rdy(rdy0);
 #pragma unroll 1
-                for (int kt = 0; kt < KT / 2; ++kt) issue(dcol, abase + kt * TC_KB, 1, kt == 0, false);
+                for (int kt = 0; kt < KT16 / 2; ++kt) issue(dcol, abase + kt * 64, 1, kt == 0, false, false, true);
                 wait_rdy(rdy0 + 1);
 #pragma unroll 1
                 for (int nh = 0; nh < 2; ++nh) {
                     for (int sg = 0; sg < SPQ; ++sg)
-                        issue(dcol + nh * NH, abase + NH + sg * S::KPS * TC_KB, 1, false, true);
+                        issue(dcol + nh * NH, abase + NH + sg * S::KPS * 64, 1, false, true, false, true);
                     commit(bar_full + 8 * (full0 + nh));
                 }
             };
@@ -539,10 +557,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     gemm_split(H, 0, RDY_R0H0, FULL_R1H0);          // linear 0: A = R0 (a), D = R1
                     gemm_split(0, H, RDY_R1H0, FULL_R0H0);          // linear 1: A = R1 (relu t), D = R0
                 } else {
-                    gemm_blk(H, 0, RDY_R0H0, KT, true, true);
+                    gemm_blk16(H, 0, RDY_R0H0);
                     commit(bar_full + 8 * FULL_R1H0);
                     commit(bar_full + 8 * FULL_R1H1);
-                    gemm_blk(0, H, RDY_R1H0, KT, true, true);
+                    gemm_blk16(0, H, RDY_R1H0);
                     commit(bar_full + 8 * FULL_R0H0);
                     commit(bar_full + 8 * FULL_R0H1);
                 }
@@ -554,11 +572,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             for (int c = 0; c < n_final; ++c) {
                 const int f = c & 1;
                 if (c >= 2) wait_rdy(RDY_F0 + f);              // epilogue drained chunk c-2
-                const uint32_t dcol = f ? fin1 : fin0;
-                const int SPC = (fin16 ? H / 64 : KT) / S::KPS;   // stages per chunk
+                const uint32_t dcol = f ? S::FIN1 : S::FIN0;
+                const bool fus = g.fused != 0;
+                const int SPC = (fus ? H / 64 : KT) / S::KPS;   // stages per chunk
                 for (int sg = 0; sg < SPC; sg += S::GROUP)
-                    issue(dcol, (fin16 ? a16 : 0u) + sg * S::KPS * TC_KB, min(S::GROUP, SPC - sg), sg == 0, true,
-                          g.fused != 0);
+                    issue(dcol, sg * S::KPS * (fus ? 64 : TC_KB), min(S::GROUP, SPC - sg), sg == 0, true, fus, fus);
                 commit(bar_full + 8 * (FULL_F0 + f));
             }
             if (dbg && lane == 0) {
@@ -672,8 +690,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     ua = fma2(ua, pk2(sc.x, sc.y), pk2(of.x, of.y));                                           \
                     ub = fma2(ub, pk2(sc.z, sc.w), pk2(of.z, of.w));                                           \
                     upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
-                    v[4 * i4] = relu_tf32(uu.x); v[4 * i4 + 1] = relu_tf32(uu.y);                              \
-                    v[4 * i4 + 2] = relu_tf32(uu.z); v[4 * i4 + 3] = relu_tf32(uu.w);                          \
+                    v[2 * i4] = pack_f16x2(fmaxf(uu.x, 0.f), fmaxf(uu.y, 0.f));                                \
+                    v[2 * i4 + 1] = pack_f16x2(fmaxf(uu.z, 0.f), fmaxf(uu.w, 0.f));                            \
                 } else if (f16mode) {                                                                          \
                     v[2 * i4] = pack_f16x2(uu.x, uu.y); v[2 * i4 + 1] = pack_f16x2(uu.z, uu.w);                \
                 } else {                                                                                       \
@@ -681,7 +699,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     v[4 * i4 + 2] = round_tf32(uu.z); v[4 * i4 + 3] = round_tf32(uu.w);                        \
                 }                                                                                              \
             }                                                                                                  \
-            if (!(HAS_NEXT) && f16mode) tc_st8(lane_addr + a16 + ((col + 16 * sub) >> 1), v);                  \
+            /* packed halves go to the first 16 of this thread's own 32 columns; the theta path keeps TF32 u */ \
+            if ((HAS_NEXT) || f16mode) tc_st8(lane_addr + col + 8 * sub, v);                                   \
             else tc_st16(lane_addr + col + 16 * sub, v);                                                       \
         }                                                                                                      \
         tc_wait_st();                                                                                          \
@@ -716,12 +735,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         float t0, t1, t2, t3;
                         upk2(ta, t0, t1);
                         upk2(tb, t2, t3);
-                        v[4 * i4] = relu_tf32(t0);
-                        v[4 * i4 + 1] = relu_tf32(t1);
-                        v[4 * i4 + 2] = relu_tf32(t2);
-                        v[4 * i4 + 3] = relu_tf32(t3);
+                        v[2 * i4] = pack_f16x2(fmaxf(t0, 0.f), fmaxf(t1, 0.f));
+                        v[2 * i4 + 1] = pack_f16x2(fmaxf(t2, 0.f), fmaxf(t3, 0.f));
                     }
-                    tc_st16(lane_addr + H + col + 16 * sub, v);
+                    tc_st8(lane_addr + H + col + 8 * sub, v);
                 }
                 tc_wait_st();
                 signal_rdy(RDY_R1H0 + hf);
@@ -774,7 +791,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             bool bad = false;
             auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * pair) : "memory"); };
             auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
-            const uint32_t fcol = pair ? fin1 : fin0;
+            const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
             for (int c = pair; c < g.N; c += 2) {
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 const int ft = __ldg(g.trf + c);
@@ -1116,15 +1133,24 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             const int kcols = std::min(H, P->Kp0 - pc * H);
             for (int kt = 0; kt < kcols / TC_KB; ++kt) append_tile(stream, p->init_w, H, K0, 0, pc * H + kt * TC_KB, H);
         }
-        // H = 256 (split schedule, see gemm_split): K-lo k-tiles of all H rows, then (rows lo, K hi) and (rows hi, K hi)
-        // as stages of KPS k-tiles of a 128-row chunk
+        // Residual-block GEMMs: FP16 tiles of 64 k.  H = 256 (split schedule, see gemm_split): the two K-lo tiles of all
+        // H rows, then (rows lo, K hi) and (rows hi, K hi) as stages of KPS tiles of a 128-row chunk.  H = 128: the two
+        // tiles of all rows.
+        auto append16 = [&](const float* W, int rows, int k0) {
+            std::vector<uint16_t> t16;
+            append_tile16(t16, W, rows, H, k0, rows);
+            const size_t base = stream.size();
+            stream.resize(base + t16.size() / 2);
+            memcpy(&stream[base], t16.data(), t16.size() * 2);
+        };
         auto append_gemm = [&](const float* W) {
+            const int KT16 = H / 64;
             if (H == 256) {
-                for (int kt = 0; kt < KT / 2; ++kt) append_tile(stream, W, H, H, 0, kt * TC_KB, H);
+                for (int kt = 0; kt < KT16 / 2; ++kt) append16(W, H, kt * 64);
                 for (int nh = 0; nh < 2; ++nh)
-                    for (int kt = KT / 2; kt < KT; ++kt) append_tile(stream, W, H, H, nh * (H / 2), kt * TC_KB, H / 2);
+                    for (int kt = KT16 / 2; kt < KT16; ++kt) append16(W + (size_t)nh * (H / 2) * H, H / 2, kt * 64);
             } else {
-                for (int kt = 0; kt < KT; ++kt) append_tile(stream, W, H, H, 0, kt * TC_KB, H);
+                for (int kt = 0; kt < KT16; ++kt) append16(W, H, kt * 64);
             }
         };
         for (int b = 0; b < nB; ++b) {
