@@ -431,19 +431,22 @@ def main():
     # TF32 tensor peak = half the measured BF16 figure (same pipe, K=8 instead of 16 per instruction)
     tensor_peak = bf16 / 2.0
     peak_note = "%s bf16_tflops_sustained / 2 (tf32)" % peak_src
-    if fused:
-        # the fused kernel runs GEMM0 + the residual blocks in TF32 and the final layer with FP16 operands (BF16-rate
-        # pipe): the roofline of the launch is the flop-weighted harmonic blend of the two peaks
+    if prec == "tf32":
+        # tensor path: GEMM0 (features) has TF32 operands, every other GEMM FP16 operands (BF16-rate pipe); on the
+        # theta path (no fused epilogue) the final layer is TF32 too.  Roofline of the launch = flop-weighted harmonic
+        # blend of the two peaks.
+        f_gemm0 = 2.0 * 2 * w["n"] * w["H"]
         f_final = 2.0 * w["H"] * w["n"] * (3 * w["nb"] + 1)
-        f_tf32 = flops_per_sample_layer(w) - f_final
-        tensor_peak = (f_tf32 + f_final) / (f_tf32 / (bf16 / 2.0) + f_final / bf16)
-        peak_note = ("%s bf16_tflops_sustained: residual blocks at /2 (tf32 operands), final layer at the full figure "
-                     "(fp16 operands), flop-weighted harmonic blend" % peak_src)
+        f_tf32 = f_gemm0 + (0.0 if fused else f_final)
+        f_f16 = flops_per_sample_layer(w) - f_tf32
+        tensor_peak = (f_tf32 + f_f16) / (f_tf32 / (bf16 / 2.0) + f_f16 / bf16)
+        peak_note = ("%s bf16_tflops_sustained for the FP16-operand GEMMs, half of it for the TF32 ones, flop-weighted "
+                     "harmonic blend" % peak_src)
     achieved = flops_pass / (pass_ms * 1e-3) / 1e12
     traffic = None
     tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tj) and prec == "tf32":
-        # ncu dram bytes per launch of this kernel (captured at 4096 rows; weights dominate and do not scale with rows)
+        # ncu dram bytes per launch of this kernel at this row count (weights dominate)
         traffic = json.load(open(tj)).get("tc_conditioner_kernel<%d>%s@%s@%d" % (w["H"], "+spline" if fused else "",
                                                                                  args.workload, xin.shape[0]))
     steps_total = world * B * (w["local"] + 1) * args.steps
@@ -452,13 +455,13 @@ def main():
         "metric": "mh_chain_steps_per_s", "value": value, "unit": "chain-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if prec == "tf32" else "f32", "data": "synthetic",
+        "dtype": "f16" if prec == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": B, "particles": n,
                    "local_steps_per_round": w["local"],
                    "flow": {"K": w["K"], "blocks": w["blocks"], "H": w["H"], "bins": w["nb"], "sigma": w["sigma"]},
                    "rho": w["rho"], "rng": "philox",
-                   "conditioner": ("tf32 operands in the residual blocks, fp16 operands in the final layer, fp32 accumulation"
-                                   if fused else prec),
+                   "conditioner": ("tf32 operands in GEMM0, fp16 operands in the residual blocks and the final layer, fp32 "
+                                   "accumulation" if fused else prec),
                    "pipelining": "proposals of round r+1 sampled on a side stream during round r",
                    "l2": "inputs larger than L2: %.0f MB of flow weights streamed per pass"
                          % (sum(p.numel() for p in model.parameters()) * 4 / 1e6),
@@ -467,7 +470,7 @@ def main():
         "gpu_launches": launches, "clocks": clk, "phases_ms": phases,
         "e2e": {"value": steps_total / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "roofline": {"bound": "tensor", "kernel": (("tc_conditioner_kernel (tcgen05 kind::tf32, fused spline epilogue)" if fused else
+        "roofline": {"bound": "tensor", "kernel": (("tc_conditioner_kernel (tcgen05 kind::f16 / kind::tf32, fused spline epilogue)" if fused else
                                  "tc_conditioner_kernel (tcgen05 kind::tf32)") if prec == "tf32"
                                 else "linear_kernel chain (fp32)") + ", one coupling layer",
                      "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
