@@ -213,6 +213,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// the same with ReLU folded into the conversion (negative inputs and NaN become +0)
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -677,12 +683,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     u0[16 * sub + 4 * i4] = uu.x; u0[16 * sub + 4 * i4 + 1] = uu.y;                            \
                     u0[16 * sub + 4 * i4 + 2] = uu.z; u0[16 * sub + 4 * i4 + 3] = uu.w;                        \
                 } else {                                                                                       \
-                    float4* hp = us4 + (size_t)(cgp * 8 + sub * 4 + i4) * 128 + r;                             \
                     if (!(INIT)) {                                                                             \
                         ua = add2(ua, pk2(hh[i4].x, hh[i4].y)); ub = add2(ub, pk2(hh[i4].z, hh[i4].w));        \
                     }                                                                                          \
                     upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
-                    *hp = uu;                                                                                  \
+                    hh[i4] = uu;   /* stored after the loop: a store here would fence the parameter loads below */ \
                 }                                                                                              \
                 if (HAS_NEXT) {                                                                                \
                     const float4 sc = *reinterpret_cast<const float4*>((PRM) + H + col + 16 * sub + 4 * i4);   \
@@ -690,14 +695,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     ua = fma2(ua, pk2(sc.x, sc.y), pk2(of.x, of.y));                                           \
                     ub = fma2(ub, pk2(sc.z, sc.w), pk2(of.z, of.w));                                           \
                     upk2(ua, uu.x, uu.y); upk2(ub, uu.z, uu.w);                                                \
-                    v[2 * i4] = pack_f16x2(fmaxf(uu.x, 0.f), fmaxf(uu.y, 0.f));                                \
-                    v[2 * i4 + 1] = pack_f16x2(fmaxf(uu.z, 0.f), fmaxf(uu.w, 0.f));                            \
+                    v[2 * i4] = pack_relu_f16x2(uu.x, uu.y);                                                   \
+                    v[2 * i4 + 1] = pack_relu_f16x2(uu.z, uu.w);                                               \
                 } else if (f16mode) {                                                                          \
                     v[2 * i4] = pack_f16x2(uu.x, uu.y); v[2 * i4 + 1] = pack_f16x2(uu.z, uu.w);                \
                 } else {                                                                                       \
                     v[4 * i4] = round_tf32(uu.x); v[4 * i4 + 1] = round_tf32(uu.y);                            \
                     v[4 * i4 + 2] = round_tf32(uu.z); v[4 * i4 + 3] = round_tf32(uu.w);                        \
                 }                                                                                              \
+            }                                                                                                  \
+            if ((HF) == 1) {                                                                                   \
+                _Pragma("unroll") for (int i4 = 0; i4 < 4; ++i4)                                               \
+                    us4[(size_t)(cgp * 8 + sub * 4 + i4) * 128 + r] = hh[i4];                                  \
             }                                                                                                  \
             /* packed halves go to the first 16 of this thread's own 32 columns; the theta path keeps TF32 u */ \
             if ((HAS_NEXT) || f16mode) tc_st8(lane_addr + col + 8 * sub, v);                                   \
@@ -735,8 +744,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         float t0, t1, t2, t3;
                         upk2(ta, t0, t1);
                         upk2(tb, t2, t3);
-                        v[2 * i4] = pack_f16x2(fmaxf(t0, 0.f), fmaxf(t1, 0.f));
-                        v[2 * i4 + 1] = pack_f16x2(fmaxf(t2, 0.f), fmaxf(t3, 0.f));
+                        v[2 * i4] = pack_relu_f16x2(t0, t1);
+                        v[2 * i4 + 1] = pack_relu_f16x2(t2, t3);
                     }
                     tc_st8(lane_addr + H + col + 8 * sub, v);
                 }
