@@ -1,24 +1,34 @@
-// Tensor-core conditioner (FS_PREC_TF32): the residual conditioner of one coupling layer
-// (NF/normflows/nets/resnet.py:7-104 in eval mode) for a 128-row tile per CTA, hand-written for
-// sm_100a: tcgen05.mma kind::tf32 with FP32 accumulators in TMEM, activations fed back to the tensor
-// core as the A operand *in TMEM* (the accumulator layout lane = row, column = feature is exactly the
-// A-operand layout, so BatchNorm/ReLU/bias run register-side between tcgen05.ld and tcgen05.st and
-// activations never touch shared memory), weights streamed from L2/HBM by TMA bulk copies
-// (cp.async.bulk) of tiles that fs_flow_create laid out in the 128B-swizzled K-major image the UMMA
-// shared-memory descriptor expects.
+// Tensor-core conditioner (FS_PREC_TF32 selects this path): the residual conditioner of one coupling layer
+// (NF/normflows/nets/resnet.py:7-104 in eval mode) and, on the fused path, the conditional spline of the layer
+// (flows/neural_spline/coupling.py:86-135, utils/splines.py:84-222) for a 128-row tile per CTA, hand-written for
+// sm_100a: tcgen05.mma with FP32 accumulators in TMEM, activations fed back to the tensor core as the A operand
+// *in TMEM* (TS mode: lane = row, so BatchNorm / ReLU / bias run register-side between tcgen05.ld and tcgen05.st and
+// activations never touch shared memory), weights streamed from L2/HBM by TMA bulk copies (cp.async.bulk) of tiles that
+// fs_flow_create laid out in the 128B-swizzled K-major image the UMMA shared-memory descriptor expects.
 //
-//   TMEM columns   R0 = [0, H)   : GEMM0 / linear-1 accumulator  -> after the epilogue: A operand `a`
-//                  R1 = [H, 2H)  : features / linear-0 accumulator -> after the epilogue: A operand relu(t)
-//                  final layer   : 128-column accumulators ping-pong (halves of R1 for H = 256, R1 / R2 for H = 128)
-//   one MMA = M 128 x N H x K 8 (N = 128 for the final layer); a region is handed to the MMA warp in two
-//   column halves, so linear 1 starts on the first half of relu(t) while the epilogue still writes the second.
-//   residual       the stream u (biases folded out) belongs to the epilogue threads: thread (quadrant q, column
-//                  group c) owns u[row 32q+lane][half*NH + 32c .. +32): half 0 in registers, half 1 in shared memory.
-//   shared memory  NSTAGE weight stages of H x 32 tf32 (H*128 bytes, = 4 MMAs, 512 clk of tensor pipe at
-//                  H = 256), u half 1, two parameter sets (BatchNorm scale/offset, folded bias) prefetched
-//                  by TMA, mbarriers.
-//   warps          0: TMA producer   1: MMA issuer   2: TMEM allocator   4..: epilogue (warp w touches TMEM
-//                  lanes 32*(w%4)..).
+//   operands       GEMM0 (periodic features -> H): kind::tf32.  Every later GEMM: kind::f16 with FP16 operands (same
+//                  11-bit significand as TF32, half the bytes, K = 16 per instruction = twice the rate).  An epilogue
+//                  thread packs the 32 features it owns into the first 16 of its own 32 accumulator columns
+//                  (cvt.rn[.relu].f16x2.f32), so the in-place hand-over never touches a column another thread still has
+//                  to read; K-block j of a 64-feature weight tile is addressed at column 32 (j / 2) + 8 (j % 2).
+//   TMEM columns   R0 = [0, H)   : GEMM0 / linear-1 accumulator  -> after the epilogue: operand `a` (packed halves)
+//                  R1 = [H, 2H)  : features / linear-0 accumulator -> after the epilogue: operand relu(t)
+//                  final layer   : two accumulators ping-pong in R1 (H = 256: H and H + 128; H = 128: R1 and 2H)
+//   schedule       H = 256: every H x H GEMM = (all columns, K lo: N = 256 MMAs) | (columns lo, K hi: N = 128) |
+//                  (columns hi, K hi): the first part needs only the low half of the operand, the accumulator's low
+//                  half completes a quarter-GEMM early; per-half FULL / RDY mbarriers hand over in both directions.
+//   residual       the stream u (biases folded out at pack time) belongs to the epilogue threads: thread (quadrant q,
+//                  column group c) owns u[row 32q+lane][half*NH + 32c .. +32): half 0 in registers, half 1 in smem.
+//   final layer    fused path: one chunk of chn <= 112 columns per transformed coordinate
+//                  [widths | pad | heights | pad | derivatives]; the epilogue warps of a quadrant form two pairs that
+//                  take alternate chunks: softmax / prefix sums / bin search / rational-quadratic evaluation in registers,
+//                  output coordinate and log-det written directly (theta is never materialised).  theta path
+//                  (fs_flow_conditioner, FS_NO_FUSE=1): TF32, 128-column chunks, coalesced stores through a per-warp
+//                  smem transpose.
+//   shared memory  NSTAGE weight stages of H*128 bytes, the second half of u (reused by the final layer), two parameter
+//                  sets (BatchNorm scale / offset, folded bias) prefetched by TMA, mbarriers, mailboxes.
+//   warps          0: TMA producer   1: MMA issuer (converged warp, elect.sync; one smem descriptor per stage)
+//                  2: TMEM allocator   4..19: epilogue (warp w touches TMEM lanes 32*(w%4)..).
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdint.h>
