@@ -220,10 +220,11 @@ __device__ __forceinline__ unsigned long long mul2s(unsigned long long a, unsign
 
 // numpy float32 floor-mod for the common case -L <= a < 2L (one shift); anything else takes np_mod.
 __device__ __forceinline__ float np_mod_near(float a, float L) {
-    if (a >= 0.0f && a < L) return a + 0.0f;            // -0.0 -> +0.0 like copysignf(0, L)
-    if (a >= L && a < 2.0f * L) return a - L;           // exact (Sterbenz), what fmodf returns
-    if (a < 0.0f && a >= -L) return a + L;              // fmodf keeps a, numpy adds the divisor (may round to L)
-    return np_mod(a, L);
+    if (!(a >= -L && a < 2.0f * L)) return np_mod(a, L);   // rare: more than one box length away
+    // a >= L: a - L is exact (Sterbenz), what fmodf returns; a < 0: fmodf keeps a and numpy adds the divisor (the sum
+    // may round to L); 0 <= a < L: unchanged, with -0.0 -> +0.0 like copysignf(0, L)
+    const float shift = (a >= L) ? -L : ((a < 0.0f) ? L : 0.0f);
+    return a + shift;
 }
 
 __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
