@@ -84,7 +84,6 @@ struct TcArgs {
     int* nan_flag;
     int* err;
     long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 16 per CTA
-    int dbg_mode;     // FS_TC_MODE (timing experiments only): 1 = epilogue skips data work, 4 = no weight copies
 };
 
 // ---------------------------------------------------------------------------
@@ -400,9 +399,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     // Bulk copies issued by ONE thread complete one at a time (~800 clk each, measured:
                     // scripts/tma_bw2.cu); copies issued by different lanes overlap -> rotate the issuing lane.
                     if (lane == (int)(t & 7)) {
-                        const uint32_t nb_ = (g.dbg_mode == 3) ? nbytes / 2 : nbytes;   // timing experiment only
-                        mbar_expect_tx(bar_wfull + 8 * stage, nb_);
-                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src, nb_, bar_wfull + 8 * stage);
+                        mbar_expect_tx(bar_wfull + 8 * stage, nbytes);
+                        tma_bulk_g2s(w_base + stage * S::STAGE_BYTES, src, nbytes, bar_wfull + 8 * stage);
                     }
                     src += nbytes;
                     __syncwarp();
@@ -1337,11 +1335,6 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* th
     g.trf = f->trf;
     g.nan_flag = nan_flag;
     g.dbg = tc_debug_buffer((rows + 127) / 128);
-    {
-        static int mode = -1;
-        if (mode < 0) { const char* e = getenv("FS_TC_MODE"); mode = e ? atoi(e) : 0; }
-        g.dbg_mode = mode;
-    }
     const int grid = (rows + 127) / 128;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
