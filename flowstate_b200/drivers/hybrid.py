@@ -7,9 +7,12 @@ resident on the GPU (BatchedMonteCarlo), take the constants as a config object /
 flags, and carry the multi-GPU hooks (chains sharded by rank, weights broadcast after
 training, gradients all-reduced in Algorithm 2).  Defaults are the reference's constants.
 
+    python -m flowstate_b200.drivers.hybrid --algorithm 0 --particles 3 --chains 100     # MCMC only
     python -m flowstate_b200.drivers.hybrid --algorithm 1 --particles 3 --chains 10
     torchrun --nproc-per-node 8 -m flowstate_b200.drivers.hybrid --algorithm 2 --particles 64 --chains 4096
 
+MCMC only (main_mcmc_only.py:176-236): equilibrate, then `production_steps` local moves per chain sampled every
+`sampling_frequency` steps; per-chain well statistics / free-energy difference from the sampled configurations.
 Algorithm 1 (main_algorithm_1.py:203-395): equilibrate -> collect local samples -> train the
 flow by forward KL -> interleave `big_move_interval` local moves with one NF global move.
 Algorithm 2 (main_algorithm_2.py:393-577): per cycle `local_steps` local moves, a short
@@ -62,6 +65,8 @@ class HybridConfig:
     cycles: int = 1000
     local_steps: int = 100
     precision: str = "tf32"
+    # MCMC only (main_mcmc_only.py:56-57: 1e7 steps over 100 chains)
+    production_steps: int = 100000
 
 
 def _dist():
@@ -144,6 +149,35 @@ def _train(model, data, cfg, epochs, optimizer=None):
     return losses
 
 
+def run_mcmc_only(cfg, device="cuda", log=print):
+    """main_mcmc_only.py:176-236 on the batched engine: equilibration, production with configurations sampled every
+    `sampling_frequency` steps, then calculate_well_statistics per chain (cumulative p_A, p_B, dF = ln(p_B / p_A))."""
+    from . import observables
+    eng, L = _init_chains(cfg, device)
+    step = _local_phase(eng, cfg.equilibration_steps, cfg)
+    samples = []                                             # centred coordinates, one [B, 2N] tensor per sample time
+    cfg_prod = dataclasses.replace(cfg, adjusting_frequency=0)   # the reference adapts during equilibration only
+    _local_phase(eng, cfg.production_steps, cfg_prod, collect=samples, step0=step)
+    B, n = eng.B, cfg.particles
+    half_box = L / 2
+    traj = torch.stack(samples, dim=1).reshape(B, len(samples), n, 2) + np.float32(half_box)   # MC-box coordinates
+    delta_f, p_a, p_b = [], [], []
+    _, state, _ = observables._classify(traj.reshape(B * len(samples), n, 2), half_box, cfg.r0)
+    state = state.reshape(B, len(samples)).cpu().numpy()
+    runs = np.arange(1, len(samples) + 1)
+    for b in range(B):
+        pa = np.cumsum(state[b] == 1) / runs
+        pb = np.cumsum(state[b] == 2) / runs
+        p_a.append(float(pa[-1]))
+        p_b.append(float(pb[-1]))
+        delta_f.append(float(np.log(pb[-1] / pa[-1])) if pa[-1] > 0 and pb[-1] > 0 else 0.0)
+    att, acc, _ = parallel.allreduce_counters(eng.attempts, eng.accepted, torch.zeros(1, device=eng.device))
+    log("%d chains x %d production steps, acceptance %.3f, mean dF %.3f" % (B, cfg.production_steps,
+                                                                         acc / max(att, 1), float(np.mean(delta_f))))
+    return {"algorithm": 0, "attempts": att, "accepted": acc, "p_a": p_a, "p_b": p_b, "delta_f": delta_f,
+            "samples_per_chain": len(samples), "engine": eng}
+
+
 def run_algorithm_1(cfg, device="cuda", log=print):
     eng, L = _init_chains(cfg, device)
     step = _local_phase(eng, cfg.equilibration_steps, cfg)
@@ -188,7 +222,7 @@ def run_algorithm_2(cfg, device="cuda", log=print):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
-    ap.add_argument("--algorithm", type=int, choices=(1, 2), default=1)
+    ap.add_argument("--algorithm", type=int, choices=(0, 1, 2), default=1, help="0 = local-displacement MCMC only")
     for f in dataclasses.fields(HybridConfig):
         if f.type in (int, float, str):
             ap.add_argument("--" + f.name.replace("_", "-"), type=f.type, default=f.default)
@@ -201,7 +235,8 @@ def main(argv=None):
         dist.init_process_group("nccl")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    out = (run_algorithm_1 if a.algorithm == 1 else run_algorithm_2)(cfg, device="cuda:%d" % local)
+    run = {0: run_mcmc_only, 1: run_algorithm_1, 2: run_algorithm_2}[a.algorithm]
+    out = run(cfg, device="cuda:%d" % local)
     if _dist()[0] == 0:
         print(json.dumps({k: v for k, v in out.items() if k not in ("engine", "model")}))
     if dist.is_initialized():

@@ -37,3 +37,23 @@ def test_algorithm_2_small():
     out = run_algorithm_2(cfg, log=lambda *a: None)
     assert out["attempts"] == 32 * (300 + 5 * 41)
     assert np.isfinite(out["final_loss"])
+
+
+def test_mcmc_only_small():
+    """BASELINE configs[0] shape: local-displacement MCMC only, per-chain well statistics from the device classifier
+    cross-checked against the oracle on the final configurations."""
+    from flowstate_b200.drivers import HybridConfig, run_mcmc_only
+    from oracle import observables_ref as obr
+    cfg = HybridConfig(particles=3, chains=12, equilibration_steps=400, adjusting_frequency=200, sampling_frequency=50,
+                       production_steps=2000)
+    out = run_mcmc_only(cfg, log=lambda *a: None)
+    assert out["attempts"] == 12 * 2400 and 0 < out["accepted"] < out["attempts"]
+    assert out["samples_per_chain"] == 40 and len(out["delta_f"]) == 12
+    assert all(0.0 <= a <= 1.0 and 0.0 <= b <= 1.0 and a + b <= 1.0 + 1e-12 for a, b in zip(out["p_a"], out["p_b"]))
+    eng = out["engine"]
+    L = float(np.float32(np.sqrt(3 / 0.03)))
+    pos = eng.pos.cpu().numpy()
+    assert (pos >= 0).all() and (pos <= L).all()
+    from flowstate_b200.drivers import observables
+    cls, _, _ = observables._classify(pos, L / 2, cfg.r0)
+    assert np.array_equal(cls.cpu().numpy(), obr.classify(pos, L / 2, cfg.r0))
