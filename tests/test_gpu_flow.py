@@ -227,3 +227,28 @@ def test_empty_and_single_row_batches():
         a, b = model.log_prob(x1), model.log_prob(x5)
         assert a.shape == (1,) and torch.isfinite(a).all()
         assert abs(a[0].item() - b[0].item()) <= 1e-6 * abs(b[0].item())      # rows are independent
+
+
+def test_tensor_path_is_deterministic_run_to_run():
+    """The fused kernel has no atomics on its data path and sums the per-row log-det in a fixed order: repeated
+    launches on the same input must agree bit for bit (a shared-memory / TMEM hand-off race would not)."""
+    torch.manual_seed(4)
+    for (n, H, nb, B) in ((32, 256, 32, 1000), (64, 128, 15, 700)):
+        bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+        model = _build(n, 3, 2, H, nb, bound, device="cuda")
+        g = torch.Generator().manual_seed(8)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.03 * torch.randn(p.shape, generator=g))
+        model = model.cuda().eval()
+        if "tf32" not in _precisions(model):
+            pytest.skip("tensor path unavailable")
+        model.precision = "tf32"
+        x = ((torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+        z = model.q0(B)
+        lq0 = model.log_prob(x)
+        xs0, ld0 = model.forward_and_log_det(z)
+        for _ in range(6):
+            assert torch.equal(model.log_prob(x), lq0)
+            xs, ld = model.forward_and_log_det(z)
+            assert torch.equal(xs, xs0) and torch.equal(ld, ld0)
