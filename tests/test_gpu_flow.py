@@ -252,3 +252,31 @@ def test_tensor_path_is_deterministic_run_to_run():
             assert torch.equal(model.log_prob(x), lq0)
             xs, ld = model.forward_and_log_det(z)
             assert torch.equal(xs, xs0) and torch.equal(ld, ld0)
+
+
+def test_concurrent_passes_on_two_streams_match_sequential():
+    """bench.py samples the next round's proposals on a side stream while the log-density pass runs: both passes share
+    the packed weights but use per-stream workspaces; results must equal the sequential ones bit for bit."""
+    torch.manual_seed(6)
+    n, bound = 32, float(np.float32(np.sqrt(32 / 0.03))) / 2
+    model = _build(n, 4, 3, 256, 32, bound, device="cuda")
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.03 * torch.randn(p.shape, generator=g))
+    model = model.cuda().eval()
+    if "tf32" not in _precisions(model):
+        pytest.skip("tensor path unavailable")
+    model.precision = "tf32"
+    x = ((torch.rand(2048, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    z = model.q0(1024)
+    lq_ref = model.log_prob(x)
+    xs_ref = model.forward(z)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for _ in range(4):
+        with torch.cuda.stream(side):
+            xs = model.forward(z)
+        lq = model.log_prob(x)
+        torch.cuda.synchronize()
+        assert torch.equal(lq, lq_ref) and torch.equal(xs, xs_ref)
