@@ -67,7 +67,7 @@ __device__ __forceinline__ float ex2_fast(float x) {
 // coordinate j at k*N + j), so the 32 lanes of a warp read consecutive addresses.
 // U coordinates of one lane at once: the binary searches (same trip count for every coordinate) and the
 // table loads of the U coordinates interleave, which hides the L1/L2 latency of the dependent knot loads.
-template <int U>
+template <int U, bool FAST = false>
 __device__ __forceinline__ void rqs_table_multi(const float (&x)[U], const bool (&valid)[U], const int (&j)[U],
                                                 const float* __restrict__ ux, const float* __restrict__ uy,
                                                 const float* __restrict__ ud, int N, int nb, float bound, bool inverse,
@@ -96,8 +96,12 @@ __device__ __forceinline__ void rqs_table_multi(const float (&x)[U], const bool 
             const float* cd = ud + j[u];
             const float xk = __ldg(cx + (size_t)sel * N), xk1 = __ldg(cx + (size_t)(sel + 1) * N);
             const float yk = __ldg(cy + (size_t)sel * N), yk1 = __ldg(cy + (size_t)(sel + 1) * N);
-            rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, __ldg(cd + (size_t)sel * N), __ldg(cd + (size_t)(sel + 1) * N),
-                    inverse, y[u], ld[u]);
+            if (FAST)
+                rq_eval_fast(x[u], xk, xk1 - xk, yk, yk1 - yk, __ldg(cd + (size_t)sel * N),
+                             __ldg(cd + (size_t)(sel + 1) * N), inverse, y[u], ld[u]);
+            else
+                rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, __ldg(cd + (size_t)sel * N),
+                        __ldg(cd + (size_t)(sel + 1) * N), inverse, y[u], ld[u]);
         }
     }
 }
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_MAXW) spline_kernel(
 
 // sampling direction, step 1: roll, inverse unconditional spline on the identity half, periodic
 // features of the NEW identity values (coupling.py:113-124)
-template <int U>
+// FAST (tensor path): MUFU-based sin / cos / log / reciprocal, ~1e-6, far inside that path's error budget
+template <int U, bool FAST>
 __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
     const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
     FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
@@ -279,13 +284,13 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
             fi[u] = valid[u] ? F.idf[j[u]] : 0;
             x[u] = valid[u] ? vr[(fi[u] + h) % F.D] : 0.f;
         }
-        rqs_table_multi<U>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, true, y, ld);
+        rqs_table_multi<U, FAST>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, true, y, ld);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!valid[u]) continue;
             out[(size_t)b * F.D + fi[u]] = y[u];
             float sn, cs;
-            sincosf(F.pf_scale * y[u], &sn, &cs);
+            if (FAST) __sincosf(F.pf_scale * y[u], &sn, &cs); else sincosf(F.pf_scale * y[u], &sn, &cs);
             A0[(size_t)b * 2 * F.N + j[u]] = cs;
             A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
             acc += ld[u];
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
 // density direction, step 1: periodic features of the identity half (utils/nn.py:125-127) and the
 // unconditional spline on the identity half, scattered + rolled by D/2 (coupling.py:86-102).  One warp per
 // row; the knot tables stay L1-resident here (no shared-memory carve-out).
-template <int U>
+template <int U, bool FAST>
 __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
     const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
     FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
@@ -323,12 +328,12 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
             fi[u] = valid[u] ? F.idf[j[u]] : 0;
             x[u] = valid[u] ? vr[fi[u]] : 0.f;
         }
-        rqs_table_multi<U>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, false, y, ld);
+        rqs_table_multi<U, FAST>(x, valid, j, ux, uy, ud, F.N, nb, F.bound, false, y, ld);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!valid[u]) continue;
             float sn, cs;
-            sincosf(F.pf_scale * x[u], &sn, &cs);
+            if (FAST) __sincosf(F.pf_scale * x[u], &sn, &cs); else sincosf(F.pf_scale * x[u], &sn, &cs);
             A0[(size_t)b * 2 * F.N + j[u]] = cs;
             A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
             out[(size_t)b * F.D + (fi[u] + h) % F.D] = y[u];
@@ -791,12 +796,14 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         float* nxt = w.v1;
         for (int li = f->K - 1; li >= 0; --li) {                        // core.py:82-85
             const fs_flow::Layer& L = f->layers[li];
-            if (f->N > 32)
-                prep_inverse_v2<4><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
-            else
-                prep_inverse_v2<1><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            {
+                const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
+                const bool fast = precision == FS_PREC_TF32;
+#define FS_PREP(U, FAST) prep_inverse_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+                if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
+                else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
+#undef FS_PREP
+            }
     fs::count_launch();
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
@@ -838,12 +845,14 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
         float* nxt = w.v1;
         for (int li = 0; li < f->K; ++li) {                              // core.py:52-55
             const fs_flow::Layer& L = f->layers[li];
-            if (f->N > 32)
-                prep_forward_v2<4><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
-            else
-                prep_forward_v2<1><<<(rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, 32 * FS_SPLINE_WARPS, 0, s>>>(
-                    cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag);
+            {
+                const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
+                const bool fast = precision == FS_PREC_TF32;
+#define FS_PREP(U, FAST) prep_forward_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+                if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
+                else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
+#undef FS_PREP
+            }
     fs::count_launch();
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
