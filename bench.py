@@ -67,60 +67,88 @@ def flops_per_sample_layer(w):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md).  Sampled in-process through NVML
+    (nvidia_ml_py, the library nvidia-smi itself uses) from a background thread every 25 ms: an external
+    `nvidia-smi -lms` poller re-initialises NVML over every GPU of the box and was measured to stall kernel submission
+    of all ranks (2 GPUs: 3.87 -> 4.5-7.6 ms per round).  Falls back to one nvidia-smi query if NVML cannot be loaded."""
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.gpu_index = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self._stop = False
+        self._thread = None
+        self._nvml = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            import threading
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self._nvml = None
+
+    @staticmethod
+    def _physical_index(local_index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if local_index < len(ids) and ids[local_index].strip().isdigit():
+                return int(ids[local_index])
+        return local_index
+
+    def _sample(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop:
+            try:
+                self._sample()
+            except Exception:
+                return
+            time.sleep(0.025)
+
+    def wait_ready(self, timeout=2.0):
+        t0 = time.time()
+        while self._thread is not None and not self.sm and time.time() - t0 < timeout:
+            time.sleep(0.005)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out["sm_mhz"] = float(np.median(sm))
-            out["sm_max_mhz"] = float(max(mx))
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+        elif self._nvml is None:
+            try:                                       # one query after the timed region (no NVML bindings available)
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                c = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=20).stdout.strip().split(",")
+                self.sm.append(float(c[0]))
+                self.mx.append(float(c[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["sm_max_mhz"] = float(max(self.mx))
+            out["samples"] = len(self.sm)
+        out["reasons"] = sorted(self.reasons)
         return out
 
-
-# ---------------------------------------------------------------------------
-# CPU baseline = the oracle port (numpy sampler + torch-CPU flow), bounded sample
-# ---------------------------------------------------------------------------
 def _cpu_local_worker(args):
     n, rho, seed, steps = args
     from oracle import energy_ref as er
@@ -304,10 +332,13 @@ def main():
         return eng.nf_big_move(cfg)
 
     # ---- device-resident timing ------------------------------------------------
-    # the clock sampler (an nvidia-smi process polling every 20 ms) is started before the warm-up rounds: spawning it
-    # and its NVML start-up stall kernel submission for tens of milliseconds, which must not land in the timed region;
-    # its samples therefore cover the warm-up rounds (same load) and the timed region
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    # clock sampler: in-process NVML thread, started (and its first sample awaited) before the warm-up rounds; its
+    # samples cover the warm-up rounds (same load) and the timed region
+    clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("FS_NO_CLOCKS")) else None
+    if clocks:
+        clocks.wait_ready()
+    if world > 1:
+        dist.barrier()
     for _ in range(args.warmup):
         one_round()
     torch.cuda.synchronize()
