@@ -280,3 +280,28 @@ def test_concurrent_passes_on_two_streams_match_sequential():
         lq = model.log_prob(x)
         torch.cuda.synchronize()
         assert torch.equal(lq, lq_ref) and torch.equal(xs, xs_ref)
+
+
+def test_round_trip_on_the_tensor_path():
+    """forward then inverse returns the base sample and cancels the log-determinant (the reference's own test style,
+    flows/neural_spline/coupling_test.py:40-59), here through both directions of the fused kernel: the density pass
+    sees the same conditioner outputs as the sampling pass that generated the point."""
+    torch.manual_seed(7)
+    for (n, H, nb) in ((32, 256, 32), (64, 128, 15)):
+        bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+        model = _build(n, 5, 3, H, nb, bound, device="cuda")
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.04 * torch.randn(p.shape, generator=g))
+        model = model.cuda().eval()
+        if "tf32" not in _precisions(model):
+            pytest.skip("tensor path unavailable")
+        model.precision = "tf32"
+        z = model.q0(900)
+        x, ld_f = model.forward_and_log_det(z)
+        z2, ld_i = model.inverse_and_log_det(x)
+        inside = (x.abs() <= bound).all(dim=1)
+        assert inside.float().mean().item() > 0.99
+        assert (z2[inside] - z[inside]).abs().max().item() < 2e-4 * bound
+        np.testing.assert_allclose(ld_i[inside].cpu().numpy(), -ld_f[inside].cpu().numpy(), rtol=2e-4, atol=2e-3)
