@@ -13,8 +13,10 @@
 //
 // This file holds the pack (BatchNorm folding, unconditional knot tables), the
 // CUDA-core FP32 conditioner (FS_PREC_FP32: reference arithmetic, used as the
-// precision yardstick for the tensor path) and the spline kernels, where one
-// warp owns one row and the nb <= 32 bins of a coordinate sit one per lane.
+// precision yardstick for the tensor path), the feature / identity-half kernels
+// (one warp per row, coordinates one per lane) and the stand-alone conditional
+// spline kernel of the paths that materialise theta; the tensor path with the
+// spline fused into the conditioner's epilogue lives in flow_tc.cu.
 #include <math.h>
 #include <string.h>
 
