@@ -198,3 +198,36 @@ def test_drop_in_top_level_import_names():
             % (ROOT, os.path.join(ROOT, "flowstate_b200")))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_observables_host_statistics_match_reference_golden(golden_dir, monkeypatch):
+    """The host half of flowstate_b200.drivers.observables (cumulative p_A / p_B / dF, g(r) normalisation) against the
+    reference's golden outputs, with the device kernels replaced by the oracle (no GPU here)."""
+    import torch
+    from flowstate_b200.drivers import observables as obs
+    from oracle import observables_ref as obr
+    g = np.load(os.path.join(golden_dir, "observables.npz"))
+
+    def fake_classify(configurations, half_box, r0):
+        cfg = np.asarray(configurations)
+        cls = obr.classify(cfg, half_box, r0)
+        state = np.where((cls == 1).all(axis=1), 1, np.where((cls == 2).all(axis=1), 2, 0)).astype(np.uint8)
+        return torch.from_numpy(cls), torch.from_numpy(state), torch.from_numpy(cfg[:, :, 0].astype(np.float64).mean(axis=1))
+
+    def fake_hist(final_samples, bound, dr):
+        return torch.from_numpy(obr.pair_histogram(np.asarray(final_samples), bound, dr).astype(np.int32))
+
+    monkeypatch.setattr(obs, "_classify", fake_classify)
+    monkeypatch.setattr(obs, "pair_histogram", fake_hist)
+    half_box, r0, start = float(g["ws_half_box"]), float(g["ws_r0"]), int(g["ws_start"])
+    avg_x, p_a, p_b, dF, runs = obs.calculate_well_statistics(g["ws_cfgs"], start, half_box, r0)
+    np.testing.assert_allclose(avg_x, g["ws_avg_x"], rtol=1e-6)
+    assert np.array_equal(p_a, g["ws_p_a"]) and np.array_equal(p_b, g["ws_p_b"])
+    np.testing.assert_allclose(dF, g["ws_dF"], rtol=0, atol=1e-15)
+    names = obs.classify_particles(g["ws_cfgs"], half_box, r0)
+    assert names.shape == g["ws_class"].shape and set(np.unique(names)) <= {"A", "B", "Outside"}
+    for tag in "abc":
+        r, gr = obs.calculate_pair_correlation(g["pc_%s_samples" % tag], int(g["pc_%s_n" % tag]),
+                                               float(g["pc_%s_bound" % tag]), float(g["pc_%s_dr" % tag]))
+        assert np.array_equal(r, g["pc_%s_r" % tag])
+        np.testing.assert_allclose(np.asarray(gr), g["pc_%s_g" % tag], rtol=1e-14, atol=0)
