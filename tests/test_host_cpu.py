@@ -231,3 +231,40 @@ def test_observables_host_statistics_match_reference_golden(golden_dir, monkeypa
                                                float(g["pc_%s_bound" % tag]), float(g["pc_%s_dr" % tag]))
         assert np.array_equal(r, g["pc_%s_r" % tag])
         np.testing.assert_allclose(np.asarray(gr), g["pc_%s_g" % tag], rtol=1e-14, atol=0)
+
+
+def test_driver_local_phase_schedule():
+    """_local_phase splits a run of local moves at the reference's adaptation / sampling boundaries
+    (main_algorithm_1.py:203-232: adjust every ADJUSTING_FREQUENCY steps, sample every SAMPLING_FREQUENCY steps,
+    both counted from the chain's first step)."""
+    import torch
+    from flowstate_b200.drivers import hybrid
+
+    class FakeEngine:
+        def __init__(self):
+            self.steps, self.adjusted_at, self.pos = 0, [], torch.zeros(2, 3, 2)
+
+        def particle_displacement(self, n):
+            assert n >= 1
+            self.steps += n
+
+        def adjust_displacement(self):
+            self.adjusted_at.append(self.steps)
+
+        def centred(self, pos):
+            return torch.full((2, 6), float(self.steps))
+
+    cfg = hybrid.HybridConfig(adjusting_frequency=300, sampling_frequency=70)
+    eng, samples = FakeEngine(), []
+    end = hybrid._local_phase(eng, 1000, cfg, collect=samples, step0=0)
+    assert end == 1000 and eng.steps == 1000
+    assert eng.adjusted_at == [300, 600, 900]
+    assert [int(t[0, 0]) for t in samples] == list(range(70, 1001, 70))
+    # continuing from a non-zero step count keeps the global phase of both schedules
+    end = hybrid._local_phase(eng, 500, cfg, collect=samples, step0=end)
+    assert end == 1500 and eng.adjusted_at == [300, 600, 900, 1200, 1500]
+    assert [int(t[0, 0]) for t in samples][-7:] == [1050, 1120, 1190, 1260, 1330, 1400, 1470]
+    # without collection only the adaptation boundaries split the run
+    eng2 = FakeEngine()
+    hybrid._local_phase(eng2, 650, hybrid.HybridConfig(adjusting_frequency=0, sampling_frequency=70))
+    assert eng2.steps == 650 and eng2.adjusted_at == []
