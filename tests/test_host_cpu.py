@@ -268,3 +268,20 @@ def test_driver_local_phase_schedule():
     eng2 = FakeEngine()
     hybrid._local_phase(eng2, 650, hybrid.HybridConfig(adjusting_frequency=0, sampling_frequency=70))
     assert eng2.steps == 650 and eng2.adjusted_at == []
+
+
+def test_bench_helpers_without_gpu():
+    """bench.py's algorithmic-flop formula reproduces SURVEY 8(a23)'s per-sample figures, and the clock sampler degrades
+    to an empty record on a machine without NVML / nvidia-smi instead of failing the run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fs_bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = bench.WORKLOADS
+    assert abs(bench.flops_per_sample_layer(w["alg1_n32"]) / 1e6 - 10.0) < 0.05       # C2: 10.0 MF
+    assert abs(bench.flops_per_sample_layer(w["alg1_n256"]) / 1e6 - 21.4) < 0.1       # C3: 21.4 MF
+    assert abs(bench.flops_per_sample_layer(w["alg2_n64"]) / 1e6 - 0.92) < 0.01       # C4: 0.92 MF
+    cs = bench.ClockSampler(0)
+    cs.wait_ready(timeout=0.2)
+    out = cs.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"} and isinstance(out["reasons"], list)
