@@ -42,7 +42,8 @@ class BatchedMonteCarlo:
     seeds:     iterable of B ints -> per-chain numpy-compatible PCG64 streams
                (chain i reproduces np.random.default_rng(seeds[i]), the reference's
                per-chain generator, monte_carlo.py:92-95); or None with
-               rng="philox" for counter-based streams keyed by the global chain id.
+               rng="philox" for counter-based streams keyed by the global chain id
+               (the throughput kernel: several chains per warp).
     """
 
     def __init__(self, particles, sim_box, temperature, num_particles, num_wells=0, V0_list=(-0.5, -0.5),
@@ -85,8 +86,8 @@ class BatchedMonteCarlo:
                 seeds = [None] * B
             words = np.array([pcg64_state_words(np.random.default_rng(s)) for s in seeds], dtype=np.uint64)
             self.pcg_state = torch.from_numpy(words.view(np.int64)).to(dev).contiguous()
-        elif rng != "philox":
-            raise ValueError("rng must be 'pcg64' or 'philox'")
+        elif rng not in ("philox", "philox_ref"):
+            raise ValueError("rng must be 'pcg64', 'philox' or 'philox_ref'")
         self.nf_model = None
         self.launches = 0          # kernels launched through this object (bench bookkeeping)
         self.refresh_energy()
@@ -103,7 +104,8 @@ class BatchedMonteCarlo:
             r.kind = _lib.FS_RNG_PCG64
             r.pcg_state = self.pcg_state.data_ptr()
         else:
-            r.kind = _lib.FS_RNG_PHILOX
+            # "philox_ref": the same counter-based draws through the reference-order parity kernel (tests)
+            r.kind = _lib.FS_RNG_PHILOX if self.rng_kind == "philox" else _lib.FS_RNG_PHILOX_REF
             r.philox_seed = self.philox_seed
             r.chain_id0 = self.chain_id0
         return r

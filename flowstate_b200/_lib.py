@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libflowstate_b200.so")
 
-FS_RNG_PCG64, FS_RNG_PHILOX, FS_RNG_REPLAY = 0, 1, 2
+FS_RNG_PCG64, FS_RNG_PHILOX, FS_RNG_REPLAY, FS_RNG_PHILOX_REF = 0, 1, 2, 3
 FS_PREC_FP32, FS_PREC_TF32 = 0, 1
 
 

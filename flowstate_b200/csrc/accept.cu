@@ -102,7 +102,7 @@ extern "C" int fs_accept_global(float* pos, const float* prop, double* E, double
     fs::accept_global_kernel<K><<<grid, 256, 0, s>>>(pos, prop, E, W, E_new, W_new, logq_old, logq_new, u, R, \
                                                      beta, attempts, accepted, accept_mask, B, N)
     if (kind == FS_RNG_PCG64) FS_LAUNCH(FS_RNG_PCG64);
-    else if (kind == FS_RNG_PHILOX) FS_LAUNCH(FS_RNG_PHILOX);
+    else if (kind == FS_RNG_PHILOX || kind == FS_RNG_PHILOX_REF) FS_LAUNCH(FS_RNG_PHILOX);
     else FS_LAUNCH(FS_RNG_REPLAY);
 #undef FS_LAUNCH
     fs::count_launch();

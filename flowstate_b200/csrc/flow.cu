@@ -647,8 +647,9 @@ static FlowDev flow_dev(const fs_flow* f) {
     return F;
 }
 
-static int run_conditioner(fs_flow* f, int li, const Workspace& w, int rows, int precision, cudaStream_t s) {
-    if (precision == FS_PREC_TF32) return tc_conditioner(f, li, w.A0, rows, w.theta, w.tc, w.tc_bytes, s);
+static int run_conditioner(fs_flow* f, int li, const Workspace& w, int rows, int precision, int* nan_flag,
+                           cudaStream_t s) {
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, li, w.A0, rows, w.theta, w.tc, w.tc_bytes, nan_flag, s);
     return conditioner_fp32(f, li, w.A0, rows, w.h, w.t, w.theta, s);
 }
 
@@ -760,7 +761,7 @@ extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features,
     Workspace w;
     carve(f, rows, precision, workspace, &w);
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision == FS_PREC_TF32) return tc_conditioner(f, layer, features, rows, theta, w.tc, w.tc_bytes, s);
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, layer, features, rows, theta, w.tc, w.tc_bytes, nullptr, s);
     return conditioner_fp32(f, layer, features, rows, w.h, w.t, theta, s);
 }
 
@@ -810,7 +811,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
-                if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+                if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
                 spline_kernel<true><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
                     cur, w.theta, nxt, w.ld, rows, F, nan_flag);
                 fs::count_launch();
@@ -859,7 +860,7 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
             if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
-                if (int r = run_conditioner(f, li, w, rows, precision, s)) return r;
+                if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
                 spline_kernel<false><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
                     cur, w.theta, nxt, w.ld, rows, F, nan_flag);
                 fs::count_launch();

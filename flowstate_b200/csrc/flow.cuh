@@ -116,7 +116,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d);
 void tc_free(fs_flow* f);
 size_t tc_workspace_bytes(const fs_flow* f, int B);
 int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void* ws, size_t ws_bytes,
-                   cudaStream_t s);
+                   int* nan_flag, cudaStream_t s);
 bool tc_has_fused(const fs_flow* f);
 int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, int rows, int direction, const float* xin, float* xout,
                           float* logdet, int* nan_flag, cudaStream_t s);

@@ -46,11 +46,9 @@ static constexpr int TC_KB = 32;          // K elements per weight tile (one 128
 
 struct TcLayer {
     float* wstream;    // all weight tiles of the layer in consumption order
-    float* b_init;     // unused (folded)
     float* bn0_s;      // [n_blocks, H]
     float* bn0_o;      // [n_blocks, H]  BatchNorm offset with the running bias folded in
     float* b0;         // [n_blocks, H]
-    float* b1;         // unused (folded)
     float* b_final;    // [n_chunks * 128]  b_f + W_f c
     float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
     void* wfused;      // fused-spline final layer, FP16 operands: per coordinate (H/64)/KPS stages of KPS tiles of
@@ -222,7 +220,8 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-// the same with ReLU folded into the conversion (negative inputs and NaN become +0)
+// the same with ReLU folded into the conversion (negative inputs become +0; out-of-range inputs become +inf and are
+// caught by the range guard of the epilogue, see hmax)
 __device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -634,6 +633,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         };
         uint32_t v[16];
         float u0[32];                            // residual stream, column half 0 (half 1 lives in shared memory)
+        // FP16 range guard: running maximum (per 16-bit half) of every operand this thread packed.  An activation
+        // beyond 65504 packs to +inf (0x7c00), a NaN to 0x7fff; either raises the caller's flag at the end of the
+        // H-wide stages, so an overflow can never be laundered through a later ReLU into finite-looking numbers.
+        uint32_t hmax = 0;
 
         if (cgp < NH / 32) {   // warps of the H-wide stages (all of them at H = 256)
         // ---- features -> R1 (A operand of GEMM0), piece by piece ----
@@ -716,6 +719,13 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 _Pragma("unroll") for (int i4 = 0; i4 < 4; ++i4)                                               \
                     us4[(size_t)(cgp * 8 + sub * 4 + i4) * 128 + r] = hh[i4];                                  \
             }                                                                                                  \
+            /* FP16 range guard: largest packed half so far (ReLU output: sign bit clear; u itself: masked) */ \
+            if (HAS_NEXT) {                                                                                    \
+                _Pragma("unroll") for (int i = 0; i < 8; i += 2) hmax = __vimax3_u16x2(hmax, v[i], v[i + 1]);  \
+            } else if (f16mode) {                                                                              \
+                _Pragma("unroll") for (int i = 0; i < 8; i += 2)                                               \
+                    hmax = __vimax3_u16x2(hmax, v[i] & 0x7fff7fffu, v[i + 1] & 0x7fff7fffu);                   \
+            }                                                                                                  \
             /* packed halves go to the first 16 of this thread's own 32 columns; the theta path keeps TF32 u */ \
             if ((HAS_NEXT) || f16mode) tc_st8(lane_addr + col + 8 * sub, v);                                   \
             else tc_st16(lane_addr + col + 16 * sub, v);                                                       \
@@ -755,6 +765,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         v[2 * i4] = pack_relu_f16x2(t0, t1);
                         v[2 * i4 + 1] = pack_relu_f16x2(t2, t3);
                     }
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) hmax = __vimax3_u16x2(hmax, v[i], v[i + 1]);
                     tc_st8(lane_addr + H + col + 8 * sub, v);
                 }
                 tc_wait_st();
@@ -778,6 +790,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             release_pset(b + 1);
         }
+        if (((hmax & 0xffffu) >= 0x7c00u || (hmax >> 16) >= 0x7c00u) && g.nan_flag) atomicOr(g.nan_flag, 2);
         }   // H-wide stages
 #undef FS_EPI_RESIDUAL
         // ---- fused final layer: one chunk = the 3nb+1 spline parameters of ONE transformed coordinate for the 128
@@ -1258,8 +1271,6 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                 L.wfused = d16;
             }
         }
-        L.b_init = nullptr;
-        L.b1 = nullptr;
         if (r) { delete P; return r; }
     }
     int* err = nullptr;
@@ -1344,8 +1355,9 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* th
     return cuda_check(cudaGetLastError(), "tc_conditioner_kernel");
 }
 
-int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, cudaStream_t s) {
-    return tc_launch(f, layer, A0, rows, theta, 0, nullptr, nullptr, nullptr, nullptr, s);
+int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, int* nan_flag,
+                   cudaStream_t s) {
+    return tc_launch(f, layer, A0, rows, theta, 0, nullptr, nullptr, nullptr, nan_flag, s);
 }
 
 bool tc_has_fused(const fs_flow* f) { return f->tc && ((TcPack*)f->tc)->chn > 0; }

@@ -12,6 +12,8 @@
 // and six warp-shuffle reductions finish the step.  Draw order per step follows
 // the reference: particle index, two displacement uniforms, and a third uniform
 // only for finite uphill moves.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fs {
@@ -184,10 +186,10 @@ __global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ po
 }
 
 
-// Throughput variant (Philox streams, no traces): the same move, with the per-step overheads trimmed -
-// one Philox block per step generated 32 steps at a time (lane l prepares step base+l, the step reads it
-// with four shuffles), energy/virial DIFFERENCES reduced instead of four separate sums, the two
-// hard-core minima through single REDUX instructions, wells behind a float32 pre-test.
+// Throughput kernel (Philox streams; what the drivers and the bench run): the same move with the per-step overheads
+// trimmed - one Philox block per step generated LPC steps at a time (lane `sub` of a chain's lane group prepares step
+// base + sub, the step reads it with four shuffles), energy / virial DIFFERENCES reduced instead of four separate
+// sums, hard-core tests by ballot, wells behind a float32 pre-test, several chains per warp.
 // packed FP32 pairs (add/sub/mul/fma.f32x2)
 __device__ __forceinline__ unsigned long long pk2s(float a, float b) {
     unsigned long long r;
@@ -227,21 +229,42 @@ __device__ __forceinline__ float np_mod_near(float a, float L) {
     return a + shift;
 }
 
+// LPC lanes of a warp own one chain (32 / LPC chains per warp): the per-step scalar work (random numbers, the
+// displacement, the floor-mod, the decision) is issued once per warp-instruction for all chains of the warp, each lane
+// walks ceil(N / LPC) partners of the moved particle, and the step finishes with a log2(LPC)-level segmented shuffle
+// sum of the energy difference and two ballots for the hard-core tests.  Chain slots in shared memory are `stride2`
+// float2 apart (stride2 * 8 bytes = 64 mod 128, so the groups of a warp read disjoint banks).
+// TRACE adds the outputs of the parity tests (accept flag, particle index, e_old / e_new reduced separately); the
+// decision arithmetic is the same code either way, so a traced run follows the untraced trajectory bit for bit.
+template <int LPC, bool TRACE>
 __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
                                                                double* __restrict__ W,
                                                                const double* __restrict__ max_disp,
                                                                long long* __restrict__ attempts,
                                                                long long* __restrict__ accepted, int B, int N,
                                                                int steps, PotDev P, double beta,
-                                                               unsigned long long seed, long long chain_id0) {
+                                                               unsigned long long seed, long long chain_id0,
+                                                               int stride2, unsigned char* __restrict__ trace_accept,
+                                                               int* __restrict__ trace_idx,
+                                                               float* __restrict__ trace_e) {
+    constexpr int CPW = 32 / LPC;                 // chains per warp
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ float2 smem[];
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (b >= B) return;
-    float2* sp = smem + (size_t)wib * N;
+    const int grp = lane / LPC, sub = lane % LPC, gl0 = grp * LPC;
+    const int b_first = (blockIdx.x * (blockDim.x >> 5) + wib) * CPW;
+    if (b_first >= B) return;
+    const bool live = b_first + grp < B;          // groups past the last chain shadow it and store nothing
+    const int b = live ? b_first + grp : B - 1;
+    float2* sp = smem + (size_t)(wib * CPW + grp) * stride2;
     float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
-    for (int i = lane; i < N; i += 32) sp[i] = gp[i];
+    const int iters = (N + LPC - 1) / LPC;
+    const float qnan = __int_as_float(0x7fc00000);
+    // Slots are padded to iters * LPC entries with NaN positions: a NaN r^2 fails the cut-off test (every term 0) and is
+    // ignored by fminf, so neither the padding nor the moved particle itself (overwritten with NaN while its partners
+    // are walked) needs a mask inside the pair loop.
+    for (int i = sub; i < iters * LPC; i += LPC) sp[i] = (i < N) ? gp[i] : make_float2(qnan, qnan);
     __syncwarp();
 
     const double md = max_disp[b];
@@ -253,13 +276,14 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const long long cid = chain_id0 + b;
     const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
     const float inf = __int_as_float(0x7f800000);
-    const float Lx = P.Lx, Ly = P.Ly, iLx = P.inv_Lx, iLy = P.inv_Ly, rc2 = P.rc2, ecut = P.e_cut;
+    const float Lx = P.Lx, Ly = P.Ly, iLx = P.inv_Lx, iLy = P.inv_Ly, rc2 = P.rc2, ecut = P.e_cut, rcore2 = P.rcore2;
     const float nbeta = -(float)beta;
-    // wells: lanes 0..3 evaluate (old, well 0), (old, well 1), (new, well 0), (new, well 1) with one code path
+    // wells: lanes 0..3 of a group evaluate (old, well 0), (old, well 1), (new, well 0), (new, well 1) with one code path
     const int nw = P.num_wells;
-    const bool well_lane = (nw == 2) ? lane < 4 : (nw == 1 ? (lane == 0 || lane == 2) : false);
-    const int well_idx = lane & 1;
-    const float well_sign = (lane & 2) ? 1.0f : -1.0f;
+    const bool well_lane = (nw == 2) ? sub < 4 : (nw == 1 ? (sub == 0 || sub == 2) : false);
+    const int well_idx = sub & 1;
+    const bool well_new = (sub & 2) != 0;
+    const unsigned gmask = (LPC == 32) ? FULL : (((1u << LPC) - 1u) << gl0);
     uint4 blk = make_uint4(0, 0, 0, 0);
     long long blk_base = -1;
     struct {
@@ -270,40 +294,43 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     K.four = pk2s(4.0f, 4.0f); K.mone = pk2s(-1.0f, -1.0f); K.mhalf = pk2s(-0.5f, -0.5f);
 
     for (int s = 0; s < steps; ++s, ++att) {
-        const long long base = att & ~31ll;
-        if (base != blk_base) {              // warp-uniform: refill the 32-step block of random numbers
-            const unsigned long long sid = (unsigned long long)(base + lane);
+        // one Philox block per step id {particle index, u1, u2, accept uniform}; a group prepares LPC steps at a time
+        // (lane `sub` the step base + sub) and reads them back by shuffles
+        const long long base = att & ~(long long)(LPC - 1);
+        if (__any_sync(FULL, base != blk_base)) {
+            const unsigned long long sid = (unsigned long long)(base + sub);
             blk = philox4x32(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), cz, cw), key);
             blk_base = base;
         }
-        const int slot = (int)(att & 31);
-        const uint32_t r_idx = __shfl_sync(0xffffffffu, blk.x, slot);
-        const uint32_t r_u1 = __shfl_sync(0xffffffffu, blk.y, slot);
-        const uint32_t r_u2 = __shfl_sync(0xffffffffu, blk.z, slot);
-        const uint32_t r_u3 = __shfl_sync(0xffffffffu, blk.w, slot);
+        const int src = gl0 + (int)(att & (LPC - 1));
+        const uint32_t r_idx = __shfl_sync(FULL, blk.x, src);
+        const uint32_t r_u1 = __shfl_sync(FULL, blk.y, src);
+        const uint32_t r_u2 = __shfl_sync(FULL, blk.z, src);
+        const uint32_t r_u3 = __shfl_sync(FULL, blk.w, src);
         const int p = (int)__umulhi(r_idx, (uint32_t)N);
         const float2 old = sp[p];
+        __syncwarp();
+        if (sub == 0) sp[p] = make_float2(qnan, qnan);       // the moved particle is not its own partner
+        // new_positions[p] += displacement (float64 add, stored float32), then % L (monte_carlo.py:161-166)
         float nx = (float)((double)old.x + ((double)r_u1 * (1.0 / 4294967296.0) - 0.5) * md);
         float ny = (float)((double)old.y + ((double)r_u2 * (1.0 / 4294967296.0) - 0.5) * md);
         nx = np_mod_near(nx, Lx);
         ny = np_mod_near(ny, Ly);
+        __syncwarp();
 
-        // pair terms of the moved particle at its old and new position (energy_calculator.py:48-108); the
-        // particle itself is masked out by an "infinite" r^2 instead of a branch
-        // (old, new) ride in the two halves of Blackwell's packed FP32 pairs (FADD2 / FMUL2 / FFMA2)
+        // pair terms of the moved particle at its old and new position (energy_calculator.py:48-108); (old, new) ride
+        // in the two halves of Blackwell's packed FP32 pairs (FADD2 / FMUL2 / FFMA2)
         float mo = 3.0e38f, mn = 3.0e38f;
         unsigned long long e2 = 0ull, w2 = 0ull;                     // (sum e_old, sum e_new), (sum w_old, sum w_new)
         const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny);
-        for (int j = lane; j < N; j += 32) {
-            const float2 q = sp[j];
-            const bool self = (j == p);
+#pragma unroll 4
+        for (int it = 0; it < iters; ++it) {
+            const float2 q = sp[sub + it * LPC];
             unsigned long long X = sub2s(PX, pk2s(q.x, q.x)), Y = sub2s(PY, pk2s(q.y, q.y));
             X = fma2s(add2s(fma2s(X, K.iLx, K.magic), K.nmagic), K.nLx, X);      // d - L rint(d / L)
             Y = fma2s(add2s(fma2s(Y, K.iLy, K.magic), K.nmagic), K.nLy, Y);
             float r2o, r2n;
             upk2s(fma2s(Y, Y, mul2s(X, X)), r2o, r2n);
-            r2o = self ? 3.0e38f : r2o;
-            r2n = self ? 3.0e38f : r2n;
             mo = fminf(mo, r2o);
             mn = fminf(mn, r2n);
             float io, in_;
@@ -321,10 +348,13 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         upk2s(w2, wo_s, wn_s);
         float de = en_s - eo_s;
         const float dw = 48.0f * (wn_s - wo_s);
-        if (well_lane) de += well_sign * well_term((lane & 2) ? nx : old.x, (lane & 2) ? ny : old.y, well_idx, P);
-        de = warp_sum(de);
-        const bool ov_o = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mo))) < P.rcore2;
-        const bool ov_n = __uint_as_float(__reduce_min_sync(0xffffffffu, __float_as_uint(mn))) < P.rcore2;
+        float wv = 0.f;
+        if (well_lane) wv = well_term(well_new ? nx : old.x, well_new ? ny : old.y, well_idx, P);
+        de += well_new ? wv : -wv;
+#pragma unroll
+        for (int o = LPC / 2; o > 0; o >>= 1) de += __shfl_xor_sync(FULL, de, o);
+        const bool ov_o = (__ballot_sync(FULL, mo < rcore2) & gmask) != 0u;
+        const bool ov_n = (__ballot_sync(FULL, mn < rcore2) & gmask) != 0u;
 
         // metropolis_acceptance_particle_move (monte_carlo.py:191-223): e_old = inf makes `new <= old` true for any
         // e_new; otherwise an overlapping new position is rejected; downhill is accepted; uphill draws
@@ -335,24 +365,44 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         bool ok = ov_o || (!ov_n && (de <= 0.f || uf < pf * 0.9999f));
         if (!ov_o && !ov_n && de > 0.f && uf >= pf * 0.9999f && uf <= pf * 1.0001f)
             ok = (double)r_u3 * (1.0 / 4294967296.0) < exp(-beta * (double)de);
+        if (TRACE) {
+            // e_old / e_new of the moved particle, reduced separately (outputs only: the decision above used `de`)
+            float eo_t = eo_s + (well_new ? 0.f : wv), en_t = en_s + (well_new ? wv : 0.f);
+#pragma unroll
+            for (int o = LPC / 2; o > 0; o >>= 1) {
+                eo_t += __shfl_xor_sync(FULL, eo_t, o);
+                en_t += __shfl_xor_sync(FULL, en_t, o);
+            }
+            if (sub == 0 && live) {
+                const size_t o = (size_t)b * steps + s;
+                if (trace_accept) trace_accept[o] = ok ? 1 : 0;
+                if (trace_idx) trace_idx[o] = p;
+                if (trace_e) {
+                    trace_e[2 * o] = ov_o ? inf : eo_t;
+                    trace_e[2 * o + 1] = ov_n ? inf : en_t;
+                }
+            }
+        }
+        if (sub == 0) sp[p] = ok ? make_float2(nx, ny) : old;
         if (ok) {
-            if (lane == 0) sp[p] = make_float2(nx, ny);
             acc += 1;
             const float big_o = ov_o ? inf : 0.f, big_n = ov_n ? inf : 0.f;
             Eb += (double)de + ((double)big_n - (double)big_o);
             Wl += (double)dw;
-            if (lane == 0) Wl += (double)big_n - (double)big_o;
+            if (sub == 0) Wl += (double)big_n - (double)big_o;
         }
         __syncwarp();
     }
-    for (int i = lane; i < N; i += 32) gp[i] = sp[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) Wl += __shfl_xor_sync(0xffffffffu, Wl, o);
-    if (lane == 0) {
-        attempts[b] = att;
-        accepted[b] += acc;
-        E[b] = Eb;
-        W[b] += Wl;
+    for (int o = LPC / 2; o > 0; o >>= 1) Wl += __shfl_xor_sync(FULL, Wl, o);
+    if (live) {
+        for (int i = sub; i < N; i += LPC) gp[i] = sp[i];
+        if (sub == 0) {
+            attempts[b] = att;
+            accepted[b] += acc;
+            E[b] = Eb;
+            W[b] += Wl;
+        }
     }
 }
 
@@ -395,6 +445,47 @@ static int launch_sweep(float* pos, double* E, double* W, const double* md, long
     return cuda_check(cudaGetLastError(), "local_sweep_kernel");
 }
 
+template <int LPC, bool TRACE>
+static int launch_fast_t(float* pos, double* E, double* W, const double* md, long long* att, long long* acc, int B,
+                         int N, int steps, const PotDev& P, double beta, unsigned long long seed, long long chain_id0,
+                         unsigned char* ta, int* ti, float* te, cudaStream_t s) {
+    constexpr int CPW = 32 / LPC;
+    // slot stride: N rounded up so that stride * 8 bytes = 64 (mod 128) - the lane groups of a warp then hit disjoint banks
+    int stride2 = (N + 15) / 16 * 16 + (CPW > 1 ? 8 : 0);       // >= ceil(N / LPC) * LPC: room for the NaN padding
+    int wpc = 4;
+    while (wpc > 1 && (size_t)wpc * CPW * stride2 * sizeof(float2) > 200 * 1024) wpc >>= 1;
+    const size_t smem = (size_t)wpc * CPW * stride2 * sizeof(float2);
+    if (smem > 227 * 1024) {
+        set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
+        return FS_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024)
+        FS_CUDA(cudaFuncSetAttribute(local_sweep_fast_kernel<LPC, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    const int cpc = wpc * CPW;
+    local_sweep_fast_kernel<LPC, TRACE><<<(B + cpc - 1) / cpc, wpc * 32, smem, s>>>(
+        pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, stride2, ta, ti, te);
+    fs::count_launch();
+    return cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
+}
+
+// lanes per chain: 8 (four chains per warp) while a CTA's 16 chain slots fit shared memory comfortably, else 32
+static int launch_fast(float* pos, double* E, double* W, const double* md, long long* att, long long* acc, int B, int N,
+                       int steps, const PotDev& P, double beta, unsigned long long seed, long long chain_id0,
+                       unsigned char* ta, int* ti, float* te, cudaStream_t s) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("FS_SWEEP_LPC"); forced = e ? atoi(e) : 0; }   // tuning knob (8 / 16 / 32)
+    int lpc = forced ? forced : (N <= 1024 ? 8 : 32);
+    const bool tr = ta || ti || te;
+#define FS_FAST(L)                                                                                                     \
+    return tr ? launch_fast_t<L, true>(pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, ta, ti, te, s) \
+              : launch_fast_t<L, false>(pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, ta, ti, te, s)
+    if (lpc == 8) { FS_FAST(8); }
+    if (lpc == 16) { FS_FAST(16); }
+    FS_FAST(32);
+#undef FS_FAST
+}
+
 }  // namespace fs
 
 extern "C" int fs_local_sweep(float* pos, double* E, double* W, const double* max_disp, long long* attempts,
@@ -416,21 +507,10 @@ extern "C" int fs_local_sweep(float* pos, double* E, double* W, const double* ma
             return fs::launch_sweep<FS_RNG_PCG64>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
                                                   trace_accept, trace_idx, trace_e, s);
         case FS_RNG_PHILOX:
-            if (!trace_accept && !trace_idx && !trace_e) {
-                int wpc = 4;
-                while (wpc > 1 && (size_t)wpc * N * sizeof(float2) > 200 * 1024) wpc >>= 1;
-                const size_t smem = (size_t)wpc * N * sizeof(float2);
-                if (smem > 227 * 1024) {
-                    fs::set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
-                    return FS_ERR_UNSUPPORTED;
-                }
-                if (smem > 48 * 1024)
-                    FS_CUDA(cudaFuncSetAttribute(fs::local_sweep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                fs::local_sweep_fast_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, s>>>(
-                    pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, rng->philox_seed, rng->chain_id0);
-                fs::count_launch();
-                return fs::cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
-            }
+            return fs::launch_fast(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, rng->philox_seed,
+                                   rng->chain_id0, trace_accept, trace_idx, trace_e, s);
+        case FS_RNG_PHILOX_REF:      // the same Philox draws through the reference-order kernel (parity tests)
+            R.kind = FS_RNG_PHILOX;
             return fs::launch_sweep<FS_RNG_PHILOX>(pos, E, W, max_disp, attempts, accepted, B, N, steps, P, beta, R,
                                                    trace_accept, trace_idx, trace_e, s);
         case FS_RNG_REPLAY:

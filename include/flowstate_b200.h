@@ -58,6 +58,7 @@ typedef struct fs_pot {
 #define FS_RNG_PCG64 0
 #define FS_RNG_PHILOX 1
 #define FS_RNG_REPLAY 2
+#define FS_RNG_PHILOX_REF 3   /* the FS_RNG_PHILOX draws through the reference-order parity kernel (tests) */
 typedef struct fs_rng {
     int                 kind;
     unsigned long long* pcg_state;

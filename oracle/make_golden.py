@@ -207,11 +207,16 @@ FLOW_SPECS = [
     ("n4_k4", 4, 4, 2, 32, 15, 0.03, 0.05, 64),       # even N: x only element-wise
     ("n32_k2", 32, 2, 3, 64, 32, 0.03, 0.02, 48),     # Alg-1 bins (32) at N=32, cut-down width
     ("n4_k23", 4, 23, 2, 32, 15, 0.03, 0.05, 32),     # Alg-2 depth and bins (K=23, nb=15), cut-down width
+    # hidden widths of the two driver architectures, so reference-generated vectors reach the tensor-core path
+    ("n8_h128", 8, 3, 2, 128, 15, 0.03, 0.05, 40),    # Alg-2 width / blocks / bins (main_algorithm_2.py:62-70)
+    ("n6_h256", 6, 2, 1, 256, 32, 0.03, 0.03, 40),    # Alg-1 width / bins (main_algorithm_1.py:63-70), one block
 ]
 
 
-def gen_flow(ref):
+def gen_flow(ref, only=None):
     for tag, n, K, blocks, H, nb, rho, sigma, B in FLOW_SPECS:
+        if only and tag not in only:
+            continue
         bound = er.box_length(n, rho) / 2
         model = build_ref_flow(ref, n, K, blocks, H, nb, bound, seed=11, sigma=sigma)
         g = torch.Generator().manual_seed(3)
@@ -370,8 +375,13 @@ def gen_observables(ref):
 
 
 def main():
+    """No arguments: every fixture.  `flow:<tag>[,<tag>]`: only those flow fixtures."""
     ref = _refimport.load()
     os.makedirs(GOLD, exist_ok=True)
+    sel = [a for a in sys.argv[1:] if a.startswith("flow:")]
+    if sel:
+        gen_flow(ref, only=set(sel[0][5:].split(",")))
+        return
     gen_energy(ref)
     gen_mc(ref)
     gen_flow(ref)

@@ -92,7 +92,7 @@ def _load_sd(g, prefix="sd__"):
     return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
 
 
-@pytest.mark.parametrize("tag", ["n3_k3", "n4_k4", "n32_k2", "n4_k23"])
+@pytest.mark.parametrize("tag", ["n3_k3", "n4_k4", "n32_k2", "n4_k23", "n8_h128", "n6_h256"])
 def test_flow(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, "flow_%s.npz" % tag))
     sd = _load_sd(g)
@@ -167,3 +167,23 @@ def test_observables_oracle_matches_reference_golden(golden_dir):
                                      float(g["pc_%s_dr" % tag]))
         assert np.array_equal(r, g["pc_%s_r" % tag])
         np.testing.assert_allclose(gr, g["pc_%s_g" % tag], rtol=1e-14, atol=0)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10 (counter, key -> output), and the word -> draw mapping of the device."""
+    from oracle import philox_ref as pr
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        got = pr.philox4x32(*[[c] for c in ctr], key[0], key[1])
+        assert tuple(int(g[0]) for g in got) == out
+    p, u = pr.step_draws(0xa4093822 | (0x299f31d0 << 32), 0x03707344_13198a2e, 0x85a308d3_243f6a88, 1, 32)
+    assert int(p[0]) == (0xd16cfe09 * 32) >> 32
+    assert u[0].tolist() == [0x94fdcceb / 2 ** 32, 0x5001e420 / 2 ** 32, 0x24126ea1 / 2 ** 32]
+    rng = pr.StepRNG(7, 3, 10, 4, 5)
+    for s in range(4):
+        assert rng.integers(5) == int(pr.step_draws(7, 3, 10 + s, 1, 5)[0][0])
+        assert rng.random(2).shape == (2,)
+    assert 0.0 <= rng.random() < 1.0
