@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the NF-MCMC sampling hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload alg1_n32|alg1_n256|alg2_n64]
-                    [--precision auto|tf32|fp32] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload alg1_n256|alg1_n32|alg2_n64]
+                    [--precision auto|tf32|fp32] [--impl ours|reference] [--no-secondary]
 
 One "step" = one hybrid Algorithm-1 round on every chain of this rank
 (hybrid_NF_MCMC/main_algorithm_1.py:381-395): BIG_MOVE_INTERVAL local
@@ -10,15 +10,24 @@ displacement moves + ONE NF-proposed global move (flow sample, total energy of
 the proposal, log q of old and new state, Metropolis accept).  The metric is MH
 chain-steps/s (every local move and every global move is one chain-step, like
 the reference's attempts counter); NF proposals + energy evals/s is reported
-beside it.  Default workload: BASELINE configs[1] (4096 chains per GPU, N=32,
-Alg-1 flow K=15/H=256/32 blocks/32 bins); chains shard over ranks with no
-data-path collective (weak scaling), flow weights are broadcast once from rank 0.
+beside it.
+
+Default workload = the north_star target, BASELINE configs[2]: Algorithm-1 hybrid
+at N = 256 particles, 8192 chains per GPU (65 536 over 8 GPUs), flow K=15 / H=256 /
+32 blocks / 32 bins, for every --gpus N (weak scaling: chains shard over ranks
+with no data-path collective, flow weights are broadcast once from rank 0).
+At N = 1 the same JSON line carries `secondary` entries for configs[1]
+(alg1_n32), configs[3] (alg2_n64, sampling side) and configs[4] (energy sweep
+N = 64..4096 against a FP32-FMA peak measured in the same run), each with its
+own roofline, plus the accept kernel's HBM figure.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -29,14 +38,32 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: particles, chains per GPU, local steps per round, flow (K, blocks, H, bins), sigma, rho
-    "alg1_n32": dict(n=32, chains=4096, local=1000, K=15, blocks=32, H=256, nb=32, sigma=0.02, rho=0.03,
-                     desc="BASELINE configs[1]: Alg 1 hybrid, 4096 chains/GPU, N=32"),
     "alg1_n256": dict(n=256, chains=8192, local=1000, K=15, blocks=32, H=256, nb=32, sigma=0.02, rho=0.03,
                       desc="BASELINE configs[2]: Alg 1 hybrid, N=256, 8192 chains/GPU (65536 over 8 GPUs)"),
+    "alg1_n32": dict(n=32, chains=4096, local=1000, K=15, blocks=32, H=256, nb=32, sigma=0.02, rho=0.03,
+                     desc="BASELINE configs[1]: Alg 1 hybrid, 4096 chains/GPU, N=32"),
     "alg2_n64": dict(n=64, chains=4096, local=100, K=23, blocks=2, H=128, nb=15, sigma=0.05, rho=0.03,
                      desc="BASELINE configs[3] sampling part: Alg 2 cycle, N=64, 100 local steps + 1 global move"),
 }
+DEFAULT_WORKLOAD = "alg1_n256"
 POT = dict(num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15)
+PHILOX_SEED = 20261018
+
+
+def workload_config(name, w):
+    """The `config` object both arms print (same keys, same values)."""
+    return {"workload": name, "desc": w["desc"], "chains_per_gpu": w["chains"], "particles": w["n"],
+            "local_steps_per_round": w["local"], "rho": w["rho"],
+            "flow": {"K": w["K"], "blocks": w["blocks"], "H": w["H"], "bins": w["nb"], "sigma": w["sigma"]},
+            "potential": {"wells": POT["num_wells"], "V0": POT["V0_list"], "r0": POT["r0"], "k": POT["k"], "T": 1.0},
+            "l2": "inputs larger than L2: the flow weights (%.0f MB FP32) are streamed in every pass"
+                  % (flow_params(w) * 4 / 1e6)}
+
+
+def flow_params(w):
+    n, H, P = w["n"], w["H"], 3 * w["nb"] + 1
+    per = (2 * n * H + H) + w["blocks"] * (2 * (H * H + H) + 4 * H) + (n * P * H + n * P) + n * (3 * w["nb"] + 1) + 2 * n
+    return w["K"] * per
 
 
 def build_flow(NF, w, bound, device, seed=0):
@@ -63,6 +90,15 @@ def build_flow(NF, w, bound, device, seed=0):
 def flops_per_sample_layer(w):
     """2 (2N H + 2 n_blocks H^2 + H N (3 nb + 1))."""
     return 2.0 * (2 * w["n"] * w["H"] + 2 * w["blocks"] * w["H"] ** 2 + w["H"] * w["n"] * (3 * w["nb"] + 1))
+
+
+def sweep_flops_per_step(n):
+    """old and new particle energy, E and W both tracked."""
+    return 27.0 * 2 * (n - 1) + 2 * 40.0
+
+
+def energy_flops(B, n):
+    return 27.0 * B * n * (n - 1) / 2 + 40.0 * B * n
 
 
 class ClockSampler:
@@ -122,6 +158,10 @@ class ClockSampler:
         while self._thread is not None and not self.sm and time.time() - t0 < timeout:
             time.sleep(0.005)
 
+    def mark(self):
+        """Start of the timed region: samples taken before this index are warm-up."""
+        self._mark = len(self.sm)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self._thread is not None:
@@ -148,6 +188,10 @@ class ClockSampler:
         out["reasons"] = sorted(self.reasons)
         return out
 
+
+# ---------------------------------------------------------------------------
+# CPU side (the reference arm and the cpu_baseline leg): oracle port on the host cores
+# ---------------------------------------------------------------------------
 def _cpu_local_worker(args):
     n, rho, seed, steps = args
     from oracle import energy_ref as er
@@ -204,18 +248,67 @@ def cpu_baseline(w, budget_s=20.0, state_dict=None, bound=None):
             "local_steps_per_s_per_core": 1.0 / t_local, "global_moves_per_s": 1.0 / t_global}
 
 
-# ---------------------------------------------------------------------------
-def run_reference(args, w):
+def parity_check(path):
+    """The checker half of `parity_checked` (runs in the CPU subprocess, oracle only): re-evaluates a small sample of
+    what the GPU arm computed right before its timed region - a traced local sweep (lock-step, every decision), the
+    total energy of proposals, the flow in both directions and the global accept rule - and returns the errors."""
+    from oracle import energy_ref as er
+    from oracle import flow_ref as fr
+    from oracle import mc_ref as mr
+    from oracle import philox_ref as pr
+    d = np.load(path + ".npz")
+    sd = torch.load(path + ".pt", map_location="cpu")
+    n, L, md = int(d["n"]), float(d["L"]), float(d["md"])
+    bound = L / 2
+    pot = er.Potential(POT["num_wells"], POT["V0_list"], POT["r0"], POT["k"])
+    out = {"decisions": 0, "flips_in_band": 0, "outside_band": 0, "sweep_energy_err": 0.0}
+    steps = d["acc"].shape[1]
+    for c in range(d["pos0"].shape[0]):
+        p_all, u_all = pr.step_draws(int(d["seed"]), int(d["chain_id0"]) + c, 0, steps, n)
+        r = mr.lockstep_check(d["pos0"][c], L, md, pot, p_all, u_all, d["acc"][c], d["idx"][c], d["e"][c])
+        out["decisions"] += steps
+        out["flips_in_band"] += r["flips_in_band"]
+        out["outside_band"] += r["outside_band"] + int(not np.array_equal(r["final"], d["posF"][c]))
+        out["sweep_energy_err"] = max(out["sweep_energy_err"], r["max_energy_err"])
+    spec = fr.FlowSpec(sd, bound)
+    with torch.no_grad():
+        xo, ldo = fr.forward_and_log_det(sd, spec, torch.from_numpy(d["z"]).double(), dtype=torch.float64)
+        lq = fr.log_prob(sd, spec, torch.from_numpy(d["lq_in"]).double(), dtype=torch.float64).numpy()
+    out["sample_err_of_bound"] = float((torch.from_numpy(d["x"]).double() - xo).abs().max() / bound)
+    out["logq_rel_err"] = float(np.max(np.abs(d["lq"] - lq) / np.abs(lq)))
+    cfg = d["cfg"]
+    e_err = 0.0
+    for b in range(cfg.shape[0]):
+        Er, _ = er.total_energy_virial(cfg[b].astype(np.float64), L, L, pot)
+        if np.isfinite(Er):
+            e_err = max(e_err, abs(float(d["E_new"][b]) - Er) / max(1.0, abs(Er)))
+        else:
+            e_err = max(e_err, 0.0 if np.isinf(d["E_new"][b]) else 1.0)
+    out["energy_rel_err"] = e_err
+    # global accept rule (monte_carlo.py:264-303) on the device's own inputs
+    B = cfg.shape[0]
+    lq_old, lq_new = d["lq"][:B].astype(np.float64), d["lq"][B:].astype(np.float64)
+    with np.errstate(over="ignore", invalid="ignore"):
+        ratio = np.exp(-(d["E_new"].astype(np.float64) - d["E_old"]) - ((-lq_new) - (-lq_old)))
+    ref_mask = (ratio >= 1.0) | (d["u"] < ratio)
+    out["accept_mismatch"] = int(np.sum(ref_mask != d["mask"].astype(bool)))
+    out["ok"] = bool(out["outside_band"] == 0 and out["sweep_energy_err"] < 1e-5 and out["logq_rel_err"] < 1e-4
+                     and out["energy_rel_err"] < 1e-5 and out["accept_mismatch"] == 0
+                     and out["sample_err_of_bound"] < 2e-4)
+    return out
+
+
+def run_reference(args, name, w):
     """--impl reference: the reference's CPU path.  The reference is pure Python and does not
     travel to the GPU box (nothing to compile into oracle/_ref), so this arm times the oracle
-    port of it on all host cores, on the same config / metric / unit."""
+    port of it on all host cores, on the same config / metric / unit.  Nothing of the product
+    package is imported here: the flow weights come from oracle/flow_init.py."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import flowstate_b200.normflows as NF
+    from oracle import flow_init
     bound = float(np.float32(np.sqrt(w["n"] / w["rho"]))) / 2
-    model = build_flow(NF, w, bound, "cpu").eval()
-    sd = {k: v for k, v in model.state_dict().items()}
+    sd = flow_init.synthetic_state_dict(w["n"], w["K"], w["blocks"], w["H"], w["nb"], w["sigma"], seed=0)
     vals = []
     base = None
     t_all = time.perf_counter()
@@ -223,19 +316,357 @@ def run_reference(args, w):
         base = cpu_baseline(w, budget_s=args.budget, state_dict=sd, bound=bound)
         if i >= args.warmup:
             vals.append(base["value"])
-        if time.perf_counter() - t_all > 240:
+        if time.perf_counter() - t_all > 200:
             break
     v = float(np.mean(vals)) if vals else base["value"]
     base["value"] = v
+    if args.parity_file:
+        try:
+            base["parity"] = parity_check(args.parity_file)
+        except Exception as ex:
+            base["parity"] = {"ok": False, "error": repr(ex)}
     line = {"impl": "reference", "metric": "mh_chain_steps_per_s", "value": v, "unit": "chain-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * (w["local"] + 1) * w["chains"] * args.gpus / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": w["chains"],
-                       "particles": w["n"], "local_steps_per_round": w["local"]},
+            "config": workload_config(name, w),
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# GPU side
+# ---------------------------------------------------------------------------
+def load_peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        return json.load(open(pk)), "measured (MEASURED_PEAKS.json)"
+    # fallback of /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6550.0, "bf16_tflops": 1630.0, "bf16_tflops_sustained": 1375.0}, "fallback (B200_PROFILING.md)"
+
+
+def fp32_peak(device_index):
+    """FP32 FMA peak measured in this run (scripts/fp32_peak.cu, built by __graft_entry__.build())."""
+    so = os.path.join(ROOT, "scripts", "libfp32_peak.so")
+    if not os.path.exists(so):
+        return None
+    lib = ctypes.CDLL(so)
+    lib.fp32_peak.restype = ctypes.c_int
+    lib.fp32_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    out = {}
+    for variant, tag in ((0, "ffma"), (1, "ffma2")):
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        if lib.fp32_peak(device_index, variant, ctypes.byref(tf), ctypes.byref(ms)) != 0:
+            return None
+        out[tag] = tf.value
+    out["peak"] = max(out["ffma"], out["ffma2"])
+    return out
+
+
+class Harness:
+    """One workload on this rank: engine + flow + the hybrid round, its timings and rooflines."""
+
+    def __init__(self, name, w, dev, rank, world, precision):
+        import flowstate_b200.MCMC as MC
+        import flowstate_b200.normflows as NF
+        from flowstate_b200 import _lib, parallel
+        self.MC, self.NF, self._lib, self.parallel = MC, NF, _lib, parallel
+        self.name, self.w, self.dev, self.rank, self.world = name, w, dev, rank, world
+        n, B = w["n"], w["chains"]
+        self.n, self.B = n, B
+        self.L = float(np.float32(np.sqrt(n / w["rho"])))
+        self.bound = self.L / 2
+        # flow: built on every rank from the same seed on CPU, then broadcast from rank 0 over NCCL
+        self.model = build_flow(NF, w, self.bound, dev).to(dev).eval()
+        self.bcast_bytes = parallel.broadcast_flow(self.model, src=0) if world > 1 else 0
+        prec = precision
+        if prec == "auto":
+            prec = "tf32"
+            try:
+                self.model.precision = "tf32"
+                self.model.log_prob(torch.zeros(2, 2 * n, device=dev))
+            except Exception:
+                prec = "fp32"
+        self.prec = prec
+        self.model.precision = prec
+        self.fused = prec == "tf32" and w["H"] in (128, 256) and w["nb"] <= 32 and not os.environ.get("FS_NO_FUSE")
+        # chains: this rank's contiguous block of global chain ids
+        self.start, _ = parallel.shard_range(B * world, rank, world)
+        pos, _ = MC.jittered_lattice(n, w["rho"], seed=1000 + self.start, batch=B)
+        self.pos0 = pos
+        self.eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(self.L), 1.0, n, initial_max_displacement=0.65,
+                                        rng="philox", philox_seed=PHILOX_SEED, chain_id0=self.start, device=dev, **POT)
+        self.eng.set_nf_model(self.model)
+        self.half32 = np.float32(self.bound)
+        torch.manual_seed(1234 + rank)
+        # Proposals do not depend on the chains (Alg 1 even pre-generates its whole pool,
+        # main_algorithm_1.py:340-343), so the sampling pass of round r+1 runs on a side stream in the shadow
+        # of round r's sweep + log-density pass; every round still does one sample pass, two log-densities,
+        # one proposal energy and `local` local moves per chain.
+        self.side = torch.cuda.Stream(device=dev)
+        self.pending = {}
+
+    # -- the round ----------------------------------------------------------
+    def launch_proposals(self, z_host=None):
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.side):
+            if z_host is None:
+                z = self.model.q0(self.B)
+            else:
+                z = torch.empty(self.B, 2 * self.n, dtype=torch.float32, device=self.dev)
+                z.copy_(z_host, non_blocking=True)
+            cfg = (self.model.forward(z).reshape(self.B, self.n, 2) + self.half32).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        cfg.record_stream(main)
+        self.pending["cfg"], self.pending["ev"] = cfg, ev
+
+    def one_round(self, z_host=None):
+        if "cfg" not in self.pending:
+            self.launch_proposals(z_host)
+        cfg, ev = self.pending.pop("cfg"), self.pending.pop("ev")
+        self.launch_proposals(z_host)                  # next round's proposals, off the critical path
+        self.eng.particle_displacement(self.w["local"])
+        torch.cuda.current_stream(self.dev).wait_event(ev)
+        return self.eng.nf_big_move(cfg)
+
+    # -- parity sample (checked by the oracle in the cpu_baseline subprocess) ---
+    def dump_parity_sample(self, path, chains=6, steps=48, rows=6):
+        MC = self.MC
+        small = MC.BatchedMonteCarlo(self.pos0[:chains], MC.SimulationBox(self.L), 1.0, self.n,
+                                     initial_max_displacement=0.65, rng="philox", philox_seed=PHILOX_SEED,
+                                     chain_id0=self.start, device=self.dev, **POT)
+        small.set_nf_model(self.model)
+        tr = small.particle_displacement(steps, trace=True)
+        posF = small.pos.clone()
+        g = torch.Generator().manual_seed(99)
+        z = ((torch.rand(chains, 2 * self.n, generator=g) * 2 - 1) * self.bound).to(self.dev)
+        x, _ = self.model.forward_and_log_det(z)
+        cfg = (x.reshape(chains, self.n, 2) + self.half32).contiguous()
+        lq_in = torch.cat([small.centred(small.pos), small.centred(cfg)])
+        lq = self.model.log_prob(lq_in)
+        E_new, _, _ = small.total_energy_virial(cfg)
+        E_old = small.E.clone()
+        u = torch.rand(chains, generator=g, dtype=torch.float64).to(self.dev)
+        mask = small.nf_big_move(cfg, u=u, logq=(lq[:chains].contiguous(), lq[chains:].contiguous()))
+        c = lambda t: t.detach().cpu().numpy()
+        np.savez(path + ".npz", n=self.n, L=self.L, md=0.65, seed=PHILOX_SEED, chain_id0=self.start,
+                 pos0=self.pos0[:chains], acc=c(tr["accept"]), idx=c(tr["idx"]), e=c(tr["e"]), posF=c(posF), z=c(z),
+                 x=c(x), cfg=c(cfg), lq_in=c(lq_in), lq=c(lq), E_new=c(E_new), E_old=c(E_old), u=c(u), mask=c(mask))
+        torch.save({k: v.cpu() for k, v in self.model.state_dict().items()}, path + ".pt")
+
+    # -- device-resident timing ---------------------------------------------
+    def time_device(self, steps, warmup, clocks=None):
+        import torch.distributed as dist
+        dev, world = self.dev, self.world
+        if world > 1:
+            dist.barrier()
+        for _ in range(warmup):
+            self.one_round()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = self._lib.lib().fs_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            self.one_round()
+        e1.record()
+        torch.cuda.synchronize()
+        launches = int(self._lib.lib().fs_launch_count() - l0)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    # -- end to end: host buffers in, host results out, copies inside the timed region ----
+    def time_e2e(self, steps):
+        """Every step uploads that step's chain positions and base noise from pinned host memory, runs the round and
+        reads positions, energies and accept mask back.  Two host-resident chain batches alternate (batch k % 2 in
+        step k, its output becoming its next input), so the host waits for the results of step k-1 while step k is
+        already queued: the copies and the launch work of consecutive steps overlap as in a real pipeline."""
+        import torch.distributed as dist
+        B, n, dev, eng = self.B, self.n, self.dev, self.eng
+        h_z = torch.empty(B, 2 * n, dtype=torch.float32).uniform_(-self.bound, self.bound).pin_memory()
+        hb = []
+        for k in range(2):
+            hp = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
+            hp.copy_(eng.pos.cpu())
+            hb.append({"pos": hp, "out_pos": torch.empty(B, n, 2, dtype=torch.float32).pin_memory(),
+                       "out_E": torch.empty(B, dtype=torch.float64).pin_memory(),
+                       "out_mask": torch.empty(B, dtype=torch.uint8).pin_memory(), "ev": None})
+
+        def e2e_round(k):
+            buf = hb[k % 2]
+            if buf["ev"] is not None:                      # results of this batch's previous step have landed
+                buf["ev"].synchronize()
+                buf["pos"].copy_(buf["out_pos"])
+            eng.pos.copy_(buf["pos"], non_blocking=True)
+            eng.refresh_energy()
+            mask = self.one_round(h_z)                     # base noise comes from the host buffer
+            buf["out_pos"].copy_(eng.pos, non_blocking=True)
+            buf["out_E"].copy_(eng.E, non_blocking=True)
+            buf["out_mask"].copy_(mask, non_blocking=True)
+            buf["ev"] = torch.cuda.Event()
+            buf["ev"].record()
+
+        for k in range(2):
+            e2e_round(k)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            e2e_round(k)
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        h2d = B * n * 2 * 4 + B * 2 * n * 4
+        d2h = B * n * 2 * 4 + B * 8 + B
+        return float(e2e_s.item()), h2d, d2h
+
+    # -- dominant kernel, timed alone ------------------------------------------
+    def conditioner_roofline(self, peaks, peak_src):
+        """One coupling layer (conditioner GEMM chain with the fused spline epilogue, fs_flow_coupling), one launch per
+        layer and pass, timed alone with CUDA events on the launching stream on the row count of the log-density pass.
+        Timed in isolation -> the burst BF16 figure is the denominator (FP16 operands run at the BF16 rate, the TF32
+        GEMM0 at half of it: flop-weighted harmonic blend)."""
+        w, eng, model, dev = self.w, self.eng, self.model, self.dev
+        xin = eng.centred(torch.cat([eng.pos, eng.pos]))
+        model.log_prob(xin)
+        pack = model._cuda_pack()
+        s = np.pi / self.bound
+        feats = torch.cat([torch.cos(xin[:, 0::2] * s), torch.sin(xin[:, 0::2] * s)], dim=1).contiguous()
+        xo, ldo = torch.zeros_like(xin), torch.zeros(xin.shape[0], device=dev)
+
+        def dominant(li):
+            if self.fused:
+                pack.coupling(li, "density", feats, xin, xo, ldo)
+            else:
+                pack.conditioner(li, feats)
+        for li in range(3):
+            dominant(li)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2 * w["K"]
+        r0.record()
+        for i in range(reps):
+            dominant(i % w["K"])          # cycles through the layers: weights stream from HBM/L2 as in a pass
+        r1.record()
+        torch.cuda.synchronize()
+        pass_ms = r0.elapsed_time(r1) / reps
+        flops_pass = flops_per_sample_layer(w) * xin.shape[0]
+        bf16 = peaks.get("bf16_tflops", 1630.0)
+        tensor_peak = bf16 / 2.0
+        note = "%s bf16_tflops (burst: kernel timed alone) / 2 (tf32)" % peak_src
+        if self.prec == "tf32":
+            f_gemm0 = 2.0 * 2 * w["n"] * w["H"]
+            f_final = 2.0 * w["H"] * w["n"] * (3 * w["nb"] + 1)
+            f_tf32 = f_gemm0 + (0.0 if self.fused else f_final)
+            f_f16 = flops_per_sample_layer(w) - f_tf32
+            tensor_peak = (f_tf32 + f_f16) / (f_tf32 / (bf16 / 2.0) + f_f16 / bf16)
+            note = ("%s bf16_tflops (burst: the kernel is timed alone) for the FP16-operand GEMMs, half of it for the "
+                    "TF32 GEMM0, flop-weighted harmonic blend" % peak_src)
+        achieved = flops_pass / (pass_ms * 1e-3) / 1e12
+        traffic = None
+        for tj in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tj)
+            if os.path.exists(tp) and self.prec == "tf32":
+                # ncu dram bytes per launch of this kernel at this row count (weights dominate)
+                traffic = json.load(open(tp)).get("tc_conditioner_kernel<%d>%s@%s@%d" % (
+                    w["H"], "+spline" if self.fused else "", self.name, xin.shape[0]))
+                if traffic is not None:
+                    break
+        kern = (("tc_conditioner_kernel (tcgen05 kind::f16 / kind::tf32, fused spline epilogue)" if self.fused else
+                 "tc_conditioner_kernel (tcgen05 kind::tf32)") if self.prec == "tf32" else "linear_kernel chain (fp32)")
+        return {"bound": "tensor", "kernel": kern + ", one coupling layer", "achieved": achieved, "peak": tensor_peak,
+                "unit": "TFLOP/s", "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": note,
+                "launch_ms": pass_ms, "rows": int(xin.shape[0]),
+                "algorithmic_flop_per_launch": flops_pass}
+
+    def phases(self, fp32=None, peaks=None):
+        """Phase split of one round (not part of the timed region) + the rooflines of the non-dominant kernels."""
+        w, eng, model, dev, B, n = self.w, self.eng, self.model, self.dev, self.B, self.n
+        out = {}
+
+        def timed(name, fn, reps=1):
+            fn()                                       # untimed first call: workspaces of this shape / stream get allocated
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                r = fn()
+            b_.record()
+            torch.cuda.synchronize()
+            out[name] = a.elapsed_time(b_) / reps
+            return r
+        timed("local_sweep_ms", lambda: eng.particle_displacement(w["local"]))
+        zz = model.q0(B)
+        cfg = timed("flow_sample_ms", lambda: (model.forward(zz).reshape(B, n, 2) + self.half32).contiguous())
+        timed("energy_total_ms", lambda: eng.total_energy_virial(cfg), reps=5)
+        xin = eng.centred(torch.cat([eng.pos, eng.pos]))
+        lq = timed("flow_log_prob_2B_ms", lambda: model.log_prob(xin))
+        E_new, W_new, _ = eng.total_energy_virial(cfg)
+        u = torch.rand(B, dtype=torch.float64, device=dev)
+        acc0 = int(eng.accepted.sum().item())
+        lqo, lqn = lq[:B].contiguous(), lq[B:].contiguous()
+        timed("accept_global_ms", lambda: eng.nf_big_move(cfg, u=u, logq=(lqo, lqn)), reps=5)
+        extra = {}
+        if fp32:
+            sw = sweep_flops_per_step(n) * B * w["local"] / (out["local_sweep_ms"] * 1e-3) / 1e12
+            extra["local_sweep"] = {"bound": "fp32", "kernel": "local_sweep_fast_kernel", "achieved": sw,
+                                    "peak": fp32["peak"], "unit": "TFLOP/s", "frac": sw / fp32["peak"],
+                                    "peak_source": "scripts/fp32_peak.cu measured in this run"}
+            en = energy_flops(B, n) / (out["energy_total_ms"] * 1e-3) / 1e12
+            extra["energy_total"] = {"bound": "fp32", "kernel": "energy_total_kernel_v2", "achieved": en,
+                                     "peak": fp32["peak"], "unit": "TFLOP/s", "frac": en / fp32["peak"],
+                                     "peak_source": "scripts/fp32_peak.cu measured in this run"}
+        if peaks:
+            # accept kernel: 8N bytes of proposal read + 8N written per accepted chain + ~40 bytes of scalars per chain
+            # (the phase above re-ran the move 6 times on the same inputs: use its acceptance count)
+            frac_acc = (int(eng.accepted.sum().item()) - acc0) / (6.0 * B)
+            bytes_ = B * (8.0 * n * (1 + frac_acc) + 40)
+            gbs = bytes_ / (out["accept_global_ms"] * 1e-3) / 1e9
+            extra["accept_global"] = {"bound": "hbm", "kernel": "accept_global_kernel", "achieved": gbs,
+                                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                      "note": "launch-latency-bound at this size (%.1f KB in %.1f us)"
+                                              % (bytes_ / 1e3, out["accept_global_ms"] * 1e3)}
+        return out, extra
+
+
+def energy_sweep(dev, fp32, MC):
+    """BASELINE configs[4]: fs_energy_total over N = 64 .. 4096 x 1k-64k configurations, against the FP32 peak measured
+    in this run.  Algorithmic flop = 27 B N (N-1) / 2 + 40 B N."""
+    rows = []
+    for n, B in ((64, 65536), (128, 32768), (256, 16384), (512, 8192), (1024, 4096), (2048, 2048), (4096, 1024)):
+        pos, L = MC.jittered_lattice(n, 0.5, seed=7, batch=64)
+        pos = torch.from_numpy(pos).to(dev).repeat(B // 64, 1, 1).contiguous()
+        eng = MC.BatchedMonteCarlo(pos[:64], MC.SimulationBox(L), 1.0, n, rng="philox", device=dev, **POT)
+        eng.total_energy_virial(pos)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        a.record()
+        for _ in range(reps):
+            eng.total_energy_virial(pos)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        tf = energy_flops(B, n) / (ms * 1e-3) / 1e12
+        rows.append({"particles": n, "configs": B, "ms": ms, "pairs_per_s": B * n * (n - 1) / 2 / (ms * 1e-3),
+                     "achieved": tf, "frac": tf / fp32["peak"] if fp32 else None})
+        del pos, eng
+    return {"metric": "pair_energy_tflops", "desc": "BASELINE configs[4]: energy-kernel sweep, rho = 0.5 jittered lattices",
+            "roofline": {"bound": "fp32", "kernel": "energy_total_kernel_v2", "unit": "TFLOP/s",
+                         "peak": fp32["peak"] if fp32 else None, "peak_detail": fp32,
+                         "peak_source": "scripts/fp32_peak.cu measured in this run",
+                         "achieved": max(r["achieved"] for r in rows),
+                         "frac": max(r["frac"] for r in rows) if fp32 else None},
+            "rows": rows}
 
 
 def main():
@@ -243,18 +674,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--workload", default="alg1_n32", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="auto", choices=["auto", "tf32", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=None, help="override chains per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads / energy sweep")
     ap.add_argument("--budget", type=float, default=6.0, help="seconds of CPU work per reference-arm step")
+    ap.add_argument("--parity-file", default=None, help="(reference arm) parity sample dumped by the GPU arm")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.chains:
         w["chains"] = args.chains
     if args.impl == "reference":
-        return run_reference(args, w)
+        return run_reference(args, args.workload, w)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -273,242 +706,82 @@ def main():
     if world > 1:
         dist.barrier()
     import flowstate_b200.MCMC as MC
-    import flowstate_b200.normflows as NF
-    from flowstate_b200 import _lib, parallel
 
-    n, B = w["n"], w["chains"]
-    L = float(np.float32(np.sqrt(n / w["rho"])))
-    bound = L / 2
-    # flow: built on every rank from the same seed on CPU, then broadcast from rank 0 over NCCL
-    model = build_flow(NF, w, bound, dev).to(dev).eval()
-    bcast_bytes = parallel.broadcast_flow(model, src=0) if world > 1 else 0
-    prec = args.precision
-    if prec == "auto":
-        prec = "tf32"
-        try:
-            model.precision = "tf32"
-            model.log_prob(torch.zeros(2, 2 * n, device=dev))
-        except Exception:
-            prec = "fp32"
-    model.precision = prec
-    # chains: this rank's contiguous block of global chain ids
-    start, _ = parallel.shard_range(B * world, rank, world)
-    pos, _ = MC.jittered_lattice(n, w["rho"], seed=1000 + start, batch=B)
-    eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, n, initial_max_displacement=0.65, rng="philox",
-                               philox_seed=20261018, chain_id0=start, device=dev, **POT)
-    eng.set_nf_model(model)
-    half32 = np.float32(bound)
-    torch.manual_seed(1234 + rank)
-
-    # Proposals do not depend on the chains (Alg 1 even pre-generates its whole pool,
-    # main_algorithm_1.py:340-343), so the sampling pass of round r+1 runs on a side stream in the shadow
-    # of round r's sweep + log-density pass; every round still does one sample pass, two log-densities,
-    # one proposal energy and `local` local moves per chain.
-    side = torch.cuda.Stream(device=dev)
-    pending = {}
-
-    def launch_proposals(z_host=None):
-        main = torch.cuda.current_stream(dev)
-        with torch.cuda.stream(side):
-            if z_host is None:
-                z = model.q0(B)
-            else:
-                z = torch.empty(B, 2 * n, dtype=torch.float32, device=dev)
-                z.copy_(z_host, non_blocking=True)
-            cfg = (model.forward(z).reshape(B, n, 2) + half32).contiguous()
-            ev = torch.cuda.Event()
-            ev.record(side)
-        cfg.record_stream(main)
-        pending["cfg"], pending["ev"] = cfg, ev
-
-    def one_round(z_host=None):
-        if "cfg" not in pending:
-            launch_proposals(z_host)
-        cfg, ev = pending.pop("cfg"), pending.pop("ev")
-        launch_proposals(z_host)                       # next round's proposals, off the critical path
-        eng.particle_displacement(w["local"])
-        torch.cuda.current_stream(dev).wait_event(ev)
-        return eng.nf_big_move(cfg)
-
-    # ---- device-resident timing ------------------------------------------------
+    peaks, peak_src = load_peaks()
+    h = Harness(args.workload, w, dev, rank, world, args.precision)
+    tmpdir = tempfile.mkdtemp(prefix="fs_parity_")
+    parity_path = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        parity_path = os.path.join(tmpdir, "sample")
+        h.dump_parity_sample(parity_path)
     # clock sampler: in-process NVML thread, started (and its first sample awaited) before the warm-up rounds; its
     # samples cover the warm-up rounds (same load) and the timed region
     clocks = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("FS_NO_CLOCKS")) else None
     if clocks:
         clocks.wait_ready()
-    if world > 1:
-        dist.barrier()
-    for _ in range(args.warmup):
-        one_round()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    l0 = _lib.lib().fs_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        one_round()
-    e1.record()
-    torch.cuda.synchronize()
-    launches = int(_lib.lib().fs_launch_count() - l0)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total, launches = h.time_device(args.steps, args.warmup)
     clk = clocks.stop() if clocks else None
+    e2e_s, h2d, d2h = h.time_e2e(args.steps)
+    fp32 = fp32_peak(local_rank) if rank == 0 else None
+    roof = h.conditioner_roofline(peaks, peak_src)
+    phases, extra = h.phases(fp32, peaks)
 
-    # ---- end to end: host buffers in, host results out, copies inside the timed region ----
-    # Every step uploads that step's chain positions and base noise from pinned host memory, runs the round and
-    # reads positions, energies and accept mask back.  Two host-resident chain batches alternate (batch k % 2 in
-    # step k, its output becoming its next input), so the host waits for the results of step k-1 while step k is
-    # already queued: the copies and the launch work of consecutive steps overlap as in a real pipeline.
-    h_z = torch.empty(B, 2 * n, dtype=torch.float32).uniform_(-bound, bound).pin_memory()
-    hb = []
-    for k in range(2):
-        hp = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
-        hp.copy_(eng.pos.cpu())
-        hb.append({"pos": hp, "out_pos": torch.empty(B, n, 2, dtype=torch.float32).pin_memory(),
-                   "out_E": torch.empty(B, dtype=torch.float64).pin_memory(),
-                   "out_mask": torch.empty(B, dtype=torch.uint8).pin_memory(), "ev": None})
-
-    def e2e_round(k):
-        buf = hb[k % 2]
-        if buf["ev"] is not None:                      # results of this batch's previous step have landed
-            buf["ev"].synchronize()
-            buf["pos"].copy_(buf["out_pos"])
-        eng.pos.copy_(buf["pos"], non_blocking=True)
-        eng.refresh_energy()
-        mask = one_round(h_z)                          # base noise comes from the host buffer
-        buf["out_pos"].copy_(eng.pos, non_blocking=True)
-        buf["out_E"].copy_(eng.E, non_blocking=True)
-        buf["out_mask"].copy_(mask, non_blocking=True)
-        buf["ev"] = torch.cuda.Event()
-        buf["ev"].record()
-
-    for k in range(2):
-        e2e_round(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_round(k)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    h2d = B * n * 2 * 4 + B * 2 * n * 4
-    d2h = B * n * 2 * 4 + B * 8 + B
-
-    # ---- roofline of the dominant kernel: the conditioner of one coupling layer (one launch per layer and pass),
-    #      timed alone with CUDA events on the launching stream, on the row count of the log-density pass ----
-    xin = eng.centred(torch.cat([eng.pos, eng.pos]))
-    model.log_prob(xin)
-    pack = model._cuda_pack()
-    feats = torch.cat([torch.cos(xin[:, 0::2] * (np.pi / bound)), torch.sin(xin[:, 0::2] * (np.pi / bound))], dim=1).contiguous()
-    # the kernel the passes launch: conditioner with the fused spline epilogue when the flow shape has it
-    # (H = 128 / 256, at most 32 bins), else the conditioner writing theta
-    fused = prec == "tf32" and w["H"] in (128, 256) and w["nb"] <= 32 and not os.environ.get("FS_NO_FUSE")
-    xo, ldo = torch.zeros_like(xin), torch.zeros(xin.shape[0], device=dev)
-
-    def dominant(li):
-        if fused:
-            pack.coupling(li, "density", feats, xin, xo, ldo)
-        else:
-            pack.conditioner(li, feats)
-    for li in range(3):
-        dominant(li)
-    torch.cuda.synchronize()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 2 * w["K"]
-    r0.record()
-    for i in range(reps):
-        dominant(i % w["K"])          # cycles through the layers: weights stream from HBM/L2 as in a pass
-    r1.record()
-    torch.cuda.synchronize()
-    pass_ms = r0.elapsed_time(r1) / reps
-    flops_pass = flops_per_sample_layer(w) * xin.shape[0]
-    # phase split of one round (not part of the timed region above)
-    phases = {}
-
-    def timed(name, fn):
-        fn()                                           # untimed first call: workspaces of this shape / stream get allocated
-        torch.cuda.synchronize()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = fn()
-        b_.record()
-        torch.cuda.synchronize()
-        phases[name] = a.elapsed_time(b_)
-        return out
-    timed("local_sweep_ms", lambda: eng.particle_displacement(w["local"]))
-    zz = model.q0(B)
-    cfg = timed("flow_sample_ms", lambda: (model.forward(zz).reshape(B, n, 2) + half32).contiguous())
-    timed("energy_total_ms", lambda: eng.total_energy_virial(cfg))
-    timed("flow_log_prob_2B_ms", lambda: model.log_prob(xin))
+    secondary = {}
+    if rank == 0 and world == 1 and not args.no_secondary:
+        del h.model, h.eng
+        h.pending.clear()
+        torch.cuda.empty_cache()
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            ws = dict(WORKLOADS[name])
+            hs = Harness(name, ws, dev, 0, 1, args.precision)
+            s_steps = 12
+            ms_s, l_s = hs.time_device(s_steps, 4)
+            e2e_ss, h2d_s, d2h_s = hs.time_e2e(s_steps)
+            tot = ws["chains"] * (ws["local"] + 1) * s_steps
+            ph, ex = hs.phases(fp32, peaks)
+            secondary[name] = {"metric": "mh_chain_steps_per_s", "value": tot / (ms_s * 1e-3), "unit": "chain-steps/s",
+                               "steps": s_steps, "warmup": 4, "ms_per_step": ms_s / s_steps, "gpu_launches": l_s,
+                               "config": workload_config(name, ws),
+                               "e2e": {"value": tot / e2e_ss, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d_s,
+                                       "d2h_bytes_per_step": d2h_s},
+                               "roofline": hs.conditioner_roofline(peaks, peak_src), "phases_ms": ph,
+                               "other_rooflines": ex}
+            del hs
+            torch.cuda.empty_cache()
+        try:
+            secondary["energy_sweep"] = energy_sweep(dev, fp32, MC)
+        except Exception as ex:      # a secondary entry must never take the line down
+            secondary["energy_sweep"] = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
-    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured" if peaks else "fallback"
-    # TF32 tensor peak = half the measured BF16 figure (same pipe, K=8 instead of 16 per instruction)
-    tensor_peak = bf16 / 2.0
-    peak_note = "%s bf16_tflops_sustained / 2 (tf32)" % peak_src
-    if prec == "tf32":
-        # tensor path: GEMM0 (features) has TF32 operands, every other GEMM FP16 operands (BF16-rate pipe); on the
-        # theta path (no fused epilogue) the final layer is TF32 too.  Roofline of the launch = flop-weighted harmonic
-        # blend of the two peaks.
-        f_gemm0 = 2.0 * 2 * w["n"] * w["H"]
-        f_final = 2.0 * w["H"] * w["n"] * (3 * w["nb"] + 1)
-        f_tf32 = f_gemm0 + (0.0 if fused else f_final)
-        f_f16 = flops_per_sample_layer(w) - f_tf32
-        tensor_peak = (f_tf32 + f_f16) / (f_tf32 / (bf16 / 2.0) + f_f16 / bf16)
-        peak_note = ("%s bf16_tflops_sustained for the FP16-operand GEMMs, half of it for the TF32 ones, flop-weighted "
-                     "harmonic blend" % peak_src)
-    achieved = flops_pass / (pass_ms * 1e-3) / 1e12
-    traffic = None
-    tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tj) and prec == "tf32":
-        # ncu dram bytes per launch of this kernel at this row count (weights dominate)
-        traffic = json.load(open(tj)).get("tc_conditioner_kernel<%d>%s@%s@%d" % (w["H"], "+spline" if fused else "",
-                                                                                 args.workload, xin.shape[0]))
+    n, B = w["n"], w["chains"]
     steps_total = world * B * (w["local"] + 1) * args.steps
     value = steps_total / (ms_total * 1e-3)
     line = {
         "metric": "mh_chain_steps_per_s", "value": value, "unit": "chain-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16" if prec == "tf32" else "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "chains_per_gpu": B, "particles": n,
-                   "local_steps_per_round": w["local"],
-                   "flow": {"K": w["K"], "blocks": w["blocks"], "H": w["H"], "bins": w["nb"], "sigma": w["sigma"]},
-                   "rho": w["rho"], "rng": "philox",
-                   "conditioner": ("tf32 operands in GEMM0, fp16 operands in the residual blocks and the final layer, fp32 "
-                                   "accumulation" if fused else prec),
-                   "pipelining": "proposals of round r+1 sampled on a side stream during round r",
-                   "l2": "inputs larger than L2: %.0f MB of flow weights streamed per pass"
-                         % (sum(p.numel() for p in model.parameters()) * 4 / 1e6),
-                   "weight_broadcast_bytes": bcast_bytes},
+        "dtype": "f16" if h.prec == "tf32" else "f32", "data": "synthetic",
+        "config": workload_config(args.workload, w),
+        "details": {"rng": "philox",
+                    "conditioner": ("tf32 operands in GEMM0, fp16 operands in the residual blocks and the final layer, "
+                                    "fp32 accumulation" if h.fused else h.prec),
+                    "pipelining": "proposals of round r+1 sampled on a side stream during round r",
+                    "weight_broadcast_bytes": h.bcast_bytes,
+                    "timed_region_ms": ms_total},
         "nf_proposals_per_s": world * B * args.steps / (ms_total * 1e-3),
         "gpu_launches": launches, "clocks": clk, "phases_ms": phases,
         "e2e": {"value": steps_total / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "roofline": {"bound": "tensor", "kernel": (("tc_conditioner_kernel (tcgen05 kind::f16 / kind::tf32, fused spline epilogue)" if fused else
-                                 "tc_conditioner_kernel (tcgen05 kind::tf32)") if prec == "tf32"
-                                else "linear_kernel chain (fp32)") + ", one coupling layer",
-                     "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                     "traffic": traffic, "peak_source": peak_note,
-                     "launch_ms": pass_ms, "rows": int(xin.shape[0])},
+        "roofline": roof, "other_rooflines": extra, "fp32_peak_tflops": fp32,
     }
+    if secondary:
+        line["secondary"] = secondary
     if not args.no_cpu_baseline and world == 1:
         # separate process: the oracle forks worker processes, which must not inherit a CUDA context
         try:
@@ -516,11 +789,18 @@ def main():
                    "--workload", args.workload, "--budget", "20"]
             if args.chains:
                 cmd += ["--chains", str(args.chains)]
+            if parity_path:
+                cmd += ["--parity-file", parity_path]
             env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
             for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
                 env.pop(k, None)
-            out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
-            line["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+            base = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+            par = base.pop("parity", None)
+            line["cpu_baseline"] = base
+            if par is not None:
+                line["parity_checked"] = bool(par.get("ok"))
+                line["parity"] = par
         except Exception as ex:     # the baseline must never take the GPU line down
             line["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(line))

@@ -28,7 +28,11 @@ struct PotDev {
     // wells: geometry in float64 (the wall k (r - r0) is steep: k = 15 turns a float32 rounding of
     // r, r0 or the centre into > 1e-5 of energy), potential.py:89-112
     double cxd[2], cyd, Lxd, Lyd, r0d, k2d;
-    float cxf[2], cyf, well_out2, well_in;   // float32 pre-test: outside -> 0, deep inside -> V0 (|2k(r-r0)| > 90)
+    // float32 pre-test: outside r0 + m the term is 0, inside r0 - m it is V0, with m = 12 / k: |2k(r - r0)| > 24 there
+    // and V0 e^-24 = 4e-10 is five orders below the 1e-5 tolerance.  well_shift_ok: the box is wide enough that a
+    // particle passing the pre-test has an unambiguous periodic image (the float32 image shift can be reused).
+    float cxf[2], cyf, well_out2, well_in;
+    int well_shift_ok;
 };
 
 inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
@@ -57,10 +61,11 @@ inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
     d.cxf[1] = (float)d.cxd[1];
     d.cyf = (float)d.cyd;
     {
-        const double m = p->k > 0 ? 45.0 / (double)p->k : 1e30;     // 2k m = 90: exp(+-90) is 0 / inf in float32
+        const double m = p->k > 0 ? 12.0 / (double)p->k : 1e30;
         const double ro = (double)p->r0 + m;
         d.well_out2 = (float)(ro * ro);
         d.well_in = (float)((double)p->r0 - m);                    // may be negative: shortcut never taken
+        d.well_shift_ok = (0.5 * (double)Lx > 1.01 * ro + 1e-3 && 0.5 * (double)Ly > 1.01 * ro + 1e-3) ? 1 : 0;
     }
     return d;
 }
@@ -120,6 +125,37 @@ __device__ __forceinline__ float wells(float x, float y, const PotDev& P) {
     if (P.num_wells >= 1) v += well_term(x, y, 0, P);
     if (P.num_wells == 2) v += well_term(x, y, 1, P);
     return v;
+}
+
+// The same term for the throughput sweep: parameters picked by selects (a dynamically indexed kernel parameter lives
+// in local memory), and on the wall the float64 geometry reuses the float32 image shift (no float64 division) when the
+// box is wide enough for it to be unambiguous (well_shift_ok).
+__device__ __forceinline__ float well_term_sel(float x, float y, int wi, const PotDev& P) {
+    const float cxf = wi ? P.cxf[1] : P.cxf[0];
+    const float v0 = wi ? P.V0[1] : P.V0[0];
+    float fx = x - cxf, fy = y - P.cyf;
+    const float nx = rint_fast(fx * P.inv_Lx), ny = rint_fast(fy * P.inv_Ly);
+    fx = __fmaf_rn(-P.Lx, nx, fx);
+    fy = __fmaf_rn(-P.Ly, ny, fy);
+    const float r2f = __fmaf_rn(fy, fy, fx * fx);
+    if (r2f > P.well_out2) return 0.0f;
+    if (P.well_in > 0.0f && r2f < P.well_in * P.well_in) return v0;
+    const double cxd = wi ? P.cxd[1] : P.cxd[0];
+    double dx = (double)x - cxd;
+    double dy = (double)y - P.cyd;
+    if (P.well_shift_ok) {
+        dx -= P.Lxd * (double)nx;
+        dy -= P.Lyd * (double)ny;
+    } else {
+        dx -= P.Lxd * rint(dx / P.Lxd);
+        dy -= P.Lyd * rint(dy / P.Lyd);
+    }
+    const double r2 = dx * dx + dy * dy;
+    const float rf = sqrtf((float)r2);
+    double r = 0.0;
+    if (rf > 0.0f) r = (double)rf + (r2 - (double)rf * (double)rf) * (double)(0.5f / rf);
+    const float a2 = (float)(P.k2d * (r - P.r0d));
+    return v0 / (1.0f + expf(a2));
 }
 
 // numpy float32 floor-mod (npy_divmodf), simulation_box.py:23-26 on a float32 state.

@@ -220,13 +220,15 @@ __device__ __forceinline__ unsigned long long mul2s(unsigned long long a, unsign
     return d;
 }
 
-// numpy float32 floor-mod for the common case -L <= a < 2L (one shift); anything else takes np_mod.
+// numpy float32 floor-mod for the common case -L <= a < 2L (one shift, no branch); anything else takes np_mod.
+__device__ __noinline__ float np_mod_far(float a, float L) { return np_mod(a, L); }
 __device__ __forceinline__ float np_mod_near(float a, float L) {
-    if (!(a >= -L && a < 2.0f * L)) return np_mod(a, L);   // rare: more than one box length away
     // a >= L: a - L is exact (Sterbenz), what fmodf returns; a < 0: fmodf keeps a and numpy adds the divisor (the sum
     // may round to L); 0 <= a < L: unchanged, with -0.0 -> +0.0 like copysignf(0, L)
     const float shift = (a >= L) ? -L : ((a < 0.0f) ? L : 0.0f);
-    return a + shift;
+    float r = a + shift;
+    if (__builtin_expect(!(a >= -L && a < 2.0f * L), 0)) r = np_mod_far(a, L);   // rare: more than one box length away
+    return r;
 }
 
 // LPC lanes of a warp own one chain (32 / LPC chains per warp): the per-step scalar work (random numbers, the
@@ -236,7 +238,7 @@ __device__ __forceinline__ float np_mod_near(float a, float L) {
 // float2 apart (stride2 * 8 bytes = 64 mod 128, so the groups of a warp read disjoint banks).
 // TRACE adds the outputs of the parity tests (accept flag, particle index, e_old / e_new reduced separately); the
 // decision arithmetic is the same code either way, so a traced run follows the untraced trajectory bit for bit.
-template <int LPC, bool TRACE>
+template <int LPC, bool TRACE, bool SKIP>
 __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
                                                                double* __restrict__ W,
                                                                const double* __restrict__ max_disp,
@@ -268,10 +270,11 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     __syncwarp();
 
     const double md = max_disp[b];
-    long long att = attempts[b];
+    const long long att0 = attempts[b];
     int acc = 0;
     double Eb = E[b];
     double Wl = 0.0;                         // this lane's share of the accepted virial differences (summed at the end)
+    float wacc = 0.f;                        // ... collected in float32 and flushed every 16 steps
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const long long cid = chain_id0 + b;
     const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
@@ -284,8 +287,8 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const int well_idx = sub & 1;
     const bool well_new = (sub & 2) != 0;
     const unsigned gmask = (LPC == 32) ? FULL : (((1u << LPC) - 1u) << gl0);
+    const uint32_t a0 = (uint32_t)att0;      // low bits of the step id: slot inside the LPC-step block of random numbers
     uint4 blk = make_uint4(0, 0, 0, 0);
-    long long blk_base = -1;
     struct {
         unsigned long long iLx, iLy, nLx, nLy, magic, nmagic, four, mone, mhalf;
     } K;
@@ -293,33 +296,47 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     K.magic = pk2s(12582912.0f, 12582912.0f); K.nmagic = pk2s(-12582912.0f, -12582912.0f);
     K.four = pk2s(4.0f, 4.0f); K.mone = pk2s(-1.0f, -1.0f); K.mhalf = pk2s(-0.5f, -0.5f);
 
-    for (int s = 0; s < steps; ++s, ++att) {
-        // one Philox block per step id {particle index, u1, u2, accept uniform}; a group prepares LPC steps at a time
-        // (lane `sub` the step base + sub) and reads them back by shuffles
-        const long long base = att & ~(long long)(LPC - 1);
-        if (__any_sync(FULL, base != blk_base)) {
-            const unsigned long long sid = (unsigned long long)(base + sub);
+    // One Philox block per step id {particle index, u1, u2, accept uniform}; a group prepares LPC steps at a time
+    // (lane `sub` the step  base + sub) and reads them back by shuffles.  The draws of step s + 1 are fetched while
+    // step s runs (they do not depend on it), which takes them off the step's dependent instruction chain.
+    int p_n;
+    double dx_n, dy_n;
+    uint32_t u3_n;
+    auto fetch = [&](int s) {
+        const uint32_t slot = (a0 + (uint32_t)s) & (LPC - 1);
+        if (__any_sync(FULL, slot == 0 || s == 0)) {          // groups of a warp whose counters are not aligned refill
+            const unsigned long long sid = (unsigned long long)(att0 + s - (long long)slot + sub);   // their own block again
             blk = philox4x32(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), cz, cw), key);
-            blk_base = base;
         }
-        const int src = gl0 + (int)(att & (LPC - 1));
+        const int src = gl0 + (int)slot;
         const uint32_t r_idx = __shfl_sync(FULL, blk.x, src);
         const uint32_t r_u1 = __shfl_sync(FULL, blk.y, src);
         const uint32_t r_u2 = __shfl_sync(FULL, blk.z, src);
-        const uint32_t r_u3 = __shfl_sync(FULL, blk.w, src);
-        const int p = (int)__umulhi(r_idx, (uint32_t)N);
+        u3_n = __shfl_sync(FULL, blk.w, src);
+        p_n = (int)__umulhi(r_idx, (uint32_t)N);
+        dx_n = ((double)r_u1 * (1.0 / 4294967296.0) - 0.5) * md;
+        dy_n = ((double)r_u2 * (1.0 / 4294967296.0) - 0.5) * md;
+    };
+    fetch(0);
+
+    for (int s = 0; s < steps; ++s) {
+        const int p = p_n;
+        const double ddx = dx_n, ddy = dy_n;
+        const uint32_t r_u3 = u3_n;
         const float2 old = sp[p];
         __syncwarp();
         if (sub == 0) sp[p] = make_float2(qnan, qnan);       // the moved particle is not its own partner
         // new_positions[p] += displacement (float64 add, stored float32), then % L (monte_carlo.py:161-166)
-        float nx = (float)((double)old.x + ((double)r_u1 * (1.0 / 4294967296.0) - 0.5) * md);
-        float ny = (float)((double)old.y + ((double)r_u2 * (1.0 / 4294967296.0) - 0.5) * md);
+        float nx = (float)((double)old.x + ddx);
+        float ny = (float)((double)old.y + ddy);
         nx = np_mod_near(nx, Lx);
         ny = np_mod_near(ny, Ly);
         __syncwarp();
+        if (s + 1 < steps) fetch(s + 1);
 
         // pair terms of the moved particle at its old and new position (energy_calculator.py:48-108); (old, new) ride
-        // in the two halves of Blackwell's packed FP32 pairs (FADD2 / FMUL2 / FFMA2)
+        // in the two halves of Blackwell's packed FP32 pairs (FADD2 / FMUL2 / FFMA2).  SKIP (dilute boxes): a trip of
+        // the warp whose 64 pairs all lie outside the cut-off contributes nothing and ends after r^2.
         float mo = 3.0e38f, mn = 3.0e38f;
         unsigned long long e2 = 0ull, w2 = 0ull;                     // (sum e_old, sum e_new), (sum w_old, sum w_new)
         const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny);
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
             Y = fma2s(add2s(fma2s(Y, K.iLy, K.magic), K.nmagic), K.nLy, Y);
             float r2o, r2n;
             upk2s(fma2s(Y, Y, mul2s(X, X)), r2o, r2n);
+            if (SKIP && !__any_sync(FULL, fminf(r2o, r2n) <= rc2)) continue;
             mo = fminf(mo, r2o);
             mn = fminf(mn, r2n);
             float io, in_;
@@ -349,7 +367,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         float de = en_s - eo_s;
         const float dw = 48.0f * (wn_s - wo_s);
         float wv = 0.f;
-        if (well_lane) wv = well_term(well_new ? nx : old.x, well_new ? ny : old.y, well_idx, P);
+        if (well_lane) wv = well_term_sel(well_new ? nx : old.x, well_new ? ny : old.y, well_idx, P);
         de += well_new ? wv : -wv;
 #pragma unroll
         for (int o = LPC / 2; o > 0; o >>= 1) de += __shfl_xor_sync(FULL, de, o);
@@ -386,19 +404,25 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         if (sub == 0) sp[p] = ok ? make_float2(nx, ny) : old;
         if (ok) {
             acc += 1;
-            const float big_o = ov_o ? inf : 0.f, big_n = ov_n ? inf : 0.f;
-            Eb += (double)de + ((double)big_n - (double)big_o);
-            Wl += (double)dw;
-            if (sub == 0) Wl += (double)big_n - (double)big_o;
+            if (__builtin_expect(ov_o || ov_n, 0)) {           // leaving (or, from an overlap, entering) the hard core
+                const float big_o = ov_o ? inf : 0.f, big_n = ov_n ? inf : 0.f;
+                Eb += (double)de + ((double)big_n - (double)big_o);
+                if (sub == 0) Wl += (double)big_n - (double)big_o;
+            } else {
+                Eb += (double)de;
+            }
+            wacc += dw;
         }
+        if ((s & 15) == 15) { Wl += (double)wacc; wacc = 0.f; }
         __syncwarp();
     }
+    Wl += (double)wacc;
 #pragma unroll
     for (int o = LPC / 2; o > 0; o >>= 1) Wl += __shfl_xor_sync(FULL, Wl, o);
     if (live) {
         for (int i = sub; i < N; i += LPC) gp[i] = sp[i];
         if (sub == 0) {
-            attempts[b] = att;
+            attempts[b] = att0 + steps;
             accepted[b] += acc;
             E[b] = Eb;
             W[b] += Wl;
@@ -445,13 +469,15 @@ static int launch_sweep(float* pos, double* E, double* W, const double* md, long
     return cuda_check(cudaGetLastError(), "local_sweep_kernel");
 }
 
-template <int LPC, bool TRACE>
+template <int LPC, bool TRACE, bool SKIP>
 static int launch_fast_t(float* pos, double* E, double* W, const double* md, long long* att, long long* acc, int B,
                          int N, int steps, const PotDev& P, double beta, unsigned long long seed, long long chain_id0,
                          unsigned char* ta, int* ti, float* te, cudaStream_t s) {
     constexpr int CPW = 32 / LPC;
     // slot stride: N rounded up so that stride * 8 bytes = 64 (mod 128) - the lane groups of a warp then hit disjoint banks
-    int stride2 = (N + 15) / 16 * 16 + (CPW > 1 ? 8 : 0);       // >= ceil(N / LPC) * LPC: room for the NaN padding
+    int stride2 = (N + 15) / 16 * 16 + (CPW > 1 ? 8 : 0);
+    const int padded = (N + LPC - 1) / LPC * LPC;                // room for the NaN padding of the last trip
+    if (stride2 < padded) stride2 = padded;
     int wpc = 4;
     while (wpc > 1 && (size_t)wpc * CPW * stride2 * sizeof(float2) > 200 * 1024) wpc >>= 1;
     const size_t smem = (size_t)wpc * CPW * stride2 * sizeof(float2);
@@ -460,10 +486,10 @@ static int launch_fast_t(float* pos, double* E, double* W, const double* md, lon
         return FS_ERR_UNSUPPORTED;
     }
     if (smem > 48 * 1024)
-        FS_CUDA(cudaFuncSetAttribute(local_sweep_fast_kernel<LPC, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FS_CUDA(cudaFuncSetAttribute(local_sweep_fast_kernel<LPC, TRACE, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     const int cpc = wpc * CPW;
-    local_sweep_fast_kernel<LPC, TRACE><<<(B + cpc - 1) / cpc, wpc * 32, smem, s>>>(
+    local_sweep_fast_kernel<LPC, TRACE, SKIP><<<(B + cpc - 1) / cpc, wpc * 32, smem, s>>>(
         pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, stride2, ta, ti, te);
     fs::count_launch();
     return cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
@@ -477,12 +503,22 @@ static int launch_fast(float* pos, double* E, double* W, const double* md, long 
     if (forced < 0) { const char* e = getenv("FS_SWEEP_LPC"); forced = e ? atoi(e) : 0; }   // tuning knob (8 / 16 / 32)
     int lpc = forced ? forced : (N <= 1024 ? 8 : 32);
     const bool tr = ta || ti || te;
-#define FS_FAST(L)                                                                                                     \
-    return tr ? launch_fast_t<L, true>(pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, ta, ti, te, s) \
-              : launch_fast_t<L, false>(pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, ta, ti, te, s)
+    // dilute boxes: most warp trips of the pair loop see no partner inside the cut-off (probability of a pair inside it
+    // is pi rc^2 / (Lx Ly); a trip holds 64 pairs) -> early-out variant
+    static int skip_forced = -1;
+    if (skip_forced < 0) { const char* e = getenv("FS_SWEEP_SKIP"); skip_forced = e ? (atoi(e) ? 1 : 0) : 2; }
+    const bool skip = skip_forced == 2 ? (64.0 * 3.14159 * P.rc2 < 0.75 * (double)P.Lx * (double)P.Ly) : skip_forced == 1;
+#define FS_FAST2(L, T, S) \
+    return launch_fast_t<L, T, S>(pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, ta, ti, te, s)
+#define FS_FAST(L)                                     \
+    do {                                               \
+        if (tr) { if (skip) FS_FAST2(L, true, true); else FS_FAST2(L, true, false); }     \
+        else { if (skip) FS_FAST2(L, false, true); else FS_FAST2(L, false, false); }      \
+    } while (0)
     if (lpc == 8) { FS_FAST(8); }
     if (lpc == 16) { FS_FAST(16); }
     FS_FAST(32);
+#undef FS_FAST2
 #undef FS_FAST
 }
 

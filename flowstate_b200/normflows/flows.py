@@ -102,6 +102,7 @@ class CircularCoupledRationalQuadraticSpline(Flow):
 
         self.prqct = _SplineCoupling(mask, net_fn, num_bins, tail_bound)
         self._pack = None
+        self.precision = "auto"      # conditioner arithmetic of the eval-mode kernels, as NormalizingFlow.precision
 
     # -- shapes -----------------------------------------------------------
     @property
@@ -160,6 +161,7 @@ class CircularCoupledRationalQuadraticSpline(Flow):
         from ._pack import FlowPack
         if self._pack is None or not self._pack.matches([self]):
             self._pack = FlowPack([self])
+        self._pack.precision = self.precision
         return self._pack
 
     def train(self, mode=True):

@@ -106,6 +106,21 @@ def particle_energy_virial(positions, p, Lx, Ly, pot):
     return float(pe), float(pw)
 
 
+def particle_energy_magnitude(positions, p, Lx, Ly, pot):
+    """sum_j |LJ(r_pj)| + |V_ext(p)|: the magnitude of the terms particle_energy_virial adds up.  A float32 evaluation
+    of the pair terms is accurate relative to THIS quantity (the total can be much smaller when attractive and
+    repulsive terms cancel); the parity tests scale their 1e-5 tolerance and the acceptance epsilon band with it."""
+    others = np.delete(positions, p, axis=0)
+    r = distances(positions[p], others, Lx, Ly)
+    if np.any(r < R_CORE):
+        return float("inf")
+    e, _ = lj_energy_virial(r)
+    m = np.sum(np.abs(e))
+    if pot.num_wells > 0:
+        m = m + abs(double_well(positions[p], Lx, Ly, pot))
+    return float(m)
+
+
 def total_energy_virial(positions, Lx, Ly, pot):
     """energy_calculator.py:121-203: sum_{i<j} LJ + sum_i V_ext; the reference
     returns (inf, inf) at the first row holding a pair closer than 0.5."""

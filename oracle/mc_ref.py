@@ -166,3 +166,65 @@ class ChainRef:
         pressure = density / self.beta + self.W / (2.0 * volume)
         return (cycle, self.E / self.n, density, pressure, self.Lx, self.Ly,
                 self.particles.copy())
+
+
+def lockstep_check(pos0, L, max_disp, pot, p_all, u_all, acc, idx=None, e=None, beta=1.0, tol_e=1e-5):
+    """Replays one chain of a device run through the reference rule, step by step, on the SAME draws.
+
+    pos0 (N,2) float32 start, p_all [S] particle indices, u_all [S,3] uniforms (two displacement uniforms and the accept
+    uniform), acc [S] the device's decisions, idx / e optional device traces (particle index, (e_old, e_new)).
+    The oracle state follows the device's decision after every step, so every decision is checked against
+    MCMC/monte_carlo.py:191-223 on the very state the device saw.
+
+    Tolerances.  Energies: |e_dev - e_ref| <= tol_e * max(1, M) with M = sum_j |LJ(r_pj)| + |V_ext| the magnitude of the
+    summed terms (= |e| when the terms share a sign; a float32 sum of cancelling pair terms cannot be more accurate than
+    that, and neither is the reference itself once its state is float32).  A decision may differ from the
+    rule only inside the epsilon band |log u - Delta| <= beta tol_e (M_old + M_new) (SURVEY.md 7.2 with |e| -> M), or
+    when a pair sits within 1e-6 of the hard-core radius (the device compares r^2, the reference r).
+    Returns dict(flips_in_band, outside_band, max_energy_err, final (N,2) float32 state)."""
+    state = np.array(pos0, dtype=np.float32)
+    flips = outside = 0
+    max_err = 0.0
+    for s in range(len(acc)):
+        p = int(p_all[s])
+        if idx is not None and int(idx[s]) != p:
+            outside += 1
+        truth = state.astype(np.float64)
+        eno, _ = er.particle_energy_virial(truth, p, L, L, pot)
+        new = state.copy()
+        new[p] += (np.asarray(u_all[s, :2], dtype=np.float64) - 0.5) * max_disp    # monte_carlo.py:161-163
+        new[p] = er.apply_pbc(new[p], L, L)
+        new64 = new.astype(np.float64)
+        enn, _ = er.particle_energy_virial(new64, p, L, L, pot)
+        mo = er.particle_energy_magnitude(truth, p, L, L, pot)
+        mn = er.particle_energy_magnitude(new64, p, L, L, pot)
+        core_band = False
+        if len(state) > 1:
+            dmin_o = np.min(er.distances(truth[p], np.delete(truth, p, 0), L, L))
+            dmin_n = np.min(er.distances(new64[p], np.delete(new64, p, 0), L, L))
+            core_band = abs(dmin_o - er.R_CORE) < 1e-6 or abs(dmin_n - er.R_CORE) < 1e-6
+        if e is not None and not core_band:
+            for got, ref, mag in ((float(e[s][0]), eno, mo), (float(e[s][1]), enn, mn)):
+                if np.isinf(got) != np.isinf(ref):
+                    outside += 1
+                elif np.isfinite(ref):
+                    max_err = max(max_err, abs(got - ref) / max(1.0, mag))
+        eps = tol_e * ((mo if np.isfinite(mo) else 0.0) + (mn if np.isfinite(mn) else 0.0))
+        if enn <= eno:
+            ref_ok = True
+            band = bool(np.isfinite(eno)) and abs(enn - eno) <= eps
+        elif np.isinf(enn):
+            ref_ok, band = False, False
+        else:
+            delta = -beta * (enn - eno)
+            u = float(u_all[s, 2])
+            ref_ok = bool(u < np.exp(delta))
+            band = (u > 0 and abs(np.log(u) - delta) <= beta * eps) or abs(enn - eno) <= eps
+        if bool(acc[s]) != ref_ok:
+            if band or core_band:
+                flips += 1
+            else:
+                outside += 1
+        if acc[s]:
+            state = new
+    return {"flips_in_band": flips, "outside_band": outside, "max_energy_err": max_err, "final": state}

@@ -5,8 +5,9 @@ the kernel bench.py and the drivers run.
     against oracle.mc_ref / energy_ref fed with the same Philox draws.  The oracle state follows the kernel's decision
     after every step, so EVERY decision of the run is checked, not only those before a first divergence: a decision
     may differ from the reference rule (MCMC/monte_carlo.py:191-223) only inside the epsilon band
-    |log u - Delta| <= beta tol_E (|e_old| + |e_new|), tol_E = 1e-5; energies within 1e-5; the final
-    positions must then be bit-equal and the counters equal.
+    |log u - Delta| <= beta tol_E (M_old + M_new), tol_E = 1e-5 (M = sum of |pair terms| + |well term|,
+    equal to |e| unless attractive and repulsive terms cancel - see oracle.mc_ref.lockstep_check); energies within
+    1e-5 of M; the final positions must then be bit-equal and the counters equal.
 (2) traced run == untraced run bit for bit (tracing must not change the trajectory).
 (3) fast kernel vs the reference-order parity kernel (local_sweep_kernel) on the same Philox draws.
 """
@@ -17,6 +18,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import energy_ref as er
+from oracle import mc_ref as mr
 from oracle import philox_ref as pr
 
 POT = er.Potential(2, [-10.0, -10.5], 1.2, 15.0)
@@ -44,46 +46,12 @@ def _start(n, rho, B, overlap):
 
 
 def _lockstep(pos0, L, md, chain_id, steps, acc, idx, e):
-    """Replays one chain through the oracle.  Returns (#decisions inside the band that differ, final positions)."""
-    state = pos0.copy()                                   # float32, like the device state
+    """One chain through oracle.mc_ref.lockstep_check on the device's own Philox draws."""
     p_all, u_all = pr.step_draws(SEED, chain_id, 0, steps, len(pos0))
-    flips = 0
-    for s in range(steps):
-        p = int(p_all[s])
-        assert idx[s] == p, ("particle index", s, idx[s], p)
-        truth = state.astype(np.float64)
-        eno, _ = er.particle_energy_virial(truth, p, L, L, POT)
-        disp = (u_all[s, :2] - 0.5) * md
-        new = state.copy()
-        new[p] += disp                                    # float64 add stored float32 (monte_carlo.py:161-163)
-        new[p] = er.apply_pbc(new[p], L, L)
-        enn, _ = er.particle_energy_virial(new.astype(np.float64), p, L, L, POT)
-        # hard-core band: the kernel tests r^2 < 0.25 in float32, the reference r < 0.5
-        dmin_o = np.min(er.distances(truth[p], np.delete(truth, p, 0), L, L))
-        dmin_n = np.min(er.distances(new.astype(np.float64)[p], np.delete(new.astype(np.float64), p, 0), L, L))
-        core_band = abs(dmin_o - 0.5) < 1e-6 or abs(dmin_n - 0.5) < 1e-6
-        for got, ref in ((e[s, 0], eno), (e[s, 1], enn)):
-            if core_band:
-                continue
-            assert np.isinf(got) == np.isinf(ref), ("overlap flag", s, got, ref)
-            if np.isfinite(ref):
-                assert abs(got - ref) <= TOL_E * max(1.0, abs(ref)), ("energy", s, got, ref)
-        if enn <= eno:
-            ref_ok, band = True, np.isfinite(eno) and abs(enn - eno) <= TOL_E * (abs(eno) + abs(enn))
-        elif np.isinf(enn):
-            ref_ok, band = False, False
-        else:
-            delta = -(enn - eno)
-            u = u_all[s, 2]
-            ref_ok = bool(u < np.exp(delta))
-            eps = TOL_E * (abs(eno) + abs(enn))
-            band = (u > 0 and abs(np.log(u) - delta) <= eps) or abs(enn - eno) <= eps
-        if bool(acc[s]) != ref_ok:
-            assert band or core_band, ("decision outside the epsilon band", s, eno, enn, u_all[s, 2])
-            flips += 1
-        if acc[s]:
-            state = new
-    return flips, state
+    r = mr.lockstep_check(pos0, L, md, POT, p_all, u_all, acc, idx, e, tol_e=TOL_E)
+    assert r["outside_band"] == 0, r
+    assert r["max_energy_err"] <= TOL_E, r
+    return r["flips_in_band"], r["final"]
 
 
 CASES = [  # n, rho, max_disp, steps, overlap start
@@ -127,7 +95,7 @@ def test_fast_kernel_lockstep_oracle(n, rho, md, steps, overlap):
         if not overlap:
             assert abs(eng.E[c].item() - Er) <= TOL_E * max(1.0, abs(Er))
     frac = acc.mean()
-    assert 0.02 < frac < 0.98, frac
+    assert 0.02 < frac < 0.999, frac       # dilute systems accept almost every move
     print("n=%d rho=%g md=%g: %d decisions checked, %d inside the epsilon band differ, acceptance %.3f"
           % (n, rho, md, 3 * steps, total_flips, frac))
 
