@@ -74,14 +74,35 @@ __device__ __forceinline__ void rq_eval(float x, float xk, float wk, float yk, f
     }
 }
 
-// Fast-math variants for the tensor-core epilogue (MUFU-based exp / log / reciprocal: ~1e-6 relative, far inside
-// the TF32 path's error budget; the FP32 path keeps the accurate ones above).
+// Fast-math variants for the tensor-core epilogue: raw MUFU exp2 / log2 / reciprocal / square root (~1e-6 relative, far
+// inside the tensor path's error budget; flush-to-zero forms, so none of the range-scaling code the C intrinsics add
+// around them; the arguments here are O(1e-9 .. 1e9)).  The FP32 path keeps the accurate ones above.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float softplus_fast(float x) {
-    return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x)));
+    return fmaxf(x, 0.0f) + 0.6931471805599453f * lg2_approx(1.0f + ex2_approx(-1.4426950408889634f * fabsf(x)));
 }
 __device__ __forceinline__ void rq_eval_fast(float x, float xk, float wk, float yk, float hk, float dk, float dk1,
                                              bool inverse, float& y, float& ld) {
-    const float sk = __fdividef(hk, wk);
+    const float sk = hk * rcp_approx(wk);
     const float t = dk + dk1 - 2.0f * sk;
     if (inverse) {
         const float dy = x - yk;
@@ -89,23 +110,24 @@ __device__ __forceinline__ void rq_eval_fast(float x, float xk, float wk, float 
         const float b = hk * dk - dy * t;
         const float c = -sk * dy;
         const float disc = fabsf(b * b - 4.0f * a * c);
-        const float root = __fdividef(2.0f * c, -b - sqrtf(disc));
+        const float root = (2.0f * c) * rcp_approx(-b - sqrt_approx(disc));
         y = root * wk + xk;
         const float tt = root * (1.0f - root);
         const float den = sk + t * tt;
         const float omr = 1.0f - root;
         const float num = (sk * sk) * (dk1 * (root * root) + 2.0f * sk * tt + dk * (omr * omr));
-        ld = -__logf(__fdividef(num, den * den));
+        const float rden = rcp_approx(den);
+        ld = -0.6931471805599453f * lg2_approx(num * rden * rden);
     } else {
-        const float th = __fdividef(x - xk, wk);
+        const float th = (x - xk) * rcp_approx(wk);
         const float tt = th * (1.0f - th);
         const float num = hk * (sk * (th * th) + dk * tt);
         const float den = sk + t * tt;
-        const float rden = __frcp_rn(den);
+        const float rden = rcp_approx(den);
         y = yk + num * rden;
         const float omt = 1.0f - th;
         const float dnum = (sk * sk) * (dk1 * (th * th) + 2.0f * sk * tt + dk * (omt * omt));
-        ld = __logf(dnum * rden * rden);
+        ld = 0.6931471805599453f * lg2_approx(dnum * rden * rden);
     }
 }
 

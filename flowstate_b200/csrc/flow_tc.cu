@@ -61,6 +61,7 @@ struct TcPack {
     int chn;           // columns of a fused final-layer chunk (0: fused path unavailable)
     size_t tiles_per_layer, tiles_before_final;
     size_t smem_bytes;
+    int* xcols;        // device [4][N]: input / output columns of the transformed coordinates, density then sampling
     std::vector<TcLayer> layers;
 };
 
@@ -78,7 +79,8 @@ struct TcArgs {
     const float* xin;      // [rows, D] layer input
     float* xout;           // [rows, D] layer output (transformed half written here)
     float* logdet;         // [rows] accumulated, or nullptr
-    const int* trf;        // [N] transformed feature indices
+    const int* xc_in;      // [N] column of the layer input read for transformed coordinate c (this direction)
+    const int* xc_out;     // [N] column of the layer output it is written to
     int* nan_flag;
     int* err;
     long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 16 per CTA
@@ -810,7 +812,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             const bool inv = (g.fused == 2);
             const int axis = isA ? (inv ? 1 : 0) : (inv ? 0 : 1);   // 0 = widths columns, 1 = heights columns
             const float c2 = g.inv_sqrt_h * 1.4426950408889634f, bound = g.bound, two_b = 2.0f * g.bound;
-            const int hD = g.D / 2;
+            const float* xrow_in = g.xin + (size_t)grow * g.D;
+            float* xrow_out = g.xout + (size_t)grow * g.D;
             const float gnum = 1.0f - kMinW * (float)nb;       // kMinW == kMinH
             const float rgnum = 1.0f / gnum, r2b = 1.0f / two_b;
             // The u buffer is dead: thread-private 128-byte rows for values a later dynamic index picks from
@@ -824,9 +827,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
             for (int c = pair; c < g.N; c += 2) {
                 float* mb = mbq + ((c >> 1) & 1) * 160;
-                const int ft = __ldg(g.trf + c);
                 float x = 0.f;
-                if (row_ok) x = __ldg(g.xin + (size_t)grow * g.D + (inv ? (ft + hD) % g.D : ft));
+                if (row_ok) x = __ldg(xrow_in + __ldg(g.xc_in + c));
                 const float* bch = g.L.b_fused + (size_t)c * g.chn;
                 float4 bias[8];                                     // in flight while the accumulator completes
 #pragma unroll
@@ -870,10 +872,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bias[i4].z, bias[i4].w)), e[4 * i4 + 2],
                          e[4 * i4 + 3]);
                 }
-                // softmax numerators and inclusive prefix sums; pad columns (>= nb) contribute exp(-inf) = 0
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (i >= nb) e[i] = -3.0e38f;
+                // softmax numerators and inclusive prefix sums; pad columns (>= nb) carry a bias of -3e38 (pack time)
+                // and contribute exp(-inf) = 0
                 float m8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(e[i], e[i + 8]), fmaxf(e[i + 16], e[i + 24]));
@@ -894,33 +894,37 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
                     const float rg = sum * rgnum;
                     const float t0 = (x + bound) * r2b * rg, dt = -kMinW * rg;
-                    // Two-level search in registers (knot conditions are monotone: true up to the bin): pick the block of
-                    // 8 bins from the knots 8, 16, 24, copy that block's prefix sums (static indices only), scan it.
+                    // Two-level search in registers without divergence (the lanes of a warp hold different rows).  The knot
+                    // conditions are monotone (true up to the bin): level 1 picks the block of 8 bins from the knots 8, 16,
+                    // 24; level 2 selects that block's nine prefix sums S[8 blk - 1 .. 8 blk + 7] with a two-predicate
+                    // select tree (static register indices only), counts the hits inside it and selects the bin's two sums.
                     auto hit = [&](int i, float s_prev) { return i < nb && s_prev <= __fmaf_rn((float)i, dt, t0); };
-                    int blk8 = 0;
-                    blk8 += hit(8, e[7]) ? 1 : 0;
-                    blk8 += hit(16, e[15]) ? 1 : 0;
-                    blk8 += hit(24, e[23]) ? 1 : 0;
-                    float w9[9];                                    // S[8 blk8 - 1 .. 8 blk8 + 7]
-                    w9[0] = 0.f;
+                    const bool h8 = hit(8, e[7]), h16 = hit(16, e[15]), h24 = hit(24, e[23]);
+                    const int blk8 = (h8 ? 1 : 0) + (h16 ? 1 : 0) + (h24 ? 1 : 0);
+                    const bool b0 = (blk8 & 1) != 0, b1 = (blk8 & 2) != 0;
+                    float w9[9];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) w9[i + 1] = e[i];
-#pragma unroll
-                    for (int bk = 1; bk < 4; ++bk)
-                        if (blk8 == bk) {
-#pragma unroll
-                            for (int i = 0; i < 9; ++i) w9[i] = e[8 * bk - 1 + i];
-                        }
+                    for (int i = 0; i < 9; ++i) {
+                        const float lo0 = (i == 0) ? 0.f : e[i - 1];      // block 0: S[-1] = 0
+                        const float lo = b0 ? e[8 + i - 1] : lo0;
+                        const float hi = b0 ? e[24 + i - 1] : e[16 + i - 1];
+                        w9[i] = b1 ? hi : lo;
+                    }
                     const int base8 = 8 * blk8;
-                    int sel = base8;
-                    float s0 = w9[0], s1 = w9[1];                   // S[sel-1], S[sel]
+                    const float t8 = __fmaf_rn((float)base8, dt, t0);
+                    int cnt = 0;
 #pragma unroll
                     for (int i = 1; i < 8; ++i)
-                        if (base8 + i < nb && w9[i] <= __fmaf_rn((float)(base8 + i), dt, t0)) {
-                            sel = base8 + i;
-                            s0 = w9[i];
-                            s1 = w9[i + 1];
-                        }
+                        cnt += (base8 + i < nb && w9[i] <= __fmaf_rn((float)i, dt, t8)) ? 1 : 0;
+                    const int sel = base8 + cnt;
+                    // S[sel - 1], S[sel] = w9[cnt], w9[cnt + 1]: three-level select trees on the bits of cnt
+                    const bool c0 = (cnt & 1) != 0, c1 = (cnt & 2) != 0, c2b = (cnt & 4) != 0;
+                    const float p01 = c0 ? w9[1] : w9[0], p23 = c0 ? w9[3] : w9[2], p45 = c0 ? w9[5] : w9[4],
+                                p67 = c0 ? w9[7] : w9[6];
+                    const float q12 = c0 ? w9[2] : w9[1], q34 = c0 ? w9[4] : w9[3], q56 = c0 ? w9[6] : w9[5],
+                                q78 = c0 ? w9[8] : w9[7];
+                    const float s0 = c2b ? (c1 ? p67 : p45) : (c1 ? p23 : p01);
+                    const float s1 = c2b ? (c1 ? q78 : q56) : (c1 ? q34 : q12);
                     const float bd0 = __ldg(bch + 64 + sel), bd1 = __ldg(bch + 65 + sel);
                     const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
                     const float right =
@@ -952,7 +956,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         else rq_eval_fast(x, aL, aW, left, right - left, mb[96], mb[128], false, y, ld);
                     }
                     if (row_ok) {
-                        g.xout[(size_t)grow * g.D + (inv ? ft : (ft + hD) % g.D)] = y;
+                        xrow_out[__ldg(g.xc_out + c)] = y;
                         acc_ld += ld;
                         bad = bad || (y != y) || (ld != ld);
                     }
@@ -1243,6 +1247,13 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
                     for (int k = 0; k < H; ++k) acc += (double)half_round(wr[k]) * c[k];
                     bfused[(size_t)j * chn + cidx] = (float)acc;
                 }
+            // pad columns of the two softmax groups: zero weights and a bias of -3e38, so their numerators are
+            // exp(-inf) = 0 without any masking in the epilogue
+            for (int j = 0; j < f->N; ++j)
+                for (int k = f->nb; k < 32; ++k) {
+                    bfused[(size_t)j * chn + k] = -3.0e38f;
+                    bfused[(size_t)j * chn + 32 + k] = -3.0e38f;
+                }
         }
         std::vector<float> psets((size_t)(nB + 1) * 3 * H, 0.f);
         for (int j = 0; j <= nB; ++j) {
@@ -1272,6 +1283,18 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             }
         }
         if (r) { delete P; return r; }
+    }
+    {   // columns read / written by the fused epilogue: density reads feature ft and writes (ft + D/2) % D (the roll,
+        // coupling.py:100-101), sampling reads the rolled input (coupling.py:113-114) and writes ft
+        std::vector<int> xc((size_t)4 * f->N);
+        for (int j = 0; j < f->N; ++j) {
+            const int ft = d->transform_features[j], rolled = (ft + f->D / 2) % f->D;
+            xc[j] = ft;
+            xc[f->N + j] = rolled;
+            xc[2 * f->N + j] = rolled;
+            xc[3 * f->N + j] = ft;
+        }
+        if (int r = tc_upload(f, xc, &P->xcols)) { delete P; return r; }
     }
     int* err = nullptr;
     if (cudaMalloc(&err, sizeof(int)) != cudaSuccess) { delete P; return FS_ERR_CUDA; }
@@ -1343,7 +1366,8 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* th
     g.xin = xin;
     g.xout = xout;
     g.logdet = logdet;
-    g.trf = f->trf;
+    g.xc_in = P->xcols + (size_t)(fused == 2 ? 2 : 0) * f->N;
+    g.xc_out = g.xc_in + f->N;
     g.nan_flag = nan_flag;
     g.dbg = tc_debug_buffer((rows + 127) / 128);
     const int grid = (rows + 127) / 128;

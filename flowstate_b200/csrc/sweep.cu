@@ -274,7 +274,6 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     int acc = 0;
     double Eb = E[b];
     double Wl = 0.0;                         // this lane's share of the accepted virial differences (summed at the end)
-    float wacc = 0.f;                        // ... collected in float32 and flushed every 16 steps
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const long long cid = chain_id0 + b;
     const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
@@ -411,12 +410,10 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
             } else {
                 Eb += (double)de;
             }
-            wacc += dw;
+            Wl += (double)dw;                                  // float64 per step: W does not depend on launch splitting
         }
-        if ((s & 15) == 15) { Wl += (double)wacc; wacc = 0.f; }
         __syncwarp();
     }
-    Wl += (double)wacc;
 #pragma unroll
     for (int o = LPC / 2; o > 0; o >>= 1) Wl += __shfl_xor_sync(FULL, Wl, o);
     if (live) {

