@@ -17,8 +17,8 @@ FS_PREC_FP32, FS_PREC_TF32 = 0, 1
 
 
 class FsPot(C.Structure):
-    _fields_ = [("num_wells", C.c_int), ("V0", C.c_float * 2), ("r0", C.c_float), ("k", C.c_float),
-                ("r_cut", C.c_float), ("r_core", C.c_float)]
+    _fields_ = [("num_wells", C.c_int), ("V0", C.c_double * 2), ("r0", C.c_double), ("k", C.c_double),
+                ("r_cut", C.c_double), ("r_core", C.c_double)]
 
 
 class FsRng(C.Structure):
@@ -61,6 +61,7 @@ _PROTOS = {
     "fs_flow_destroy": (None, [_P]),
     "fs_flow_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "fs_flow_conditioner": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, C.c_int, _P]),
+    "fs_target_energy": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(FsPot), _P, _P, _P]),
     "fs_classify_wells": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     "fs_pair_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
     "fs_flow_has_tensor_path": (C.c_int, [_P]),

@@ -38,12 +38,12 @@ struct PotDev {
 inline PotDev make_pot(const fs_pot* p, float Lx, float Ly) {
     PotDev d;
     d.num_wells = p->num_wells;
-    d.V0[0] = p->V0[0];
-    d.V0[1] = p->V0[1];
-    d.r0 = p->r0;
-    d.k = p->k;
-    d.rc2 = p->r_cut * p->r_cut;
-    d.rcore2 = p->r_core * p->r_core;
+    d.V0[0] = (float)p->V0[0];
+    d.V0[1] = (float)p->V0[1];
+    d.r0 = (float)p->r0;
+    d.k = (float)p->k;
+    d.rc2 = (float)(p->r_cut * p->r_cut);
+    d.rcore2 = (float)(p->r_core * p->r_core);
     double s6 = pow(1.0 / (double)p->r_cut, 6.0);
     d.e_cut = (float)(4.0 * (s6 * s6 - s6));          // potential.py:21-26
     d.Lx = Lx;

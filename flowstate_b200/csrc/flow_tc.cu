@@ -317,7 +317,9 @@ struct TcCfg {
     static constexpr int P_OFF = U_OFF + U_BYTES;
     static constexpr int BAR_OFF = P_OFF + 2 * PSET_FLOATS * 4;
     static constexpr int MB_OFF = BAR_OFF + 512;             // fused epilogue mailboxes: 8 pair groups x 2 x 5 x 32 floats
-    static constexpr int TOTAL = MB_OFF + 8 * 320 * 4;
+    static constexpr int BIAS_SLOTS = 8;                     // fused final layer: ring of per-coordinate bias vectors
+    static constexpr int BIAS_OFF = MB_OFF + 8 * 320 * 4;    // (<= 128 floats each), filled by the TMA producer
+    static constexpr int TOTAL = BIAS_OFF + BIAS_SLOTS * 512;
 };
 
 template <int H>
@@ -341,8 +343,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     const uint32_t bar_free1 = bar_rdy + 48;                    // [1]  MMA -> epilogue (feature piece consumed)
     const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 144);
-    static_assert(16 * NSTAGE + 148 <= 512, "barrier area overflow");
+    const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pair (bias of a chunk landed)
+    const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pair -> TMA
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 136 + 16 * S::BIAS_SLOTS);
+    static_assert(16 * NSTAGE + 140 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
+    const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
     float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
     const int warp = threadIdx.x >> 5;
@@ -361,6 +366,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
             mbar_init(bar_pempty + 8 * i, S::BLK_WARPS);
+        }
+        for (int i = 0; i < S::BIAS_SLOTS; ++i) {
+            mbar_init(bar_bfull + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 2);                   // the two warps of the pair that owns the chunk
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -417,7 +426,19 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             if (g.fused) {                                                        // final layer, FP16 tiles of 64 k
                 src = (const uint8_t*)g.L.wfused;
-                stream((unsigned long long)g.N * ((H / 64) / S::KPS), (uint32_t)(S::KPS * g.chn * 128));
+                // per coordinate chunk: its bias vector into the ring (the epilogue pair reads it from shared memory: no
+                // global loads on its serial chain), then its weight stages
+                for (int c = 0; c < g.N; ++c) {
+                    const int slot = c % S::BIAS_SLOTS;
+                    mbar_wait(bar_bempty + 8 * slot, ((c / S::BIAS_SLOTS) & 1) ^ 1, g.err, 8);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_bfull + 8 * slot, (uint32_t)g.chn * 4);
+                        tma_bulk_g2s(bias_base + slot * 512, g.L.b_fused + (size_t)c * g.chn, (uint32_t)g.chn * 4,
+                                     bar_bfull + 8 * slot);
+                    }
+                    __syncwarp();
+                    stream((unsigned long long)((H / 64) / S::KPS), (uint32_t)(S::KPS * g.chn * 128));
+                }
             } else {
                 stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
             }
@@ -829,10 +850,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 float x = 0.f;
                 if (row_ok) x = __ldg(xrow_in + __ldg(g.xc_in + c));
-                const float* bch = g.L.b_fused + (size_t)c * g.chn;
-                float4 bias[8];                                     // in flight while the accumulator completes
-#pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) bias[i4] = __ldg(reinterpret_cast<const float4*>(bch + 32 * axis) + i4);
+                const int bslot = c % S::BIAS_SLOTS;
+                const float* bch = reinterpret_cast<const float*>(smem + S::BIAS_OFF) + bslot * 128;
+                mbar_wait(bar_bfull + 8 * bslot, (c / S::BIAS_SLOTS) & 1, g.err, 9);
                 wait_full(FULL_F0 + pair);
                 if (dbg_me) t_mark = clock64();
                 float e[32];
@@ -868,9 +888,13 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 if (dbg_me) { t_m2 = clock64(); t_f1 += t_m2 - t_mark; }
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
-                    upk2(add2(pk2(e[4 * i4], e[4 * i4 + 1]), pk2(bias[i4].x, bias[i4].y)), e[4 * i4], e[4 * i4 + 1]);
-                    upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bias[i4].z, bias[i4].w)), e[4 * i4 + 2],
-                         e[4 * i4 + 3]);
+                    const float4 bb = reinterpret_cast<const float4*>(bch + 32 * axis)[i4];   // broadcast LDS.128
+                    upk2(add2(pk2(e[4 * i4], e[4 * i4 + 1]), pk2(bb.x, bb.y)), e[4 * i4], e[4 * i4 + 1]);
+                    upk2(add2(pk2(e[4 * i4 + 2], e[4 * i4 + 3]), pk2(bb.z, bb.w)), e[4 * i4 + 2], e[4 * i4 + 3]);
+                }
+                if (!isA) {                                         // warp B is done with the bias; warp A after its picks
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_bempty + 8 * bslot);
                 }
                 // softmax numerators and inclusive prefix sums; pad columns (>= nb) carry a bias of -3e38 (pack time)
                 // and contribute exp(-inf) = 0
@@ -925,7 +949,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                                 q78 = c0 ? w9[8] : w9[7];
                     const float s0 = c2b ? (c1 ? p67 : p45) : (c1 ? p23 : p01);
                     const float s1 = c2b ? (c1 ? q78 : q56) : (c1 ? q34 : q12);
-                    const float bd0 = __ldg(bch + 64 + sel), bd1 = __ldg(bch + 65 + sel);
+                    const float bd0 = bch[64 + sel], bd1 = bch[65 + sel];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_bempty + 8 * bslot);
                     const float left = __fmaf_rn(two_b, __fmaf_rn(gs, s0, kMinW * (float)sel), -bound);
                     const float right =
                         (sel == nb - 1) ? bound : __fmaf_rn(two_b, __fmaf_rn(gs, s1, kMinW * (float)(sel + 1)), -bound);

@@ -16,9 +16,10 @@ MCMC only (main_mcmc_only.py:176-236): equilibrate, then `production_steps` loca
 Algorithm 1 (main_algorithm_1.py:203-395): equilibrate -> collect local samples -> train the
 flow by forward KL -> interleave `big_move_interval` local moves with one NF global move.
 Algorithm 2 (main_algorithm_2.py:393-577): per cycle `local_steps` local moves, a short
-forward-KL training pass on the newest samples, one NF global move per chain.  (The
-reference also evaluates a reverse-KL term whose weight 1-ALPHA is 0, main_algorithm_2.py:52;
-it is left out.)
+training pass on the newest samples, one NF global move per chain.  The loss is
+alpha * forward KL + (1 - alpha) * reverse KL against NF.Energy.DoubleWellLJ; with the
+reference's ALPHA = 1.0 (main_algorithm_2.py:52) the reverse-KL term has weight 0 and is
+not evaluated.
 """
 import argparse
 import dataclasses
@@ -36,8 +37,10 @@ from .. import parallel
 
 @dataclasses.dataclass
 class HybridConfig:
+    """Defaults = Algorithm 1's constants (main_algorithm_1.py:33-73); HybridConfig.preset(algorithm) applies the other
+    drivers' constants (main_algorithm_2.py:33-76, main_mcmc_only.py:40-60) on top."""
     particles: int = 3
-    chains: int = 10                 # total over all ranks
+    chains: int = 10                 # total over all ranks (NUM_MC_RUNS)
     rho: float = 0.03
     temperature: float = 1.0
     V0_list: tuple = (-10.0, -10.5)
@@ -48,7 +51,11 @@ class HybridConfig:
     adjusting_frequency: int = 5000
     sampling_frequency: int = 150
     master_seed: int = 42
-    # flow (Alg-1 defaults: K=15, H=256, NUM_BINS passed as num_blocks -> 32 blocks, 32 bins)
+    # random streams of the chains: "philox" = counter-based streams keyed by the global chain id (the throughput kernel,
+    # results independent of the number of GPUs); "pcg64" = numpy-compatible per-chain generators seeded
+    # master_seed + chain id like the reference (monte_carlo.py:92-95; the replay / parity kernel)
+    rng: str = "philox"
+    # flow (Alg-1: K=15, H=256, NUM_BINS passed as num_blocks -> 32 blocks, 32 bins; main_algorithm_1.py:63-70, 282)
     K: int = 15
     blocks: int = 32
     hidden: int = 256
@@ -64,9 +71,29 @@ class HybridConfig:
     # Alg 2
     cycles: int = 1000
     local_steps: int = 100
-    precision: str = "tf32"
+    alpha: float = 1.0               # loss = alpha * forward KL + (1 - alpha) * reverse KL (main_algorithm_2.py:52, 321)
+    precision: str = "auto"          # conditioner arithmetic of the eval-mode kernels: auto | tf32 | fp32
     # MCMC only (main_mcmc_only.py:56-57: 1e7 steps over 100 chains)
     production_steps: int = 100000
+
+    @staticmethod
+    def preset(algorithm, **overrides):
+        cfg = HybridConfig(**PRESETS[int(algorithm)])
+        return dataclasses.replace(cfg, **overrides)
+
+
+PRESETS = {
+    # main_mcmc_only.py:33-60
+    0: dict(chains=100, production_steps=100000),
+    # main_algorithm_1.py:33-73
+    1: dict(),
+    # main_algorithm_2.py:33-76: 100 chains, K=23, H=128, 2 blocks, 15 bins, Adam lr 5.435e-4 wd 9.586e-5, batch 256,
+    # one epoch per cycle on the newest 1000 samples (100 local steps per chain sampled every 10), no adaptation during
+    # the cycles (ADJUSTING_FREQUENCY 10000 > EQUILIBRATION_STEPS 5000)
+    2: dict(chains=100, K=23, blocks=2, hidden=128, bins=15, lr=0.000543510751759681,
+            weight_decay=9.5857178422352e-05, batch_size=256, epochs=1, training_samples=1000, sampling_frequency=10,
+            adjusting_frequency=10000, cycles=1000, local_steps=100),
+}
 
 
 def _dist():
@@ -85,10 +112,13 @@ def _init_chains(cfg, device):
         init = MC.initialise_low_left if (start + i) % 2 == 0 else MC.initialise_low_right
         p, _ = init(cfg.particles, cfg.rho)
         pos[i] = p.astype(np.float32)
-    seeds = [cfg.master_seed + start + i for i in range(count)]
-    eng = MC.BatchedMonteCarlo(pos, box, cfg.temperature, cfg.particles, num_wells=2, V0_list=list(cfg.V0_list),
-                               r0=cfg.r0, k=cfg.k, initial_max_displacement=cfg.max_displacement, seeds=seeds,
-                               device=device)
+    kw = dict(num_wells=2, V0_list=list(cfg.V0_list), r0=cfg.r0, k=cfg.k,
+              initial_max_displacement=cfg.max_displacement, device=device)
+    if cfg.rng == "pcg64":
+        kw.update(seeds=[cfg.master_seed + start + i for i in range(count)])
+    else:
+        kw.update(rng="philox", philox_seed=cfg.master_seed, chain_id0=start)
+    eng = MC.BatchedMonteCarlo(pos, box, cfg.temperature, cfg.particles, **kw)
     return eng, L
 
 
@@ -98,8 +128,15 @@ def _build_flow(cfg, L, device):
     D = 2 * cfg.particles
     layers = [NF.flows.CircularCoupledRationalQuadraticSpline(D, cfg.blocks, cfg.hidden, range(D), num_bins=cfg.bins,
                                                               tail_bound=bound) for _ in range(cfg.K)]
-    model = NF.NormalizingFlow(base, layers).to(device)
+    target = NF.Energy.DoubleWellLJ(D, cfg.particles, cfg.temperature, bound, V0_list=list(cfg.V0_list), r0=cfg.r0,
+                                    k=cfg.k)                                     # main_algorithm_2.py:282-285
+    model = NF.NormalizingFlow(base, layers, target).to(device)
     model.precision = cfg.precision
+    # every rank starts from rank 0's weights (gradients are averaged, so the replicas then stay identical); the
+    # proposal / permutation generator is seeded per rank so chains on different GPUs see different base noise
+    parallel.broadcast_flow(model, src=0)
+    rank, _ = _dist()
+    torch.manual_seed(cfg.master_seed + 7919 * (rank + 1))
     return model
 
 
@@ -123,20 +160,35 @@ def _local_phase(eng, steps, cfg, collect=None, step0=0):
 
 
 def _train(model, data, cfg, epochs, optimizer=None):
-    """Forward-KL training (main_algorithm_1.py:297-320); gradients are all-reduced over ranks."""
+    """Forward-KL training (main_algorithm_1.py:297-320, main_algorithm_2.py:437-452); gradients are all-reduced over
+    ranks between backward and the optimizer step.  The number of collectives is the same on every rank: the number of
+    minibatches per epoch is the minimum over ranks (ranks may own different numbers of chains), and the reference's
+    "skip a NaN / Inf loss" decision (main_algorithm_1.py:310-315) is taken collectively."""
     model.train()
     opt = optimizer or torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay)
+    _, world = _dist()
+    n_batches = torch.tensor([max(0, -(-(data.shape[0] - 1) // cfg.batch_size))], device=data.device)
+    if world > 1:
+        dist.all_reduce(n_batches, op=dist.ReduceOp.MIN)
+    n_batches = int(n_batches.item())
+    use_reverse = cfg.alpha < 1.0
     losses = []
     for _ in range(epochs):
         perm = torch.randperm(data.shape[0], device=data.device)
         tot, nb = 0.0, 0
-        for i in range(0, data.shape[0] - 1, cfg.batch_size):
-            batch = data[perm[i:i + cfg.batch_size]]
-            if batch.shape[0] < 2:
-                continue
+        for bi in range(n_batches):
+            batch = data[perm[bi * cfg.batch_size:(bi + 1) * cfg.batch_size]]
             opt.zero_grad()
-            loss = model.forward_kld(batch)
-            if torch.isnan(loss) or torch.isinf(loss):        # main_algorithm_1.py:310-315
+            usable = batch.shape[0] >= 2                       # BatchNorm needs two rows
+            if usable:
+                loss = model.forward_kld(batch)
+                if use_reverse:                                # main_algorithm_2.py:446-448
+                    energy_loss, _ = model.reverse_kld(cfg.batch_size)
+                    loss = cfg.alpha * loss + (1.0 - cfg.alpha) * energy_loss
+            bad = torch.tensor([0.0 if usable and bool(torch.isfinite(loss)) else 1.0], device=data.device)
+            if world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if bad.item() > 0:                                 # every rank skips this step together
                 continue
             loss.backward()
             parallel.allreduce_gradients(model)
@@ -183,7 +235,8 @@ def run_algorithm_1(cfg, device="cuda", log=print):
     step = _local_phase(eng, cfg.equilibration_steps, cfg)
     samples = []
     per_chain = max(1, -(-cfg.training_samples // cfg.chains))
-    _local_phase(eng, per_chain * cfg.sampling_frequency, cfg, collect=samples, step0=step)
+    cfg_prod = dataclasses.replace(cfg, adjusting_frequency=0)   # the reference adapts during equilibration only
+    _local_phase(eng, per_chain * cfg.sampling_frequency, cfg_prod, collect=samples, step0=step)   # (main_algorithm_1.py:203-210 vs 245-252)
     data = torch.cat(samples, dim=0)
     model = _build_flow(cfg, L, device)
     t0 = time.time()
@@ -201,19 +254,34 @@ def run_algorithm_1(cfg, device="cuda", log=print):
             "model": model}
 
 
+def _collect(eng, steps, cfg):
+    """`steps` local moves per chain, configurations (centred coordinates) sampled every cfg.sampling_frequency."""
+    samples = []
+    sf = max(1, cfg.sampling_frequency)
+    for s in range(0, steps, sf):
+        n = min(sf, steps - s)
+        eng.particle_displacement(n)
+        if n == sf:
+            samples.append(eng.centred(eng.pos).clone())
+    return torch.cat(samples, dim=0) if samples else eng.centred(eng.pos).clone()
+
+
 def run_algorithm_2(cfg, device="cuda", log=print):
+    """main_algorithm_2.py:209-577: equilibrate, initial training on `training_samples` configurations, then per cycle
+    `local_steps` local moves per chain (sampled every `sampling_frequency`), `epochs` of training on the new samples
+    with a fresh Adam (main_algorithm_2.py:440), one NF global move per chain."""
     eng, L = _init_chains(cfg, device)
     _local_phase(eng, cfg.equilibration_steps, cfg)
     model = _build_flow(cfg, L, device)
     eng.set_nf_model(model)
-    big_acc, last = 0, float("nan")
+    # initial training set: INITIAL_TRAINING_NUM_SAMPLES / (NUM_MC_RUNS / SAMPLING_FREQUENCY) steps per chain
+    # (main_algorithm_2.py:240-252)
+    init_steps = max(cfg.sampling_frequency, int(cfg.training_samples / (cfg.chains / cfg.sampling_frequency)))
+    last = _train(model, _collect(eng, init_steps, cfg), cfg, cfg.epochs)[-1]
+    big_acc = 0
     for cycle in range(cfg.cycles):
-        samples = []
-        for s in range(0, cfg.local_steps, 10):               # SAMPLING_FREQUENCY = 10 in Alg 2 (main_algorithm_2.py:59)
-            eng.particle_displacement(min(10, cfg.local_steps - s))
-            samples.append(eng.centred(eng.pos).clone())
-        data = torch.cat(samples, dim=0)
-        last = _train(model, data, cfg, 1)[-1]                # new Adam every cycle (main_algorithm_2.py:440)
+        data = _collect(eng, cfg.local_steps, cfg)
+        last = _train(model, data, cfg, cfg.epochs)[-1]
         big_acc += int(eng.nf_big_move().sum().item())
     att, acc, big = parallel.allreduce_counters(eng.attempts, eng.accepted, torch.tensor([big_acc], device=eng.device))
     return {"algorithm": 2, "attempts": att, "accepted": acc, "big_move_accepts": big,
@@ -223,12 +291,12 @@ def run_algorithm_2(cfg, device="cuda", log=print):
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--algorithm", type=int, choices=(0, 1, 2), default=1, help="0 = local-displacement MCMC only")
-    for f in dataclasses.fields(HybridConfig):
-        if f.type in (int, float, str):
-            ap.add_argument("--" + f.name.replace("_", "-"), type=f.type, default=f.default)
+    scalar = [f for f in dataclasses.fields(HybridConfig) if f.type in (int, float, str)]
+    for f in scalar:                                          # default None: taken from the algorithm's preset
+        ap.add_argument("--" + f.name.replace("_", "-"), type=f.type, default=None)
     a = ap.parse_args(argv)
-    cfg = HybridConfig(**{f.name: getattr(a, f.name) for f in dataclasses.fields(HybridConfig)
-                          if f.type in (int, float, str)})
+    cfg = HybridConfig.preset(a.algorithm, **{f.name: getattr(a, f.name) for f in scalar
+                                              if getattr(a, f.name) is not None})
     import os
     if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -34,12 +34,12 @@ extern "C" {
  * (num_wells, V0_list, r0, k), MCMC/potential.py:3 (cutoff 2.5, shifted),
  * MCMC/energy_calculator.py:73,150 (hard core r < 0.5 -> inf). */
 typedef struct fs_pot {
-    int   num_wells;   /* 0, 1 or 2 */
-    float V0[2];
-    float r0;
-    float k;
-    float r_cut;       /* 2.5 */
-    float r_core;      /* 0.5 */
+    int    num_wells;   /* 0, 1 or 2 */
+    double V0[2];       /* the reference keeps these as Python floats (float64): r0 = 1.2 is not a float32 value, */
+    double r0;          /* and the steep wall (k = 15) turns its float32 rounding into 4e-6 of energy            */
+    double k;
+    double r_cut;       /* 2.5 */
+    double r_core;      /* 0.5 */
 } fs_pot;
 
 /* Random source of the Metropolis kernels.
@@ -214,6 +214,16 @@ int fs_flow_forward(fs_flow* flow, const float* z, int B, double out_shift,
 /* Development aid (FS_TC_DEBUG=1): wait-cycle counters of the last tensor-core conditioner launch,
  * 16 int64 per CTA; returns the number of CTAs copied to `host`. */
 int fs_tc_debug_read(long long* host, int max_ctas);
+
+/* ---- training target of Algorithm 2 ---------------------------------------------------- */
+
+/* SimpleLJ._energy / DoubleWellLJ._energy (NF/normflows/Energy/SimpleLJ.py:15-39, 114-128), the target energy of
+ * NormalizingFlow.reverse_kld (NF/normflows/core.py:139-141): x [B, n_particles, 2] centred coordinates ->
+ * E [B] = (soft-core LJ over the n + 1 particles incl. one at the origin, coordinates wrapped, no minimum image)
+ * / temperature + double well (pot->num_wells = 0: SimpleLJ).  dEdx [B, 2 n_particles] (nullable) = gradient of E
+ * with respect to x, for autograd.  pot: V0, r0, k of the wells (r_cut / r_core unused), host pointer, may be NULL. */
+int fs_target_energy(const float* x, int B, int n_particles, double bound, double temperature,
+                     const fs_pot* pot /*host*/, float* E, float* dEdx, void* stream);
 
 /* ---- observables of sampled configurations ------------------------------------------- */
 

@@ -83,3 +83,26 @@ def load_hybrid_utils():
     spec.loader.exec_module(mod)
     _loaded["hybrid_utils"] = mod
     return mod
+
+
+class cuda_zeros_on_cpu:
+    """The reference's SimpleLJ._energy creates its zero particle with device='cuda' unconditionally
+    (NF/normflows/Energy/SimpleLJ.py:21) and moves it to x.device right after; on this GPU-less container the
+    allocation itself fails.  Inside this context torch.zeros(..., device='cuda') allocates on the CPU instead -
+    an environment stand-in (like the matplotlib stubs above), the reference's code runs unmodified."""
+
+    def __enter__(self):
+        import torch
+        self._torch = torch
+        self._orig = torch.zeros
+
+        def zeros(*a, **k):
+            if str(k.get("device", "")) == "cuda":
+                k["device"] = "cpu"
+            return self._orig(*a, **k)
+        torch.zeros = zeros
+        return self
+
+    def __exit__(self, *exc):
+        self._torch.zeros = self._orig
+        return False

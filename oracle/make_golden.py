@@ -374,6 +374,39 @@ def gen_observables(ref):
     print("observables.npz:", len(out), "arrays")
 
 
+def gen_target(ref):
+    """Training target of Algorithm 2: NF.Energy.DoubleWellLJ._energy (NF/normflows/Energy/SimpleLJ.py:42-128) and its
+    gradient by the reference's own autograd, on float32 centred configurations incl. soft-core pairs (r <= 0.82),
+    particles near the origin particle, in the wells, and outside the box (wrapped by the reference)."""
+    NF = ref["normflows"]
+    out = {}
+    names = []
+    for tag, n, rho, T in (("n3", 3, 0.03, 1.0), ("n8", 8, 0.1, 1.0), ("n64", 64, 0.03, 0.7)):
+        bound = er.box_length(n, rho) / 2
+        tgt = NF.Energy.DoubleWellLJ(2 * n, n, T, bound, V0_list=[-10.0, -10.5], r0=1.2, k=15)
+        g = torch.Generator().manual_seed(17 + n)
+        B = 24
+        x = (torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound
+        x[0, :4] = torch.tensor([0.3, 0.1, 0.75, 0.2])            # soft-core pair and a particle next to the origin one
+        x[1, :2] = torch.tensor([-bound / 2 + 1.1, 0.2])           # on the wall of the left well
+        x[2, :2] = torch.tensor([bound / 2, 0.05])                 # inside the right well
+        x[3, 0] = bound * 1.3                                      # outside the box: wrapped (:19-20)
+        x[4, :4] = torch.tensor([bound - 0.2, 1.0, -bound + 0.2, 1.0])   # neighbours across the boundary: NO minimum image
+        xr = x.clone().requires_grad_(True)
+        with _refimport.cuda_zeros_on_cpu():
+            E = tgt._energy(xr)
+            (grad,) = torch.autograd.grad(E.sum(), xr)
+            lj = NF.Energy.SimpleLJ._energy(tgt, x.clone())
+            dw = tgt.double_well_potential(x.clone().view(B, n, 2))
+        out.update({tag + "__x": x.numpy(), tag + "__E": E.detach().numpy(), tag + "__grad": grad.numpy(),
+                    tag + "__lj": lj.numpy(), tag + "__dw": dw.numpy(), tag + "__bound": np.float64(bound),
+                    tag + "__T": np.float64(T), tag + "__n": np.int64(n)})
+        names.append(tag)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLD, "target_energy.npz"), **out)
+    print("target_energy: %d cases" % len(names))
+
+
 def main():
     """No arguments: every fixture.  `flow:<tag>[,<tag>]`: only those flow fixtures."""
     ref = _refimport.load()
@@ -382,12 +415,16 @@ def main():
     if sel:
         gen_flow(ref, only=set(sel[0][5:].split(",")))
         return
+    if "target" in sys.argv[1:]:
+        gen_target(ref)
+        return
     gen_energy(ref)
     gen_mc(ref)
     gen_flow(ref)
     gen_global(ref)
     gen_init(ref)
     gen_observables(ref)
+    gen_target(ref)
 
 
 if __name__ == "__main__":

@@ -32,11 +32,43 @@ def test_algorithm_1_small():
 def test_algorithm_2_small():
     from flowstate_b200.drivers import HybridConfig, run_algorithm_2
     torch.manual_seed(0)
-    cfg = HybridConfig(particles=4, chains=32, equilibration_steps=300, adjusting_frequency=10000, K=2, blocks=2,
-                       hidden=128, bins=8, lr=1e-3, batch_size=64, cycles=5, local_steps=40)
+    cfg = HybridConfig.preset(2, particles=4, chains=32, equilibration_steps=300, K=2, blocks=2, hidden=128, bins=8,
+                              lr=1e-3, batch_size=64, cycles=5, local_steps=40, training_samples=128)
     out = run_algorithm_2(cfg, log=lambda *a: None)
-    assert out["attempts"] == 32 * (300 + 5 * 41)
+    # equilibration + initial training set (128 / (32 / 10) = 40 steps per chain) + 5 cycles of 40 local + 1 global move
+    assert out["attempts"] == 32 * (300 + 40 + 5 * 41)
     assert np.isfinite(out["final_loss"])
+    # with a reverse-KL share (ALPHA < 1, main_algorithm_2.py:446-448) the DoubleWellLJ target kernel is on the path
+    cfg_r = HybridConfig.preset(2, particles=4, chains=32, equilibration_steps=100, K=2, blocks=2, hidden=128, bins=8,
+                                lr=1e-3, batch_size=64, cycles=2, local_steps=40, training_samples=128, alpha=0.5)
+    out_r = run_algorithm_2(cfg_r, log=lambda *a: None)
+    assert np.isfinite(out_r["final_loss"])
+
+
+def test_presets_match_the_reference_drivers():
+    """--algorithm 2 with defaults builds the reference's Alg-2 flow (main_algorithm_2.py:33-76: K = 23, H = 128,
+    2 blocks, 15 bins, Adam 5.435e-4 / 9.586e-5, batch 256) on the throughput RNG; Algorithm 1 keeps K = 15, H = 256,
+    32 blocks (NUM_BINS in the num_blocks slot, main_algorithm_1.py:282), 32 bins."""
+    from flowstate_b200.drivers import HybridConfig, hybrid
+    c2 = HybridConfig.preset(2)
+    assert (c2.K, c2.hidden, c2.blocks, c2.bins, c2.batch_size, c2.chains) == (23, 128, 2, 15, 256, 100)
+    assert abs(c2.lr - 5.43510751759681e-4) < 1e-18 and abs(c2.weight_decay - 9.5857178422352e-05) < 1e-18
+    assert c2.rng == "philox" and c2.precision == "auto" and c2.sampling_frequency == 10
+    L = float(np.float32(np.sqrt(c2.particles / c2.rho)))
+    m = hybrid._build_flow(c2, L, "cuda")
+    net = m.flows[0].prqct.transform_net
+    assert len(m.flows) == 23 and net.hidden_features == 128 and len(net.blocks) == 2 and m.flows[0].prqct.num_bins == 15
+    assert type(m.p).__name__ == "DoubleWellLJ"
+    c1 = HybridConfig.preset(1)
+    assert (c1.K, c1.hidden, c1.blocks, c1.bins, c1.batch_size, c1.lr) == (15, 256, 32, 32, 512, 1e-4)
+    c0 = HybridConfig.preset(0)
+    assert c0.chains == 100 and c0.production_steps == 100000
+    # CLI: only explicitly given flags override the preset
+    import argparse  # noqa: F401
+    eng, _ = hybrid._init_chains(HybridConfig.preset(1, chains=6), "cuda")
+    assert eng.rng_kind == "philox" and eng.B == 6
+    eng2, _ = hybrid._init_chains(HybridConfig.preset(1, chains=6, rng="pcg64"), "cuda")
+    assert eng2.rng_kind == "pcg64" and eng2.pcg_state is not None
 
 
 def test_mcmc_only_small():

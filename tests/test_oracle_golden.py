@@ -187,3 +187,19 @@ def test_philox_known_answers():
         assert rng.integers(5) == int(pr.step_draws(7, 3, 10 + s, 1, 5)[0][0])
         assert rng.random(2).shape == (2,)
     assert 0.0 <= rng.random() < 1.0
+
+
+def test_target_energy_oracle_matches_reference_golden(golden_dir):
+    """oracle/target_ref.py against NF.Energy.DoubleWellLJ._energy of the reference and its autograd gradient."""
+    from oracle import target_ref as tr
+    g = np.load(os.path.join(golden_dir, "target_energy.npz"))
+    for tag in g["names"]:
+        x = torch.from_numpy(g[tag + "__x"])
+        n, b, T = int(g[tag + "__n"]), float(g[tag + "__bound"]), float(g[tag + "__T"])
+        E32 = tr.double_well_lj_energy(x, n, T, b, [-10.0, -10.5], 1.2, 15).numpy()
+        np.testing.assert_allclose(E32, g[tag + "__E"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(tr.simple_lj_energy(x, n, T, b).numpy(), g[tag + "__lj"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_allclose(tr.double_well(x, n, b, [-10.0, -10.5], 1.2, 15).numpy(), g[tag + "__dw"],
+                                   rtol=2e-6, atol=2e-6)
+        _, grad = tr.energy_and_grad(x, n, T, b, [-10.0, -10.5], 1.2, 15, dtype=torch.float32)
+        np.testing.assert_allclose(grad.numpy(), g[tag + "__grad"], rtol=1e-4, atol=1e-4)
