@@ -59,6 +59,7 @@ _PROTOS = {
     "fs_tc_debug_read": (C.c_int, [_P, C.c_int]),
     "fs_flow_create": (C.c_int, [C.POINTER(FsFlowDesc), C.POINTER(_P)]),
     "fs_flow_destroy": (None, [_P]),
+    "fs_flow_update": (C.c_int, [_P, C.POINTER(FsFlowDesc), _P]),
     "fs_flow_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "fs_flow_conditioner": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, C.c_int, _P]),
     "fs_target_energy": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(FsPot), _P, _P, _P]),

@@ -32,6 +32,8 @@ struct fs_flow {
     void* tc;   // tensor-core pack (flow_tc.cu), or nullptr
     int* tc_err;   // device error word written by the tensor kernel's watchdog
     int sm_count;
+    void* repack_tab = nullptr;        // fs_flow_update: device table of per-layer pointers (repack.cu)
+    double* repack_scratch = nullptr;  // ... and its float64 scratch
 };
 
 namespace fs {
@@ -130,6 +132,29 @@ __device__ __forceinline__ void rq_eval_fast(float x, float xk, float wk, float 
         ld = 0.6931471805599453f * lg2_approx(dnum * rden * rden);
     }
 }
+
+// ---- tensor-core pack (flow_tc.cu fills it, repack.cu refreshes it on the device) ----
+static constexpr int TC_KB = 32;          // K elements per TF32 weight tile (one 128-byte swizzle atom per row)
+struct TcLayer {
+    float* wstream;    // all weight tiles of the layer in consumption order
+    float* bn0_s;      // [n_blocks, H]
+    float* bn0_o;      // [n_blocks, H]  BatchNorm offset with the running bias folded in
+    float* b0;         // [n_blocks, H]
+    float* b_final;    // [n_chunks * 128]  b_f + W_f c
+    float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
+    void* wfused;      // fused-spline final layer, FP16 operands: per coordinate (H/64)/KPS stages of KPS tiles of
+                       // [chn rows x 64 k] halves (half the bytes and twice the MMA rate of TF32, same 11-bit significand)
+    float* b_fused;    // [N][chn] (+ 32 floats of padding), folded with the FP16-rounded weights
+};
+
+struct TcPack {
+    int H, NH, Kp0, n_pieces, n_chunks, nstage;
+    int chn;           // columns of a fused final-layer chunk (0: fused path unavailable)
+    size_t tiles_per_layer, tiles_before_final;
+    size_t smem_bytes;
+    int* xcols;        // device [4][N]: input / output columns of the transformed coordinates, density then sampling
+    std::vector<TcLayer> layers;
+};
 
 // final-layer rows/bias permuted to parameter-major order (row k*N + j), see flow.cu
 void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b);

@@ -42,29 +42,6 @@
 
 namespace fs {
 
-static constexpr int TC_KB = 32;          // K elements per weight tile (one 128-byte swizzle atom per row)
-
-struct TcLayer {
-    float* wstream;    // all weight tiles of the layer in consumption order
-    float* bn0_s;      // [n_blocks, H]
-    float* bn0_o;      // [n_blocks, H]  BatchNorm offset with the running bias folded in
-    float* b0;         // [n_blocks, H]
-    float* b_final;    // [n_chunks * 128]  b_f + W_f c
-    float* psets;      // [n_blocks + 1][3][H]: set 0 = {-, s_0, o'_0}; set b+1 = {b0'_b, s_{b+1}, o'_{b+1}}
-    void* wfused;      // fused-spline final layer, FP16 operands: per coordinate (H/64)/KPS stages of KPS tiles of
-                       // [chn rows x 64 k] halves (half the bytes and twice the MMA rate of TF32, same 11-bit significand)
-    float* b_fused;    // [N][chn] (+ 32 floats of padding), folded with the FP16-rounded weights
-};
-
-struct TcPack {
-    int H, NH, Kp0, n_pieces, n_chunks, nstage;
-    int chn;           // columns of a fused final-layer chunk (0: fused path unavailable)
-    size_t tiles_per_layer, tiles_before_final;
-    size_t smem_bytes;
-    int* xcols;        // device [4][N]: input / output columns of the transformed coordinates, density then sampling
-    std::vector<TcLayer> layers;
-};
-
 struct TcArgs {
     const float* A0;       // [rows, K0]
     float* theta;          // [rows, NP]
@@ -343,8 +320,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     const uint32_t bar_free1 = bar_rdy + 48;                    // [1]  MMA -> epilogue (feature piece consumed)
     const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
-    const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pair (bias of a chunk landed)
-    const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pair -> TMA
+    const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pairs (bias of a chunk landed)
+    const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pairs -> TMA
     uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 136 + 16 * S::BIAS_SLOTS);
     static_assert(16 * NSTAGE + 140 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
     const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
@@ -369,7 +346,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         }
         for (int i = 0; i < S::BIAS_SLOTS; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
-            mbar_init(bar_bempty + 8 * i, 2);                   // the two warps of the pair that owns the chunk
+            mbar_init(bar_bempty + 8 * i, EPI_WARPS / 2);       // the pair that owns the chunk, in each of the four lane quadrants
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }

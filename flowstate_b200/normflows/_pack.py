@@ -114,6 +114,73 @@ class FlowPack:
                 pass
             self._h = None
 
+    # -- device-side refresh after the parameters changed (fs_flow_update) -----
+    def _layer_sources(self, layer):
+        """Source tensors of one layer in the order of the flat staging buffer (fs_layer_params order, the per-block
+        tensors in [block, j] order so each stack is contiguous)."""
+        c = layer.prqct
+        net = c.transform_net
+        bns = [blk.batch_norm_layers[j] for blk in net.blocks for j in (0, 1)]
+        lins = [blk.linear_layers[j] for blk in net.blocks for j in (0, 1)]
+        u = c.unconditional_transform
+        groups = [[net.initial_layer.weight], [net.initial_layer.bias], [b.weight for b in bns], [b.bias for b in bns],
+                  [b.running_mean for b in bns], [b.running_var for b in bns], [l.weight for l in lins],
+                  [l.bias for l in lins], [net.final_layer.weight], [net.final_layer.bias],
+                  [u.unnormalized_widths], [u.unnormalized_heights], [u.unnormalized_derivatives]]
+        return groups
+
+    def update(self, layers):
+        """Refreshes the packed weights from the layers' current parameters without leaving the device: one
+        multi-tensor copy into a flat staging buffer (the stacks fs_layer_params expects), then fs_flow_update."""
+        names = ("init_w", "init_b", "bn_w", "bn_b", "bn_mean", "bn_var", "lin_w", "lin_b", "final_w", "final_b",
+                 "un_w", "un_h", "un_d")
+        srcs, sizes = [], []
+        for layer in layers:
+            groups = self._layer_sources(layer)
+            sizes.append([[t.numel() for t in g] for g in groups])
+            srcs.extend(t.detach() for g in groups for t in g)
+        total = sum(n for lay in sizes for g in lay for n in g)
+        if getattr(self, "_flat", None) is None or self._flat.numel() != total:
+            self._flat = torch.empty(total, dtype=torch.float32, device=self.device)
+            views, offs, off = [], [], 0
+            for lay in sizes:
+                lay_offs = []
+                for g in lay:
+                    lay_offs.append(off)
+                    for n in g:
+                        views.append(self._flat[off:off + n])
+                        off += n
+                offs.append(lay_offs)
+            self._flat_views, self._flat_offs = views, offs
+        torch._foreach_copy_(self._flat_views, [t.reshape(-1).float() if t.dtype != torch.float32 else t.reshape(-1)
+                                                for t in srcs])
+        arr = (_lib.FsLayerParams * self.K)()
+        base = self._flat.data_ptr()
+        for i in range(self.K):
+            for name, off in zip(names, self._flat_offs[i]):
+                setattr(arr[i], name, base + 4 * off)
+        d = _lib.FsFlowDesc()
+        d.K, d.N, d.H, d.n_blocks, d.nb = self.K, self.N, self.H, self.n_blocks, self.nb
+        d.bound = self.bound
+        l0 = layers[0].prqct
+        d.bn_eps = float(l0.transform_net.blocks[0].batch_norm_layers[0].eps) if self.n_blocks else 1e-3
+        d.layers = C.cast(arr, C.POINTER(_lib.FsLayerParams))
+        _lib.check(_lib.lib().fs_flow_update(self._h, C.byref(d), _lib.stream_ptr(self.device)))
+        self._sig = self._signature(layers)
+        self.updates = getattr(self, "updates", 0) + 1
+
+    def same_shape(self, layers):
+        if len(layers) != self.K:
+            return False
+        for l in layers:
+            c = l.prqct
+            net = c.transform_net
+            if (c.features != self.D or net.hidden_features != self.H or c.num_bins != self.nb
+                    or len(net.blocks) != self.n_blocks or float(c.tail_bound) != self.bound
+                    or net.initial_layer.weight.device != self.device):
+                return False
+        return True
+
     @staticmethod
     def _signature(layers):
         # a few sentinel tensors per layer: optimizer steps and load_state_dict touch all of them

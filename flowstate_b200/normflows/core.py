@@ -31,26 +31,30 @@ class NormalizingFlow(nn.Module):
     def _cuda_pack(self):
         from ._pack import FlowPack
         layers = list(self.flows)
-        if self._pack is None or not self._pack.matches(layers):
+        if self._pack is None or not self._pack.same_shape(layers):
             self._pack = FlowPack(layers)
+        elif not self._pack.matches(layers):
+            # parameters changed (optimizer step, load_state_dict): refresh the packed weights on the device
+            # (fs_flow_update) instead of packing on the host again - Algorithm 2 does this every cycle
+            self._pack.update(layers)
         self._pack.precision = self.precision
         return self._pack
 
     def repack(self):
-        """Drop the packed inference weights (call after editing parameters in place in eval mode)."""
-        self._pack = None
+        """Mark the packed inference weights stale (call after editing parameters in a way that does not bump tensor
+        versions); the next eval-mode call refreshes them on the device."""
+        if self._pack is not None:
+            self._pack._sig = None
         for f in self.flows:
-            if hasattr(f, "_pack"):
-                f._pack = None
+            if getattr(f, "_pack", None) is not None:
+                f._pack._sig = None
 
     def train(self, mode=True):
-        if mode:
-            self._pack = None
+        # the pack survives train(): the next eval-mode call sees the bumped tensor versions and refreshes it in place
         return super().train(mode)
 
     def load_state_dict(self, *a, **k):
-        self.repack()
-        return super().load_state_dict(*a, **k)
+        return super().load_state_dict(*a, **k)    # in-place copies bump the tensor versions -> refreshed on next use
 
     def _apply(self, fn, *a, **k):
         self.repack()

@@ -159,15 +159,12 @@ class CircularCoupledRationalQuadraticSpline(Flow):
     # -- public interface -------------------------------------------------
     def _cuda_pack(self):
         from ._pack import FlowPack
-        if self._pack is None or not self._pack.matches([self]):
+        if self._pack is None or not self._pack.same_shape([self]):
             self._pack = FlowPack([self])
+        elif not self._pack.matches([self]):
+            self._pack.update([self])
         self._pack.precision = self.precision
         return self._pack
-
-    def train(self, mode=True):
-        if mode:
-            self._pack = None
-        return super().train(mode)
 
     def forward(self, z, context=None):
         self._check(z)

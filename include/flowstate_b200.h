@@ -177,6 +177,14 @@ int fs_flow_create(const fs_flow_desc* desc /*host*/, fs_flow** out);
 void fs_flow_destroy(fs_flow* flow);
 size_t fs_flow_workspace_bytes(const fs_flow* flow, int B, int precision);
 
+/* Re-packs `flow` in place from parameters that live on the DEVICE: `desc` has the shapes of the descriptor the flow
+ * was created from, but the pointers inside desc->layers[] are device pointers (identity_features / transform_features
+ * are ignored).  Every packed buffer (BatchNorm / bias folding, FP32 matrices, swizzled TF32 / FP16 tile streams, knot
+ * tables) is recomputed by a few kernels on `stream`: no device-to-host copy, no allocation after the first call.
+ * This is what `model.eval()` after an optimizer step amounts to in Algorithm 2, once per training cycle
+ * (hybrid_NF_MCMC/main_algorithm_2.py:450-451 -> 476). */
+int fs_flow_update(fs_flow* flow, const fs_flow_desc* desc /*host struct, device pointers in layers*/, void* stream);
+
 /* ResidualNet.forward of the conditioner of layer `layer`  (NF/normflows/nets/resnet.py:92-104, eval mode)
  * on ready-made periodic features [rows, 2N] (NF/normflows/utils/nn.py:120-137) -> theta [rows, 3 nb + 1, N]:
  * the library keeps the spline parameters parameter-major (the reference's column j (3nb+1) + k is k N + j here). */

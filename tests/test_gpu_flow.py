@@ -420,3 +420,39 @@ def test_fp16_operand_range_is_guarded():
     err = ((lq - ref).abs() / ref.abs()).max().item()
     print("FP16-subnormal weights: tensor path vs fp32 path %.2e" % err)
     assert err < 1e-4
+
+
+@pytest.mark.parametrize("n,K,blocks,H,nb", [(32, 3, 4, 256, 32), (64, 4, 2, 128, 15), (5, 3, 2, 64, 8), (40, 2, 1, 256, 20)])
+def test_device_side_update_equals_a_fresh_pack(n, K, blocks, H, nb):
+    """fs_flow_update (the per-cycle refresh of Algorithm 2: optimizer step -> eval) must give what fs_flow_create
+    gives on the same parameters, on both conditioner paths and in both directions, without rebuilding the pack."""
+    model, bound, g = _perturbed(n, K, blocks, H, nb, 0.03, seed=11)
+    model = model.cuda().eval()
+    x = ((torch.rand(300, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    z = ((torch.rand(300, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    model.log_prob(x)                                    # pack created on the host from the initial parameters
+    pack = model._cuda_pack()
+    with torch.no_grad():                                # an "optimizer step": every tensor changes in place
+        for p in model.parameters():
+            p.add_(0.02 * torch.randn(p.shape, generator=g).cuda())
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.add_(0.05 * torch.randn(buf.shape, generator=g).cuda())
+            elif name.endswith("running_var"):
+                buf.mul_(1.1)
+    fresh = _build(n, K, blocks, H, nb, bound, device="cpu")
+    fresh.load_state_dict({k: v.cpu() for k, v in model.state_dict().items()})
+    fresh = fresh.cuda().eval()
+    for prec in _precisions(fresh):
+        model.precision = fresh.precision = prec
+        a, b = model.log_prob(x), fresh.log_prob(x)
+        assert model._cuda_pack() is pack and getattr(pack, "updates", 0) >= 1      # refreshed in place, not rebuilt
+        xa, la = model.forward_and_log_det(z)
+        xb, lb = fresh.forward_and_log_det(z)
+        err = ((a - b).abs() / b.abs()).max().item()
+        print("N=%d H=%d %s: updated vs fresh pack: log q %.2e, sample %.2e" % (n, H, prec, err, (xa - xb).abs().max().item() / bound))
+        assert err < 2e-6 and (xa - xb).abs().max().item() < 2e-6 * bound and (la - lb).abs().max().item() < 2e-4
+    # train() / eval() round trip keeps the pack (and its device buffers)
+    model.train()
+    model.eval()
+    assert model._cuda_pack() is pack
