@@ -17,7 +17,8 @@ at N = 256 particles, 8192 chains per GPU (65 536 over 8 GPUs), flow K=15 / H=25
 32 blocks / 32 bins, for every --gpus N (weak scaling: chains shard over ranks
 with no data-path collective, flow weights are broadcast once from rank 0).
 At N = 1 the same JSON line carries `secondary` entries for configs[1]
-(alg1_n32), configs[3] (alg2_n64, sampling side) and configs[4] (energy sweep
+(alg1_n32), configs[3] (alg2_n64: the WHOLE Algorithm-2 cycle - local moves,
+training step with gradient all-reduce, device-side re-pack, global move) and configs[4] (energy sweep
 N = 64..4096 against a FP32-FMA peak measured in the same run), each with its
 own roofline, plus the accept kernel's HBM figure.
 """
@@ -42,8 +43,14 @@ WORKLOADS = {
                       desc="BASELINE configs[2]: Alg 1 hybrid, N=256, 8192 chains/GPU (65536 over 8 GPUs)"),
     "alg1_n32": dict(n=32, chains=4096, local=1000, K=15, blocks=32, H=256, nb=32, sigma=0.02, rho=0.03,
                      desc="BASELINE configs[1]: Alg 1 hybrid, 4096 chains/GPU, N=32"),
+    # Algorithm 2 (main_algorithm_2.py:393-577): every cycle = 100 local moves per chain sampled every 10 steps,
+    # one epoch of training on UPDATE_NUM_SAMPLES = 1000 of the new configurations (4 minibatches of 256, new Adam,
+    # lr 5.435e-4, wd 9.586e-5), eval -> device-side re-pack, one NF global move per chain.  Under N GPUs every rank
+    # trains on its own 1000 samples and the flat gradient bucket is all-reduced (NCCL, SUM / N) once per optimizer step.
     "alg2_n64": dict(n=64, chains=4096, local=100, K=23, blocks=2, H=128, nb=15, sigma=0.05, rho=0.03,
-                     desc="BASELINE configs[3] sampling part: Alg 2 cycle, N=64, 100 local steps + 1 global move"),
+                     train=dict(samples=1000, batch=256, lr=0.000543510751759681, wd=9.5857178422352e-05, every=10),
+                     desc="BASELINE configs[3]: Alg 2 whole cycle, N=64: 100 local steps + training step (4 x 256, "
+                          "gradient all-reduce) + re-pack + 1 global move"),
 }
 DEFAULT_WORKLOAD = "alg1_n256"
 POT = dict(num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15)
@@ -57,7 +64,8 @@ def workload_config(name, w):
             "flow": {"K": w["K"], "blocks": w["blocks"], "H": w["H"], "bins": w["nb"], "sigma": w["sigma"]},
             "potential": {"wells": POT["num_wells"], "V0": POT["V0_list"], "r0": POT["r0"], "k": POT["k"], "T": 1.0},
             "l2": "inputs larger than L2: the flow weights (%.0f MB FP32) are streamed in every pass"
-                  % (flow_params(w) * 4 / 1e6)}
+                  % (flow_params(w) * 4 / 1e6),
+            "train": w.get("train")}
 
 
 def flow_params(w):
@@ -406,6 +414,11 @@ class Harness:
         # one proposal energy and `local` local moves per chain.
         self.side = torch.cuda.Stream(device=dev)
         self.pending = {}
+        self.trainer = None
+        if w.get("train"):
+            from flowstate_b200.drivers.training import FlowTrainer
+            t = w["train"]
+            self.trainer = FlowTrainer(self.model, t["lr"], t["wd"], 1.0, t["batch"], use_graph=True)
 
     # -- the round ----------------------------------------------------------
     def launch_proposals(self, z_host=None):
@@ -422,7 +435,49 @@ class Harness:
         cfg.record_stream(main)
         self.pending["cfg"], self.pending["ev"] = cfg, ev
 
+    def train_cycle(self, z_host=None, timers=None):
+        """One Algorithm-2 cycle (main_algorithm_2.py:393-548)."""
+        w, eng, model, t = self.w, self.eng, self.model, self.w["train"]
+
+        def mark(name):
+            if timers is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                timers.append((name, ev))
+        mark("start")
+        snaps = []
+        for s0 in range(0, w["local"], t["every"]):            # SAMPLING_FREQUENCY = 10 (main_algorithm_2.py:59, 403-412)
+            eng.particle_displacement(min(t["every"], w["local"] - s0))
+            snaps.append(eng.centred(eng.pos))
+        pool = torch.cat(snaps)
+        data = pool[torch.randint(0, pool.shape[0], (t["samples"],), device=self.dev)]
+        mark("local_sweep+collect")
+        model.train()
+        self.trainer.fresh_optimizer()                         # new Adam every cycle (main_algorithm_2.py:440)
+        perm = torch.randperm(data.shape[0], device=self.dev)
+        for bi in range(0, data.shape[0], t["batch"]):
+            self.trainer.step(data[perm[bi:bi + t["batch"]]])
+        model.eval()
+        mark("train")
+        if self.world > 1:
+            self.parallel.broadcast_flow(model, src=0)         # rank 0's BatchNorm statistics everywhere
+        mark("broadcast")
+        model._cuda_pack()                                     # device-side re-pack (fs_flow_update)
+        mark("repack")
+        if z_host is None:
+            z = model.q0(self.B)
+        else:
+            z = torch.empty(self.B, 2 * self.n, dtype=torch.float32, device=self.dev)
+            z.copy_(z_host, non_blocking=True)
+        cfg = (model.forward(z).reshape(self.B, self.n, 2) + self.half32).contiguous()
+        mark("flow_sample")
+        mask = eng.nf_big_move(cfg)
+        mark("global_move")
+        return mask
+
     def one_round(self, z_host=None):
+        if self.trainer is not None:
+            return self.train_cycle(z_host)
         if "cfg" not in self.pending:
             self.launch_proposals(z_host)
         cfg, ev = self.pending.pop("cfg"), self.pending.pop("ev")
@@ -592,6 +647,30 @@ class Harness:
         """Phase split of one round (not part of the timed region) + the rooflines of the non-dominant kernels."""
         w, eng, model, dev, B, n = self.w, self.eng, self.model, self.dev, self.B, self.n
         out = {}
+        if self.trainer is not None:                           # Algorithm-2 cycle: split of one whole cycle
+            self.train_cycle()
+            torch.cuda.synchronize()
+            timers = []
+            self.train_cycle(timers=timers)
+            torch.cuda.synchronize()
+            for (_, a), (name, b_) in zip(timers, timers[1:]):
+                out["cycle_" + name + "_ms"] = a.elapsed_time(b_)
+            tr = self.trainer
+            out["train_steps_per_cycle"] = -(-w["train"]["samples"] // w["train"]["batch"])
+            out["gradient_bucket_bytes"] = int(tr.flat.numel() * 4) if tr.flat is not None else 0
+            if self.world > 1:
+                import torch.distributed as dist
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.all_reduce(tr.flat)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(5):
+                    dist.all_reduce(tr.flat)
+                b_.record()
+                torch.cuda.synchronize()
+                out["allreduce_ms"] = a.elapsed_time(b_) / 5
+                out["allreduce_collective"] = "ncclAllReduce(sum) of the flat float32 gradient bucket, one per optimizer step"
+                out["allreduce_busbw_gbs"] = (2 * (self.world - 1) / self.world) * out["gradient_bucket_bytes"] / (out["allreduce_ms"] * 1e-3) / 1e9
 
         def timed(name, fn, reps=1):
             fn()                                       # untimed first call: workspaces of this shape / stream get allocated

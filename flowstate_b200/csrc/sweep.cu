@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(128) local_sweep_kernel(float* __restrict__ po
 // Throughput kernel (Philox streams; what the drivers and the bench run): the same move with the per-step overheads
 // trimmed - one Philox block per step generated LPC steps at a time (lane `sub` of a chain's lane group prepares step
 // base + sub, the step reads it with four shuffles), energy / virial DIFFERENCES reduced instead of four separate
-// sums, hard-core tests by ballot, wells behind a float32 pre-test, several chains per warp.
+// sums, hard-core tests by ballot, wells behind a float32 pre-test, several chains per warp, an exact minimum image
+// for close pairs.
 // packed FP32 pairs (add/sub/mul/fma.f32x2)
 __device__ __forceinline__ unsigned long long pk2s(float a, float b) {
     unsigned long long r;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
                                                                float* __restrict__ trace_e) {
     constexpr int CPW = 32 / LPC;                 // chains per warp
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ float2 smem[];
+    extern __shared__ float4 smem4[];
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int grp = lane / LPC, sub = lane % LPC, gl0 = grp * LPC;
@@ -259,14 +260,27 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     if (b_first >= B) return;
     const bool live = b_first + grp < B;          // groups past the last chain shadow it and store nothing
     const int b = live ? b_first + grp : B - 1;
-    float2* sp = smem + (size_t)(wib * CPW + grp) * stride2;
+    // Chain state in shared memory: per particle (x, y, cx, cy) with c = x - L [x > L / 2], the same point seen from the
+    // box centre.  The minimum image of a difference is whichever of x_i - x_j and c_i - c_j is smaller in magnitude
+    // (both lie in {d, d +- L}, and one of them has |.| <= L / 2); for a close pair the smaller one is a difference of
+    // nearby float32 numbers and therefore exact - the rint-based form subtracts at magnitude L first and loses up to
+    // ulp(L) / r of relative accuracy on pairs that straddle the periodic boundary (1e-5 of r^-12 at L = 11).
+    float4* sp = smem4 + (size_t)(wib * CPW + grp) * stride2;
     float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
     const int iters = (N + LPC - 1) / LPC;
     const float qnan = __int_as_float(0x7fc00000);
+    const float hLx = 0.5f * P.Lx, hLy = 0.5f * P.Ly;
     // Slots are padded to iters * LPC entries with NaN positions: a NaN r^2 fails the cut-off test (every term 0) and is
     // ignored by fminf, so neither the padding nor the moved particle itself (overwritten with NaN while its partners
     // are walked) needs a mask inside the pair loop.
-    for (int i = sub; i < iters * LPC; i += LPC) sp[i] = (i < N) ? gp[i] : make_float2(qnan, qnan);
+    for (int i = sub; i < iters * LPC; i += LPC) {
+        float4 v = make_float4(qnan, qnan, qnan, qnan);
+        if (i < N) {
+            const float2 g = gp[i];
+            v = make_float4(g.x, g.y, g.x - (g.x > hLx ? P.Lx : 0.f), g.y - (g.y > hLy ? P.Ly : 0.f));
+        }
+        sp[i] = v;
+    }
     __syncwarp();
 
     const double md = max_disp[b];
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const long long cid = chain_id0 + b;
     const uint32_t cz = (uint32_t)cid, cw = (uint32_t)((unsigned long long)cid >> 32);
     const float inf = __int_as_float(0x7f800000);
-    const float Lx = P.Lx, Ly = P.Ly, iLx = P.inv_Lx, iLy = P.inv_Ly, rc2 = P.rc2, ecut = P.e_cut, rcore2 = P.rcore2;
+    const float Lx = P.Lx, Ly = P.Ly, rc2 = P.rc2, ecut = P.e_cut, rcore2 = P.rcore2;
     const float nbeta = -(float)beta;
     // wells: lanes 0..3 of a group evaluate (old, well 0), (old, well 1), (new, well 0), (new, well 1) with one code path
     const int nw = P.num_wells;
@@ -289,10 +303,8 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const uint32_t a0 = (uint32_t)att0;      // low bits of the step id: slot inside the LPC-step block of random numbers
     uint4 blk = make_uint4(0, 0, 0, 0);
     struct {
-        unsigned long long iLx, iLy, nLx, nLy, magic, nmagic, four, mone, mhalf;
+        unsigned long long four, mone, mhalf;
     } K;
-    K.iLx = pk2s(iLx, iLx); K.iLy = pk2s(iLy, iLy); K.nLx = pk2s(-Lx, -Lx); K.nLy = pk2s(-Ly, -Ly);
-    K.magic = pk2s(12582912.0f, 12582912.0f); K.nmagic = pk2s(-12582912.0f, -12582912.0f);
     K.four = pk2s(4.0f, 4.0f); K.mone = pk2s(-1.0f, -1.0f); K.mhalf = pk2s(-0.5f, -0.5f);
 
     // One Philox block per step id {particle index, u1, u2, accept uniform}; a group prepares LPC steps at a time
@@ -322,9 +334,9 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         const int p = p_n;
         const double ddx = dx_n, ddy = dy_n;
         const uint32_t r_u3 = u3_n;
-        const float2 old = sp[p];
+        const float4 old = sp[p];
         __syncwarp();
-        if (sub == 0) sp[p] = make_float2(qnan, qnan);       // the moved particle is not its own partner
+        if (sub == 0) sp[p] = make_float4(qnan, qnan, qnan, qnan);       // the moved particle is not its own partner
         // new_positions[p] += displacement (float64 add, stored float32), then % L (monte_carlo.py:161-166)
         float nx = (float)((double)old.x + ddx);
         float ny = (float)((double)old.y + ddy);
@@ -338,15 +350,21 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         // the warp whose 64 pairs all lie outside the cut-off contributes nothing and ends after r^2.
         float mo = 3.0e38f, mn = 3.0e38f;
         unsigned long long e2 = 0ull, w2 = 0ull;                     // (sum e_old, sum e_new), (sum w_old, sum w_new)
-        const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny);
+        const float cnx = nx - (nx > hLx ? Lx : 0.f), cny = ny - (ny > hLy ? Ly : 0.f);
+        const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny), PCX = pk2s(old.z, cnx),
+                                 PCY = pk2s(old.w, cny);
 #pragma unroll 4
         for (int it = 0; it < iters; ++it) {
-            const float2 q = sp[sub + it * LPC];
-            unsigned long long X = sub2s(PX, pk2s(q.x, q.x)), Y = sub2s(PY, pk2s(q.y, q.y));
-            X = fma2s(add2s(fma2s(X, K.iLx, K.magic), K.nmagic), K.nLx, X);      // d - L rint(d / L)
-            Y = fma2s(add2s(fma2s(Y, K.iLy, K.magic), K.nmagic), K.nLy, Y);
-            float r2o, r2n;
-            upk2s(fma2s(Y, Y, mul2s(X, X)), r2o, r2n);
+            const float4 q = sp[sub + it * LPC];
+            // both candidates of the minimum image per axis, squared; the smaller one is the image (see above)
+            const unsigned long long X0 = sub2s(PX, pk2s(q.x, q.x)), X1 = sub2s(PCX, pk2s(q.z, q.z));
+            const unsigned long long Y0 = sub2s(PY, pk2s(q.y, q.y)), Y1 = sub2s(PCY, pk2s(q.w, q.w));
+            float ax0, bx0, ax1, bx1, ay0, by0, ay1, by1;
+            upk2s(mul2s(X0, X0), ax0, bx0);
+            upk2s(mul2s(X1, X1), ax1, bx1);
+            upk2s(mul2s(Y0, Y0), ay0, by0);
+            upk2s(mul2s(Y1, Y1), ay1, by1);
+            const float r2o = fminf(ax0, ax1) + fminf(ay0, ay1), r2n = fminf(bx0, bx1) + fminf(by0, by1);
             if (SKIP && !__any_sync(FULL, fminf(r2o, r2n) <= rc2)) continue;
             mo = fminf(mo, r2o);
             mn = fminf(mn, r2n);
@@ -400,7 +418,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
                 }
             }
         }
-        if (sub == 0) sp[p] = ok ? make_float2(nx, ny) : old;
+        if (sub == 0) sp[p] = ok ? make_float4(nx, ny, cnx, cny) : old;
         if (ok) {
             acc += 1;
             if (__builtin_expect(ov_o || ov_n, 0)) {           // leaving (or, from an overlap, entering) the hard core
@@ -417,7 +435,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
 #pragma unroll
     for (int o = LPC / 2; o > 0; o >>= 1) Wl += __shfl_xor_sync(FULL, Wl, o);
     if (live) {
-        for (int i = sub; i < N; i += LPC) gp[i] = sp[i];
+        for (int i = sub; i < N; i += LPC) gp[i] = make_float2(sp[i].x, sp[i].y);
         if (sub == 0) {
             attempts[b] = att0 + steps;
             accepted[b] += acc;
@@ -471,13 +489,11 @@ static int launch_fast_t(float* pos, double* E, double* W, const double* md, lon
                          int N, int steps, const PotDev& P, double beta, unsigned long long seed, long long chain_id0,
                          unsigned char* ta, int* ti, float* te, cudaStream_t s) {
     constexpr int CPW = 32 / LPC;
-    // slot stride: N rounded up so that stride * 8 bytes = 64 (mod 128) - the lane groups of a warp then hit disjoint banks
-    int stride2 = (N + 15) / 16 * 16 + (CPW > 1 ? 8 : 0);
-    const int padded = (N + LPC - 1) / LPC * LPC;                // room for the NaN padding of the last trip
-    if (stride2 < padded) stride2 = padded;
+    // slot stride (float4 units): N rounded up to whole trips of the lane group (room for the NaN padding)
+    const int stride2 = (N + LPC - 1) / LPC * LPC;
     int wpc = 4;
-    while (wpc > 1 && (size_t)wpc * CPW * stride2 * sizeof(float2) > 200 * 1024) wpc >>= 1;
-    const size_t smem = (size_t)wpc * CPW * stride2 * sizeof(float2);
+    while (wpc > 1 && (size_t)wpc * CPW * stride2 * sizeof(float4) > 200 * 1024) wpc >>= 1;
+    const size_t smem = (size_t)wpc * CPW * stride2 * sizeof(float4);
     if (smem > 227 * 1024) {
         set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
         return FS_ERR_UNSUPPORTED;
@@ -498,7 +514,7 @@ static int launch_fast(float* pos, double* E, double* W, const double* md, long 
                        unsigned char* ta, int* ti, float* te, cudaStream_t s) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("FS_SWEEP_LPC"); forced = e ? atoi(e) : 0; }   // tuning knob (8 / 16 / 32)
-    int lpc = forced ? forced : (N <= 1024 ? 8 : 32);
+    int lpc = forced ? forced : (N <= 768 ? 8 : 32);
     const bool tr = ta || ti || te;
     // dilute boxes: most warp trips of the pair loop see no partner inside the cut-off (probability of a pair inside it
     // is pi rc^2 / (Lx Ly); a trip holds 64 pairs) -> early-out variant

@@ -73,6 +73,7 @@ class HybridConfig:
     local_steps: int = 100
     alpha: float = 1.0               # loss = alpha * forward KL + (1 - alpha) * reverse KL (main_algorithm_2.py:52, 321)
     precision: str = "auto"          # conditioner arithmetic of the eval-mode kernels: auto | tf32 | fp32
+    cuda_graph: int = 1              # replay the training pass from a CUDA graph (0: eager autograd)
     # MCMC only (main_mcmc_only.py:56-57: 1e7 steps over 100 chains)
     production_steps: int = 100000
 
@@ -159,42 +160,31 @@ def _local_phase(eng, steps, cfg, collect=None, step0=0):
     return step0 + done
 
 
-def _train(model, data, cfg, epochs, optimizer=None):
-    """Forward-KL training (main_algorithm_1.py:297-320, main_algorithm_2.py:437-452); gradients are all-reduced over
-    ranks between backward and the optimizer step.  The number of collectives is the same on every rank: the number of
-    minibatches per epoch is the minimum over ranks (ranks may own different numbers of chains), and the reference's
-    "skip a NaN / Inf loss" decision (main_algorithm_1.py:310-315) is taken collectively."""
+def _train(model, data, cfg, epochs, trainer=None):
+    """Training (main_algorithm_1.py:297-320, main_algorithm_2.py:437-452) through drivers.training.FlowTrainer: forward +
+    backward replayed from a CUDA graph, ONE all-reduce of the flat gradient bucket per optimizer step, fused Adam, a new
+    optimizer per call (the reference creates a new Adam every cycle, main_algorithm_2.py:440).  The number of
+    collectives is the same on every rank: the number of minibatches per epoch is the minimum over ranks (ranks may own
+    different numbers of chains), and the reference's "skip a NaN / Inf loss" decision (main_algorithm_1.py:310-315) is
+    taken collectively.  Ends in eval mode with rank 0's weights and BatchNorm statistics on every rank."""
+    from .training import FlowTrainer
     model.train()
-    opt = optimizer or torch.optim.Adam(model.parameters(), lr=cfg.lr, weight_decay=cfg.weight_decay)
+    tr = trainer or FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph)
+    tr.fresh_optimizer()
     _, world = _dist()
     n_batches = torch.tensor([max(0, -(-(data.shape[0] - 1) // cfg.batch_size))], device=data.device)
     if world > 1:
         dist.all_reduce(n_batches, op=dist.ReduceOp.MIN)
     n_batches = int(n_batches.item())
-    use_reverse = cfg.alpha < 1.0
     losses = []
     for _ in range(epochs):
         perm = torch.randperm(data.shape[0], device=data.device)
         tot, nb = 0.0, 0
         for bi in range(n_batches):
-            batch = data[perm[bi * cfg.batch_size:(bi + 1) * cfg.batch_size]]
-            opt.zero_grad()
-            usable = batch.shape[0] >= 2                       # BatchNorm needs two rows
-            if usable:
-                loss = model.forward_kld(batch)
-                if use_reverse:                                # main_algorithm_2.py:446-448
-                    energy_loss, _ = model.reverse_kld(cfg.batch_size)
-                    loss = cfg.alpha * loss + (1.0 - cfg.alpha) * energy_loss
-            bad = torch.tensor([0.0 if usable and bool(torch.isfinite(loss)) else 1.0], device=data.device)
-            if world > 1:
-                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-            if bad.item() > 0:                                 # every rank skips this step together
-                continue
-            loss.backward()
-            parallel.allreduce_gradients(model)
-            opt.step()
-            tot += float(loss.detach())
-            nb += 1
+            loss = tr.step(data[perm[bi * cfg.batch_size:(bi + 1) * cfg.batch_size]])
+            if loss is not None:
+                tot += loss
+                nb += 1
         losses.append(tot / max(nb, 1))
     model.eval()
     parallel.broadcast_flow(model, src=0)
@@ -276,12 +266,14 @@ def run_algorithm_2(cfg, device="cuda", log=print):
     eng.set_nf_model(model)
     # initial training set: INITIAL_TRAINING_NUM_SAMPLES / (NUM_MC_RUNS / SAMPLING_FREQUENCY) steps per chain
     # (main_algorithm_2.py:240-252)
+    from .training import FlowTrainer
+    trainer = FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph)
     init_steps = max(cfg.sampling_frequency, int(cfg.training_samples / (cfg.chains / cfg.sampling_frequency)))
-    last = _train(model, _collect(eng, init_steps, cfg), cfg, cfg.epochs)[-1]
+    last = _train(model, _collect(eng, init_steps, cfg), cfg, cfg.epochs, trainer)[-1]
     big_acc = 0
     for cycle in range(cfg.cycles):
         data = _collect(eng, cfg.local_steps, cfg)
-        last = _train(model, data, cfg, cfg.epochs)[-1]
+        last = _train(model, data, cfg, cfg.epochs, trainer)[-1]          # graphs are reused, the optimizer is new
         big_acc += int(eng.nf_big_move().sum().item())
     att, acc, big = parallel.allreduce_counters(eng.attempts, eng.accepted, torch.tensor([big_acc], device=eng.device))
     return {"algorithm": 2, "attempts": att, "accepted": acc, "big_move_accepts": big,

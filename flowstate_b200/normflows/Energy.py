@@ -76,7 +76,7 @@ class SimpleLJ(nn.Module):
         return E, g
 
     def _energy(self, x):
-        x = x.reshape(x.shape[0], -1)
+        x = x.reshape(x.shape[0], self._dim)
         if x.requires_grad and torch.is_grad_enabled():
             return _TargetEnergyFn.apply(x, self)
         return self._launch(x, False)[0]
@@ -104,5 +104,5 @@ class DoubleWellLJ(SimpleLJ):
 
     def double_well_potential(self, positions):
         """SimpleLJ.py:61-112 alone (wells only), summed over the particles of each configuration."""
-        x = positions.reshape(positions.shape[0], -1)
+        x = positions.reshape(positions.shape[0], self._dim)
         return self._launch(x, False)[0] - self._launch(x, False, wells=False)[0]

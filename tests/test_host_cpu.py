@@ -184,6 +184,51 @@ def test_world_size_2_broadcast_and_gradient_allreduce():
         assert att == 7 and acc == 3
 
 
+def _trainer_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from flowstate_b200 import parallel
+    from flowstate_b200.drivers import hybrid
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(5)                                   # same initial weights, as _build_flow broadcasts them
+        model = _build(3, 2, 2, 16, 8, 5.0)
+        cfg = hybrid.HybridConfig.preset(2, particles=3, K=2, blocks=2, hidden=16, bins=8, batch_size=8, epochs=2,
+                                         lr=1e-2, cuda_graph=0)
+        g = torch.Generator().manual_seed(40 + rank)
+        rows = 30 if rank == 0 else 19                         # unequal data: 4 vs 3 minibatches -> 3 on both ranks
+        data = (torch.rand(rows, 6, generator=g) * 2 - 1) * 5
+        if rank == 1:
+            data[8:16] = float("nan")                          # a non-finite loss on ONE rank: both must skip that step
+        torch.manual_seed(9)                                   # same permutations on both ranks (keeps the NaN batch aligned)
+        losses = hybrid._train(model, data, cfg, cfg.epochs)
+        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        gathered = [torch.zeros_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        ret[rank] = (all(torch.equal(gathered[0], t) for t in gathered), bool(torch.isfinite(flat).all()),
+                     [float(x) for x in losses], model.training)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_trainer_keeps_collectives_aligned():
+    """drivers.training.FlowTrainer through hybrid._train on two gloo ranks with unequal sample counts and a NaN batch on
+    one rank: no deadlock, identical finite weights afterwards (rank-invariant collective count, collective
+    skip decision)."""
+    import torch.multiprocessing as mp
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_trainer_worker, args=(world, port, ret), nprocs=world, join=True)
+        res = dict(ret)
+    for r in range(world):
+        same, finite, losses, training = res[r]
+        assert same and finite and not training
+        assert len(losses) == 2 and all(np.isfinite(l) for l in losses)
+
+
 def test_drop_in_top_level_import_names():
     """The reference drivers do `import normflows as NF; import MCMC as MC`
     (hybrid_NF_MCMC/main_algorithm_1.py:29-30): both names must resolve to this package when its
