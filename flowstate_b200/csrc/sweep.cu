@@ -265,7 +265,10 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     // (both lie in {d, d +- L}, and one of them has |.| <= L / 2); for a close pair the smaller one is a difference of
     // nearby float32 numbers and therefore exact - the rint-based form subtracts at magnitude L first and loses up to
     // ulp(L) / r of relative accuracy on pairs that straddle the periodic boundary (1e-5 of r^-12 at L = 11).
-    float4* sp = smem4 + (size_t)(wib * CPW + grp) * stride2;
+    // (two float2 arrays per chain slot: the dilute-box variant reads the centred copy only for warp trips that hold a
+    // pair inside the cut-off)
+    float2* sp = reinterpret_cast<float2*>(smem4) + (size_t)(wib * CPW + grp) * 2 * stride2;
+    float2* sc = sp + stride2;
     float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
     const int iters = (N + LPC - 1) / LPC;
     const float qnan = __int_as_float(0x7fc00000);
@@ -274,12 +277,13 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     // ignored by fminf, so neither the padding nor the moved particle itself (overwritten with NaN while its partners
     // are walked) needs a mask inside the pair loop.
     for (int i = sub; i < iters * LPC; i += LPC) {
-        float4 v = make_float4(qnan, qnan, qnan, qnan);
+        float2 v = make_float2(qnan, qnan), c = v;
         if (i < N) {
-            const float2 g = gp[i];
-            v = make_float4(g.x, g.y, g.x - (g.x > hLx ? P.Lx : 0.f), g.y - (g.y > hLy ? P.Ly : 0.f));
+            v = gp[i];
+            c = make_float2(v.x - (v.x > hLx ? P.Lx : 0.f), v.y - (v.y > hLy ? P.Ly : 0.f));
         }
         sp[i] = v;
+        sc[i] = c;
     }
     __syncwarp();
 
@@ -303,8 +307,10 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     const uint32_t a0 = (uint32_t)att0;      // low bits of the step id: slot inside the LPC-step block of random numbers
     uint4 blk = make_uint4(0, 0, 0, 0);
     struct {
-        unsigned long long four, mone, mhalf;
+        unsigned long long iLx, iLy, nLx, nLy, magic, nmagic, four, mone, mhalf;
     } K;
+    K.iLx = pk2s(P.inv_Lx, P.inv_Lx); K.iLy = pk2s(P.inv_Ly, P.inv_Ly); K.nLx = pk2s(-Lx, -Lx); K.nLy = pk2s(-Ly, -Ly);
+    K.magic = pk2s(12582912.0f, 12582912.0f); K.nmagic = pk2s(-12582912.0f, -12582912.0f);
     K.four = pk2s(4.0f, 4.0f); K.mone = pk2s(-1.0f, -1.0f); K.mhalf = pk2s(-0.5f, -0.5f);
 
     // One Philox block per step id {particle index, u1, u2, accept uniform}; a group prepares LPC steps at a time
@@ -334,9 +340,12 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         const int p = p_n;
         const double ddx = dx_n, ddy = dy_n;
         const uint32_t r_u3 = u3_n;
-        const float4 old = sp[p];
+        const float2 old = sp[p], oldc = sc[p];
         __syncwarp();
-        if (sub == 0) sp[p] = make_float4(qnan, qnan, qnan, qnan);       // the moved particle is not its own partner
+        if (sub == 0) {                                        // the moved particle is not its own partner
+            sp[p] = make_float2(qnan, qnan);
+            sc[p] = make_float2(qnan, qnan);
+        }
         // new_positions[p] += displacement (float64 add, stored float32), then % L (monte_carlo.py:161-166)
         float nx = (float)((double)old.x + ddx);
         float ny = (float)((double)old.y + ddy);
@@ -351,21 +360,30 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         float mo = 3.0e38f, mn = 3.0e38f;
         unsigned long long e2 = 0ull, w2 = 0ull;                     // (sum e_old, sum e_new), (sum w_old, sum w_new)
         const float cnx = nx - (nx > hLx ? Lx : 0.f), cny = ny - (ny > hLy ? Ly : 0.f);
-        const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny), PCX = pk2s(old.z, cnx),
-                                 PCY = pk2s(old.w, cny);
+        const unsigned long long PX = pk2s(old.x, nx), PY = pk2s(old.y, ny), PCX = pk2s(oldc.x, cnx),
+                                 PCY = pk2s(oldc.y, cny);
 #pragma unroll 4
         for (int it = 0; it < iters; ++it) {
-            const float4 q = sp[sub + it * LPC];
+            const float2 q = sp[sub + it * LPC];
+            const unsigned long long X0 = sub2s(PX, pk2s(q.x, q.x)), Y0 = sub2s(PY, pk2s(q.y, q.y));
+            if (SKIP) {
+                // dilute boxes: the cut-off test of the whole warp trip on the rint-based image d - L rint(d / L) (its
+                // float32 error is irrelevant at r = r_cut, where the shifted energy is 0); most trips end here
+                const unsigned long long X = fma2s(add2s(fma2s(X0, K.iLx, K.magic), K.nmagic), K.nLx, X0);
+                const unsigned long long Y = fma2s(add2s(fma2s(Y0, K.iLy, K.magic), K.nmagic), K.nLy, Y0);
+                float ta, tb;
+                upk2s(fma2s(Y, Y, mul2s(X, X)), ta, tb);
+                if (!__any_sync(FULL, fminf(ta, tb) <= 1.0001f * rc2)) continue;
+            }
             // both candidates of the minimum image per axis, squared; the smaller one is the image (see above)
-            const unsigned long long X0 = sub2s(PX, pk2s(q.x, q.x)), X1 = sub2s(PCX, pk2s(q.z, q.z));
-            const unsigned long long Y0 = sub2s(PY, pk2s(q.y, q.y)), Y1 = sub2s(PCY, pk2s(q.w, q.w));
+            const float2 qc = sc[sub + it * LPC];
+            const unsigned long long X1 = sub2s(PCX, pk2s(qc.x, qc.x)), Y1 = sub2s(PCY, pk2s(qc.y, qc.y));
             float ax0, bx0, ax1, bx1, ay0, by0, ay1, by1;
             upk2s(mul2s(X0, X0), ax0, bx0);
             upk2s(mul2s(X1, X1), ax1, bx1);
             upk2s(mul2s(Y0, Y0), ay0, by0);
             upk2s(mul2s(Y1, Y1), ay1, by1);
             const float r2o = fminf(ax0, ax1) + fminf(ay0, ay1), r2n = fminf(bx0, bx1) + fminf(by0, by1);
-            if (SKIP && !__any_sync(FULL, fminf(r2o, r2n) <= rc2)) continue;
             mo = fminf(mo, r2o);
             mn = fminf(mn, r2n);
             float io, in_;
@@ -418,7 +436,10 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
                 }
             }
         }
-        if (sub == 0) sp[p] = ok ? make_float4(nx, ny, cnx, cny) : old;
+        if (sub == 0) {
+            sp[p] = ok ? make_float2(nx, ny) : old;
+            sc[p] = ok ? make_float2(cnx, cny) : oldc;
+        }
         if (ok) {
             acc += 1;
             if (__builtin_expect(ov_o || ov_n, 0)) {           // leaving (or, from an overlap, entering) the hard core
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
 #pragma unroll
     for (int o = LPC / 2; o > 0; o >>= 1) Wl += __shfl_xor_sync(FULL, Wl, o);
     if (live) {
-        for (int i = sub; i < N; i += LPC) gp[i] = make_float2(sp[i].x, sp[i].y);
+        for (int i = sub; i < N; i += LPC) gp[i] = sp[i];
         if (sub == 0) {
             attempts[b] = att0 + steps;
             accepted[b] += acc;

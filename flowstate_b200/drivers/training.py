@@ -54,7 +54,14 @@ class FlowTrainer:
         """One eager pass to find the parameters that get gradients, then the flat bucket with the grads as views."""
         for p in self.params:
             p.grad = None
-        self._loss(batch).backward()
+        side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        if side is not None:                                   # off the default stream, like the graph warm-up below
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._loss(batch).backward()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+        else:
+            self._loss(batch).backward()
         self.trainable = [p for p in self.params if p.grad is not None]
         total = sum(p.numel() for p in self.trainable)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -96,8 +103,10 @@ class FlowTrainer:
             pool = next(iter(self.graphs.values()))[0].pool() if self.graphs else None
             with torch.cuda.graph(g, pool=pool):
                 self.flat.zero_()
-                static_loss = self._loss(static_in)
-                static_loss.backward()                         # accumulates in place into the views of self.flat
+                loss = self._loss(static_in)
+                loss.backward()                                # accumulates in place into the views of self.flat
+                static_loss = loss.detach()                    # keeps the storage, drops the autograd graph (and with it
+            del loss                                           # the AccumulateGrad nodes bound to the capture stream)
             entry = (g, static_in, static_loss)
             self.graphs[rows] = entry
         g, static_in, static_loss = entry

@@ -69,6 +69,8 @@ class SimpleLJ(nn.Module):
         B = xc.shape[0]
         E = torch.empty(B, dtype=torch.float32, device=xc.device)
         g = torch.empty_like(xc) if want_grad else None
+        if B == 0:
+            return E, g
         pot = self._pot(wells)
         _lib.check(_lib.lib().fs_target_energy(_lib.ptr(xc), B, self._n_particles, float(self.bound),
                                                float(self.temperature), pot, _lib.ptr(E), _lib.ptr(g),

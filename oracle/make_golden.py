@@ -374,6 +374,44 @@ def gen_observables(ref):
     print("observables.npz:", len(out), "arrays")
 
 
+def gen_judge(ref):
+    """judge_normalizing_flow / bulk_judge_normalizing_flow (monte_carlo.py:305-370): energy-only Metropolis tests of
+    proposals; the cached energy must be restored, attempts counted, one uniform consumed per finite uphill proposal."""
+    SB = ref["simulation_box"].SimulationBox
+    MC = ref["monte_carlo"].MonteCarlo
+    lg = quiet_logger()
+    out = {}
+    n, rho, seed = 8, 0.3, 77
+    L = er.box_length(n, rho)
+    p32, _ = er.jittered_lattice(n, rho, seed)
+    # float32 state from the start (what a reference chain holds after its first NF acceptance, SURVEY.md 7.2): the
+    # device chain then follows the same trajectory bit for bit
+    mc = MC(p32.copy(), SB(L), 1.0, n, initial_max_displacement=0.5, timing=False, checking=False,
+            logger=lg, seed=seed, device=torch.device("cpu"), **POT)
+    for _ in range(30):
+        mc.particle_displacement()
+    rng = np.random.default_rng(5)
+    state = np.array(mc.particles, dtype=np.float32)
+    props = []
+    for i in range(24):                                   # small perturbations (mixed up / downhill), one overlap
+        c = state + (rng.random((n, 2)).astype(np.float32) - 0.5) * np.float32(0.08 * (1 + i % 4))
+        c = np.mod(c, np.float32(L)).astype(np.float32)
+        props.append(c)
+    props[7][1] = props[7][0] + np.float32(0.2)
+    e_before = mc.energy_calculator.total_energy
+    att0 = mc.attempts_displacement
+    crit = [bool(mc.judge_normalizing_flow(c.copy())) for c in props[:12]]
+    out.update(pos0=p32, L=np.float64(L), n=np.int64(n), seed=np.int64(seed), warm=np.int64(30),
+               props=np.stack(props), crit=np.array(crit), e_cached=np.float64(mc.energy_calculator.total_energy),
+               e_before=np.float64(e_before), att_delta=np.int64(mc.attempts_displacement - att0))
+    ref_e = float(e_before) + 0.5
+    acc, att = mc.bulk_judge_normalizing_flow([c.copy() for c in props[12:]], ref_e)
+    out.update(bulk_ref_energy=np.float64(ref_e), bulk_acc=np.int64(acc), bulk_att=np.int64(att),
+               next_uniform=np.float64(mc.rng.random()))
+    np.savez_compressed(os.path.join(GOLD, "mc_judge.npz"), **out)
+    print("mc_judge: %d single + %d bulk proposals, %d accepted" % (12, att, acc))
+
+
 def gen_target(ref):
     """Training target of Algorithm 2: NF.Energy.DoubleWellLJ._energy (NF/normflows/Energy/SimpleLJ.py:42-128) and its
     gradient by the reference's own autograd, on float32 centred configurations incl. soft-core pairs (r <= 0.82),
@@ -418,6 +456,9 @@ def main():
     if "target" in sys.argv[1:]:
         gen_target(ref)
         return
+    if "judge" in sys.argv[1:]:
+        gen_judge(ref)
+        return
     gen_energy(ref)
     gen_mc(ref)
     gen_flow(ref)
@@ -425,6 +466,7 @@ def main():
     gen_init(ref)
     gen_observables(ref)
     gen_target(ref)
+    gen_judge(ref)
 
 
 if __name__ == "__main__":

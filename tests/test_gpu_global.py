@@ -179,3 +179,30 @@ def test_second_device_binding():
             assert eng.pos.device == torch.device(dev)
             outs.append(eng.pos.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_judge_and_bulk_judge_match_reference(golden_dir):
+    """MonteCarlo.judge_normalizing_flow / bulk_judge_normalizing_flow (monte_carlo.py:305-370) against outputs of the
+    reference on the same seed: criteria, restored cached energy, attempts counter, and the position of the numpy
+    generator afterwards (one uniform per finite uphill proposal)."""
+    import logging
+    import flowstate_b200.MCMC as MC
+    g = np.load(os.path.join(golden_dir, "mc_judge.npz"))
+    n, L, seed = int(g["n"]), float(g["L"]), int(g["seed"])
+    lg = logging.getLogger("fs_quiet_judge")
+    lg.setLevel(logging.CRITICAL)
+    mc = MC.MonteCarlo(g["pos0"], MC.SimulationBox(L), 1.0, n, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15,
+                       initial_max_displacement=0.5, logger=lg, seed=seed)
+    for _ in range(int(g["warm"])):
+        mc.particle_displacement()
+    e0 = mc.energy_calculator.total_energy
+    assert abs(e0 - float(g["e_before"])) <= 1e-5 * max(1.0, abs(float(g["e_before"])))
+    att0 = mc.attempts_displacement
+    props = g["props"]
+    crit = [bool(mc.judge_normalizing_flow(c.copy())) for c in props[:12]]
+    assert crit == [bool(c) for c in g["crit"]]
+    assert mc.energy_calculator.total_energy == e0                  # cache restored (:326-327)
+    assert mc.attempts_displacement - att0 == int(g["att_delta"])
+    acc, att = mc.bulk_judge_normalizing_flow([c.copy() for c in props[12:]], float(g["bulk_ref_energy"]))
+    assert (acc, att) == (int(g["bulk_acc"]), int(g["bulk_att"]))
+    assert mc.rng.random() == float(g["next_uniform"])              # same number of uniforms consumed
