@@ -823,10 +823,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * pair) : "memory"); };
             auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
             const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
+            // The layer input of this row for the coordinate of chunk c is a dependent load (column table -> x) of two
+            // L2 latencies; issued at the top of chunk c it would stall the in-order warp for ~1 k clk before it even
+            // looks at the accumulator.  Both loads run one own-chunk ahead instead: x of chunk c + 2 is requested while
+            // chunk c is processed, its column index one chunk earlier still.
+            int col_n2 = (pair + 2 < g.N) ? __ldg(g.xc_in + pair + 2) : 0;
+            float x_nxt = (row_ok && pair < g.N) ? __ldg(xrow_in + __ldg(g.xc_in + pair)) : 0.f;
             for (int c = pair; c < g.N; c += 2) {
                 float* mb = mbq + ((c >> 1) & 1) * 160;
-                float x = 0.f;
-                if (row_ok) x = __ldg(xrow_in + __ldg(g.xc_in + c));
+                const float x = x_nxt;
+                if (c + 2 < g.N) x_nxt = row_ok ? __ldg(xrow_in + col_n2) : 0.f;
+                if (c + 4 < g.N) col_n2 = __ldg(g.xc_in + c + 4);
+                const int col_out = isA ? 0 : __ldg(g.xc_out + c);   // requested now, needed at the end of the chunk
                 const int bslot = c % S::BIAS_SLOTS;
                 const float* bch = reinterpret_cast<const float*>(smem + S::BIAS_OFF) + bslot * 128;
                 mbar_wait(bar_bfull + 8 * bslot, (c / S::BIAS_SLOTS) & 1, g.err, 9);
@@ -959,7 +967,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         else rq_eval_fast(x, aL, aW, left, right - left, mb[96], mb[128], false, y, ld);
                     }
                     if (row_ok) {
-                        xrow_out[__ldg(g.xc_out + c)] = y;
+                        xrow_out[col_out] = y;
                         acc_ld += ld;
                         bad = bad || (y != y) || (ld != ld);
                     }

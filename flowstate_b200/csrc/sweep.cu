@@ -529,13 +529,13 @@ static int launch_fast_t(float* pos, double* E, double* W, const double* md, lon
     return cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
 }
 
-// lanes per chain: 8 (four chains per warp) while a CTA's 16 chain slots fit shared memory comfortably, else 32
+// lanes per chain: 8 (four chains per warp) for small systems, 16 for medium ones, else 32
 static int launch_fast(float* pos, double* E, double* W, const double* md, long long* att, long long* acc, int B, int N,
                        int steps, const PotDev& P, double beta, unsigned long long seed, long long chain_id0,
                        unsigned char* ta, int* ti, float* te, cudaStream_t s) {
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("FS_SWEEP_LPC"); forced = e ? atoi(e) : 0; }   // tuning knob (8 / 16 / 32)
-    int lpc = forced ? forced : (N <= 768 ? 8 : 32);
+    int lpc = forced ? forced : (N <= 128 ? 8 : (N <= 768 ? 16 : 32));   // measured: N = 32 / 64: 8, N = 256: 16
     const bool tr = ta || ti || te;
     // dilute boxes: most warp trips of the pair loop see no partner inside the cut-off (probability of a pair inside it
     // is pi rc^2 / (Lx Ly); a trip holds 64 pairs) -> early-out variant

@@ -106,13 +106,11 @@ def _dist():
 def _init_chains(cfg, device):
     rank, world = _dist()
     start, count = parallel.shard_range(cfg.chains, rank, world)
+    # even chains start in the left well, odd chains in the right one (main_algorithm_1.py:149-165); the box length is
+    # rounded to float32 so the device and any float64 re-evaluation see the same box
+    pos, _ = MC.initialise_chains(count, cfg.particles, cfg.rho, first_chain=start)
     L = float(np.float32(np.sqrt(cfg.particles / cfg.rho)))
     box = MC.SimulationBox(L)
-    pos = np.empty((count, cfg.particles, 2), np.float32)
-    for i in range(count):                       # even chains start in the left well, odd in the right (main_algorithm_1.py:149-165)
-        init = MC.initialise_low_left if (start + i) % 2 == 0 else MC.initialise_low_right
-        p, _ = init(cfg.particles, cfg.rho)
-        pos[i] = p.astype(np.float32)
     kw = dict(num_wells=2, V0_list=list(cfg.V0_list), r0=cfg.r0, k=cfg.k,
               initial_max_displacement=cfg.max_displacement, device=device)
     if cfg.rng == "pcg64":

@@ -412,6 +412,38 @@ def gen_judge(ref):
     print("mc_judge: %d single + %d bulk proposals, %d accepted" % (12, att, acc))
 
 
+def gen_initialise(ref):
+    """MCMC/initialise.py: initialise_low_left / right (N = 1..12) and initialise_fcc on a few shapes.  The module
+    imports matplotlib for its plots; inert stand-ins are registered first (as for hybrid_NF_MCMC/utils.py)."""
+    import importlib.util
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location("fs_ref_initialise",
+                                                  os.path.join(_refimport.REF_ROOT, "MCMC", "initialise.py"))
+    ini = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ini)
+    out = {}
+    for n in range(1, 13):
+        for rho in (0.03, 0.5):
+            for side, fn in (("L", ini.initialise_low_left), ("R", ini.initialise_low_right)):
+                p, box = fn(n, rho, 1.0)
+                out["low%s_n%d_rho%g" % (side, n, rho)] = np.asarray(p, dtype=np.float64)
+                out["low%s_n%d_rho%g_box" % (side, n, rho)] = np.array([box.box_size_x, box.box_size_y])
+    p, box = ini.initialise_low_left(6, 0.5, 2.0)
+    out["lowL_n6_rho0.5_ar2"] = np.asarray(p, dtype=np.float64)
+    out["lowL_n6_rho0.5_ar2_box"] = np.array([box.box_size_x, box.box_size_y])
+    for n, rho, ar in ((48, 0.5, 1.5), (32, 0.03, 1.0), (7, 0.3, 1.0), (256, 0.5, 1.0)):
+        with ref["quiet"]():
+            p, box = ini.initialise_fcc(n, rho, ar)
+        out["fcc_n%d_rho%g_ar%g" % (n, rho, ar)] = np.asarray(p, dtype=np.float64)
+        out["fcc_n%d_rho%g_ar%g_box" % (n, rho, ar)] = np.array([box.box_size_x, box.box_size_y])
+    np.savez_compressed(os.path.join(GOLD, "initialise.npz"), **out)
+    print("initialise.npz:", len(out), "arrays")
+
+
 def gen_target(ref):
     """Training target of Algorithm 2: NF.Energy.DoubleWellLJ._energy (NF/normflows/Energy/SimpleLJ.py:42-128) and its
     gradient by the reference's own autograd, on float32 centred configurations incl. soft-core pairs (r <= 0.82),
@@ -459,6 +491,9 @@ def main():
     if "judge" in sys.argv[1:]:
         gen_judge(ref)
         return
+    if "initialise" in sys.argv[1:]:
+        gen_initialise(ref)
+        return
     gen_energy(ref)
     gen_mc(ref)
     gen_flow(ref)
@@ -467,6 +502,7 @@ def main():
     gen_observables(ref)
     gen_target(ref)
     gen_judge(ref)
+    gen_initialise(ref)
 
 
 if __name__ == "__main__":

@@ -330,3 +330,33 @@ def test_bench_helpers_without_gpu():
     cs.wait_ready(timeout=0.2)
     out = cs.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"} and isinstance(out["reasons"], list)
+
+
+def test_initialisers_match_reference_golden(golden_dir):
+    """MCMC/initialise.py:8-305 restated: every low-left / low-right grid for N = 1..12 and the FCC-like lattices,
+    bit-identical to arrays produced by the reference's own functions (oracle/make_golden.py: gen_initialise)."""
+    import flowstate_b200.MCMC as MC
+    g = np.load(os.path.join(golden_dir, "initialise.npz"))
+    checked = 0
+    for k in g.files:
+        if k.endswith("_box"):
+            continue
+        parts = k.split("_")
+        n, rho = int(parts[1][1:]), float(parts[2][3:])
+        if k.startswith("low"):
+            fn = MC.initialise_low_left if k[3] == "L" else MC.initialise_low_right
+            p, box = fn(n, rho, 2.0 if k.endswith("ar2") else 1.0)
+        else:
+            p, box = MC.initialise_fcc(n, rho, float(parts[3][2:]))
+        assert np.array_equal(p, g[k]), k
+        assert np.array_equal([box.box_size_x, box.box_size_y], g[k + "_box"]), k
+        checked += 1
+    assert checked == 53
+    with pytest.raises(ValueError):
+        MC.initialise_low_left(13, 0.03)
+    pos, box = MC.initialise_chains(5, 3, 0.03, first_chain=2)
+    left, _ = MC.initialise_low_left(3, 0.03)
+    right, _ = MC.initialise_low_right(3, 0.03)
+    assert pos.shape == (5, 3, 2) and pos.dtype == np.float32
+    assert np.array_equal(pos[0], left.astype(np.float32)) and np.array_equal(pos[1], right.astype(np.float32))
+    assert np.array_equal(pos[2], pos[0]) and abs(box.box_size_x - 10.0) < 1e-12
