@@ -63,3 +63,45 @@ def spline(x, uw, uh, ud, bound, inverse):
         num = s * s * (d1 * th * th + 2 * s * tt + d0 * (1 - th) ** 2)
         ld = torch.log(num) - 2 * torch.log(den)
     return torch.where(inside, y, x), torch.where(inside, ld, torch.zeros_like(ld))
+
+
+class _FusedSplineFn(torch.autograd.Function):
+    """Density-direction spline through fs_spline_train_fwd / fs_spline_train_bwd (one kernel each instead of ~80
+    element-wise autograd kernels per direction).  theta: [B, N, 3 nb + 1] (conditional) or [N, 3 nb + 1] (parameters
+    shared by all rows: the unconditional spline; its gradient is summed over the rows)."""
+
+    @staticmethod
+    def forward(ctx, x, theta, bound, nb, scale):
+        from ._bridge import _lib
+        x = x.contiguous()
+        theta = theta.contiguous()
+        B, N = x.shape
+        shared = theta.dim() == 2
+        y = torch.empty_like(x)
+        ld = torch.empty_like(x)
+        _lib.check(_lib.lib().fs_spline_train_fwd(_lib.ptr(x), _lib.ptr(theta), 0 if shared else N * (3 * nb + 1), B, N, nb,
+                                                  float(bound), float(scale), _lib.ptr(y), _lib.ptr(ld),
+                                                  _lib.stream_ptr(x.device)))
+        ctx.save_for_backward(x, theta)
+        ctx.meta = (float(bound), int(nb), float(scale), shared)
+        return y, ld
+
+    @staticmethod
+    def backward(ctx, gy, gld):
+        from ._bridge import _lib
+        x, theta = ctx.saved_tensors
+        bound, nb, scale, shared = ctx.meta
+        B, N = x.shape
+        gy = gy.contiguous()
+        gld = gld.contiguous()
+        gx = torch.empty_like(x)
+        gt = torch.empty(B, N, 3 * nb + 1, dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().fs_spline_train_bwd(_lib.ptr(x), _lib.ptr(theta), 0 if shared else N * (3 * nb + 1), B, N, nb,
+                                                  bound, scale, _lib.ptr(gy), _lib.ptr(gld), _lib.ptr(gx), _lib.ptr(gt),
+                                                  _lib.stream_ptr(x.device)))
+        return gx, (gt.sum(0) if shared else gt), None, None, None
+
+
+def fused_spline(x, theta, bound, nb, scale):
+    """(y, log|dy/dx|) of the density-direction spline on CUDA float32 tensors; differentiable."""
+    return _FusedSplineFn.apply(x, theta, bound, nb, scale)

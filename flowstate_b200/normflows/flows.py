@@ -103,6 +103,7 @@ class CircularCoupledRationalQuadraticSpline(Flow):
         self.prqct = _SplineCoupling(mask, net_fn, num_bins, tail_bound)
         self._pack = None
         self.precision = "auto"      # conditioner arithmetic of the eval-mode kernels, as NormalizingFlow.precision
+        self.fused_training = True   # train mode on CUDA: splines through fs_spline_train_fwd / _bwd (False: torch ops)
 
     # -- shapes -----------------------------------------------------------
     @property
@@ -134,9 +135,19 @@ class CircularCoupledRationalQuadraticSpline(Flow):
     def _density_torch(self, x):
         c = self.prqct
         ident, tr = x[:, c.identity_features], x[:, c.transform_features]
-        uw, uh, ud = self._params(ident)
-        tr2, ld = _spline_torch.spline(tr, uw, uh, ud, self.bound, False)
-        id2, ld_id = self._uncond(ident, False)
+        if x.is_cuda and x.dtype == torch.float32 and self.fused_training:
+            # training on the device: both splines through the hand-written forward / backward kernels
+            nb = c.num_bins
+            theta = c.transform_net(ident).reshape(x.shape[0], len(c.transform_features), 3 * nb + 1)
+            tr2, ld = _spline_torch.fused_spline(tr, theta, self.bound, nb,
+                                                 1.0 / math.sqrt(c.transform_net.hidden_features))
+            u = c.unconditional_transform
+            shared = torch.cat([u.unnormalized_widths, u.unnormalized_heights, u.unnormalized_derivatives], dim=1)
+            id2, ld_id = _spline_torch.fused_spline(ident, shared, self.bound, nb, 1.0)
+        else:
+            uw, uh, ud = self._params(ident)
+            tr2, ld = _spline_torch.spline(tr, uw, uh, ud, self.bound, False)
+            id2, ld_id = self._uncond(ident, False)
         out = torch.empty_like(x)
         out[:, c.identity_features] = id2
         out[:, c.transform_features] = tr2

@@ -233,6 +233,20 @@ int fs_tc_debug_read(long long* host, int max_ctas);
 int fs_target_energy(const float* x, int B, int n_particles, double bound, double temperature,
                      const fs_pot* pot /*host*/, float* E, float* dEdx, void* stream);
 
+/* Rational-quadratic spline of the density direction for TRAINING, and its reverse-mode derivative
+ * (unconstrained_rational_quadratic_spline / rational_quadratic_spline, NF/normflows/utils/splines.py:16-161, 203-222,
+ * as autograd differentiates them under NormalizingFlow.forward_kld, NF/normflows/core.py:88-108).
+ * x [rows, N]; the parameters of coordinate j of row r are the 3 nb + 1 floats at theta + r * theta_row_stride + j (3 nb + 1)
+ * = [nb widths | nb heights | nb + 1 derivatives] (theta_row_stride = 0: shared by all rows, the unconditional spline);
+ * width / height logits are multiplied by `scale` (1 / sqrt(hidden) for the conditional spline, coupling.py:340-342).
+ * fwd: y, logdet [rows, N].  bwd: grad_x [rows, N] and grad_theta [rows, N, 3 nb + 1] from grad_y, grad_logdet [rows, N]
+ * (the forward is recomputed; sum grad_theta over rows when the parameters are shared). */
+int fs_spline_train_fwd(const float* x, const float* theta, long long theta_row_stride, int rows, int N, int nb,
+                        double bound, double scale, float* y, float* logdet, void* stream);
+int fs_spline_train_bwd(const float* x, const float* theta, long long theta_row_stride, int rows, int N, int nb,
+                        double bound, double scale, const float* grad_y, const float* grad_logdet,
+                        float* grad_x, float* grad_theta, void* stream);
+
 /* ---- observables of sampled configurations ------------------------------------------- */
 
 /* classify_particles + the per-configuration part of calculate_well_statistics

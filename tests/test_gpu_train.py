@@ -1,0 +1,99 @@
+"""GPU: the training path on the device - hand-written spline forward / backward kernels (fs_spline_train_fwd / _bwd)
+against autograd through the torch restatement of utils/splines.py, the forward-KL gradient of a whole flow against the
+oracle's autograd on the CPU, and the CUDA-graph trainer against eager steps."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(n, K, blocks, H, nb, bound):
+    import flowstate_b200.normflows as NF
+    base = NF.Energy.UniformParticle(n, 2, bound, device="cuda")
+    layers = [NF.flows.CircularCoupledRationalQuadraticSpline(2 * n, blocks, H, range(2 * n), num_bins=nb,
+                                                              tail_bound=bound) for _ in range(K)]
+    return NF.NormalizingFlow(base, layers)
+
+
+@pytest.mark.parametrize("nb,N,B,shared", [(15, 64, 256, False), (32, 32, 100, False), (8, 5, 33, True), (15, 64, 256, True)])
+def test_fused_spline_matches_torch_autograd(nb, N, B, shared):
+    from flowstate_b200.normflows import _spline_torch as st
+    g = torch.Generator().manual_seed(3)
+    bound, P = 7.5, 3 * nb + 1
+    x = ((torch.rand(B, N, generator=g) * 2 - 1) * bound).cuda()
+    x[0, 0] = bound                      # on the upper edge: last bin
+    x[1, 1] = -bound
+    x[2, 2] = 1.3 * bound                # outside: identity, zero log-det, gradient 1
+    theta = (torch.randn((N, P) if shared else (B, N, P), generator=g) * (1.0 if shared else 3.0)).cuda()
+    scale = 1.0 if shared else 1.0 / np.sqrt(128.0)
+    gy = torch.randn(B, N, generator=g).cuda()
+    gl = torch.randn(B, N, generator=g).cuda()
+
+    def ref(xx, th):
+        t = th[None].expand(B, N, P) if shared else th
+        return st.spline(xx, t[..., :nb] * scale, t[..., nb:2 * nb] * scale, t[..., 2 * nb:], bound, False)
+    xr, tr = x.clone().double().requires_grad_(True), theta.clone().double().requires_grad_(True)
+    yr, lr = ref(xr, tr)
+    gxr, gtr = torch.autograd.grad((yr * gy.double()).sum() + (lr * gl.double()).sum(), (xr, tr))
+    xf, tf = x.clone().requires_grad_(True), theta.clone().requires_grad_(True)
+    yf, lf = st.fused_spline(xf, tf, bound, nb, scale)
+    gxf, gtf = torch.autograd.grad((yf * gy).sum() + (lf * gl).sum(), (xf, tf))
+    assert (yf.double() - yr).abs().max().item() < 2e-5 * bound
+    assert (lf.double() - lr).abs().max().item() < 2e-4
+    sx = gxr.abs().max().item()
+    stt = gtr.abs().max().item()
+    print("nb=%d shared=%s: grad_x err %.2e of %.2e, grad_theta err %.2e of %.2e"
+          % (nb, shared, (gxf.double() - gxr).abs().max().item(), sx, (gtf.double() - gtr).abs().max().item(), stt))
+    assert (gxf.double() - gxr).abs().max().item() < 2e-4 * max(1.0, sx)
+    assert (gtf.double() - gtr).abs().max().item() < 2e-4 * max(1.0, stt)
+
+
+def test_forward_kld_gradient_fused_vs_torch_path():
+    """Loss and gradient of NormalizingFlow.forward_kld in train mode (BatchNorm batch statistics) with the fused spline
+    kernels, against the same pass through the torch-op splines."""
+    torch.manual_seed(0)
+    n, K, blocks, H, nb, bound = 8, 3, 2, 32, 8, 8.0
+    model = _build(n, K, blocks, H, nb, bound)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    model = model.cuda().train()
+    x = ((torch.rand(64, 2 * n) * 2 - 1) * bound).cuda()
+    losses, grads = {}, {}
+    for fused in (True, False):
+        for f in model.flows:
+            f.fused_training = fused
+        model.zero_grad()
+        # same BatchNorm running-stat side effects in both runs do not matter: batch statistics are used
+        loss = model.forward_kld(x)
+        loss.backward()
+        losses[fused] = float(loss)
+        grads[fused] = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+    assert abs(losses[True] - losses[False]) < 1e-4 * max(1.0, abs(losses[False]))
+    scale = grads[False].abs().max().item()
+    err = (grads[True] - grads[False]).abs().max().item()
+    print("forward_kld: loss %.6f / %.6f, gradient err %.2e of %.2e" % (losses[True], losses[False], err, scale))
+    assert err < 2e-3 * scale
+    # (the torch path used as the yardstick is itself pinned on the CPU against the reference, tests/test_host_cpu.py)
+
+
+def test_graph_trainer_matches_eager_steps():
+    from flowstate_b200.drivers.training import FlowTrainer
+    n, K, blocks, H, nb, bound = 6, 2, 2, 32, 8, 6.0
+    xs = [((torch.rand(48, 2 * n, generator=torch.Generator().manual_seed(10 + i)) * 2 - 1) * bound).cuda()
+          for i in range(4)]
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(1)
+        model = _build(n, K, blocks, H, nb, bound)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.05 * torch.randn_like(p))
+        model = model.cuda().train()
+        tr = FlowTrainer(model, 1e-3, 1e-4, 1.0, 48, use_graph=graph)
+        losses = [tr.step(x) for x in xs]
+        out[graph] = (losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone())
+    la, lb = out[False][0], out[True][0]
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(la, lb)), (la, lb)
+    assert (out[False][1] - out[True][1]).abs().max().item() < 1e-4
