@@ -66,6 +66,9 @@ _PROTOS = {
     "fs_spline_train_fwd": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _P, _P, _P]),
     "fs_spline_train_bwd": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _P, _P,
                                       _P, _P, _P]),
+    "fs_affine_coupling": (C.c_int, [_P, C.c_longlong, _P, _P, C.c_longlong, C.c_int, _P, C.c_longlong, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, _P, _P]),
+    "fs_periodic_shift": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "fs_classify_wells": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, _P, _P]),
     "fs_pair_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
     "fs_flow_has_tensor_path": (C.c_int, [_P]),

@@ -190,3 +190,8 @@ class CircularCoupledRationalQuadraticSpline(Flow):
             return self._density_torch(z)
         x, ld, _ = self._cuda_pack().inverse(z)
         return x, ld.view(-1)
+
+
+# affine (RealNVP) coupling and periodic flows under the reference's names
+from .affine import (AffineCoupling, AffineCouplingBlock, MaskedAffineFlow, Merge, PeriodicShift,  # noqa: E402,F401
+                     PeriodicWrap, Split)

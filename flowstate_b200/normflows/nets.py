@@ -56,3 +56,56 @@ class ResidualNet(nn.Module):
         for block in self.blocks:
             t = block(t)
         return self.final_layer(t)
+
+
+class MLP(nn.Module):
+    """nets/mlp.py:5-58: Linear / LeakyReLU stack, optional output function; the conditioner of the affine flows."""
+
+    def __init__(self, layers, leaky=0.0, score_scale=None, output_fn=None, output_scale=None, init_zeros=False,
+                 dropout=None):
+        super().__init__()
+        net = nn.ModuleList([])
+        for k in range(len(layers) - 2):
+            net.append(nn.Linear(layers[k], layers[k + 1]))
+            net.append(nn.LeakyReLU(leaky))
+        if dropout is not None:
+            net.append(nn.Dropout(p=dropout))
+        net.append(nn.Linear(layers[-2], layers[-1]))
+        if init_zeros:
+            nn.init.zeros_(net[-1].weight)
+            nn.init.zeros_(net[-1].bias)
+        if output_fn is not None:
+            if score_scale is not None:
+                net.append(_ConstScale(score_scale))
+            if output_fn == "sigmoid":
+                net.append(nn.Sigmoid())
+            elif output_fn == "relu":
+                net.append(nn.ReLU())
+            elif output_fn == "tanh":
+                net.append(nn.Tanh())
+            elif output_fn == "clampexp":
+                net.append(_ClampExp())
+            if output_scale is not None:
+                net.append(_ConstScale(output_scale))
+        self.net = nn.Sequential(*net)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class _ConstScale(nn.Module):
+    """utils/nn.py ConstScaleLayer"""
+
+    def __init__(self, scale=1.0):
+        super().__init__()
+        self.register_buffer("scale", torch.tensor(scale))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class _ClampExp(nn.Module):
+    """utils/nn.py ClampExp: exp(min(x, 0)), i.e. exp clamped to at most 1"""
+
+    def forward(self, x):
+        return torch.min(torch.exp(x), torch.tensor(1.0, device=x.device, dtype=x.dtype))

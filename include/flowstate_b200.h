@@ -247,6 +247,25 @@ int fs_spline_train_bwd(const float* x, const float* theta, long long theta_row_
                         double bound, double scale, const float* grad_y, const float* grad_logdet,
                         float* grad_x, float* grad_theta, void* stream);
 
+/* ---- affine (RealNVP) coupling and periodic shifts ----------------------------------------- */
+
+/* MaskedAffineFlow.forward / inverse (NF/normflows/flows/affine/coupling.py:163-229) and the element-wise half of
+ * AffineCoupling.forward / inverse (:99-160).  z, out [rows, n] with row strides; mask [n] (1 = feature unchanged) or
+ * NULL (all n features transformed); scale / shift read at row * row_stride + j * elem_stride (elem_stride 2 for
+ * AffineCoupling's interleaved parameters), NULL = none.  scale_map 0 = exp, 1 = sigmoid, 2 = sigmoid_inv;
+ * inverse != 0 applies the inverse map; nan_rule != 0 turns non-finite parameters into NaN (MaskedAffineFlow).
+ * logdet [rows] (nullable) is WRITTEN (sum over the n features). */
+int fs_affine_coupling(const float* z, long long z_row_stride, const float* mask, const float* scale,
+                       long long scale_row_stride, int scale_elem_stride, const float* shift,
+                       long long shift_row_stride, int shift_elem_stride, int rows, int n, int scale_map, int inverse,
+                       int nan_rule, float* out, long long out_row_stride, float* logdet, void* stream);
+
+/* PeriodicShift.forward / inverse, PeriodicWrap.inverse (NF/normflows/flows/periodic.py:6-73): out = z with
+ * remainder(z + shift + bound, 2 bound) - bound on the columns with col_slot[col] = s >= 0 (bound[s], shift[s];
+ * col_slot = -1 leaves a column unchanged). */
+int fs_periodic_shift(const float* z, int rows, int D, const int* col_slot, const float* bound, const float* shift,
+                      float* out, void* stream);
+
 /* ---- observables of sampled configurations ------------------------------------------- */
 
 /* classify_particles + the per-configuration part of calculate_well_statistics

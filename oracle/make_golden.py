@@ -444,6 +444,90 @@ def gen_initialise(ref):
     print("initialise.npz:", len(out), "arrays")
 
 
+def gen_affine(ref):
+    """RealNVP-style flows of the vendored normflows (flows/affine/coupling.py:99-268, flows/periodic.py:6-73,
+    nets/mlp.py): a MaskedAffineFlow stack with PeriodicShift layers in between, AffineCouplingBlocks with the three scale
+    maps, PeriodicWrap; layer by layer forward / inverse outputs and log-determinants, and the container's log_prob."""
+    NF = ref["normflows"]
+    torch.manual_seed(31)
+    D, bound, B = 12, 4.5, 40
+    g = torch.Generator().manual_seed(32)
+    out = {"D": np.int64(D), "bound": np.float64(bound)}
+    b = torch.tensor([1.0 if i % 2 == 0 else 0.0 for i in range(D)])
+    flows = []
+    for i in range(4):
+        s_net = NF.nets.MLP([D, 2 * D, D], init_zeros=True)
+        t_net = NF.nets.MLP([D, 2 * D, D], init_zeros=True)
+        flows.append(NF.flows.MaskedAffineFlow(b if i % 2 == 0 else 1 - b, t_net, s_net))
+        flows.append(NF.flows.PeriodicShift(list(range(0, D, 3)), bound=bound, shift=0.37 * (i + 1)))
+    with ref["quiet"]():
+        base = NF.Energy.UniformParticle(D // 2, 2, bound, device="cpu")
+    model = NF.NormalizingFlow(base, flows)
+    with torch.no_grad():
+        for prm in model.parameters():
+            prm.add_(0.04 * torch.randn(prm.shape, generator=g))
+    model.eval()
+    z = (torch.rand(B, D, generator=g) * 2 - 1) * bound
+    x = (torch.rand(B, D, generator=g) * 2 - 1) * bound
+    with torch.no_grad():
+        zz, lds = z.clone(), []
+        for i, f in enumerate(model.flows):
+            zz, ld = f(zz)
+            out["stack_fwd_%d" % i] = zz.numpy().copy()
+            lds.append(ld.numpy().copy())
+        out["stack_fwd_ld"] = np.stack(lds)
+        xx, lds = x.clone(), []
+        for i in range(len(model.flows) - 1, -1, -1):
+            xx, ld = model.flows[i].inverse(xx)
+            out["stack_inv_%d" % i] = xx.numpy().copy()
+            lds.append(ld.numpy().copy())
+        out["stack_inv_ld"] = np.stack(lds)
+        out["stack_log_prob"] = model.log_prob(x.clone()).numpy()
+        zi, ldi = model.inverse_and_log_det(x.clone())
+        out["stack_inv_total_ld"] = ldi.numpy()
+    out["stack_z"], out["stack_x"] = z.numpy(), x.numpy()
+    for k, v in model.state_dict().items():
+        out["stack_sd__" + k] = v.numpy().copy()          # (copy: the NaN case below edits a weight in place)
+    # non-finite parameter -> NaN (coupling.py:199-202)
+    with torch.no_grad():
+        zbig = z.clone()
+        zbig[0, 0] = 1e30
+        model.flows[0].s.net[-1].weight.mul_(1e12)
+        y, ld = model.flows[0](zbig)
+        out["nan_in"], out["nan_out"], out["nan_ld"] = zbig.numpy(), y.numpy(), ld.numpy()
+        out["nan_last_w"] = model.flows[0].s.net[-1].weight.numpy().copy()
+    # AffineCouplingBlock with the three scale maps, both split modes
+    for sm in ("exp", "sigmoid", "sigmoid_inv"):
+        for mode in ("channel", "channel_inv"):
+            pm = NF.nets.MLP([D // 2, 16, D], init_zeros=True)
+            blk = NF.flows.AffineCouplingBlock(pm, scale=True, scale_map=sm, split_mode=mode)
+            with torch.no_grad():
+                for prm in blk.parameters():
+                    prm.add_(0.08 * torch.randn(prm.shape, generator=g))
+                yf, lf = blk(z.clone())
+                yi, li = blk.inverse(x.clone())
+            tag = "blk_%s_%s" % (sm, mode)
+            out[tag + "_fwd"], out[tag + "_fwd_ld"], out[tag + "_inv"], out[tag + "_inv_ld"] = (
+                yf.numpy(), lf.numpy(), yi.numpy(), li.numpy())
+            for k, v in blk.state_dict().items():
+                out[tag + "_sd__" + k] = v.numpy()
+    pm = NF.nets.MLP([D // 2, 16, D // 2], init_zeros=True)
+    blk = NF.flows.AffineCouplingBlock(pm, scale=False)
+    with torch.no_grad():
+        for prm in blk.parameters():
+            prm.add_(0.2 * torch.randn(prm.shape, generator=g))
+        yf, lf = blk(z.clone())
+    out["blk_noscale_fwd"], out["blk_noscale_fwd_ld"] = yf.numpy(), lf.numpy()
+    for k, v in blk.state_dict().items():
+        out["blk_noscale_sd__" + k] = v.numpy()
+    wrap = NF.flows.PeriodicWrap(list(range(1, D, 2)), bound=bound)
+    far = z * 3.0
+    with torch.no_grad():
+        out["wrap_in"], out["wrap_inv"] = far.numpy(), wrap.inverse(far.clone())[0].numpy()
+    np.savez_compressed(os.path.join(GOLD, "affine.npz"), **out)
+    print("affine.npz:", len(out), "arrays")
+
+
 def gen_target(ref):
     """Training target of Algorithm 2: NF.Energy.DoubleWellLJ._energy (NF/normflows/Energy/SimpleLJ.py:42-128) and its
     gradient by the reference's own autograd, on float32 centred configurations incl. soft-core pairs (r <= 0.82),
@@ -494,6 +578,9 @@ def main():
     if "initialise" in sys.argv[1:]:
         gen_initialise(ref)
         return
+    if "affine" in sys.argv[1:]:
+        gen_affine(ref)
+        return
     gen_energy(ref)
     gen_mc(ref)
     gen_flow(ref)
@@ -503,6 +590,7 @@ def main():
     gen_target(ref)
     gen_judge(ref)
     gen_initialise(ref)
+    gen_affine(ref)
 
 
 if __name__ == "__main__":

@@ -203,3 +203,48 @@ def test_target_energy_oracle_matches_reference_golden(golden_dir):
                                    rtol=2e-6, atol=2e-6)
         _, grad = tr.energy_and_grad(x, n, T, b, [-10.0, -10.5], 1.2, 15, dtype=torch.float32)
         np.testing.assert_allclose(grad.numpy(), g[tag + "__grad"], rtol=1e-4, atol=1e-4)
+
+
+def test_affine_oracle_matches_reference_golden(golden_dir):
+    """oracle/affine_ref.py against layer-by-layer outputs of the reference's MaskedAffineFlow / PeriodicShift stack,
+    AffineCouplingBlocks (three scale maps, two split modes) and PeriodicWrap."""
+    from oracle import affine_ref as ar
+    g = np.load(os.path.join(golden_dir, "affine.npz"))
+    D, bound = int(g["D"]), float(g["bound"])
+    sd = {k[len("stack_sd__"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("stack_sd__")}
+    z = torch.from_numpy(g["stack_z"])
+    for i in range(8):
+        if i % 2 == 0:
+            b = sd["flows.%d.b" % i][0]
+            s = ar.mlp(sd, "flows.%d.s." % i, b * z)
+            t = ar.mlp(sd, "flows.%d.t." % i, b * z)
+            z, ld = ar.masked_affine(z, b, s, t, False)
+            np.testing.assert_allclose(ld.numpy(), g["stack_fwd_ld"][i], rtol=1e-5, atol=1e-6)
+        else:
+            z = ar.periodic_shift(z, list(range(0, D, 3)), bound, 0.37 * (i // 2 + 1))
+        np.testing.assert_allclose(z.numpy(), g["stack_fwd_%d" % i], rtol=1e-5, atol=1e-5)
+    x = torch.from_numpy(g["stack_x"])
+    tot = torch.zeros(len(x))
+    for i in range(7, -1, -1):
+        if i % 2 == 0:
+            b = sd["flows.%d.b" % i][0]
+            x, ld = ar.masked_affine(x, b, ar.mlp(sd, "flows.%d.s." % i, b * x), ar.mlp(sd, "flows.%d.t." % i, b * x), True)
+            tot = tot + ld
+        else:
+            x = ar.periodic_shift(x, list(range(0, D, 3)), bound, -0.37 * (i // 2 + 1))
+        np.testing.assert_allclose(x.numpy(), g["stack_inv_%d" % i], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(tot.numpy(), g["stack_inv_total_ld"], rtol=1e-5, atol=1e-5)
+    for sm in ("exp", "sigmoid", "sigmoid_inv"):
+        for mode in ("channel", "channel_inv"):
+            tag = "blk_%s_%s" % (sm, mode)
+            bsd = {k[len(tag + "_sd__"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + "_sd__")}
+            zz = torch.from_numpy(g["stack_z"])
+            a, c = zz.chunk(2, dim=1)
+            z1, z2 = (a, c) if mode == "channel" else (c, a)
+            out, ld = ar.affine_coupling(z2, ar.mlp(bsd, "flows.1.param_map.", z1), sm, False)
+            y = torch.cat([z1, out] if mode == "channel" else [out, z1], 1)
+            np.testing.assert_allclose(y.numpy(), g[tag + "_fwd"], rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(ld.numpy(), g[tag + "_fwd_ld"], rtol=1e-5, atol=1e-5)
+    far = torch.from_numpy(g["wrap_in"])
+    np.testing.assert_allclose(ar.periodic_shift(far, list(range(1, D, 2)), bound, 0.0).numpy(), g["wrap_inv"],
+                               rtol=1e-6, atol=1e-6)
