@@ -9,6 +9,8 @@
 // particle i meets i+1 .. i+floor((N-1)/2), plus i+N/2 for the first half when N
 // is even - every unordered pair exactly once and every thread the same trip
 // count.  FP32 on the CUDA cores; cross-thread sums are finished in FP64.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace fs {
@@ -356,7 +358,9 @@ static int launch_total(const float* pos, int B, int N, const PotDev& P, float* 
     constexpr int GROUPS = 256 / G;
     int grid = (B + GROUPS - 1) / GROUPS;
     const size_t smem2 = (size_t)GROUPS * 8 * N * sizeof(float);
-    if (smem2 <= 112 * 1024) {                           // packed variant while two blocks per SM still fit
+    static long v2max = -1;                              // tuning knob: largest tile (bytes) of the packed variant
+    if (v2max < 0) { const char* e = getenv("FS_ENERGY_V2MAX"); v2max = e ? atol(e) : 112 * 1024; }
+    if ((long)smem2 <= v2max) {                          // packed variant while two blocks per SM still fit
         if (smem2 > 48 * 1024)
             FS_CUDA(cudaFuncSetAttribute(energy_total_kernel_v2<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         energy_total_kernel_v2<G><<<grid, 256, smem2, s>>>(pos, B, N, P, E, W, ov);
@@ -387,9 +391,13 @@ extern "C" int fs_energy_total(const float* pos, int B, int N, float Lx, float L
     fs::PotDev P = fs::make_pot(pot, Lx, Ly);
     cudaStream_t s = (cudaStream_t)stream;
     // group size: about half a particle per thread keeps the cyclic loops long enough
-    if (N <= 48) return fs::launch_total<32>(pos, B, N, P, E, W, overlap, s);
-    if (N <= 96) return fs::launch_total<64>(pos, B, N, P, E, W, overlap, s);
-    if (N <= 192) return fs::launch_total<128>(pos, B, N, P, E, W, overlap, s);
+    static int g_forced = -1;                            // tuning knob (32 / 64 / 128 / 256)
+    if (g_forced < 0) { const char* e = getenv("FS_ENERGY_G"); g_forced = e ? atoi(e) : 0; }
+    int G = N <= 48 ? 32 : (N <= 96 ? 64 : (N <= 192 ? 128 : 256));
+    if (g_forced) G = g_forced;
+    if (G == 32) return fs::launch_total<32>(pos, B, N, P, E, W, overlap, s);
+    if (G == 64) return fs::launch_total<64>(pos, B, N, P, E, W, overlap, s);
+    if (G == 128) return fs::launch_total<128>(pos, B, N, P, E, W, overlap, s);
     return fs::launch_total<256>(pos, B, N, P, E, W, overlap, s);
 }
 
