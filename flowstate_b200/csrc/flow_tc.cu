@@ -582,9 +582,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             wait_rdy(RDY_R0H0);
             wait_rdy(RDY_R0H1);
             const int n_final = g.fused ? g.N : g.n_chunks;
+            const long long t_final0 = dbg ? clock64() : 0;
+            long long w_rdyf = 0;
             for (int c = 0; c < n_final; ++c) {
                 const int f = c & 1;
-                if (c >= 2) wait_rdy(RDY_F0 + f);              // epilogue drained chunk c-2
+                if (c >= 2) {                                   // epilogue drained chunk c-2
+                    const long long w0 = w_ready;
+                    wait_rdy(RDY_F0 + f);
+                    w_rdyf += w_ready - w0;
+                }
                 const uint32_t dcol = f ? S::FIN1 : S::FIN0;
                 const bool fus = g.fused != 0;
                 const int SPC = (fus ? H / 64 : KT) / S::KPS;   // stages per chunk
@@ -597,6 +603,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 dbg[16 * blockIdx.x + 2] = w_weights;
                 dbg[16 * blockIdx.x + 3] = clock64() - t_start;
                 dbg[16 * blockIdx.x + 6] = t_issue;
+                dbg[16 * blockIdx.x + 14] = clock64() - t_final0;     // final layer: whole phase of the MMA warp
+                dbg[16 * blockIdx.x + 15] = w_rdyf;                   // ... of which waiting for a drained accumulator
             }
         }
     } else {
