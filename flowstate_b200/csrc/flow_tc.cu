@@ -420,8 +420,14 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
             }
             if (dbg && lane == 0) dbg[16 * blockIdx.x + 0] = w_empty;
-        } else if (warp == 1) {
+        } else if (warp == 1 || (warp == 3 && g.fused)) {
             // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+            // Warp 1 issues GEMM0 and the residual blocks.  In the fused final layer a SECOND issuer (warp 3, on another
+            // scheduler) takes the odd coordinate chunks: the chunks of the two issuers use different accumulators and
+            // different weight stages, and the in-kernel timers showed the single issuer - not the tensor pipe (≈ 0.9 k
+            // clk of MMAs per chunk) and not the epilogue (≈ 80 clk per chunk waiting for a drained accumulator) - to be
+            // what sets the chunk period: ≈ 2.0 k clk of its own instruction stream per chunk.
+            const bool second = (warp == 3);
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
             const uint32_t idesc_blk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
             const uint32_t idesc_fin = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
@@ -534,6 +540,17 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     issue(dcol, abase + kt * 64, 1, kt == 0, false, false, true);
                 }
             };
+            auto skip_stages = [&](int n) {                    // stages consumed by the other issuer
+                for (int i = 0; i < n; ++i)
+                    if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
+            };
+            if (second) {
+                // position of the weight ring and parities of the R0 hand-over at the start of the final layer
+                const unsigned long long consumed = (unsigned long long)(g.Kp0 / TC_KB) + (unsigned long long)g.n_blocks * 2ull * (H / 64);
+                stage = (uint32_t)(consumed % NSTAGE);
+                wphase = (uint32_t)((consumed / NSTAGE) & 1ull);
+                ph_rdy = (g.n_blocks & 1) ? ((1u << RDY_R0H0) | (1u << RDY_R0H1)) : 0u;
+            } else {
             // ---- GEMM0: features (R1) -> R0 ----
             for (int p = 0; p < g.n_pieces; ++p) {
                 const int kcols = min(H, g.Kp0 - p * H);
@@ -578,13 +595,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     commit(bar_full + 8 * FULL_R0H1);
                 }
             }
+            }   // !second
             // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
             wait_rdy(RDY_R0H0);
             wait_rdy(RDY_R0H1);
             const int n_final = g.fused ? g.N : g.n_chunks;
             const long long t_final0 = dbg ? clock64() : 0;
             long long w_rdyf = 0;
-            for (int c = 0; c < n_final; ++c) {
+            const bool fus = g.fused != 0;
+            const int SPC = (fus ? H / 64 : KT) / S::KPS;       // stages per chunk
+            const int c_step = fus ? 2 : 1;                     // fused: this issuer's chunks are those of its parity
+            if (second) skip_stages(SPC);                       // chunk 0 belongs to the first issuer
+            for (int c = second ? 1 : 0; c < n_final; c += c_step) {
                 const int f = c & 1;
                 if (c >= 2) {                                   // epilogue drained chunk c-2
                     const long long w0 = w_ready;
@@ -592,13 +614,12 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     w_rdyf += w_ready - w0;
                 }
                 const uint32_t dcol = f ? S::FIN1 : S::FIN0;
-                const bool fus = g.fused != 0;
-                const int SPC = (fus ? H / 64 : KT) / S::KPS;   // stages per chunk
                 for (int sg = 0; sg < SPC; sg += S::GROUP)
                     issue(dcol, sg * S::KPS * (fus ? 64 : TC_KB), min(S::GROUP, SPC - sg), sg == 0, true, fus, fus);
                 commit(bar_full + 8 * (FULL_F0 + f));
+                if (fus) skip_stages(SPC);                      // the other issuer's chunk
             }
-            if (dbg && lane == 0) {
+            if (dbg && lane == 0 && !second) {
                 dbg[16 * blockIdx.x + 1] = w_ready;
                 dbg[16 * blockIdx.x + 2] = w_weights;
                 dbg[16 * blockIdx.x + 3] = clock64() - t_start;
