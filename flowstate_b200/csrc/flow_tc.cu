@@ -322,8 +322,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
     const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pairs (bias of a chunk landed)
     const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pairs -> TMA
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 136 + 16 * S::BIAS_SLOTS);
-    static_assert(16 * NSTAGE + 140 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
+    const uint32_t bar_fstart = bar_bempty + 8 * S::BIAS_SLOTS; // [1] first MMA issuer -> second: the final layer may start
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 144 + 16 * S::BIAS_SLOTS);
+    static_assert(16 * NSTAGE + 148 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
     const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
     float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
@@ -344,6 +345,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_pfull + 8 * i, 1);
             mbar_init(bar_pempty + 8 * i, S::BLK_WARPS);
         }
+        mbar_init(bar_fstart, 1);
         for (int i = 0; i < S::BIAS_SLOTS; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, EPI_WARPS / 2);       // the pair that owns the chunk, in each of the four lane quadrants
@@ -545,11 +547,12 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
             };
             if (second) {
-                // position of the weight ring and parities of the R0 hand-over at the start of the final layer
+                // position of the weight ring at the start of the final layer.  The second issuer must not look at any
+                // barrier the blocks cycled through before the first issuer says so (a parity wait cannot tell phase n
+                // from phase n + 2): it sleeps on bar_fstart, a single-use barrier.
                 const unsigned long long consumed = (unsigned long long)(g.Kp0 / TC_KB) + (unsigned long long)g.n_blocks * 2ull * (H / 64);
                 stage = (uint32_t)(consumed % NSTAGE);
                 wphase = (uint32_t)((consumed / NSTAGE) & 1ull);
-                ph_rdy = (g.n_blocks & 1) ? ((1u << RDY_R0H0) | (1u << RDY_R0H1)) : 0u;
             } else {
             // ---- GEMM0: features (R1) -> R0 ----
             for (int p = 0; p < g.n_pieces; ++p) {
@@ -597,8 +600,17 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             }   // !second
             // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
-            wait_rdy(RDY_R0H0);
-            wait_rdy(RDY_R0H1);
+            if (!second) {
+                wait_rdy(RDY_R0H0);
+                wait_rdy(RDY_R0H1);
+                if (g.fused) {                                  // wake the second issuer
+                    if (elect_one()) mbar_arrive(bar_fstart);
+                    __syncwarp();
+                }
+            } else {
+                mbar_wait(bar_fstart, 0, g.err, 10);
+                tc_fence_after();
+            }
             const int n_final = g.fused ? g.N : g.n_chunks;
             const long long t_final0 = dbg ? clock64() : 0;
             long long w_rdyf = 0;

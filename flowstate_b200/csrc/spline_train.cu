@@ -24,6 +24,7 @@ static constexpr float kTMin = 1e-3f;   // min bin width / height / derivative (
 struct SplineBin {
     int k;              // selected bin
     float c0, c1;       // cumulative sizes at knots k and k + 1 (before the affine map to [-bound, bound])
+    float p0, p1;       // sums of the softmax probabilities below knots k and k + 1
     float lo, hi;       // knots k and k + 1
 };
 
@@ -41,10 +42,17 @@ __device__ __forceinline__ void softmax_norm(const float* __restrict__ u, int nb
 __device__ __forceinline__ void axis_knots(const float* __restrict__ u, int nb, float scale, float m, float rz, float bound,
                                            int k, SplineBin& b) {
     const float c = 1.0f - kTMin * nb;
-    float cum = 0.f;
-    for (int i = 0; i < k; ++i) cum += kTMin + c * expf(u[i] * scale - m) * rz;
+    float cum = 0.f, ps = 0.f;
+    for (int i = 0; i < k; ++i) {
+        const float p = expf(u[i] * scale - m) * rz;
+        cum += kTMin + c * p;
+        ps += p;
+    }
+    const float pk = expf(u[k] * scale - m) * rz;
     b.c0 = cum;
-    b.c1 = cum + kTMin + c * expf(u[k] * scale - m) * rz;
+    b.c1 = cum + kTMin + c * pk;
+    b.p0 = ps;
+    b.p1 = ps + pk;
     b.k = k;
     b.lo = (k == 0) ? -bound : 2.0f * bound * b.c0 - bound;
     b.hi = (k == nb - 1) ? bound : 2.0f * bound * b.c1 - bound;
@@ -170,8 +178,7 @@ __global__ void __launch_bounds__(128) spline_train_kernel(const float* __restri
     const float c = 1.0f - kTMin * nb, two_b = 2.0f * bound;
     {
         const float G0 = (k == 0) ? 0.f : two_b * x0_b, G1 = (k == nb - 1) ? 0.f : two_b * x1_b;
-        const float P0 = (bw.c0 - kTMin * k) / c, P1 = (bw.c1 - kTMin * (k + 1)) / c;     // sums of softmax probabilities
-        const float dot = G0 * P0 + G1 * P1;
+        const float dot = G0 * bw.p0 + G1 * bw.p1;
         for (int i = 0; i < nb; ++i) {
             const float p = expf(u[i] * scale - mw) * rzw;
             gt[i] = scale * c * p * ((i < k ? G0 : 0.f) + (i < k + 1 ? G1 : 0.f) - dot);
@@ -179,8 +186,7 @@ __global__ void __launch_bounds__(128) spline_train_kernel(const float* __restri
     }
     {
         const float G0 = (k == 0) ? 0.f : two_b * y0_b, G1 = (k == nb - 1) ? 0.f : two_b * y1_b;
-        const float P0 = (bh.c0 - kTMin * k) / c, P1 = (bh.c1 - kTMin * (k + 1)) / c;
-        const float dot = G0 * P0 + G1 * P1;
+        const float dot = G0 * bh.p0 + G1 * bh.p1;
         for (int i = 0; i < nb; ++i) {
             const float p = expf(u[nb + i] * scale - mh) * rzh;
             gt[nb + i] = scale * c * p * ((i < k ? G0 : 0.f) + (i < k + 1 ? G1 : 0.f) - dot);
