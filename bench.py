@@ -597,10 +597,11 @@ class Harness:
         s = np.pi / self.bound
         feats = torch.cat([torch.cos(xin[:, 0::2] * s), torch.sin(xin[:, 0::2] * s)], dim=1).contiguous()
         xo, ldo = torch.zeros_like(xin), torch.zeros(xin.shape[0], device=dev)
+        feats_t = pack.tile_features(feats) if self.fused else None   # the layout the full passes hand to the kernel
 
         def dominant(li):
             if self.fused:
-                pack.coupling(li, "density", feats, xin, xo, ldo)
+                pack.coupling(li, "density", feats_t, xin, xo, ldo, tiled=True)
             else:
                 pack.conditioner(li, feats)
         for li in range(3):

@@ -50,8 +50,8 @@ def build(force=False, verbose=False):
                "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        if os.environ.get("FS_TC_TIMERS") == "1":       # in-kernel timers for scripts/tc_debug.py (development only)
-            cmd.insert(1, "-DFS_TC_TIMERS=1")
+        if os.environ.get("FS_TC_TIMERS") in ("1", "2"):   # in-kernel timers for scripts/tc_debug.py (development only;
+            cmd.insert(1, "-DFS_TC_TIMERS=" + os.environ["FS_TC_TIMERS"])   # 2: slots 11-13 hold a timeline instead)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

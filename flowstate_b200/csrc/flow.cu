@@ -293,8 +293,13 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_forward_v2(
             out[(size_t)b * F.D + fi[u]] = y[u];
             float sn, cs;
             if (FAST) __sincosf(F.pf_scale * y[u], &sn, &cs); else sincosf(F.pf_scale * y[u], &sn, &cs);
-            A0[(size_t)b * 2 * F.N + j[u]] = cs;
-            A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            if (FAST) {           // tensor path: row-tiled feature layout (a0_tiled), coalesced for its lane = row loads
+                A0[a0_tiled(b, j[u], 2 * F.N)] = cs;
+                A0[a0_tiled(b, F.N + j[u], 2 * F.N)] = sn;
+            } else {
+                A0[(size_t)b * 2 * F.N + j[u]] = cs;
+                A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            }
             acc += ld[u];
             bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
         }
@@ -336,8 +341,13 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
             if (!valid[u]) continue;
             float sn, cs;
             if (FAST) __sincosf(F.pf_scale * x[u], &sn, &cs); else sincosf(F.pf_scale * x[u], &sn, &cs);
-            A0[(size_t)b * 2 * F.N + j[u]] = cs;
-            A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            if (FAST) {           // tensor path: row-tiled feature layout (a0_tiled), coalesced for its lane = row loads
+                A0[a0_tiled(b, j[u], 2 * F.N)] = cs;
+                A0[a0_tiled(b, F.N + j[u], 2 * F.N)] = sn;
+            } else {
+                A0[(size_t)b * 2 * F.N + j[u]] = cs;
+                A0[(size_t)b * 2 * F.N + F.N + j[u]] = sn;
+            }
             out[(size_t)b * F.D + (fi[u] + h) % F.D] = y[u];
             acc += ld[u];
             bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
@@ -627,7 +637,8 @@ static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspac
     };
     float* v0 = (float*)take((size_t)Bc * f->D * 4);
     float* v1 = (float*)take((size_t)Bc * f->D * 4);
-    float* A0 = (float*)take((size_t)Bc * 2 * f->N * 4);
+    // features: row-major [Bc][2N] on the FP32 path, row-tiled (a0_tiled: 128-row tiles, quads of 4 features) on the tensor path
+    float* A0 = (float*)take((size_t)((Bc + 127) / 128 * 128) * ((2 * f->N + 3) / 4 * 4) * 4);
     const bool fp32 = precision != FS_PREC_TF32;                   // hidden activations live in TMEM on the tensor path
     float* h = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
     float* t = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
@@ -649,7 +660,7 @@ static FlowDev flow_dev(const fs_flow* f) {
 
 static int run_conditioner(fs_flow* f, int li, const Workspace& w, int rows, int precision, int* nan_flag,
                            cudaStream_t s) {
-    if (precision == FS_PREC_TF32) return tc_conditioner(f, li, w.A0, rows, w.theta, w.tc, w.tc_bytes, nan_flag, s);
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, li, w.A0, true, rows, w.theta, w.tc, w.tc_bytes, nan_flag, s);
     return conditioner_fp32(f, li, w.A0, rows, w.h, w.t, w.theta, s);
 }
 
@@ -761,7 +772,7 @@ extern "C" int fs_flow_conditioner(fs_flow* f, int layer, const float* features,
     Workspace w;
     carve(f, rows, precision, workspace, &w);
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision == FS_PREC_TF32) return tc_conditioner(f, layer, features, rows, theta, w.tc, w.tc_bytes, nullptr, s);
+    if (precision == FS_PREC_TF32) return tc_conditioner(f, layer, features, false, rows, theta, w.tc, w.tc_bytes, nullptr, s);
     return conditioner_fp32(f, layer, features, rows, w.h, w.t, theta, s);
 }
 
@@ -769,12 +780,43 @@ extern "C" int fs_flow_has_tensor_path(const fs_flow* f) { return (f && f->tc) ?
 
 extern "C" int fs_flow_coupling(fs_flow* f, int layer, int direction, const float* features, const float* xin,
                                 float* xout, float* logdet, int rows, int* nan_flag, void* stream) {
+    const bool tiled = (direction & FS_FEATURES_TILED) != 0;
+    direction &= ~FS_FEATURES_TILED;
     if (!f || !features || !xin || !xout || rows < 0 || layer < 0 || layer >= f->K || (direction != 1 && direction != 2)) {
         set_error("fs_flow_coupling: invalid argument");
         return FS_ERR_INVALID;
     }
     if (rows == 0) return FS_OK;
-    return tc_conditioner_spline(f, layer, features, rows, direction, xin, xout, logdet, nan_flag, (cudaStream_t)stream);
+    return tc_conditioner_spline(f, layer, features, tiled, rows, direction, xin, xout, logdet, nan_flag,
+                                 (cudaStream_t)stream);
+}
+
+// [rows, K0] row-major -> the row-tiled layout the tensor path reads (a0_tiled); the full passes write that layout
+// directly from their feature kernels, this is for callers of fs_flow_coupling that hold a row-major matrix.
+__global__ void tile_features_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int K0) {
+    const size_t n = (size_t)rows * K0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / K0), k = (int)(i % K0);
+        out[a0_tiled(b, k, K0)] = in[i];
+    }
+}
+
+extern "C" size_t fs_flow_tiled_features_bytes(int rows, int K0) {
+    if (rows <= 0 || K0 <= 0) return 0;
+    return (size_t)((rows + 127) / 128 * 128) * (size_t)((K0 + 3) / 4 * 4) * 4;
+}
+
+extern "C" int fs_flow_tile_features(const float* features, int rows, int K0, float* tiled, void* stream) {
+    if (rows < 0 || K0 <= 0 || (rows > 0 && (!features || !tiled))) {
+        set_error("fs_flow_tile_features: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (rows == 0) return FS_OK;
+    const size_t n = (size_t)rows * K0;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+    tile_features_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(features, tiled, rows, K0);
+    fs::count_launch();
+    return cuda_check(cudaGetLastError(), "tile_features_kernel");
 }
 
 extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shift, float* z, float* logdet,
@@ -809,7 +851,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             }
     fs::count_launch();
             if (fused) {
-                if (int r = tc_conditioner_spline(f, li, w.A0, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
+                if (int r = tc_conditioner_spline(f, li, w.A0, true, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
                 if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
                 spline_kernel<true><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(
@@ -858,7 +900,7 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
             }
     fs::count_launch();
             if (fused) {
-                if (int r = tc_conditioner_spline(f, li, w.A0, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
+                if (int r = tc_conditioner_spline(f, li, w.A0, true, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
                 if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
                 spline_kernel<false><<<spline_grid(f, rows), 32 * spline_warps(f), spline_smem_bytes(f), s>>>(

@@ -156,15 +156,23 @@ struct TcPack {
     std::vector<TcLayer> layers;
 };
 
+// Feature matrix of the tensor path: element (row b, feature k) of a [rows][K0] matrix, stored as 128-row tiles of
+// quads: [b / 128][k / 4][b % 128][k % 4].  The conditioner's epilogue threads own one row each (TMEM lane = row), so a
+// warp's float4 load of quad k/4 touches 32 consecutive rows = 512 contiguous bytes; the row-major layout made every
+// one of those loads 32 separate sectors (117 k clk of LSU wavefronts per tile at K0 = 512, measured in-kernel).
+__host__ __device__ inline size_t a0_tiled(int b, int k, int K0) {
+    return ((((size_t)(b >> 7) * (size_t)((K0 + 3) >> 2) + (size_t)(k >> 2)) * 128 + (size_t)(b & 127)) << 2) + (size_t)(k & 3);
+}
+
 // final-layer rows/bias permuted to parameter-major order (row k*N + j), see flow.cu
 void permute_final(const fs_layer_params* p, int N, int P, int H, std::vector<float>& w, std::vector<float>& b);
 // tensor-core path (flow_tc.cu)
 int tc_pack(fs_flow* f, const fs_flow_desc* d);
 void tc_free(fs_flow* f);
 size_t tc_workspace_bytes(const fs_flow* f, int B);
-int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void* ws, size_t ws_bytes,
-                   int* nan_flag, cudaStream_t s);
+int tc_conditioner(fs_flow* f, int layer, const float* A0, bool tiled, int rows, float* theta, void* ws,
+                   size_t ws_bytes, int* nan_flag, cudaStream_t s);
 bool tc_has_fused(const fs_flow* f);
-int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, int rows, int direction, const float* xin, float* xout,
-                          float* logdet, int* nan_flag, cudaStream_t s);
+int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, bool tiled, int rows, int direction, const float* xin,
+                          float* xout, float* logdet, int* nan_flag, cudaStream_t s);
 }  // namespace fs

@@ -43,7 +43,8 @@
 namespace fs {
 
 struct TcArgs {
-    const float* A0;       // [rows, K0]
+    const float* A0;       // [rows, K0] row-major, or row-tiled (a0_tiled, flow.cuh) when a0_tiled != 0
+    int a0_tiled;
     float* theta;          // [rows, NP]
     int rows, K0, NP;
     int Kp0, n_pieces, n_blocks, n_chunks;
@@ -693,22 +694,48 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const int col = hf * NH + cgp * 32;              // column inside R1
                 if (col < kcols) {
                     const int k0 = p * H + col;
-                    const float* src = g.A0 + (size_t)grow * g.K0 + k0;
+                    if (g.a0_tiled) {
+                        // row-tiled features (a0_tiled): quad k / 4 of the tile's 128 rows is 2 KB contiguous
+                        const float4* src = reinterpret_cast<const float4*>(g.A0) +
+                                            ((size_t)blockIdx.x * (size_t)((g.K0 + 3) >> 2) + (size_t)(k0 >> 2)) * 128 + r;
+                        float4 q4[8];
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = 0.f;
-                            if (row_ok && k0 + 16 * sub + i < g.K0) x = __ldg(src + 16 * sub + i);
-                            v[i] = to_tf32(x);
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            q4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (row_ok && k0 + 4 * i4 < g.K0) q4[i4] = __ldg(src + (size_t)i4 * 128);
                         }
-                        tc_st16(lane_addr + H + col + 16 * sub, v);
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                            for (int i4 = 0; i4 < 4; ++i4) {
+                                const float4 t = q4[4 * sub + i4];
+                                const int k = k0 + 16 * sub + 4 * i4;     // K0 = 2N is even: a quad holds 4 or 2 features
+                                v[4 * i4] = to_tf32(t.x);
+                                v[4 * i4 + 1] = to_tf32(t.y);
+                                v[4 * i4 + 2] = to_tf32(k + 2 < g.K0 ? t.z : 0.f);
+                                v[4 * i4 + 3] = to_tf32(k + 3 < g.K0 ? t.w : 0.f);
+                            }
+                            tc_st16(lane_addr + H + col + 16 * sub, v);
+                        }
+                    } else {                                     // caller's row-major matrix (single-layer entry points)
+                        const float* src = g.A0 + (size_t)grow * g.K0 + k0;
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                float x = 0.f;
+                                if (row_ok && k0 + 16 * sub + i < g.K0) x = __ldg(src + 16 * sub + i);
+                                v[i] = to_tf32(x);
+                            }
+                            tc_st16(lane_addr + H + col + 16 * sub, v);
+                        }
                     }
                 }
                 tc_wait_st();
                 signal_rdy(RDY_R1H0 + hf);
             }
         }
+        if (FS_TC_TIMERS == 2 && dbg_me) t_f1 = clock64() - e_start;   // timeline: features packed
         // ---- residual-stream step on R0 (u = h - c, c = biases so far, folded at pack time):
         //      u (+)= D ; operand = relu(s u + o')   (or u itself in front of the final layer) ----
 #define FS_EPI_RESIDUAL(HF, PRM, HAS_NEXT, INIT)                                                               \
@@ -779,6 +806,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
         FS_EPI_RESIDUAL(0, pbuf, true, true)
         wait_full(FULL_R0H1);
         FS_EPI_RESIDUAL(1, pbuf, true, true)
+        if (FS_TC_TIMERS == 2 && dbg_me) t_f2 = clock64() - e_start;   // timeline: first residual step done
         release_pset(0);
         // ---- residual blocks ----
         for (int b = 0; b < g.n_blocks; ++b) {
@@ -831,6 +859,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             }
             release_pset(b + 1);
         }
+        if (FS_TC_TIMERS == 2 && dbg_me) t_f3 = clock64() - e_start;   // timeline: trunk done
         if (((hmax & 0xffffu) >= 0x7c00u || (hmax >> 16) >= 0x7c00u) && g.nan_flag) atomicOr(g.nan_flag, 2);
         }   // H-wide stages
 #undef FS_EPI_RESIDUAL
@@ -911,7 +940,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #pragma unroll
                 for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
                 signal_rdy(RDY_F0 + pair);                          // accumulator drained
-                if (dbg_me) { t_m2 = clock64(); t_f1 += t_m2 - t_mark; }
+                if (dbg_me) { t_m2 = clock64(); if (FS_TC_TIMERS != 2) t_f1 += t_m2 - t_mark; }
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {
                     const float4 bb = reinterpret_cast<const float4*>(bch + 32 * axis)[i4];   // broadcast LDS.128
@@ -939,7 +968,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     e[i] = sum;
                 }
                 const float gs = gnum * __frcp_rn(sum);
-                if (dbg_me) { const long long tt = clock64(); t_f2 += tt - t_m2; t_m2 = tt; }
+                if (dbg_me) { const long long tt = clock64(); if (FS_TC_TIMERS != 2) t_f2 += tt - t_m2; t_m2 = tt; }
                 if (isA) {                                          // last knot <= x (utils/splines.py:11-13)
                     // x >= knot_i = 2b (gs S[i-1] + min i) - b   <=>   S[i-1] <= (t - min i) / gs,  t = (x + b) / 2b
                     const float rg = sum * rgnum;
@@ -988,7 +1017,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     mb[64] = right - left;
                     mb[96] = kMinD + softplus_fast(dk);
                     mb[128] = kMinD + softplus_fast(dk1);
-                    if (dbg_me) t_f3 += clock64() - t_m2;
+                    if (dbg_me && FS_TC_TIMERS != 2) t_f3 += clock64() - t_m2;
                     pair_sync();
                 } else {
 #pragma unroll
@@ -1384,8 +1413,8 @@ static long long* tc_debug_buffer(int ctas) {
     return g_dbg;
 }
 
-static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* theta, int fused, const float* xin,
-                     float* xout, float* logdet, int* nan_flag, cudaStream_t s) {
+static int tc_launch(fs_flow* f, int layer, const float* A0, bool tiled, int rows, float* theta, int fused,
+                     const float* xin, float* xout, float* logdet, int* nan_flag, cudaStream_t s) {
     TcPack* P = (TcPack*)f->tc;
     if (!P) {
         set_error("tensor-core conditioner not available for this flow shape (H=%d, blocks=%d)", f->H, f->n_blocks);
@@ -1397,6 +1426,7 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* th
     }
     TcArgs g;
     g.A0 = A0;
+    g.a0_tiled = tiled ? 1 : 0;
     g.theta = theta;
     g.rows = rows;
     g.K0 = 2 * f->N;
@@ -1431,9 +1461,9 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, int rows, float* th
     return cuda_check(cudaGetLastError(), "tc_conditioner_kernel");
 }
 
-int tc_conditioner(fs_flow* f, int layer, const float* A0, int rows, float* theta, void*, size_t, int* nan_flag,
-                   cudaStream_t s) {
-    return tc_launch(f, layer, A0, rows, theta, 0, nullptr, nullptr, nullptr, nan_flag, s);
+int tc_conditioner(fs_flow* f, int layer, const float* A0, bool tiled, int rows, float* theta, void*, size_t,
+                   int* nan_flag, cudaStream_t s) {
+    return tc_launch(f, layer, A0, tiled, rows, theta, 0, nullptr, nullptr, nullptr, nan_flag, s);
 }
 
 bool tc_has_fused(const fs_flow* f) { return f->tc && ((TcPack*)f->tc)->chn > 0; }
@@ -1441,9 +1471,9 @@ bool tc_has_fused(const fs_flow* f) { return f->tc && ((TcPack*)f->tc)->chn > 0;
 // conditioner + conditional spline of the transformed half in one kernel: direction 1 = density (coupling.py:86-102),
 // 2 = sampling (coupling.py:126-135).  Reads the layer input xin, writes the transformed half of xout and
 // accumulates the log-determinant.
-int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, int rows, int direction, const float* xin, float* xout,
-                          float* logdet, int* nan_flag, cudaStream_t s) {
-    return tc_launch(f, layer, A0, rows, nullptr, direction, xin, xout, logdet, nan_flag, s);
+int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, bool tiled, int rows, int direction, const float* xin,
+                          float* xout, float* logdet, int* nan_flag, cudaStream_t s) {
+    return tc_launch(f, layer, A0, tiled, rows, nullptr, direction, xin, xout, logdet, nan_flag, s);
 }
 
 }  // namespace fs

@@ -265,17 +265,29 @@ class FlowPack:
                                                   _lib.ptr(ws), ws.numel(), prec, _lib.stream_ptr(features.device)))
         return theta
 
-    def coupling(self, layer, direction, features, xin, xout=None, logdet=None):
+    def tile_features(self, features):
+        """Row-major periodic features [rows, 2N] -> the row-tiled layout the tensor path reads (fs_flow_tile_features);
+        pass the result to coupling(..., tiled=True)."""
+        features = _lib.require_cuda(features, "features")
+        rows, k0 = features.shape
+        nbytes = _lib.lib().fs_flow_tiled_features_bytes(int(rows), int(k0))
+        out = torch.zeros(nbytes // 4, dtype=torch.float32, device=features.device)
+        _lib.check(_lib.lib().fs_flow_tile_features(_lib.ptr(features), int(rows), int(k0), _lib.ptr(out),
+                                                    _lib.stream_ptr(features.device)))
+        return out
+
+    def coupling(self, layer, direction, features, xin, xout=None, logdet=None, tiled=False):
         """Conditioner + conditional spline of the transformed half of one layer in one kernel (fused
-        tensor-core path; coupling.py:86-102 density / 126-135 sampling).  Returns (xout, logdet)."""
+        tensor-core path; coupling.py:86-102 density / 126-135 sampling).  Returns (xout, logdet).
+        tiled: `features` is the output of tile_features (the layout the full passes use) instead of [rows, 2N]."""
         features = _lib.require_cuda(features, "features")
         xin = _lib.require_cuda(xin, "xin")
-        rows = features.shape[0]
+        rows = xin.shape[0]
         if xout is None:
             xout = torch.zeros_like(xin)
         if logdet is None:
             logdet = torch.zeros(rows, dtype=torch.float32, device=xin.device)
-        code = {"density": 1, "sampling": 2}[direction]
+        code = {"density": 1, "sampling": 2}[direction] | (0x10 if tiled else 0)
         _lib.check(_lib.lib().fs_flow_coupling(self._h, int(layer), code, _lib.ptr(features), _lib.ptr(xin),
                                                _lib.ptr(xout), _lib.ptr(logdet), rows, _lib.ptr(self._nan),
                                                _lib.stream_ptr(xin.device)))

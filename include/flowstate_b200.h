@@ -204,6 +204,15 @@ int fs_flow_has_tensor_path(const fs_flow* flow);
 int fs_flow_coupling(fs_flow* flow, int layer, int direction, const float* features, const float* xin, float* xout,
                      float* logdet, int rows, int* nan_flag, void* stream);
 
+/* Feature layout of the tensor path.  fs_flow_inverse / fs_flow_forward keep the periodic features of a chunk in
+ * 128-row tiles of quads, element (row b, feature k) at [b / 128][k / 4][b % 128][k % 4], so that the kernel's
+ * row-per-thread loads are coalesced.  A caller of fs_flow_coupling that already holds the features in that layout
+ * (fs_flow_tile_features converts a row-major [rows, K0] matrix; fs_flow_tiled_features_bytes sizes the buffer) passes
+ * direction | FS_FEATURES_TILED; without the flag the row-major matrix is read as it is (slower feature stage). */
+#define FS_FEATURES_TILED 0x10
+size_t fs_flow_tiled_features_bytes(int rows, int K0);
+int fs_flow_tile_features(const float* features, int rows, int K0, float* tiled, void* stream);
+
 /* NormalizingFlow.inverse_and_log_det / log_prob  (NF/normflows/core.py:71-86,198-214):
  * x [B, D] -> z [B, D], logdet [B]; x_in = x - in_shift (MC-box -> centred coords,
  * MCMC/monte_carlo.py:251-258).  logq (nullable) = logdet + UniformParticle.log_prob(z)

@@ -34,6 +34,6 @@ n = (rows + 127) // 128
 buf = (C.c_longlong * (16 * n))()
 got = _lib.lib().fs_tc_debug_read(buf, n)
 a = np.array(buf[: 16 * got]).reshape(got, 16)
-names = ["producer wait-empty", "mma wait-operand", "mma wait-weights", "mma total", "epi wait-accum", "epi total", "mma issue+commit", "epi residual half 0", "epi residual half 1", "epi relu (2 halves)", "epi final chunks", "fused A: loads+signal", "fused A: bias+softmax", "fused A: search+derivs", "mma final phase", "mma final: wait drained acc"]
+names = ["producer wait-empty", "mma wait-operand", "mma wait-weights", "mma total", "epi wait-accum", "epi total", "mma issue+commit", "epi residual half 0", "epi residual half 1", "epi relu (2 halves)", "epi final chunks", "fused A: loads+signal | T2: features packed", "fused A: bias+softmax | T2: first residual done", "fused A: search+derivs | T2: trunk done", "mma final phase", "mma final: wait drained acc"]
 for i, nm in enumerate(names):
-    print("%-22s mean %10.0f  min %10.0f  max %10.0f clk" % (nm, a[:, i].mean(), a[:, i].min(), a[:, i].max()))
+    print("%-48s mean %10.0f  min %10.0f  max %10.0f clk" % (nm, a[:, i].mean(), a[:, i].min(), a[:, i].max()))

@@ -176,6 +176,12 @@ def test_fused_spline_epilogue_matches_unfused(monkeypatch):
     h = n                                                # roll by D/2
     cols = [(t + h) % (2 * n) for t in trf]
     assert (xo[:, cols] - y_ref[:, cols]).abs().max().item() < 2e-5 * bound
+    # the row-tiled feature layout of the full passes (FS_FEATURES_TILED) is the same arithmetic: bit-identical
+    xo_t, ld_t = pack.coupling(1, "density", pack.tile_features(feats), x, tiled=True)
+    assert torch.equal(xo_t, xo) and torch.equal(ld_t, ld)
+    xs_r, _ = pack.coupling(1, "sampling", feats, x)
+    xs_t, _ = pack.coupling(1, "sampling", pack.tile_features(feats), x, tiled=True)
+    assert torch.equal(xs_t, xs_r)
 
 
 def test_sample_and_base_distribution():
