@@ -74,6 +74,7 @@ class HybridConfig:
     alpha: float = 1.0               # loss = alpha * forward KL + (1 - alpha) * reverse KL (main_algorithm_2.py:52, 321)
     precision: str = "auto"          # conditioner arithmetic of the eval-mode kernels: auto | tf32 | fp32
     cuda_graph: int = 1              # replay the training pass from a CUDA graph (0: eager autograd)
+    sync_bn: int = 0                 # N > 1 GPUs: BatchNorm batch statistics over all ranks' batches (SyncBatchNorm)
     # MCMC only (main_mcmc_only.py:56-57: 1e7 steps over 100 chains)
     production_steps: int = 100000
 
@@ -167,7 +168,8 @@ def _train(model, data, cfg, epochs, trainer=None):
     taken collectively.  Ends in eval mode with rank 0's weights and BatchNorm statistics on every rank."""
     from .training import FlowTrainer
     model.train()
-    tr = trainer or FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph)
+    tr = trainer or FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph,
+                                   sync_bn=cfg.sync_bn)
     tr.fresh_optimizer()
     _, world = _dist()
     n_batches = torch.tensor([max(0, -(-(data.shape[0] - 1) // cfg.batch_size))], device=data.device)
@@ -265,7 +267,8 @@ def run_algorithm_2(cfg, device="cuda", log=print):
     # initial training set: INITIAL_TRAINING_NUM_SAMPLES / (NUM_MC_RUNS / SAMPLING_FREQUENCY) steps per chain
     # (main_algorithm_2.py:240-252)
     from .training import FlowTrainer
-    trainer = FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph)
+    trainer = FlowTrainer(model, cfg.lr, cfg.weight_decay, cfg.alpha, cfg.batch_size, use_graph=cfg.cuda_graph,
+                                   sync_bn=cfg.sync_bn)
     init_steps = max(cfg.sampling_frequency, int(cfg.training_samples / (cfg.chains / cfg.sampling_frequency)))
     last = _train(model, _collect(eng, init_steps, cfg), cfg, cfg.epochs, trainer)[-1]
     big_acc = 0

@@ -14,7 +14,12 @@ Here the same step runs with
     copies - the hook point is between backward and optimizer.step (main_algorithm_2.py:450-451);
   * a fused multi-tensor Adam (torch.optim.Adam(fused=True)); a new optimizer per call of `fresh_optimizer`, like the
     reference's new Adam every cycle (main_algorithm_2.py:440);
-  * the reference's "skip the step when the loss is NaN / Inf" decision taken collectively over the ranks.
+  * the reference's "skip the step when the loss is NaN / Inf" decision taken collectively over the ranks;
+  * optionally (sync_bn=True, N > 1 GPUs) train-mode BatchNorm statistics taken over the union of the ranks' batches
+    (torch.nn.SyncBatchNorm, same state_dict keys): the N-GPU step then equals the single-process step on the
+    concatenated batch; without it every rank normalises with its own batch (DDP's default semantics)
+    and rank 0's running statistics are broadcast before sampling.  The synchronised pass runs eagerly (its
+    collectives sit inside the forward and backward passes).
 Parameters that never receive a gradient (PeriodicFeaturesElementwise.weights) keep grad = None, so
 Adam skips them exactly like the reference's.
 """
@@ -29,7 +34,11 @@ def _world():
 
 
 class FlowTrainer:
-    def __init__(self, model, lr, weight_decay=0.0, alpha=1.0, reverse_batch=256, use_graph=True):
+    def __init__(self, model, lr, weight_decay=0.0, alpha=1.0, reverse_batch=256, use_graph=True, sync_bn=False):
+        self.sync_bn = bool(sync_bn) and _world() > 1
+        if self.sync_bn:                                       # children are replaced in place; parameters are kept
+            torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            use_graph = False
         self.model = model
         self.lr, self.weight_decay, self.alpha, self.reverse_batch = lr, weight_decay, alpha, reverse_batch
         self.params = [p for p in model.parameters() if p.requires_grad]

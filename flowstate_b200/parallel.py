@@ -23,26 +23,35 @@ def _flat(tensors):
     return torch.cat([t.reshape(-1) for t in tensors]) if tensors else torch.empty(0)
 
 
+def _broadcast_flat(tensors, src, group):
+    """cat -> ONE broadcast -> multi-tensor scatter back (a handful of kernels however many tensors there are)."""
+    if not tensors:
+        return 0
+    dtype = tensors[0].dtype
+    flat = torch.cat([t.detach().reshape(-1).to(dtype) for t in tensors])
+    dist.broadcast(flat, src=src, group=group)
+    views = [v.view(t.shape) for v, t in zip(flat.split([t.numel() for t in tensors]), tensors)]
+    with torch.no_grad():
+        same = [i for i, t in enumerate(tensors) if t.dtype == dtype]
+        torch._foreach_copy_([tensors[i].detach() for i in same], [views[i] for i in same])
+        for i, t in enumerate(tensors):
+            if t.dtype != dtype:
+                t.copy_(views[i].to(t.dtype))
+    return flat.numel() * flat.element_size()
+
+
 def broadcast_flow(model, src=0, group=None):
-    """One flat broadcast of every parameter and buffer (BatchNorm statistics included)
-    from `src`; call after training on rank `src` / before sampling."""
+    """Every parameter and buffer (BatchNorm statistics and their integer batch counters included) from `src`: one
+    flat broadcast for the floating-point tensors, one for the integer buffers; call after training on rank `src` /
+    before sampling.  Returns the bytes broadcast."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
     ts = [t for t in list(model.parameters()) + list(model.buffers()) if t.is_floating_point()]
     ints = [t for t in model.buffers() if not t.is_floating_point()]
-    flat = _flat([t.detach().float() for t in ts])
-    dist.broadcast(flat, src=src, group=group)
-    off = 0
-    with torch.no_grad():
-        for t in ts:
-            n = t.numel()
-            t.copy_(flat[off:off + n].reshape(t.shape).to(t.dtype))
-            off += n
-        for t in ints:
-            dist.broadcast(t, src=src, group=group)
+    nbytes = _broadcast_flat(ts, src, group) + _broadcast_flat(ints, src, group)
     if hasattr(model, "repack"):
         model.repack()
-    return flat.numel() * 4
+    return nbytes
 
 
 def allreduce_gradients(model, group=None, average=True):
@@ -57,11 +66,8 @@ def allreduce_gradients(model, group=None, average=True):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
-    off = 0
-    for p in ps:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].reshape(p.shape))
-        off += n
+    torch._foreach_copy_([p.grad for p in ps],
+                         [v.view(p.shape) for v, p in zip(flat.split([p.numel() for p in ps]), ps)])
     return flat.numel() * 4
 
 
