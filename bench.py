@@ -460,7 +460,8 @@ class Harness:
         model.eval()
         mark("train")
         if self.world > 1:
-            self.parallel.broadcast_flow(model, src=0)         # rank 0's BatchNorm statistics everywhere
+            # parameters are identical by construction (all-reduced gradients): only rank 0's BatchNorm statistics move
+            self.parallel.broadcast_flow(model, src=0, buffers_only=True)
         mark("broadcast")
         model._cuda_pack()                                     # device-side re-pack (fs_flow_update)
         mark("repack")

@@ -262,8 +262,8 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 
 // barrier ids.  full: MMA -> epilogue (accumulator complete).  rdy: epilogue -> MMA (operand half written, or
 // final-layer accumulator drained).
-enum { FULL_R0H0 = 0, FULL_R0H1 = 1, FULL_R1H0 = 2, FULL_R1H1 = 3, FULL_F0 = 4, FULL_F1 = 5 };
-enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F1 = 5 };
+enum { FULL_R0H0 = 0, FULL_R0H1 = 1, FULL_R1H0 = 2, FULL_R1H1 = 3, FULL_F0 = 4, FULL_F1 = 5, FULL_F2 = 6, N_FULL = 7 };
+enum { RDY_R0H0 = 0, RDY_R0H1 = 1, RDY_R1H0 = 2, RDY_R1H1 = 3, RDY_F0 = 4, RDY_F1 = 5, RDY_F2 = 6, N_RDY = 7 };
 
 // In-kernel wait/phase timers (scripts/tc_debug.py): compiled in only with -DFS_TC_TIMERS=1; the clock reads sit in
 // the issue loops and cost the single MMA-issuing warp real time.
@@ -285,8 +285,19 @@ struct TcCfg {
     static constexpr int FCH = 128;                          // final-layer chunk width (MMA N)
     static constexpr bool SPLIT = (H == 256);                // block GEMMs as N = 128 quarter-GEMMs (see gemm_split)
     static constexpr int KPS = STAGE_BYTES / (FCH * 128);    // final-layer k-tiles per stage
-    static constexpr int FIN0 = H;                           // TMEM column of final accumulator 0
+    static constexpr int FIN0 = H;                           // TMEM column of final accumulator 0 (theta path: two, ping-pong)
     static constexpr int FIN1 = (H == 256) ? H + 128 : 2 * H;
+    // Fused final layer: THREE accumulators in rotation (chunk c -> accumulator c % 3) while the two epilogue pairs
+    // still alternate (chunk c -> pair c % 2), so the tensor pipe works one chunk ahead of the pairs instead of
+    // idling until the pair that owns its only other accumulator has read it out.  H = 256 has no room for a third
+    // accumulator next to the operand's scattered hand-over layout, so the LAST residual step writes the packed
+    // operand compactly into the (dead) low half of R1, features 2j, 2j+1 in column H + j, and the accumulators
+    // take R0 and the high half of R1.  H = 128: operand stays in R0, accumulators at 128 / 256 / 384.
+    static constexpr bool COMPACT = (H == 256);
+    static constexpr int FA = COMPACT ? H : 0;               // operand column of the fused final layer
+    static constexpr int FINF0 = COMPACT ? 0 : 128;
+    static constexpr int FINF1 = COMPACT ? 128 : 256;
+    static constexpr int FINF2 = 384;
     static constexpr int TMEM_COLS = 512;
     static constexpr int PSET_FLOATS = 3 * H;                // per parameter set: b0' | s | o'
     static constexpr int U_OFF = NSTAGE * STAGE_BYTES;       // second column half of the residual stream: [NH/4][128] float4;
@@ -316,16 +327,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     // barrier map (8 bytes each)
     const uint32_t bar_wfull = bar_base;                        // [NSTAGE] TMA -> MMA
     const uint32_t bar_wempty = bar_base + 8 * NSTAGE;          // [NSTAGE] MMA -> TMA
-    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [6]
-    const uint32_t bar_rdy = bar_full + 48;                     // [6]
-    const uint32_t bar_free1 = bar_rdy + 48;                    // [1]  MMA -> epilogue (feature piece consumed)
+    const uint32_t bar_full = bar_base + 16 * NSTAGE;           // [N_FULL]
+    const uint32_t bar_rdy = bar_full + 8 * N_FULL;             // [N_RDY]
+    const uint32_t bar_free1 = bar_rdy + 8 * N_RDY;             // [1]  MMA -> epilogue (feature piece consumed)
     const uint32_t bar_pfull = bar_free1 + 8;                   // [2]  TMA -> epilogue (parameter set landed)
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
     const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pairs (bias of a chunk landed)
     const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pairs -> TMA
-    const uint32_t bar_fstart = bar_bempty + 8 * S::BIAS_SLOTS; // [1] first MMA issuer -> second: the final layer may start
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 144 + 16 * S::BIAS_SLOTS);
-    static_assert(16 * NSTAGE + 148 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 8 * (N_FULL + N_RDY) + 40 + 16 * S::BIAS_SLOTS);
+    static_assert(16 * NSTAGE + 8 * (N_FULL + N_RDY) + 44 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
     const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
     float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
@@ -338,15 +348,14 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_wfull + 8 * i, 1);
             mbar_init(bar_wempty + 8 * i, 1);
         }
-        for (int i = 0; i < 6; ++i) mbar_init(bar_full + 8 * i, 1);
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < N_FULL; ++i) mbar_init(bar_full + 8 * i, 1);
+        for (int i = 0; i < N_RDY; ++i)
             mbar_init(bar_rdy + 8 * i, i < RDY_F0 ? S::BLK_WARPS : (g.fused ? EPI_WARPS / 2 : EPI_WARPS));
         mbar_init(bar_free1, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_pfull + 8 * i, 1);
             mbar_init(bar_pempty + 8 * i, S::BLK_WARPS);
         }
-        mbar_init(bar_fstart, 1);
         for (int i = 0; i < S::BIAS_SLOTS; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, EPI_WARPS / 2);       // the pair that owns the chunk, in each of the four lane quadrants
@@ -423,14 +432,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 stream((unsigned long long)g.n_chunks * (KT / S::KPS), S::STAGE_BYTES);
             }
             if (dbg && lane == 0) dbg[16 * blockIdx.x + 0] = w_empty;
-        } else if (warp == 1 || (warp == 3 && g.fused)) {
+        } else if (warp == 1) {
             // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-            // Warp 1 issues GEMM0 and the residual blocks.  In the fused final layer a SECOND issuer (warp 3, on another
-            // scheduler) takes the odd coordinate chunks: the chunks of the two issuers use different accumulators and
-            // different weight stages, and the in-kernel timers showed the single issuer - not the tensor pipe (≈ 0.9 k
-            // clk of MMAs per chunk) and not the epilogue (≈ 80 clk per chunk waiting for a drained accumulator) - to be
-            // what sets the chunk period: ≈ 2.0 k clk of its own instruction stream per chunk.
-            const bool second = (warp == 3);
             // instruction descriptors: D=F32, A=B=TF32, both K-major, M = 128, N = H (blocks) / 128 (final layer)
             const uint32_t idesc_blk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | (8u << 24);
             const uint32_t idesc_fin = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(S::FCH >> 3) << 17) | (8u << 24);
@@ -504,7 +507,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 #pragma unroll
                                         for (int j = 0; j < 4; ++j)
                                             tc_mma_ts_f16(tmem + dcol,
-                                                          tmem + acol + 64 * (i * S::KPS + kk) + 32 * (j >> 1) + 8 * (j & 1),
+                                                          (S::COMPACT && fus)
+                                                              ? tmem + acol + 32 * (i * S::KPS + kk) + 8 * j
+                                                              : tmem + acol + 64 * (i * S::KPS + kk) + 32 * (j >> 1) + 8 * (j & 1),
                                                           desc(kk * tile + 32 * j), fus ? idesc_f16 : idesc_q16,
                                                           (first && i == 0 && kk == 0 && j == 0) ? 0u : 1u);
                                 } else {
@@ -543,18 +548,6 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     issue(dcol, abase + kt * 64, 1, kt == 0, false, false, true);
                 }
             };
-            auto skip_stages = [&](int n) {                    // stages consumed by the other issuer
-                for (int i = 0; i < n; ++i)
-                    if (++stage == NSTAGE) { stage = 0; wphase ^= 1; }
-            };
-            if (second) {
-                // position of the weight ring at the start of the final layer.  The second issuer must not look at any
-                // barrier the blocks cycled through before the first issuer says so (a parity wait cannot tell phase n
-                // from phase n + 2): it sleeps on bar_fstart, a single-use barrier.
-                const unsigned long long consumed = (unsigned long long)(g.Kp0 / TC_KB) + (unsigned long long)g.n_blocks * 2ull * (H / 64);
-                stage = (uint32_t)(consumed % NSTAGE);
-                wphase = (uint32_t)((consumed / NSTAGE) & 1ull);
-            } else {
             // ---- GEMM0: features (R1) -> R0 ----
             for (int p = 0; p < g.n_pieces; ++p) {
                 const int kcols = min(H, g.Kp0 - p * H);
@@ -599,40 +592,31 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     commit(bar_full + 8 * FULL_R0H1);
                 }
             }
-            }   // !second
-            // ---- final layer: A = R0 (u), D = 128-column accumulators ping-pong, chunk after chunk ----
-            if (!second) {
-                wait_rdy(RDY_R0H0);
-                wait_rdy(RDY_R0H1);
-                if (g.fused) {                                  // wake the second issuer
-                    if (elect_one()) mbar_arrive(bar_fstart);
-                    __syncwarp();
-                }
-            } else {
-                mbar_wait(bar_fstart, 0, g.err, 10);
-                tc_fence_after();
-            }
+            // ---- final layer: A = R0 (u).  theta path: 128-column accumulators ping-pong, chunk after chunk.  Fused
+            //      path: one chunk per transformed coordinate, three accumulators in rotation (see TcCfg). ----
+            wait_rdy(RDY_R0H0);
+            wait_rdy(RDY_R0H1);
             const int n_final = g.fused ? g.N : g.n_chunks;
             const long long t_final0 = dbg ? clock64() : 0;
             long long w_rdyf = 0;
             const bool fus = g.fused != 0;
             const int SPC = (fus ? H / 64 : KT) / S::KPS;       // stages per chunk
-            const int c_step = fus ? 2 : 1;                     // fused: this issuer's chunks are those of its parity
-            if (second) skip_stages(SPC);                       // chunk 0 belongs to the first issuer
-            for (int c = second ? 1 : 0; c < n_final; c += c_step) {
-                const int f = c & 1;
-                if (c >= 2) {                                   // epilogue drained chunk c-2
+            const int n_acc = fus ? 3 : 2;
+            const uint32_t astep = fus ? (S::COMPACT ? 32u : 64u) : (uint32_t)TC_KB;   // operand columns per k-tile
+            int f = 0;                                          // accumulator of chunk c: c % n_acc
+            for (int c = 0; c < n_final; ++c) {
+                if (c >= n_acc) {                               // the epilogue drained chunk c - n_acc
                     const long long w0 = w_ready;
                     wait_rdy(RDY_F0 + f);
                     w_rdyf += w_ready - w0;
                 }
-                const uint32_t dcol = f ? S::FIN1 : S::FIN0;
+                const uint32_t dcol = fus ? (f == 0 ? S::FINF0 : (f == 1 ? S::FINF1 : S::FINF2)) : (f ? S::FIN1 : S::FIN0);
                 for (int sg = 0; sg < SPC; sg += S::GROUP)
-                    issue(dcol, sg * S::KPS * (fus ? 64 : TC_KB), min(S::GROUP, SPC - sg), sg == 0, true, fus, fus);
+                    issue(dcol, (fus ? S::FA : 0) + sg * S::KPS * astep, min(S::GROUP, SPC - sg), sg == 0, true, fus, fus);
                 commit(bar_full + 8 * (FULL_F0 + f));
-                if (fus) skip_stages(SPC);                      // the other issuer's chunk
+                if (++f == n_acc) f = 0;
             }
-            if (dbg && lane == 0 && !second) {
+            if (dbg && lane == 0) {
                 dbg[16 * blockIdx.x + 1] = w_ready;
                 dbg[16 * blockIdx.x + 2] = w_weights;
                 dbg[16 * blockIdx.x + 3] = clock64() - t_start;
@@ -795,7 +779,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     hmax = __vimax3_u16x2(hmax, v[i] & 0x7fff7fffu, v[i + 1] & 0x7fff7fffu);                   \
             }                                                                                                  \
             /* packed halves go to the first 16 of this thread's own 32 columns; the theta path keeps TF32 u */ \
-            if ((HAS_NEXT) || f16mode) tc_st8(lane_addr + col + 8 * sub, v);                                   \
+            /* the fused final layer's operand (H = 256): compact, features 2j, 2j+1 in column H + j (see TcCfg) */ \
+            if (HAS_NEXT) tc_st8(lane_addr + col + 8 * sub, v);                                                \
+            else if (f16mode) tc_st8(lane_addr + (S::COMPACT ? H + (col >> 1) : col) + 8 * sub, v);            \
             else tc_st16(lane_addr + col + 16 * sub, v);                                                       \
         }                                                                                                      \
         tc_wait_st();                                                                                          \
@@ -892,14 +878,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             bool bad = false;
             auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q + 4 * pair) : "memory"); };
             auto pick = [&](int i) { return myrow[(((i >> 2) ^ (lane & 7)) << 2) | (i & 3)]; };
-            const uint32_t fcol = pair ? S::FIN1 : S::FIN0;
             // The layer input of this row for the coordinate of chunk c is a dependent load (column table -> x) of two
             // L2 latencies; issued at the top of chunk c it would stall the in-order warp for ~1 k clk before it even
             // looks at the accumulator.  Both loads run one own-chunk ahead instead: x of chunk c + 2 is requested while
             // chunk c is processed, its column index one chunk earlier still.
             int col_n2 = (pair + 2 < g.N) ? __ldg(g.xc_in + pair + 2) : 0;
             float x_nxt = (row_ok && pair < g.N) ? __ldg(xrow_in + __ldg(g.xc_in + pair)) : 0.f;
+            // chunk c = 3 k + a lives in accumulator a; the k-th completion of FULL_F[a] has parity k & 1.  The pair sees
+            // only every other completion of a barrier, but the one before (chunk c - 3, the other pair's) is older
+            // than chunk c - 2, which this pair has already consumed: the parity wait cannot alias.
+            int acc_a = pair, acc_k = 0;
             for (int c = pair; c < g.N; c += 2) {
+                const uint32_t fcol = acc_a == 0 ? S::FINF0 : (acc_a == 1 ? S::FINF1 : S::FINF2);
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 const float x = x_nxt;
                 if (c + 2 < g.N) x_nxt = row_ok ? __ldg(xrow_in + col_n2) : 0.f;
@@ -908,7 +898,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const int bslot = c % S::BIAS_SLOTS;
                 const float* bch = reinterpret_cast<const float*>(smem + S::BIAS_OFF) + bslot * 128;
                 mbar_wait(bar_bfull + 8 * bslot, (c / S::BIAS_SLOTS) & 1, g.err, 9);
-                wait_full(FULL_F0 + pair);
+                mbar_wait(bar_full + 8 * (FULL_F0 + acc_a), acc_k & 1, g.err, 4, dbg_me ? &w_full : nullptr);
+                tc_fence_after();
                 if (dbg_me) t_mark = clock64();
                 float e[32];
                 float d32 = 0.f;
@@ -939,7 +930,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 tc_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) e[16 + i] = __uint_as_float(v[i]);
-                signal_rdy(RDY_F0 + pair);                          // accumulator drained
+                signal_rdy(RDY_F0 + acc_a);                         // accumulator drained
+                if (acc_a == 0) acc_a = 2; else { --acc_a; ++acc_k; }   // chunk c + 2
                 if (dbg_me) { t_m2 = clock64(); if (FS_TC_TIMERS != 2) t_f1 += t_m2 - t_mark; }
 #pragma unroll
                 for (int i4 = 0; i4 < 8; ++i4) {

@@ -187,7 +187,8 @@ def _train(model, data, cfg, epochs, trainer=None):
                 nb += 1
         losses.append(tot / max(nb, 1))
     model.eval()
-    parallel.broadcast_flow(model, src=0)
+    if not tr.sync_bn:            # parameters followed the all-reduced gradients on every rank; the BatchNorm running
+        parallel.broadcast_flow(model, src=0, buffers_only=True)   # statistics are per rank unless synchronised
     return losses
 
 

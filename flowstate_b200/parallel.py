@@ -40,13 +40,16 @@ def _broadcast_flat(tensors, src, group):
     return flat.numel() * flat.element_size()
 
 
-def broadcast_flow(model, src=0, group=None):
+def broadcast_flow(model, src=0, group=None, buffers_only=False):
     """Every parameter and buffer (BatchNorm statistics and their integer batch counters included) from `src`: one
     flat broadcast for the floating-point tensors, one for the integer buffers; call after training on rank `src` /
-    before sampling.  Returns the bytes broadcast."""
+    before sampling.  buffers_only: the parameters are already identical on every rank (they started identical and
+    every optimizer step used the all-reduced gradient bucket), only the per-rank BatchNorm running statistics need
+    rank `src`'s values.  Returns the bytes broadcast."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 0
-    ts = [t for t in list(model.parameters()) + list(model.buffers()) if t.is_floating_point()]
+    ts = [t for t in ([] if buffers_only else list(model.parameters())) + list(model.buffers())
+          if t.is_floating_point()]
     ints = [t for t in model.buffers() if not t.is_floating_point()]
     nbytes = _broadcast_flat(ts, src, group) + _broadcast_flat(ints, src, group)
     if hasattr(model, "repack"):
