@@ -359,6 +359,129 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
 }
 
 
+// Both prep steps with the knot tables staged in shared memory (the kernel the flow passes launch when the tables of
+// a 32-coordinate slice fit: nb <= 62).  prep_*_v2 gather the knots straight from global memory: after the first
+// probe of the bin search every lane of a warp asks for a different table row, ~20 sectors per request, and the
+// kernel sits on the LSU's wavefront rate (ncu r02b: 8 wavefronts per element, 40 us per launch at 8192 x 256).
+// Here a block of 8 warps owns 32 rows and walks the identity coordinates in slices of 32 (lane = coordinate, every
+// lane four rows at once: the U independent chains of rqs_table_multi).  The slice's tables [x | y | d][nb+1][32]
+// are copied by cp.async into one of two shared buffers while the previous slice is computed; knot k of the lane's
+// coordinate is word 32 k + lane: bank = lane whatever k, no conflicts.  Sums run over the same elements in the same
+// order as prep_*_v2 (lane-strided coordinates, then the warp tree): results are bit-identical.
+// DENSITY: true = prep_inverse (coupling.py:86-102), false = prep_forward (coupling.py:113-124).
+#define FS_PREP3_WARPS 8
+#define FS_PREP3_ROWS 4
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+template <bool FAST, bool DENSITY>
+__global__ void __launch_bounds__(32 * FS_PREP3_WARPS) prep_v3(
+    const float* __restrict__ v, float* __restrict__ out, float* __restrict__ A0, float* __restrict__ logdet, int rows,
+    FlowDev F, const float* __restrict__ ux, const float* __restrict__ uy, const float* __restrict__ ud,
+    int* nan_flag) {
+    extern __shared__ float prep_tab[];
+    constexpr int U = FS_PREP3_ROWS;
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = F.nb, nk = nb + 1, N = F.N, D = F.D, h = D / 2;
+    const int tsz = 3 * nk * 32;                                   // floats per buffer
+    const int n_slices = (N + 31) >> 5;
+    const int b0 = (blockIdx.x * FS_PREP3_WARPS + wib) * U;
+    auto stage = [&](int sl, int buf) {
+        float* dst = prep_tab + buf * tsz;
+        for (int i = threadIdx.x; i < tsz; i += 32 * FS_PREP3_WARPS) {
+            const int t = i / (nk * 32), r = i - t * nk * 32, k = r >> 5, j = 32 * sl + (r & 31);
+            const float* src = t == 0 ? ux : (t == 1 ? uy : ud);
+            if (j < N) cp_async4(dst + i, src + (size_t)k * N + j);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, 0);
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = 0.f;
+    bool bad = false;
+    for (int sl = 0; sl < n_slices; ++sl) {
+        if (sl + 1 < n_slices) {
+            stage(sl + 1, (sl + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this slice has landed, the next one is in flight
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* tx = prep_tab + (sl & 1) * tsz + lane;
+        const float* ty = tx + nk * 32;
+        const float* td = ty + nk * 32;
+        const float* ks = DENSITY ? tx : ty;                      // density: spline forward (search x knots); sampling: inverse
+        const int j = 32 * sl + lane;
+        const bool vj = j < N;
+        const int fi = vj ? F.idf[j] : 0;
+        float x[U], y[U], ld[U];
+        bool valid[U];
+        int lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            valid[u] = vj && (b0 + u < rows);
+            x[u] = valid[u] ? v[(size_t)(b0 + u) * D + (DENSITY ? fi : (fi + h) % D)] : 0.f;
+            lo[u] = 0;
+            hi[u] = nb;
+        }
+        for (int span = nb; span > 1; span = (span + 1) >> 1) {   // same trip count for every chain (rqs_table_multi)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (hi[u] - lo[u] > 1) {
+                    const int mid = (lo[u] + hi[u]) >> 1;
+                    if (x[u] >= ks[mid * 32]) lo[u] = mid; else hi[u] = mid;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            y[u] = x[u];
+            ld[u] = 0.f;
+            if (valid[u] && x[u] >= -F.bound && x[u] <= F.bound) {
+                const int sel = lo[u];
+                const float xk = tx[sel * 32], xk1 = tx[(sel + 1) * 32];
+                const float yk = ty[sel * 32], yk1 = ty[(sel + 1) * 32];
+                if (FAST)
+                    rq_eval_fast(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, y[u], ld[u]);
+                else
+                    rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, y[u], ld[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            const int b = b0 + u;
+            const float arg = F.pf_scale * (DENSITY ? x[u] : y[u]);   // features of the identity VALUES the conditioner sees
+            float sn, cs;
+            if (FAST) __sincosf(arg, &sn, &cs); else sincosf(arg, &sn, &cs);
+            if (FAST) {
+                A0[a0_tiled(b, j, 2 * N)] = cs;
+                A0[a0_tiled(b, N + j, 2 * N)] = sn;
+            } else {
+                A0[(size_t)b * 2 * N + j] = cs;
+                A0[(size_t)b * 2 * N + N + j] = sn;
+            }
+            out[(size_t)b * D + (DENSITY ? (fi + h) % D : fi)] = y[u];
+            acc[u] += ld[u];
+            bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
+        }
+        __syncthreads();                                           // the buffer of slice sl is re-filled next iteration
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float a = warp_sum_f(acc[u]);
+        if (lane == 0 && logdet && b0 + u < rows) logdet[b0 + u] += a;
+    }
+    if (bad && nan_flag) atomicOr(nan_flag, 1);
+}
+static inline size_t prep3_smem(const fs_flow* f) { return (size_t)2 * 3 * (f->nb + 1) * 32 * 4; }
+static inline unsigned prep3_grid(int rows) {
+    return (unsigned)((rows + FS_PREP3_WARPS * FS_PREP3_ROWS - 1) / (FS_PREP3_WARPS * FS_PREP3_ROWS));
+}
+
+
 // warps per block of spline_kernel: one per 32-coordinate chunk of a row, at most FS_SPLINE_MAXW
 static int spline_warps(const fs_flow* f) {
     const int nchunk = (f->N + 31) / 32;
@@ -845,8 +968,11 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
                 const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
                 const bool fast = precision == FS_PREC_TF32;
 #define FS_PREP(U, FAST) prep_inverse_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-                if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
+#define FS_PREP3(FAST) prep_v3<FAST, true><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+                if (prep3_smem(f) <= 48 * 1024 && !getenv("FS_PREP_V2")) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
+                else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
+#undef FS_PREP3
 #undef FS_PREP
             }
     fs::count_launch();
@@ -894,8 +1020,11 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
                 const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
                 const bool fast = precision == FS_PREC_TF32;
 #define FS_PREP(U, FAST) prep_forward_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-                if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
+#define FS_PREP3(FAST) prep_v3<FAST, false><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+                if (prep3_smem(f) <= 48 * 1024 && !getenv("FS_PREP_V2")) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
+                else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
+#undef FS_PREP3
 #undef FS_PREP
             }
     fs::count_launch();

@@ -184,6 +184,34 @@ def test_fused_spline_epilogue_matches_unfused(monkeypatch):
     assert torch.equal(xs_t, xs_r)
 
 
+@pytest.mark.parametrize("n,H,nb", [(40, 256, 32), (3, 32, 8), (64, 128, 15)])
+def test_prep_kernel_with_staged_tables_is_bit_identical(monkeypatch, n, H, nb):
+    """prep_v3 (knot tables staged in shared memory, 32 rows per block) against prep_*_v2 (FS_PREP_V2=1: tables
+    gathered from global memory, one warp per row): same elements summed in the same order -> identical bits, in both
+    directions and on both conditioner paths, ragged coordinate slices (40 = 32 + 8, 3) and ragged row blocks."""
+    bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+    model = _build(n, 3, 2, H, nb, bound, device="cuda")
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+    model = model.cuda().eval()
+    B = 77
+    x = ((torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    x[1, 0] = bound * 1.2                                # identity coordinate outside the interval
+    z = model.q0(B)
+    for prec in _precisions(model):
+        model.precision = prec
+        lq3 = model.log_prob(x)
+        xs3, ld3 = model.forward_and_log_det(z)
+        monkeypatch.setenv("FS_PREP_V2", "1")
+        lq2 = model.log_prob(x)
+        xs2, ld2 = model.forward_and_log_det(z)
+        monkeypatch.delenv("FS_PREP_V2")
+        assert torch.equal(lq3, lq2) and torch.equal(xs3, xs2) and torch.equal(ld3, ld2), prec
+    model.precision = "fp32"
+
+
 def test_sample_and_base_distribution():
     g = torch.Generator().manual_seed(0)
     model = _build(4, 2, 2, 32, 8, 5.0, device="cuda").cuda().eval()
