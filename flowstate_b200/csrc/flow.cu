@@ -371,9 +371,8 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
 // DENSITY: true = prep_inverse (coupling.py:86-102), false = prep_forward (coupling.py:113-124).
 #define FS_PREP3_WARPS 8
 #define FS_PREP3_ROWS 4
-__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 template <bool FAST, bool DENSITY>
 __global__ void __launch_bounds__(32 * FS_PREP3_WARPS) prep_v3(
@@ -387,87 +386,107 @@ __global__ void __launch_bounds__(32 * FS_PREP3_WARPS) prep_v3(
     const int tsz = 3 * nk * 32;                                   // floats per buffer
     const int n_slices = (N + 31) >> 5;
     const int b0 = (blockIdx.x * FS_PREP3_WARPS + wib) * U;
+    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(prep_tab) + 4u * (unsigned)lane;
     auto stage = [&](int sl, int buf) {
-        float* dst = prep_tab + buf * tsz;
-        for (int i = threadIdx.x; i < tsz; i += 32 * FS_PREP3_WARPS) {
-            const int t = i / (nk * 32), r = i - t * nk * 32, k = r >> 5, j = 32 * sl + (r & 31);
-            const float* src = t == 0 ? ux : (t == 1 ? uy : ud);
-            if (j < N) cp_async4(dst + i, src + (size_t)k * N + j);
+        if (32 * sl + lane < N) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {                           // knot row k of the slice: 32 consecutive floats
+                const float* src = (t == 0 ? ux : (t == 1 ? uy : ud)) + 32 * sl + lane + wib * N;
+                unsigned dst = tab_s + 4u * (unsigned)(buf * tsz + (t * nk + wib) * 32);
+                for (int k = wib; k < nk; k += FS_PREP3_WARPS, src += FS_PREP3_WARPS * N, dst += 128u * FS_PREP3_WARPS)
+                    cp_async4(dst, src);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // branch-free bin search: the largest index <= nb - 1 whose knot is <= x, bit by bit from the top
+    // (same answer as the halving search of rqs_table_multi on monotone knots; NaN -> 0 in both)
+    int top = 1;
+    while (2 * top <= nb - 1) top *= 2;
     stage(0, 0);
     float acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) acc[u] = 0.f;
     bool bad = false;
+    // the layer input of a slice is a dependent load (index table -> row): both run one slice ahead of the arithmetic
+    auto column = [&](int sl) {
+        const int j = 32 * sl + lane;
+        return (sl < n_slices && j < N) ? __ldg(F.idf + j) : -1;
+    };
+    const float* vrow = v + (size_t)b0 * D;
+    float* orow = out + (size_t)b0 * D;
+    // feature (row b, column k) of the tensor path sits at tile_base(b) + 512 (k / 4) + k % 4 (a0_tiled, flow.cuh)
+    float* arow = FAST ? A0 + ((size_t)(b0 >> 7) * (size_t)((2 * N + 3) >> 2) * 512 + (size_t)(b0 & 127) * 4)
+                       : A0 + (size_t)b0 * 2 * N;                  // the 4 rows of a warp never straddle a 128-row tile
+    auto rolled = [&](int fi) { const int c = fi + h; return c >= D ? c - D : c; };
+    auto fetch = [&](int fi, float (&xn)[U]) {
+        const int c = DENSITY ? fi : rolled(fi);
+#pragma unroll
+        for (int u = 0; u < U; ++u) xn[u] = (fi >= 0 && b0 + u < rows) ? vrow[u * D + c] : 0.f;
+    };
+    int fi_cur = column(0), fi_nxt = column(1);
+    float x_nxt[U];
+    fetch(fi_cur, x_nxt);
     for (int sl = 0; sl < n_slices; ++sl) {
-        if (sl + 1 < n_slices) {
-            stage(sl + 1, (sl + 1) & 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");   // this slice has landed, the next one is in flight
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");       // slice sl has landed (this thread's copies)
+        __syncthreads();                                           // ... everybody's; and slice sl - 1 is no longer read
+        if (sl + 1 < n_slices) stage(sl + 1, (sl + 1) & 1);        // overlaps the arithmetic below
         const float* tx = prep_tab + (sl & 1) * tsz + lane;
         const float* ty = tx + nk * 32;
         const float* td = ty + nk * 32;
         const float* ks = DENSITY ? tx : ty;                      // density: spline forward (search x knots); sampling: inverse
         const int j = 32 * sl + lane;
-        const bool vj = j < N;
-        const int fi = vj ? F.idf[j] : 0;
+        const int fi = fi_cur;
         float x[U], y[U], ld[U];
         bool valid[U];
-        int lo[U], hi[U];
+        int lo[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            valid[u] = vj && (b0 + u < rows);
-            x[u] = valid[u] ? v[(size_t)(b0 + u) * D + (DENSITY ? fi : (fi + h) % D)] : 0.f;
+            valid[u] = fi >= 0 && (b0 + u < rows);
+            x[u] = x_nxt[u];
             lo[u] = 0;
-            hi[u] = nb;
         }
-        for (int span = nb; span > 1; span = (span + 1) >> 1) {   // same trip count for every chain (rqs_table_multi)
+        fi_cur = fi_nxt;
+        fetch(fi_cur, x_nxt);                                      // slice sl + 1
+        fi_nxt = column(sl + 2);
+        for (int step = top; step >= 1; step >>= 1) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (hi[u] - lo[u] > 1) {
-                    const int mid = (lo[u] + hi[u]) >> 1;
-                    if (x[u] >= ks[mid * 32]) lo[u] = mid; else hi[u] = mid;
-                }
+                const int cand = lo[u] + step;                     // <= 2 top - 1 <= nb: inside the nb + 1 rows staged
+                const bool ok = cand <= nb - 1 && x[u] >= ks[cand * 32];
+                lo[u] = ok ? cand : lo[u];
             }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            y[u] = x[u];
-            ld[u] = 0.f;
-            if (valid[u] && x[u] >= -F.bound && x[u] <= F.bound) {
-                const int sel = lo[u];
-                const float xk = tx[sel * 32], xk1 = tx[(sel + 1) * 32];
-                const float yk = ty[sel * 32], yk1 = ty[(sel + 1) * 32];
-                if (FAST)
-                    rq_eval_fast(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, y[u], ld[u]);
-                else
-                    rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, y[u], ld[u]);
-            }
+        for (int u = 0; u < U; ++u) {                              // evaluated for every lane, selected afterwards
+            const int sel = lo[u];
+            const float xk = tx[sel * 32], xk1 = tx[(sel + 1) * 32];
+            const float yk = ty[sel * 32], yk1 = ty[(sel + 1) * 32];
+            float yy, ll;
+            if (FAST)
+                rq_eval_fast(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, yy, ll);
+            else
+                rq_eval(x[u], xk, xk1 - xk, yk, yk1 - yk, td[sel * 32], td[(sel + 1) * 32], !DENSITY, yy, ll);
+            const bool inside = x[u] >= -F.bound && x[u] <= F.bound;   // utils/splines.py:24, 38-39
+            y[u] = inside ? yy : x[u];
+            ld[u] = inside ? ll : 0.f;
         }
+        const int oc = DENSITY ? rolled(fi) : fi;
+        const int kc = FAST ? ((j >> 2) * 512 + (j & 3)) : j;                         // cos feature j, sin feature N + j
+        const int ksn = FAST ? (((N + j) >> 2) * 512 + ((N + j) & 3)) : N + j;
+        const int ustep = FAST ? 4 : 2 * N;                                           // next row
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (!valid[u]) continue;
-            const int b = b0 + u;
             const float arg = F.pf_scale * (DENSITY ? x[u] : y[u]);   // features of the identity VALUES the conditioner sees
             float sn, cs;
             if (FAST) __sincosf(arg, &sn, &cs); else sincosf(arg, &sn, &cs);
-            if (FAST) {
-                A0[a0_tiled(b, j, 2 * N)] = cs;
-                A0[a0_tiled(b, N + j, 2 * N)] = sn;
-            } else {
-                A0[(size_t)b * 2 * N + j] = cs;
-                A0[(size_t)b * 2 * N + N + j] = sn;
-            }
-            out[(size_t)b * D + (DENSITY ? (fi + h) % D : fi)] = y[u];
+            arow[u * ustep + kc] = cs;
+            arow[u * ustep + ksn] = sn;
+            orow[u * D + oc] = y[u];
             acc[u] += ld[u];
             bad = bad || (y[u] != y[u]) || (ld[u] != ld[u]);
         }
-        __syncthreads();                                           // the buffer of slice sl is re-filled next iteration
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -477,6 +496,13 @@ __global__ void __launch_bounds__(32 * FS_PREP3_WARPS) prep_v3(
     if (bad && nan_flag) atomicOr(nan_flag, 1);
 }
 static inline size_t prep3_smem(const fs_flow* f) { return (size_t)2 * 3 * (f->nb + 1) * 32 * 4; }
+// measured on B200 (scripts/kernel_times.py, us per launch, v3 / v2): N = 256: 44 / 52 (16384 rows, density), 32 / 36
+// (8192 rows, sampling); N = 32: 8.1 / 7.2 -> one slice has nothing to overlap the staging with.  FS_PREP_V2=1 / FS_PREP_V3=1
+// force either (the tests compare them bit for bit).
+static inline bool use_prep3(const fs_flow* f) {
+    if (prep3_smem(f) > 48 * 1024 || getenv("FS_PREP_V2")) return false;
+    return f->N > 32 || getenv("FS_PREP_V3");
+}
 static inline unsigned prep3_grid(int rows) {
     return (unsigned)((rows + FS_PREP3_WARPS * FS_PREP3_ROWS - 1) / (FS_PREP3_WARPS * FS_PREP3_ROWS));
 }
@@ -969,7 +995,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
                 const bool fast = precision == FS_PREC_TF32;
 #define FS_PREP(U, FAST) prep_inverse_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
 #define FS_PREP3(FAST) prep_v3<FAST, true><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-                if (prep3_smem(f) <= 48 * 1024 && !getenv("FS_PREP_V2")) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
+                if (use_prep3(f)) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
                 else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
 #undef FS_PREP3
@@ -1021,7 +1047,7 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
                 const bool fast = precision == FS_PREC_TF32;
 #define FS_PREP(U, FAST) prep_forward_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
 #define FS_PREP3(FAST) prep_v3<FAST, false><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-                if (prep3_smem(f) <= 48 * 1024 && !getenv("FS_PREP_V2")) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
+                if (use_prep3(f)) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
                 else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
 #undef FS_PREP3

@@ -202,8 +202,10 @@ def test_prep_kernel_with_staged_tables_is_bit_identical(monkeypatch, n, H, nb):
     z = model.q0(B)
     for prec in _precisions(model):
         model.precision = prec
+        monkeypatch.setenv("FS_PREP_V3", "1")
         lq3 = model.log_prob(x)
         xs3, ld3 = model.forward_and_log_det(z)
+        monkeypatch.delenv("FS_PREP_V3")
         monkeypatch.setenv("FS_PREP_V2", "1")
         lq2 = model.log_prob(x)
         xs2, ld2 = model.forward_and_log_det(z)
