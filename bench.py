@@ -109,6 +109,26 @@ def energy_flops(B, n):
     return 27.0 * B * n * (n - 1) / 2 + 40.0 * B * n
 
 
+class quiet_host:
+    """Timed regions run with the cyclic garbage collector paused (collected right before): a generation-2 collection
+    of this process's heap takes 60-130 ms (measured: one round of 3.4 ms took 86 ms, always a single round of a run),
+    during which no kernel is submitted and the GPU runs dry.  Reference counting still frees everything the rounds
+    allocate; nothing in the timed loop creates cycles."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self._was = gc.isenabled()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+        return False
+
+
 class ClockSampler:
     """SM clock and throttle reasons during the timed region (B200_PROFILING.md).  Sampled in-process through NVML
     (nvidia_ml_py, the library nvidia-smi itself uses) from a background thread every 25 ms: an external
@@ -526,12 +546,19 @@ class Harness:
         l0 = self._lib.lib().fs_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            self.one_round()
-        e1.record()
-        torch.cuda.synchronize()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        with quiet_host():
+            e0.record()
+            for i in range(steps):
+                self.one_round()
+                marks[i].record()
+            e1.record()
+            torch.cuda.synchronize()
         launches = int(self._lib.lib().fs_launch_count() - l0)
+        # per-round times (main stream), for the record: the headline stays e0 -> e1 over exactly `steps` rounds
+        self.step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(steps)]
+        if os.environ.get("FS_BENCH_TRACE"):
+            print("[bench] %s per-round ms: %s" % (self.name, ["%.2f" % t for t in self.step_ms]), file=sys.stderr)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.barrier()
@@ -574,11 +601,12 @@ class Harness:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for k in range(steps):
-            e2e_round(k)
-        torch.cuda.synchronize()
-        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        with quiet_host():
+            t0 = time.perf_counter()
+            for k in range(steps):
+                e2e_round(k)
+            torch.cuda.synchronize()
+            e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if self.world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         h2d = B * n * 2 * 4 + B * 2 * n * 4
@@ -824,6 +852,8 @@ def main():
             ph, ex = hs.phases(fp32, peaks)
             secondary[name] = {"metric": "mh_chain_steps_per_s", "value": tot / (ms_s * 1e-3), "unit": "chain-steps/s",
                                "steps": s_steps, "warmup": 4, "ms_per_step": ms_s / s_steps, "gpu_launches": l_s,
+                               "step_ms_min_median_max": [min(hs.step_ms), sorted(hs.step_ms)[len(hs.step_ms) // 2],
+                                                          max(hs.step_ms)],
                                "config": workload_config(name, ws),
                                "e2e": {"value": tot / e2e_ss, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d_s,
                                        "d2h_bytes_per_step": d2h_s},
@@ -854,7 +884,8 @@ def main():
                                     "fp32 accumulation" if h.fused else h.prec),
                     "pipelining": "proposals of round r+1 sampled on a side stream during round r",
                     "weight_broadcast_bytes": h.bcast_bytes,
-                    "timed_region_ms": ms_total},
+                    "timed_region_ms": ms_total,
+                    "step_ms_min_median_max": [min(h.step_ms), sorted(h.step_ms)[len(h.step_ms) // 2], max(h.step_ms)]},
         "nf_proposals_per_s": world * B * args.steps / (ms_total * 1e-3),
         "gpu_launches": launches, "clocks": clk, "phases_ms": phases,
         "e2e": {"value": steps_total / e2e_s, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,

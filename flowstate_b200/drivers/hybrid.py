@@ -105,6 +105,11 @@ def _dist():
 
 
 def _init_chains(cfg, device):
+    # Everything allocated so far (imports, modules) goes to the collector's permanent generation: a full collection of
+    # this heap in the middle of a run stalls kernel submission for ~0.1 s (bench.py: quiet_host).
+    import gc
+    gc.collect()
+    gc.freeze()
     rank, world = _dist()
     start, count = parallel.shard_range(cfg.chains, rank, world)
     # even chains start in the left well, odd chains in the right one (main_algorithm_1.py:149-165); the box length is
