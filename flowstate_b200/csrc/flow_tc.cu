@@ -281,7 +281,7 @@ struct TcCfg {
     static constexpr int THREADS = 128 + 32 * EPI_WARPS;
     static constexpr int STAGE_BYTES = H * 128;              // H rows x 32 tf32
     static constexpr int NSTAGE = (H == 256) ? 4 : 8;
-    static constexpr int GROUP = (H == 256) ? 1 : 2;         // stages issued per barrier batch (>= 512 clk of MMAs)
+    static constexpr int GROUP = 2;                            // stages issued per barrier batch (>= 512 clk of MMAs)
     static constexpr int FCH = 128;                          // final-layer chunk width (MMA N)
     static constexpr bool SPLIT = (H == 256);                // block GEMMs as N = 128 quarter-GEMMs (see gemm_split)
     static constexpr int KPS = STAGE_BYTES / (FCH * 128);    // final-layer k-tiles per stage
