@@ -534,7 +534,8 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ v
                                                      const float* __restrict__ logdet,
                                                      float* __restrict__ logdet_out, float* __restrict__ logq,
                                                      int rows, int D, float bound, float base_logc,
-                                                     double shift) {
+                                                     double shift, const float* __restrict__ ld_part = nullptr,
+                                                     int n_part = 0, size_t part_stride = 0) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (b >= rows) return;
@@ -546,7 +547,8 @@ __global__ void __launch_bounds__(256) finish_kernel(const float* __restrict__ v
     }
     inb = __all_sync(0xffffffffu, inb);
     if (lane == 0) {
-        const float ld = logdet[b];
+        float ld = logdet[b];
+        for (int i = 0; i < n_part; ++i) ld += ld_part[(size_t)i * part_stride + b];   // layer-parallel pass: fixed order
         if (logdet_out) logdet_out[b] = ld;
         if (logq) logq[b] = inb ? ld + base_logc : -__int_as_float(0x7f800000);
     }
@@ -774,7 +776,19 @@ struct Workspace {
     float *v0, *v1, *A0, *h, *t, *theta, *ld;
     void* tc;
     size_t tc_bytes;
+    // layer-parallel pass (layer_parallel()): K feature matrices a0_stride floats apart, K log-det partials of Bc
+    // floats, the chunk counters of the launch
+    size_t a0_stride;
+    float* ldp;
+    int* flags;
 };
+
+// One launch for the conditioners of all K layers of a pass (tc_conditioner_spline_all): the fused tensor path on a
+// flow whose identity coordinates stay identity coordinates under the roll (every even-N configuration, SURVEY.md
+// A.4-Q2).  FS_NO_LP=1 keeps one launch per layer (read per call so tests can compare the two).
+static bool layer_parallel(const fs_flow* f, int precision) {
+    return fused_path(f, precision) && tc_layer_parallel_ok(f);
+}
 
 static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspace* w) {
     const int Bc = chunk_rows(f, B);
@@ -787,7 +801,9 @@ static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspac
     float* v0 = (float*)take((size_t)Bc * f->D * 4);
     float* v1 = (float*)take((size_t)Bc * f->D * 4);
     // features: row-major [Bc][2N] on the FP32 path, row-tiled (a0_tiled: 128-row tiles, quads of 4 features) on the tensor path
-    float* A0 = (float*)take((size_t)((Bc + 127) / 128 * 128) * ((2 * f->N + 3) / 4 * 4) * 4);
+    const bool lp = layer_parallel(f, precision);
+    const size_t a0_floats = (size_t)((Bc + 127) / 128 * 128) * ((2 * f->N + 3) / 4 * 4);
+    float* A0 = (float*)take(a0_floats * 4 * (lp ? f->K : 1));
     const bool fp32 = precision != FS_PREC_TF32;                   // hidden activations live in TMEM on the tensor path
     float* h = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
     float* t = (float*)take(fp32 ? (size_t)Bc * f->H * 4 : 0);
@@ -795,7 +811,9 @@ static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspac
     float* ld = (float*)take((size_t)Bc * 4);
     size_t tcb = precision == FS_PREC_TF32 ? tc_workspace_bytes(f, Bc) : 0;
     void* tc = take(tcb);
-    if (w) *w = Workspace{v0, v1, A0, h, t, th, ld, tc, tcb};
+    float* ldp = (float*)take(lp ? (size_t)f->K * Bc * 4 : 0);
+    int* flags = (int*)take(lp ? tc_lp_flag_ints(f, Bc) * 4 : 0);
+    if (w) *w = Workspace{v0, v1, A0, h, t, th, ld, tc, tcb, a0_floats, ldp, flags};
     return off;
 }
 
@@ -988,13 +1006,19 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
         float* cur = w.v0;
         float* nxt = w.v1;
+        const bool lp = layer_parallel(f, precision);
+        if (lp) {
+            FS_CUDA(cudaMemsetAsync(w.ldp, 0, (size_t)f->K * Bc * 4, s));
+            FS_CUDA(cudaMemsetAsync(w.flags, 0, tc_lp_flag_ints(f, Bc) * 4, s));
+        }
         for (int li = f->K - 1; li >= 0; --li) {                        // core.py:82-85
             const fs_flow::Layer& L = f->layers[li];
+            float* const a0 = w.A0 + (lp ? (size_t)(f->K - 1 - li) * w.a0_stride : 0);
             {
                 const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
                 const bool fast = precision == FS_PREC_TF32;
-#define FS_PREP(U, FAST) prep_inverse_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-#define FS_PREP3(FAST) prep_v3<FAST, true><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+#define FS_PREP(U, FAST) prep_inverse_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, a0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+#define FS_PREP3(FAST) prep_v3<FAST, true><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, a0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
                 if (use_prep3(f)) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
                 else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
@@ -1002,7 +1026,9 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
 #undef FS_PREP
             }
     fs::count_launch();
-            if (fused) {
+            if (lp) {
+                // identity columns only: the conditioners of all layers follow in one launch below
+            } else if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, true, rows, 1, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
                 if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
@@ -1012,9 +1038,14 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
             }
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
+        if (lp)
+            if (int r = tc_conditioner_spline_all(f, 1, rows, w.A0, w.a0_stride, w.v0, w.v1, w.ldp, (size_t)Bc, w.flags,
+                                                  nan_flag, s))
+                return r;
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, z ? z + (size_t)r0 * f->D : nullptr, w.ld,
                                                      logdet ? logdet + r0 : nullptr, logq ? logq + r0 : nullptr,
-                                                     rows, f->D, f->bound_f, f->base_logc, 0.0);
+                                                     rows, f->D, f->bound_f, f->base_logc, 0.0, w.ldp,
+                                                     lp ? f->K : 0, (size_t)Bc);
     fs::count_launch();
         FS_CUDA(cudaGetLastError());
     }
@@ -1040,13 +1071,19 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
         FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
         float* cur = w.v0;
         float* nxt = w.v1;
+        const bool lp = layer_parallel(f, precision);
+        if (lp) {
+            FS_CUDA(cudaMemsetAsync(w.ldp, 0, (size_t)f->K * Bc * 4, s));
+            FS_CUDA(cudaMemsetAsync(w.flags, 0, tc_lp_flag_ints(f, Bc) * 4, s));
+        }
         for (int li = 0; li < f->K; ++li) {                              // core.py:52-55
             const fs_flow::Layer& L = f->layers[li];
+            float* const a0 = w.A0 + (lp ? (size_t)li * w.a0_stride : 0);
             {
                 const unsigned pg = (rows + FS_SPLINE_WARPS - 1) / FS_SPLINE_WARPS, pb = 32 * FS_SPLINE_WARPS;
                 const bool fast = precision == FS_PREC_TF32;
-#define FS_PREP(U, FAST) prep_forward_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
-#define FS_PREP3(FAST) prep_v3<FAST, false><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, w.A0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+#define FS_PREP(U, FAST) prep_forward_v2<U, FAST><<<pg, pb, 0, s>>>(cur, nxt, a0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
+#define FS_PREP3(FAST) prep_v3<FAST, false><<<prep3_grid(rows), 32 * FS_PREP3_WARPS, prep3_smem(f), s>>>(cur, nxt, a0, w.ld, rows, F, L.u_x, L.u_y, L.u_d, nan_flag)
                 if (use_prep3(f)) { if (fast) FS_PREP3(true); else FS_PREP3(false); }
                 else if (f->N > 32) { if (fast) FS_PREP(4, true); else FS_PREP(4, false); }
                 else { if (fast) FS_PREP(1, true); else FS_PREP(1, false); }
@@ -1054,7 +1091,9 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
 #undef FS_PREP
             }
     fs::count_launch();
-            if (fused) {
+            if (lp) {
+                // identity columns only: the conditioners of all layers follow in one launch below
+            } else if (fused) {
                 if (int r = tc_conditioner_spline(f, li, w.A0, true, rows, 2, cur, nxt, w.ld, nan_flag, s)) return r;
             } else {
                 if (int r = run_conditioner(f, li, w, rows, precision, nan_flag, s)) return r;
@@ -1064,9 +1103,14 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
             }
             float* tmp = cur; cur = nxt; nxt = tmp;
         }
+        if (lp)
+            if (int r = tc_conditioner_spline_all(f, 2, rows, w.A0, w.a0_stride, w.v0, w.v1, w.ldp, (size_t)Bc, w.flags,
+                                                  nan_flag, s))
+                return r;
         finish_kernel<<<(rows + 7) / 8, 256, 0, s>>>(cur, x + (size_t)r0 * f->D, w.ld,
                                                      logdet ? logdet + r0 : nullptr, nullptr, rows, f->D,
-                                                     f->bound_f, f->base_logc, out_shift);
+                                                     f->bound_f, f->base_logc, out_shift, w.ldp, lp ? f->K : 0,
+                                                     (size_t)Bc);
     fs::count_launch();
         FS_CUDA(cudaGetLastError());
     }

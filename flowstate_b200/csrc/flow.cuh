@@ -154,6 +154,8 @@ struct TcPack {
     size_t smem_bytes;
     int* xcols;        // device [4][N]: input / output columns of the transformed coordinates, density then sampling
     std::vector<TcLayer> layers;
+    TcLayer* layers_dev = nullptr;   // the same table on the device (layer-parallel launches index it by CTA)
+    bool lp_ok = false;              // identity set closed under the roll: all conditioner inputs known up front
 };
 
 // Feature matrix of the tensor path: element (row b, feature k) of a [rows][K0] matrix, stored as 128-row tiles of
@@ -175,4 +177,8 @@ int tc_conditioner(fs_flow* f, int layer, const float* A0, bool tiled, int rows,
 bool tc_has_fused(const fs_flow* f);
 int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, bool tiled, int rows, int direction, const float* xin,
                           float* xout, float* logdet, int* nan_flag, cudaStream_t s);
+bool tc_layer_parallel_ok(const fs_flow* f);
+size_t tc_lp_flag_ints(const fs_flow* f, int rows);
+int tc_conditioner_spline_all(fs_flow* f, int direction, int rows, const float* A0, size_t a0_stride, float* buf0,
+                              float* buf1, float* ldp, size_t ld_stride, int* flags, int* nan_flag, cudaStream_t s);
 }  // namespace fs

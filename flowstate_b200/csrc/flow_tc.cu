@@ -62,6 +62,17 @@ struct TcArgs {
     int* nan_flag;
     int* err;
     long long* dbg;   // optional per-CTA wait-cycle counters (FS_TC_DEBUG=1), 16 per CTA
+    // Layer-parallel launch (lp_layers > 0, fused path only): CTA b works on layer step b / tiles (layer
+    // lp_rev ? lp_layers - 1 - step : step) of row tile b % tiles.  Every conditioner input is known up front (the
+    // identity coordinates only ever go through the unconditional splines: SURVEY.md A.4-Q2), so the GEMM stacks of all
+    // layers are independent; only the spline of the transformed coordinates is a chain, and that is ordered per
+    // (tile, lane quadrant, pair) by the chunk counters in `flags`: step s reads what step s - 1 has published.
+    const TcLayer* Ls;     // device array [lp_layers]
+    int lp_layers, lp_rev, tiles;
+    unsigned long long a0_stride, ld_stride;   // floats between the feature matrices / log-det partials of two steps
+    float* buf0;           // activations: step s reads buf[s & 1] and writes buf[(s + 1) & 1] (transformed columns only)
+    float* buf1;
+    int* flags;            // [lp_layers][tiles][4 quadrants][2 pairs]: chunks of that pair written so far
 };
 
 // ---------------------------------------------------------------------------
@@ -341,7 +352,11 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * 128;
+    const int lp = g.lp_layers;
+    const int step = lp ? (int)blockIdx.x / g.tiles : 0;
+    const int tile = lp ? (int)blockIdx.x - step * g.tiles : (int)blockIdx.x;
+    const TcLayer L = lp ? g.Ls[g.lp_rev ? lp - 1 - step : step] : g.L;
+    const int row0 = tile * 128;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
@@ -376,7 +391,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     if (warp < 4) {
         if (warp == 0) {
             // ===================== TMA producer: parameter sets + the layer's weight stages, in order =====================
-            const uint8_t* src = (const uint8_t*)g.L.wstream;
+            const uint8_t* src = (const uint8_t*)L.wstream;
             uint32_t stage = 0, phase = 0;
             long long w_empty = 0;
             unsigned long long t = 0;
@@ -387,7 +402,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 pph ^= 1u << bsel;
                 if (elect_one()) {
                     mbar_expect_tx(bar_pfull + 8 * bsel, S::PSET_FLOATS * 4);
-                    tma_bulk_g2s(p_base + bsel * S::PSET_FLOATS * 4, g.L.psets + (size_t)j * S::PSET_FLOATS,
+                    tma_bulk_g2s(p_base + bsel * S::PSET_FLOATS * 4, L.psets + (size_t)j * S::PSET_FLOATS,
                                  S::PSET_FLOATS * 4, bar_pfull + 8 * bsel);
                 }
                 __syncwarp();
@@ -414,7 +429,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 stream(2ull * (H / 64), S::STAGE_BYTES);           // two GEMMs of H/64 FP16 stages
             }
             if (g.fused) {                                                        // final layer, FP16 tiles of 64 k
-                src = (const uint8_t*)g.L.wfused;
+                src = (const uint8_t*)L.wfused;
                 // per coordinate chunk: its bias vector into the ring (the epilogue pair reads it from shared memory: no
                 // global loads on its serial chain), then its weight stages
                 for (int c = 0; c < g.N; ++c) {
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     mbar_wait(bar_bempty + 8 * slot, ((c / S::BIAS_SLOTS) & 1) ^ 1, g.err, 8);
                     if (elect_one()) {
                         mbar_expect_tx(bar_bfull + 8 * slot, (uint32_t)g.chn * 4);
-                        tma_bulk_g2s(bias_base + slot * 512, g.L.b_fused + (size_t)c * g.chn, (uint32_t)g.chn * 4,
+                        tma_bulk_g2s(bias_base + slot * 512, L.b_fused + (size_t)c * g.chn, (uint32_t)g.chn * 4,
                                      bar_bfull + 8 * slot);
                     }
                     __syncwarp();
@@ -680,8 +695,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                     const int k0 = p * H + col;
                     if (g.a0_tiled) {
                         // row-tiled features (a0_tiled): quad k / 4 of the tile's 128 rows is 2 KB contiguous
-                        const float4* src = reinterpret_cast<const float4*>(g.A0) +
-                                            ((size_t)blockIdx.x * (size_t)((g.K0 + 3) >> 2) + (size_t)(k0 >> 2)) * 128 + r;
+                        const float4* src = reinterpret_cast<const float4*>(g.A0 + (size_t)step * g.a0_stride) +
+                                            ((size_t)tile * (size_t)((g.K0 + 3) >> 2) + (size_t)(k0 >> 2)) * 128 + r;
                         float4 q4[8];
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
@@ -866,8 +881,27 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             const bool inv = (g.fused == 2);
             const int axis = isA ? (inv ? 1 : 0) : (inv ? 0 : 1);   // 0 = widths columns, 1 = heights columns
             const float c2 = g.inv_sqrt_h * 1.4426950408889634f, bound = g.bound, two_b = 2.0f * g.bound;
-            const float* xrow_in = g.xin + (size_t)grow * g.D;
-            float* xrow_out = g.xout + (size_t)grow * g.D;
+            const float* xrow_in = (lp ? ((step & 1) ? g.buf1 : g.buf0) : g.xin) + (size_t)grow * g.D;
+            float* xrow_out = (lp ? ((step & 1) ? g.buf0 : g.buf1) : g.xout) + (size_t)grow * g.D;
+            float* const ld_out = g.logdet ? g.logdet + (size_t)step * g.ld_stride : nullptr;
+            // layer-parallel launch: chunk counters of this (tile, quadrant, pair) in the previous / this step
+            const int fidx = ((step * g.tiles + tile) * 4 + q) * 2 + pair;
+            const int* flag_in = (lp && step > 0) ? g.flags + (fidx - g.tiles * 8) : nullptr;
+            int* flag_out = (lp && step < lp - 1) ? g.flags + fidx : nullptr;
+            int seen = 0;                                      // chunks of the previous step known to be published
+            auto need = [&](int cc) {                          // the layer input of chunk cc (this pair's) is visible
+                const int want = (cc >> 1) + 1;
+                if (flag_in && seen < want) {
+                    unsigned spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag_in) : "memory");
+                        if (++spins > 4000000u) { if (g.err) atomicExch(g.err, 11); break; }
+                    } while (seen < want);
+                }
+            };
+            auto xload = [&](int col) {                        // another CTA of this launch may have written it: not .nc
+                return lp ? __ldcg(xrow_in + col) : __ldg(xrow_in + col);
+            };
             const float gnum = 1.0f - kMinW * (float)nb;       // kMinW == kMinH
             const float rgnum = 1.0f / gnum, r2b = 1.0f / two_b;
             // The u buffer is dead: thread-private 128-byte rows for values a later dynamic index picks from
@@ -883,7 +917,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // looks at the accumulator.  Both loads run one own-chunk ahead instead: x of chunk c + 2 is requested while
             // chunk c is processed, its column index one chunk earlier still.
             int col_n2 = (pair + 2 < g.N) ? __ldg(g.xc_in + pair + 2) : 0;
-            float x_nxt = (row_ok && pair < g.N) ? __ldg(xrow_in + __ldg(g.xc_in + pair)) : 0.f;
+            if (pair < g.N) need(pair);
+            float x_nxt = (row_ok && pair < g.N) ? xload(__ldg(g.xc_in + pair)) : 0.f;
             // chunk c = 3 k + a lives in accumulator a; the k-th completion of FULL_F[a] has parity k & 1.  The pair sees
             // only every other completion of a barrier, but the one before (chunk c - 3, the other pair's) is older
             // than chunk c - 2, which this pair has already consumed: the parity wait cannot alias.
@@ -892,7 +927,10 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const uint32_t fcol = acc_a == 0 ? S::FINF0 : (acc_a == 1 ? S::FINF1 : S::FINF2);
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 const float x = x_nxt;
-                if (c + 2 < g.N) x_nxt = row_ok ? __ldg(xrow_in + col_n2) : 0.f;
+                if (c + 2 < g.N) {
+                    need(c + 2);
+                    x_nxt = row_ok ? xload(col_n2) : 0.f;
+                }
                 if (c + 4 < g.N) col_n2 = __ldg(g.xc_in + c + 4);
                 const int col_out = isA ? 0 : __ldg(g.xc_out + c);   // requested now, needed at the end of the chunk
                 const int bslot = c % S::BIAS_SLOTS;
@@ -1033,13 +1071,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         acc_ld += ld;
                         bad = bad || (y != y) || (ld != ld);
                     }
+                    if (flag_out) {                                 // publish chunk c to the next step's CTA of this tile
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flag_out), "r"((c >> 1) + 1) : "memory");
+                    }
                 }
                 if (dbg_me) t_fin += clock64() - t_mark;
             }
             if (!isA) {                                             // the two B warps of a quadrant: fixed-order sum
                 if (pair == 1) mbq[0] = acc_ld;                     // pair 1's mailbox is idle now
                 asm volatile("bar.sync %0, 64;" ::"r"(9 + q) : "memory");
-                if (pair == 0 && row_ok && g.logdet) g.logdet[grow] += acc_ld + mbq[320];
+                if (pair == 0 && row_ok && ld_out) ld_out[grow] += acc_ld + mbq[320];
             }
             if (bad && g.nan_flag) atomicOr(g.nan_flag, 1);
         } else {
@@ -1074,7 +1117,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 __syncwarp();
                 const int ocol = c * S::FCH + col + 4 * slot;          // this lane's 4 columns
                 if (vec_ok && c * S::FCH + col + 32 <= g.NP) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(g.L.b_final + ocol));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(L.b_final + ocol));
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = 4 * i + rsub;
@@ -1093,7 +1136,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         const float tv[4] = {t.x, t.y, t.z, t.w};
                         if (gr < g.rows)
                             for (int e = 0; e < 4; ++e)
-                                if (ocol + e < g.NP) g.theta[(size_t)gr * g.NP + ocol + e] = tv[e] + __ldg(g.L.b_final + ocol + e);
+                                if (ocol + e < g.NP) g.theta[(size_t)gr * g.NP + ocol + e] = tv[e] + __ldg(L.b_final + ocol + e);
                     }
                 }
                 __syncwarp();
@@ -1368,6 +1411,24 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             xc[3 * f->N + j] = ft;
         }
         if (int r = tc_upload(f, xc, &P->xcols)) { delete P; return r; }
+        // Layer-parallel launches need the identity set to be closed under the roll by D/2 (then the conditioner inputs
+        // of all layers follow from the unconditional splines alone) and disjoint from the transformed set.
+        std::vector<char> is_id((size_t)f->D, 0);
+        for (int j = 0; j < f->N; ++j) is_id[d->identity_features[j]] = 1;
+        bool closed = P->chn > 0 && f->D == 2 * f->N;
+        for (int j = 0; j < f->N && closed; ++j)
+            closed = is_id[(d->identity_features[j] + f->D / 2) % f->D] && !is_id[d->transform_features[j]];
+        P->lp_ok = closed;
+    }
+    {   // device copy of the per-layer pointer table (the buffers behind it are re-packed in place by fs_flow_update)
+        void* dl = nullptr;
+        if (cudaMalloc(&dl, sizeof(TcLayer) * P->layers.size()) != cudaSuccess) { delete P; return FS_ERR_CUDA; }
+        f->allocs.push_back(dl);
+        if (cudaMemcpy(dl, P->layers.data(), sizeof(TcLayer) * P->layers.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete P;
+            return FS_ERR_CUDA;
+        }
+        P->layers_dev = (TcLayer*)dl;
     }
     int* err = nullptr;
     if (cudaMalloc(&err, sizeof(int)) != cudaSuccess) { delete P; return FS_ERR_CUDA; }
@@ -1444,6 +1505,12 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, bool tiled, int row
     g.xc_out = g.xc_in + f->N;
     g.nan_flag = nan_flag;
     g.dbg = tc_debug_buffer((rows + 127) / 128);
+    g.Ls = nullptr;
+    g.lp_layers = g.lp_rev = 0;
+    g.tiles = (rows + 127) / 128;
+    g.a0_stride = g.ld_stride = 0;
+    g.buf0 = g.buf1 = nullptr;
+    g.flags = nullptr;
     const int grid = (rows + 127) / 128;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
@@ -1466,6 +1533,69 @@ bool tc_has_fused(const fs_flow* f) { return f->tc && ((TcPack*)f->tc)->chn > 0;
 int tc_conditioner_spline(fs_flow* f, int layer, const float* A0, bool tiled, int rows, int direction, const float* xin,
                           float* xout, float* logdet, int* nan_flag, cudaStream_t s) {
     return tc_launch(f, layer, A0, tiled, rows, nullptr, direction, xin, xout, logdet, nan_flag, s);
+}
+
+bool tc_layer_parallel_ok(const fs_flow* f) {
+    return f->tc && ((TcPack*)f->tc)->lp_ok && ((TcPack*)f->tc)->chn > 0 && f->K >= 2 && !getenv("FS_NO_LP");
+}
+
+size_t tc_lp_flag_ints(const fs_flow* f, int rows) { return (size_t)f->K * (size_t)((rows + 127) / 128) * 8; }
+
+// All K coupling layers of one pass in ONE launch of K x tiles CTAs (see TcArgs).  direction 1: density (layers
+// K-1 .. 0), 2: sampling (0 .. K-1).  A0: K row-tiled feature matrices a0_stride floats apart, in step order; buf0 holds
+// the input of step 0; ldp: K log-det partials ld_stride floats apart (zeroed by the caller, summed by finish_kernel);
+// flags: tc_lp_flag_ints() ints, zeroed by the caller.
+int tc_conditioner_spline_all(fs_flow* f, int direction, int rows, const float* A0, size_t a0_stride, float* buf0,
+                              float* buf1, float* ldp, size_t ld_stride, int* flags, int* nan_flag, cudaStream_t s) {
+    TcPack* P = (TcPack*)f->tc;
+    if (!P || !P->chn || !P->lp_ok) {
+        set_error("layer-parallel conditioner launch not available for this flow");
+        return FS_ERR_UNSUPPORTED;
+    }
+    TcArgs g;
+    g.A0 = A0;
+    g.a0_tiled = 1;
+    g.theta = nullptr;
+    g.rows = rows;
+    g.K0 = 2 * f->N;
+    g.NP = f->N * f->P;
+    g.Kp0 = P->Kp0;
+    g.n_pieces = P->n_pieces;
+    g.n_blocks = f->n_blocks;
+    g.n_chunks = P->n_chunks;
+    g.n_tiles = P->tiles_per_layer;
+    g.L = P->layers[0];
+    g.err = f->tc_err;
+    g.fused = direction;
+    g.N = f->N;
+    g.D = f->D;
+    g.nb = f->nb;
+    g.chn = P->chn;
+    g.bound = f->bound_f;
+    g.inv_sqrt_h = f->inv_sqrt_h;
+    g.xin = nullptr;
+    g.xout = nullptr;
+    g.logdet = ldp;
+    g.xc_in = P->xcols + (size_t)(direction == 2 ? 2 : 0) * f->N;
+    g.xc_out = g.xc_in + f->N;
+    g.nan_flag = nan_flag;
+    g.tiles = (rows + 127) / 128;
+    g.dbg = tc_debug_buffer(g.tiles * f->K);
+    g.Ls = P->layers_dev;
+    g.lp_layers = f->K;
+    g.lp_rev = direction == 1 ? 1 : 0;
+    g.a0_stride = a0_stride;
+    g.ld_stride = ld_stride;
+    g.buf0 = buf0;
+    g.buf1 = buf1;
+    g.flags = flags;
+    const int grid = g.tiles * f->K;
+    if (P->H == 256)
+        tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
+    else
+        tc_conditioner_kernel<128><<<grid, TcCfg<128>::THREADS, P->smem_bytes, s>>>(g);
+    fs::count_launch();
+    return cuda_check(cudaGetLastError(), "tc_conditioner_kernel (layer-parallel)");
 }
 
 }  // namespace fs

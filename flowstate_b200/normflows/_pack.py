@@ -205,7 +205,8 @@ class FlowPack:
     # -- calls ------------------------------------------------------------
     def _workspace(self, B, prec):
         # one buffer per (batch, precision, path, stream): passes issued on different streams may overlap
-        key = (B, prec, bool(os.environ.get("FS_NO_FUSE")), torch.cuda.current_stream(self.device).cuda_stream)
+        key = (B, prec, bool(os.environ.get("FS_NO_FUSE")), bool(os.environ.get("FS_NO_LP")),
+               torch.cuda.current_stream(self.device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None:
             n = _lib.lib().fs_flow_workspace_bytes(self._h, B, prec)

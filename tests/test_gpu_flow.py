@@ -214,6 +214,39 @@ def test_prep_kernel_with_staged_tables_is_bit_identical(monkeypatch, n, H, nb):
     model.precision = "fp32"
 
 
+@pytest.mark.parametrize("n,K,blocks,H,nb,B", [(40, 5, 2, 256, 32, 300), (64, 4, 2, 128, 15, 700), (6, 7, 1, 128, 8, 129),
+                                                 (5, 3, 2, 128, 8, 200)])
+def test_layer_parallel_pass_matches_layer_by_layer(monkeypatch, n, K, blocks, H, nb, B):
+    """Even N: the conditioners of all K layers run in ONE launch of K x tiles CTAs, the spline chain ordered by
+    per-(tile, quadrant, pair) chunk counters in global memory; FS_NO_LP=1 keeps one launch per layer.
+    Same kernel arithmetic on the same inputs: coordinates must be bit-identical, log-dets equal up to the order in which
+    the per-layer partial sums are added.  N = 5 (odd: the roll swaps the coordinate parity) must fall back silently."""
+    bound = float(np.float32(np.sqrt(n / 0.03))) / 2
+    model = _build(n, K, blocks, H, nb, bound, device="cuda")
+    g = torch.Generator().manual_seed(21)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+    model = model.cuda().eval()
+    if "tf32" not in _precisions(model):
+        pytest.skip("tensor path unavailable")
+    model.precision = "tf32"
+    x = ((torch.rand(B, 2 * n, generator=g) * 2 - 1) * bound).cuda()
+    x[2, 1] = bound * 1.3                                # transformed coordinate outside the interval
+    z = model.q0(B)
+    for _ in range(2):                                   # twice: the chunk counters are re-armed per pass
+        z_lp, ld_lp = model.inverse_and_log_det(x)
+        xs_lp, lds_lp = model.forward_and_log_det(z)
+    monkeypatch.setenv("FS_NO_LP", "1")
+    z_seq, ld_seq = model.inverse_and_log_det(x)
+    xs_seq, lds_seq = model.forward_and_log_det(z)
+    monkeypatch.delenv("FS_NO_LP")
+    assert torch.equal(z_lp, z_seq) and torch.equal(xs_lp, xs_seq)
+    scale = 1.0 + ld_seq.abs().max().item()
+    assert (ld_lp - ld_seq).abs().max().item() < 2e-6 * scale
+    assert (lds_lp - lds_seq).abs().max().item() < 2e-6 * (1.0 + lds_seq.abs().max().item())
+
+
 def test_sample_and_base_distribution():
     g = torch.Generator().manual_seed(0)
     model = _build(4, 2, 2, 32, 8, 5.0, device="cuda").cuda().eval()
