@@ -73,6 +73,7 @@ _PROTOS = {
     "fs_pair_histogram": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _P, _P]),
     "fs_flow_has_tensor_path": (C.c_int, [_P]),
     "fs_flow_coupling": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
+    "fs_flow_coupling_all": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_tiled_features_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fs_flow_tile_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "fs_flow_inverse": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),

@@ -958,6 +958,30 @@ extern "C" int fs_flow_coupling(fs_flow* f, int layer, int direction, const floa
                                  (cudaStream_t)stream);
 }
 
+// The conditioners + conditional splines of ALL K layers of a pass in one launch (what fs_flow_inverse / fs_flow_forward
+// do after their K feature kernels; exposed for benchmarks and tests).  features: K row-tiled matrices in step order
+// (density: layers K-1 .. 0; sampling: 0 .. K-1), fs_flow_tiled_features_bytes(rows, 2N) bytes apart; buf0 [rows, D] holds
+// the input (its transformed columns are read), the steps ping-pong between buf0 and buf1 and step K-1 writes
+// buf[K & 1]; logdet_parts [K, rows] receives one partial per step; scratch: K * ceil(rows / 128) * 8 ints.
+extern "C" int fs_flow_coupling_all(fs_flow* f, int direction, const float* features, float* buf0, float* buf1,
+                                    float* logdet_parts, int* scratch, int rows, int* nan_flag, void* stream) {
+    if (!f || !features || !buf0 || !buf1 || !logdet_parts || !scratch || rows < 0 || (direction != 1 && direction != 2)) {
+        set_error("fs_flow_coupling_all: invalid argument");
+        return FS_ERR_INVALID;
+    }
+    if (rows == 0) return FS_OK;
+    if (!tc_layer_parallel_ok(f)) {
+        set_error("fs_flow_coupling_all: this flow has no layer-parallel path (fused tensor path, identity set closed under the roll)");
+        return FS_ERR_UNSUPPORTED;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    FS_CUDA(cudaMemsetAsync(logdet_parts, 0, (size_t)f->K * rows * 4, s));
+    FS_CUDA(cudaMemsetAsync(scratch, 0, tc_lp_flag_ints(f, rows) * 4, s));
+    const size_t stride = (size_t)((rows + 127) / 128 * 128) * ((2 * f->N + 3) / 4 * 4);
+    return tc_conditioner_spline_all(f, direction, rows, features, stride, buf0, buf1, logdet_parts, (size_t)rows, scratch,
+                                     nan_flag, s);
+}
+
 // [rows, K0] row-major -> the row-tiled layout the tensor path reads (a0_tiled); the full passes write that layout
 // directly from their feature kernels, this is for callers of fs_flow_coupling that hold a row-major matrix.
 __global__ void tile_features_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int K0) {

@@ -73,6 +73,7 @@ struct TcArgs {
     float* buf0;           // activations: step s reads buf[s & 1] and writes buf[(s + 1) & 1] (transformed columns only)
     float* buf1;
     int* flags;            // [lp_layers][tiles][4 quadrants][2 pairs]: chunks of that pair written so far
+    const int* xc_dep;     // [N] chunk of the previous step that writes the column chunk c reads (the roll shifts it by N/2)
 };
 
 // ---------------------------------------------------------------------------
@@ -888,15 +889,20 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             const int fidx = ((step * g.tiles + tile) * 4 + q) * 2 + pair;
             const int* flag_in = (lp && step > 0) ? g.flags + (fidx - g.tiles * 8) : nullptr;
             int* flag_out = (lp && step < lp - 1) ? g.flags + fidx : nullptr;
-            int seen = 0;                                      // chunks of the previous step known to be published
-            auto need = [&](int cc) {                          // the layer input of chunk cc (this pair's) is visible
-                const int want = (cc >> 1) + 1;
-                if (flag_in && seen < want) {
+            int seen0 = 0, seen1 = 0;                          // chunks of the previous step known to be published, per pair
+            auto need = [&](int cc) {                          // the layer input of chunk cc has been written
+                if (!flag_in) return;
+                const int j = __ldg(g.xc_dep + cc);            // ... by chunk j of the previous step (pair j & 1)
+                const int want = (j >> 1) + 1;
+                int seen = (j & 1) ? seen1 : seen0;
+                if (seen < want) {
+                    const int* fl = flag_in - pair + (j & 1);
                     unsigned spins = 0;
                     do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag_in) : "memory");
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
                         if (++spins > 4000000u) { if (g.err) atomicExch(g.err, 11); break; }
                     } while (seen < want);
+                    if (j & 1) seen1 = seen; else seen0 = seen;
                 }
             };
             auto xload = [&](int col) {                        // another CTA of this launch may have written it: not .nc
@@ -1402,7 +1408,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     }
     {   // columns read / written by the fused epilogue: density reads feature ft and writes (ft + D/2) % D (the roll,
         // coupling.py:100-101), sampling reads the rolled input (coupling.py:113-114) and writes ft
-        std::vector<int> xc((size_t)4 * f->N);
+        std::vector<int> xc((size_t)6 * f->N, -1);
         for (int j = 0; j < f->N; ++j) {
             const int ft = d->transform_features[j], rolled = (ft + f->D / 2) % f->D;
             xc[j] = ft;
@@ -1410,6 +1416,16 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             xc[2 * f->N + j] = rolled;
             xc[3 * f->N + j] = ft;
         }
+        // rows 4, 5 (layer-parallel launches): the chunk of the previous step that writes the column chunk c reads
+        bool deps_ok = true;
+        for (int dir = 0; dir < 2; ++dir)
+            for (int c = 0; c < f->N; ++c) {
+                const int col = xc[(size_t)(2 * dir) * f->N + c];
+                int j = 0;
+                while (j < f->N && xc[(size_t)(2 * dir + 1) * f->N + j] != col) ++j;
+                if (j == f->N) { deps_ok = false; j = 0; }
+                xc[(size_t)(4 + dir) * f->N + c] = j;
+            }
         if (int r = tc_upload(f, xc, &P->xcols)) { delete P; return r; }
         // Layer-parallel launches need the identity set to be closed under the roll by D/2 (then the conditioner inputs
         // of all layers follow from the unconditional splines alone) and disjoint from the transformed set.
@@ -1418,7 +1434,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         bool closed = P->chn > 0 && f->D == 2 * f->N;
         for (int j = 0; j < f->N && closed; ++j)
             closed = is_id[(d->identity_features[j] + f->D / 2) % f->D] && !is_id[d->transform_features[j]];
-        P->lp_ok = closed;
+        P->lp_ok = closed && deps_ok;
     }
     {   // device copy of the per-layer pointer table (the buffers behind it are re-packed in place by fs_flow_update)
         void* dl = nullptr;
@@ -1511,6 +1527,7 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, bool tiled, int row
     g.a0_stride = g.ld_stride = 0;
     g.buf0 = g.buf1 = nullptr;
     g.flags = nullptr;
+    g.xc_dep = nullptr;
     const int grid = (rows + 127) / 128;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
@@ -1589,6 +1606,7 @@ int tc_conditioner_spline_all(fs_flow* f, int direction, int rows, const float* 
     g.buf0 = buf0;
     g.buf1 = buf1;
     g.flags = flags;
+    g.xc_dep = P->xcols + (size_t)(direction == 2 ? 5 : 4) * f->N;
     const int grid = g.tiles * f->K;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);

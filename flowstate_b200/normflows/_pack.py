@@ -294,6 +294,22 @@ class FlowPack:
                                                _lib.stream_ptr(xin.device)))
         return xout, logdet
 
+    def coupling_all(self, direction, features_all, buf0, buf1=None):
+        """All K layers' conditioners + conditional splines in one launch (fs_flow_coupling_all).  features_all: flat
+        tensor of K tiled feature matrices in step order (tile_features per layer, concatenated).  Returns
+        (buf holding the result, logdet partials [K, rows])."""
+        buf0 = _lib.require_cuda(buf0, "buf0")
+        rows = buf0.shape[0]
+        if buf1 is None:
+            buf1 = torch.zeros_like(buf0)
+        parts = torch.empty(self.K, rows, dtype=torch.float32, device=buf0.device)
+        scratch = torch.empty(self.K * ((rows + 127) // 128) * 8, dtype=torch.int32, device=buf0.device)
+        code = {"density": 1, "sampling": 2}[direction]
+        _lib.check(_lib.lib().fs_flow_coupling_all(self._h, code, _lib.ptr(features_all), _lib.ptr(buf0), _lib.ptr(buf1),
+                                                   _lib.ptr(parts), _lib.ptr(scratch), rows, _lib.ptr(self._nan),
+                                                   _lib.stream_ptr(buf0.device)))
+        return (buf1 if self.K & 1 else buf0), parts
+
     def check_nan(self):
         """Surfaces the device-side NaN flag like the reference's ValueError (utils/splines.py:176-183)."""
         if int(self._nan.item()):
