@@ -66,13 +66,13 @@ struct TcArgs {
     // lp_rev ? lp_layers - 1 - step : step) of row tile b % tiles.  Every conditioner input is known up front (the
     // identity coordinates only ever go through the unconditional splines: SURVEY.md A.4-Q2), so the GEMM stacks of all
     // layers are independent; only the spline of the transformed coordinates is a chain, and that is ordered per
-    // (tile, lane quadrant, pair) by the chunk counters in `flags`: step s reads what step s - 1 has published.
+    // (tile, pair) by the chunk counters in `flags`: step s reads what step s - 1 has published.
     const TcLayer* Ls;     // device array [lp_layers]
     int lp_layers, lp_rev, tiles;
     unsigned long long a0_stride, ld_stride;   // floats between the feature matrices / log-det partials of two steps
     float* buf0;           // activations: step s reads buf[s & 1] and writes buf[(s + 1) & 1] (transformed columns only)
     float* buf1;
-    int* flags;            // [lp_layers][tiles][4 quadrants][2 pairs]: chunks of that pair written so far
+    int* flags;            // [lp_layers][tiles][2 pairs]: chunks of that pair written (by all four lane quadrants) so far
     const int* xc_dep;     // [N] chunk of the previous step that writes the column chunk c reads (the roll shifts it by N/2)
 };
 
@@ -346,8 +346,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
     const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pairs (bias of a chunk landed)
     const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pairs -> TMA
-    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 8 * (N_FULL + N_RDY) + 40 + 16 * S::BIAS_SLOTS);
-    static_assert(16 * NSTAGE + 8 * (N_FULL + N_RDY) + 44 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
+    const uint32_t bar_pub = bar_bempty + 8 * S::BIAS_SLOTS;    // [2] layer-parallel launch: pair p's B warps wrote a chunk
+    uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 8 * (N_FULL + N_RDY) + 56 + 16 * S::BIAS_SLOTS);
+    static_assert(16 * NSTAGE + 8 * (N_FULL + N_RDY) + 60 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
     const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
     float4* us4 = reinterpret_cast<float4*>(smem + S::U_OFF);   // u of column half 1: [col/4][row]
 
@@ -376,6 +377,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, EPI_WARPS / 2);       // the pair that owns the chunk, in each of the four lane quadrants
         }
+        mbar_init(bar_pub, 4);                                  // the pair's B warp of each lane quadrant
+        mbar_init(bar_pub + 8, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -640,6 +643,18 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 dbg[16 * blockIdx.x + 14] = clock64() - t_final0;     // final layer: whole phase of the MMA warp
                 dbg[16 * blockIdx.x + 15] = w_rdyf;                   // ... of which waiting for a drained accumulator
             }
+        } else if (warp == 3 && lp && step < lp - 1 && g.fused) {
+            // ===================== publisher (layer-parallel launch) =====================
+            // The next step's CTA of this row tile reads the coordinates this CTA writes.  The B warps only arrive on a
+            // CTA-scope mbarrier after their stores; the device-scope fence (an L2 round trip per chunk) is paid here, off
+            // the epilogue's chain: mbarrier (release / acquire at CTA scope) -> fence.gpu -> flag, so the B warps' stores
+            // are ordered before the flag for whoever acquires it.
+            int* fl = g.flags + (size_t)(step * g.tiles + tile) * 2;
+            for (int c = 0; c < g.N; ++c) {
+                mbar_wait(bar_pub + 8 * (c & 1), (c >> 1) & 1, g.err, 12);
+                __threadfence();
+                if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(fl + (c & 1)), "r"((c >> 1) + 1) : "memory");
+            }
         }
     } else {
         // ===================== epilogue warps =====================
@@ -886,9 +901,8 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             float* xrow_out = (lp ? ((step & 1) ? g.buf0 : g.buf1) : g.xout) + (size_t)grow * g.D;
             float* const ld_out = g.logdet ? g.logdet + (size_t)step * g.ld_stride : nullptr;
             // layer-parallel launch: chunk counters of this (tile, quadrant, pair) in the previous / this step
-            const int fidx = ((step * g.tiles + tile) * 4 + q) * 2 + pair;
-            const int* flag_in = (lp && step > 0) ? g.flags + (fidx - g.tiles * 8) : nullptr;
-            int* flag_out = (lp && step < lp - 1) ? g.flags + fidx : nullptr;
+            const int* flag_in = (lp && step > 0) ? g.flags + (size_t)((step - 1) * g.tiles + tile) * 2 : nullptr;
+            const bool publish = lp && step < lp - 1;
             int seen0 = 0, seen1 = 0;                          // chunks of the previous step known to be published, per pair
             auto need = [&](int cc) {                          // the layer input of chunk cc has been written
                 if (!flag_in) return;
@@ -896,7 +910,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const int want = (j >> 1) + 1;
                 int seen = (j & 1) ? seen1 : seen0;
                 if (seen < want) {
-                    const int* fl = flag_in - pair + (j & 1);
+                    const int* fl = flag_in + (j & 1);
                     unsigned spins = 0;
                     do {
                         asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
@@ -1077,10 +1091,9 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         acc_ld += ld;
                         bad = bad || (y != y) || (ld != ld);
                     }
-                    if (flag_out) {                                 // publish chunk c to the next step's CTA of this tile
-                        __threadfence();
+                    if (publish) {                                  // chunk c of this quadrant is written: tell the publisher
                         __syncwarp();
-                        if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flag_out), "r"((c >> 1) + 1) : "memory");
+                        if (lane == 0) mbar_arrive(bar_pub + 8 * pair);
                     }
                 }
                 if (dbg_me) t_fin += clock64() - t_mark;
