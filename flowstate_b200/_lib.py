@@ -74,6 +74,7 @@ _PROTOS = {
     "fs_flow_has_tensor_path": (C.c_int, [_P]),
     "fs_flow_coupling": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_coupling_all": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
+    "fs_flow_uses_layer_parallel": (C.c_int, [_P, C.c_int, C.c_int]),
     "fs_flow_tiled_features_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fs_flow_tile_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "fs_flow_inverse": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),

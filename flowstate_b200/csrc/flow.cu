@@ -789,6 +789,30 @@ struct Workspace {
 static bool layer_parallel(const fs_flow* f, int precision) {
     return fused_path(f, precision) && tc_layer_parallel_ok(f);
 }
+// ... used for a pass of `rows` rows when it pays.  A step's CTA runs its GEMM stack at once but starts its spline
+// chunks only when the previous step of its row tile has finished, so a CTA may idle on its SM for up to one
+// final-layer time.  That is free while every CTA of the launch is resident anyway (K x tiles <= SMs); beyond that
+// the wait disappears when the previous step's CTA was dispatched early enough: tiles / SMs of a kernel time earlier,
+// against the fraction of a kernel the trunk (GEMM0 + residual blocks) takes.  Measured (profiles/r02_layer_parallel.md):
+// alg1_n32 passes 1.5 x faster, alg1_n256 (final layer 61 % of the flops, 64 / 128 tiles) no gain -> one launch per layer.
+// FS_LP_MAX_TILES overrides the tile limit (development).
+static bool layer_parallel_rows(const fs_flow* f, int precision, int rows) {
+    if (!layer_parallel(f, precision)) return false;
+    const int tiles = (rows + 127) / 128;
+    if (const char* e = getenv("FS_LP_MAX_TILES")) return tiles <= atoi(e);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    if (tiles > 96) return false;
+    if (f->K * tiles <= sms) return true;
+    const double trunk = 2.0 * (2.0 * f->N) * f->H + 4.0 * f->n_blocks * (double)f->H * f->H;
+    const double fin = 2.0 * f->H * (double)f->N * (3.0 * f->nb + 1.0);
+    return (double)tiles / sms + trunk / (trunk + fin) >= 1.0;
+}
 
 static size_t carve(const fs_flow* f, int B, int precision, void* base, Workspace* w) {
     const int Bc = chunk_rows(f, B);
@@ -1030,7 +1054,7 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
         FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
         float* cur = w.v0;
         float* nxt = w.v1;
-        const bool lp = layer_parallel(f, precision);
+        const bool lp = layer_parallel_rows(f, precision, rows);
         if (lp) {
             FS_CUDA(cudaMemsetAsync(w.ldp, 0, (size_t)f->K * Bc * 4, s));
             FS_CUDA(cudaMemsetAsync(w.flags, 0, tc_lp_flag_ints(f, Bc) * 4, s));
@@ -1076,6 +1100,12 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
     return FS_OK;
 }
 
+extern "C" int fs_flow_uses_layer_parallel(const fs_flow* f, int rows, int precision) {
+    if (!f || rows <= 0) return 0;
+    const int Bc = chunk_rows(f, rows);
+    return layer_parallel_rows(f, precision, rows < Bc ? rows : Bc) ? 1 : 0;
+}
+
 extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_shift, float* x, float* logdet,
                                int* nan_flag, void* workspace, size_t workspace_bytes, int precision,
                                void* stream) {
@@ -1095,7 +1125,7 @@ extern "C" int fs_flow_forward(fs_flow* f, const float* zin, int B, double out_s
         FS_CUDA(cudaMemsetAsync(w.ld, 0, (size_t)rows * 4, s));
         float* cur = w.v0;
         float* nxt = w.v1;
-        const bool lp = layer_parallel(f, precision);
+        const bool lp = layer_parallel_rows(f, precision, rows);
         if (lp) {
             FS_CUDA(cudaMemsetAsync(w.ldp, 0, (size_t)f->K * Bc * 4, s));
             FS_CUDA(cudaMemsetAsync(w.flags, 0, tc_lp_flag_ints(f, Bc) * 4, s));

@@ -65,15 +65,17 @@ struct TcArgs {
     // Layer-parallel launch (lp_layers > 0, fused path only): CTA b works on layer step b / tiles (layer
     // lp_rev ? lp_layers - 1 - step : step) of row tile b % tiles.  Every conditioner input is known up front (the
     // identity coordinates only ever go through the unconditional splines: SURVEY.md A.4-Q2), so the GEMM stacks of all
-    // layers are independent; only the spline of the transformed coordinates is a chain, and that is ordered per
-    // (tile, pair) by the chunk counters in `flags`: step s reads what step s - 1 has published.
+    // layers are independent; only the spline of the transformed coordinates is a chain.  It is ordered per (tile, lane
+    // quadrant) by ONE counter in `flags`: the two B warps of the quadrant bump it (after a device-scope fence) when
+    // they have written their last coordinate, and step s starts its first chunk only when step s - 1 shows 2.  (A
+    // per-chunk hand-over was tried: the consumer then stalls in the middle of its chunk loop, which turned out not to
+    // be repeatable run to run at H = 128; with one wait in front of the loop the loop itself is the single-layer one.)
     const TcLayer* Ls;     // device array [lp_layers]
     int lp_layers, lp_rev, tiles;
     unsigned long long a0_stride, ld_stride;   // floats between the feature matrices / log-det partials of two steps
     float* buf0;           // activations: step s reads buf[s & 1] and writes buf[(s + 1) & 1] (transformed columns only)
     float* buf1;
-    int* flags;            // [lp_layers][tiles][2 pairs]: chunks of that pair written (by all four lane quadrants) so far
-    const int* xc_dep;     // [N] chunk of the previous step that writes the column chunk c reads (the roll shifts it by N/2)
+    int* flags;            // [lp_layers][tiles][4 lane quadrants]: B warps of that quadrant that have finished the step
 };
 
 // ---------------------------------------------------------------------------
@@ -346,7 +348,6 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
     const uint32_t bar_pempty = bar_pfull + 16;                 // [2]  epilogue -> TMA
     const uint32_t bar_bfull = bar_pempty + 16;                 // [BIAS_SLOTS] TMA -> epilogue pairs (bias of a chunk landed)
     const uint32_t bar_bempty = bar_bfull + 8 * S::BIAS_SLOTS;  // [BIAS_SLOTS] epilogue pairs -> TMA
-    const uint32_t bar_pub = bar_bempty + 8 * S::BIAS_SLOTS;    // [2] layer-parallel launch: pair p's B warps wrote a chunk
     uint32_t* tmem_slot = (uint32_t*)(smem + S::BAR_OFF + 16 * NSTAGE + 8 * (N_FULL + N_RDY) + 56 + 16 * S::BIAS_SLOTS);
     static_assert(16 * NSTAGE + 8 * (N_FULL + N_RDY) + 60 + 16 * S::BIAS_SLOTS <= 512, "barrier area overflow");
     const uint32_t bias_base = smem_u32(smem + S::BIAS_OFF);
@@ -377,8 +378,6 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, EPI_WARPS / 2);       // the pair that owns the chunk, in each of the four lane quadrants
         }
-        mbar_init(bar_pub, 4);                                  // the pair's B warp of each lane quadrant
-        mbar_init(bar_pub + 8, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -643,18 +642,6 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 dbg[16 * blockIdx.x + 14] = clock64() - t_final0;     // final layer: whole phase of the MMA warp
                 dbg[16 * blockIdx.x + 15] = w_rdyf;                   // ... of which waiting for a drained accumulator
             }
-        } else if (warp == 3 && lp && step < lp - 1 && g.fused) {
-            // ===================== publisher (layer-parallel launch) =====================
-            // The next step's CTA of this row tile reads the coordinates this CTA writes.  The B warps only arrive on a
-            // CTA-scope mbarrier after their stores; the device-scope fence (an L2 round trip per chunk) is paid here, off
-            // the epilogue's chain: mbarrier (release / acquire at CTA scope) -> fence.gpu -> flag, so the B warps' stores
-            // are ordered before the flag for whoever acquires it.
-            int* fl = g.flags + (size_t)(step * g.tiles + tile) * 2;
-            for (int c = 0; c < g.N; ++c) {
-                mbar_wait(bar_pub + 8 * (c & 1), (c >> 1) & 1, g.err, 12);
-                __threadfence();
-                if (lane == 0) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(fl + (c & 1)), "r"((c >> 1) + 1) : "memory");
-            }
         }
     } else {
         // ===================== epilogue warps =====================
@@ -900,25 +887,24 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             const float* xrow_in = (lp ? ((step & 1) ? g.buf1 : g.buf0) : g.xin) + (size_t)grow * g.D;
             float* xrow_out = (lp ? ((step & 1) ? g.buf0 : g.buf1) : g.xout) + (size_t)grow * g.D;
             float* const ld_out = g.logdet ? g.logdet + (size_t)step * g.ld_stride : nullptr;
-            // layer-parallel launch: chunk counters of this (tile, quadrant, pair) in the previous / this step
-            const int* flag_in = (lp && step > 0) ? g.flags + (size_t)((step - 1) * g.tiles + tile) * 2 : nullptr;
+            // layer-parallel launch: the previous step must have written every coordinate of these 32 rows (both of its
+            // pairs) before this warp reads its first one - and, the other way round, nothing of the previous step still
+            // reads the buffer this step writes
             const bool publish = lp && step < lp - 1;
-            int seen0 = 0, seen1 = 0;                          // chunks of the previous step known to be published, per pair
-            auto need = [&](int cc) {                          // the layer input of chunk cc has been written
-                if (!flag_in) return;
-                const int j = __ldg(g.xc_dep + cc);            // ... by chunk j of the previous step (pair j & 1)
-                const int want = (j >> 1) + 1;
-                int seen = (j & 1) ? seen1 : seen0;
-                if (seen < want) {
-                    const int* fl = flag_in + (j & 1);
-                    unsigned spins = 0;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
-                        if (++spins > 4000000u) { if (g.err) atomicExch(g.err, 11); break; }
-                    } while (seen < want);
-                    if (j & 1) seen1 = seen; else seen0 = seen;
+            if (lp && step > 0) {
+                const int* fl = g.flags + (size_t)((step - 1) * g.tiles + tile) * 4 + q;
+                int seen;
+                unsigned spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
+                    if (seen >= 2) break;
+                    __nanosleep(400);
+                    if (++spins > 8000000u) {
+                        if (g.err) atomicExch(g.err, 11);
+                        __trap();
+                    }
                 }
-            };
+            }
             auto xload = [&](int col) {                        // another CTA of this launch may have written it: not .nc
                 return lp ? __ldcg(xrow_in + col) : __ldg(xrow_in + col);
             };
@@ -937,7 +923,6 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
             // looks at the accumulator.  Both loads run one own-chunk ahead instead: x of chunk c + 2 is requested while
             // chunk c is processed, its column index one chunk earlier still.
             int col_n2 = (pair + 2 < g.N) ? __ldg(g.xc_in + pair + 2) : 0;
-            if (pair < g.N) need(pair);
             float x_nxt = (row_ok && pair < g.N) ? xload(__ldg(g.xc_in + pair)) : 0.f;
             // chunk c = 3 k + a lives in accumulator a; the k-th completion of FULL_F[a] has parity k & 1.  The pair sees
             // only every other completion of a barrier, but the one before (chunk c - 3, the other pair's) is older
@@ -947,10 +932,7 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                 const uint32_t fcol = acc_a == 0 ? S::FINF0 : (acc_a == 1 ? S::FINF1 : S::FINF2);
                 float* mb = mbq + ((c >> 1) & 1) * 160;
                 const float x = x_nxt;
-                if (c + 2 < g.N) {
-                    need(c + 2);
-                    x_nxt = row_ok ? xload(col_n2) : 0.f;
-                }
+                if (c + 2 < g.N) x_nxt = row_ok ? xload(col_n2) : 0.f;
                 if (c + 4 < g.N) col_n2 = __ldg(g.xc_in + c + 4);
                 const int col_out = isA ? 0 : __ldg(g.xc_out + c);   // requested now, needed at the end of the chunk
                 const int bslot = c % S::BIAS_SLOTS;
@@ -1091,12 +1073,15 @@ __global__ void __launch_bounds__(TcCfg<H>::THREADS, 1) tc_conditioner_kernel(Tc
                         acc_ld += ld;
                         bad = bad || (y != y) || (ld != ld);
                     }
-                    if (publish) {                                  // chunk c of this quadrant is written: tell the publisher
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_pub + 8 * pair);
-                    }
                 }
                 if (dbg_me) t_fin += clock64() - t_mark;
+            }
+            if (!isA && publish) {                                  // every coordinate of this pair is written: release the
+                __threadfence();                                    // next step's warps of this lane quadrant
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(g.flags + (size_t)(step * g.tiles + tile) * 4 + q)
+                                 : "memory");
             }
             if (!isA) {                                             // the two B warps of a quadrant: fixed-order sum
                 if (pair == 1) mbq[0] = acc_ld;                     // pair 1's mailbox is idle now
@@ -1421,7 +1406,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
     }
     {   // columns read / written by the fused epilogue: density reads feature ft and writes (ft + D/2) % D (the roll,
         // coupling.py:100-101), sampling reads the rolled input (coupling.py:113-114) and writes ft
-        std::vector<int> xc((size_t)6 * f->N, -1);
+        std::vector<int> xc((size_t)4 * f->N, -1);
         for (int j = 0; j < f->N; ++j) {
             const int ft = d->transform_features[j], rolled = (ft + f->D / 2) % f->D;
             xc[j] = ft;
@@ -1429,16 +1414,6 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
             xc[2 * f->N + j] = rolled;
             xc[3 * f->N + j] = ft;
         }
-        // rows 4, 5 (layer-parallel launches): the chunk of the previous step that writes the column chunk c reads
-        bool deps_ok = true;
-        for (int dir = 0; dir < 2; ++dir)
-            for (int c = 0; c < f->N; ++c) {
-                const int col = xc[(size_t)(2 * dir) * f->N + c];
-                int j = 0;
-                while (j < f->N && xc[(size_t)(2 * dir + 1) * f->N + j] != col) ++j;
-                if (j == f->N) { deps_ok = false; j = 0; }
-                xc[(size_t)(4 + dir) * f->N + c] = j;
-            }
         if (int r = tc_upload(f, xc, &P->xcols)) { delete P; return r; }
         // Layer-parallel launches need the identity set to be closed under the roll by D/2 (then the conditioner inputs
         // of all layers follow from the unconditional splines alone) and disjoint from the transformed set.
@@ -1447,7 +1422,7 @@ int tc_pack(fs_flow* f, const fs_flow_desc* d) {
         bool closed = P->chn > 0 && f->D == 2 * f->N;
         for (int j = 0; j < f->N && closed; ++j)
             closed = is_id[(d->identity_features[j] + f->D / 2) % f->D] && !is_id[d->transform_features[j]];
-        P->lp_ok = closed && deps_ok;
+        P->lp_ok = closed;
     }
     {   // device copy of the per-layer pointer table (the buffers behind it are re-packed in place by fs_flow_update)
         void* dl = nullptr;
@@ -1540,7 +1515,6 @@ static int tc_launch(fs_flow* f, int layer, const float* A0, bool tiled, int row
     g.a0_stride = g.ld_stride = 0;
     g.buf0 = g.buf1 = nullptr;
     g.flags = nullptr;
-    g.xc_dep = nullptr;
     const int grid = (rows + 127) / 128;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);
@@ -1569,7 +1543,7 @@ bool tc_layer_parallel_ok(const fs_flow* f) {
     return f->tc && ((TcPack*)f->tc)->lp_ok && ((TcPack*)f->tc)->chn > 0 && f->K >= 2 && !getenv("FS_NO_LP");
 }
 
-size_t tc_lp_flag_ints(const fs_flow* f, int rows) { return (size_t)f->K * (size_t)((rows + 127) / 128) * 8; }
+size_t tc_lp_flag_ints(const fs_flow* f, int rows) { return (size_t)f->K * (size_t)((rows + 127) / 128) * 4; }
 
 // All K coupling layers of one pass in ONE launch of K x tiles CTAs (see TcArgs).  direction 1: density (layers
 // K-1 .. 0), 2: sampling (0 .. K-1).  A0: K row-tiled feature matrices a0_stride floats apart, in step order; buf0 holds
@@ -1619,7 +1593,6 @@ int tc_conditioner_spline_all(fs_flow* f, int direction, int rows, const float* 
     g.buf0 = buf0;
     g.buf1 = buf1;
     g.flags = flags;
-    g.xc_dep = P->xcols + (size_t)(direction == 2 ? 5 : 4) * f->N;
     const int grid = g.tiles * f->K;
     if (P->H == 256)
         tc_conditioner_kernel<256><<<grid, TcCfg<256>::THREADS, P->smem_bytes, s>>>(g);

@@ -310,6 +310,10 @@ class FlowPack:
                                                    _lib.stream_ptr(buf0.device)))
         return (buf1 if self.K & 1 else buf0), parts
 
+    def uses_layer_parallel(self, rows):
+        """True when log_prob / sample passes of `rows` rows run as one layer-parallel launch (fs_flow_uses_layer_parallel)."""
+        return bool(_lib.lib().fs_flow_uses_layer_parallel(self._h, int(rows), _PREC[self.resolved_precision()]))
+
     def check_nan(self):
         """Surfaces the device-side NaN flag like the reference's ValueError (utils/splines.py:176-183)."""
         if int(self._nan.item()):

@@ -205,9 +205,11 @@ int fs_flow_coupling(fs_flow* flow, int layer, int direction, const float* featu
                      float* logdet, int rows, int* nan_flag, void* stream);
 
 /* All K coupling layers of a pass in ONE launch of K x ceil(rows / 128) thread blocks (the schedule fs_flow_inverse /
- * fs_flow_forward use on the fused tensor path when the identity features stay identity features under the roll by D/2 -
- * every even-N configuration of the reference's drivers, SURVEY.md A.4-Q2: the conditioner inputs of all layers then
- * follow from the unconditional splines alone and only the spline chain of the transformed features is sequential).
+ * fs_flow_forward use on the fused tensor path when it pays - fs_flow_uses_layer_parallel - and the identity features
+ * stay identity features under the roll by D/2 - every even-N configuration of the reference's drivers, SURVEY.md
+ * A.4-Q2: the conditioner inputs of all layers then follow from the unconditional splines alone and only the spline
+ * chain of the transformed features is sequential: a step's thread block starts its spline chunks when the previous
+ * step of its row tile has written all of its coordinates).
  * features: K row-tiled feature matrices (FS_FEATURES_TILED layout) in step order - density (direction 1): layers
  * K-1 .. 0, sampling (2): 0 .. K-1 - fs_flow_tiled_features_bytes(rows, 2N) bytes apart; buf0 [rows, D]: input (only its
  * transformed columns are read); the steps alternate between buf0 and buf1, the last one writes buf[K & 1];
@@ -215,6 +217,10 @@ int fs_flow_coupling(fs_flow* flow, int layer, int direction, const float* featu
  * FS_ERR_UNSUPPORTED when the flow has no such path. */
 int fs_flow_coupling_all(fs_flow* flow, int direction, const float* features, float* buf0, float* buf1,
                          float* logdet_parts, int* scratch, int rows, int* nan_flag, void* stream);
+
+/* 1 when fs_flow_inverse / fs_flow_forward run a pass of `rows` rows at `precision` as one layer-parallel launch, 0 when
+ * they launch layer by layer (no such path for the flow, or one launch per layer already fills the GPU). */
+int fs_flow_uses_layer_parallel(const fs_flow* flow, int rows, int precision);
 
 /* Feature layout of the tensor path.  fs_flow_inverse / fs_flow_forward keep the periodic features of a chunk in
  * 128-row tiles of quads, element (row b, feature k) at [b / 128][k / 4][b % 128][k % 4], so that the kernel's
