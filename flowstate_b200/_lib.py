@@ -27,6 +27,14 @@ class FsRng(C.Structure):
                 ("idx_stride", C.c_int), ("u_stride", C.c_int), ("replay_cursor", C.c_void_p)]
 
 
+class FsTrainDesc(C.Structure):
+    _fields_ = [("K", C.c_int), ("N", C.c_int), ("H", C.c_int), ("n_blocks", C.c_int), ("nb", C.c_int),
+                ("bound", C.c_double), ("feature_scale", C.c_double), ("bn_eps", C.c_double),
+                ("bn_momentum", C.c_double), ("transform_features", C.POINTER(C.c_int)),
+                ("identity_features", C.POINTER(C.c_int)), ("params", C.POINTER(C.c_void_p)),
+                ("grads", C.POINTER(C.c_void_p)), ("bn_running", C.POINTER(C.c_void_p))]
+
+
 class FsLayerParams(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("init_w", "init_b", "bn_w", "bn_b", "bn_mean", "bn_var", "lin_w",
                                           "lin_b", "final_w", "final_b", "un_w", "un_h", "un_d")]
@@ -75,6 +83,9 @@ _PROTOS = {
     "fs_flow_coupling": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_coupling_all": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_uses_layer_parallel": (C.c_int, [_P, C.c_int, C.c_int]),
+    "fs_train_create": (C.c_int, [_P, _P]),
+    "fs_train_destroy": (None, [_P]),
+    "fs_train_forward_kld": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "fs_flow_tiled_features_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "fs_flow_tile_features": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "fs_flow_inverse": (C.c_int, [_P, _P, C.c_int, C.c_double, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, _P]),

@@ -182,10 +182,12 @@ struct Pk2Consts {
     unsigned long long invLx, invLy, nLx, nLy, magic, nmagic;
 };
 
-// two pairs: X = (dx_a, dx_c), Y = (dy_a, dy_c) before the minimum image
+// two pairs: X = (dx_a, dx_c), Y = (dy_a, dy_c) before the minimum image.  The FP32 pipe is what bounds the kernel
+// (ncu: 68 % busy, every packed instruction holds it for two cycles), so whatever can run elsewhere does: the cut-off
+// is a select on r^-6 and the in-range count an integer add (ALU pipe) instead of a 0/1 factor and a packed add -
+// 14 packed instructions (7 per axis pair) per two pairs instead of 16.
 __device__ __forceinline__ void pair_sums_x2(unsigned long long X, unsigned long long Y, const Pk2Consts& C, float rc2,
-                                             unsigned long long& a12, unsigned long long& a6,
-                                             unsigned long long& cnt, float& r2min) {
+                                             unsigned long long& a12, unsigned long long& a6, int& cnt, float& r2min) {
     unsigned long long t = add2f(add2f(mul2f(X, C.invLx), C.magic), C.nmagic);
     X = fma2f(t, C.nLx, X);
     t = add2f(add2f(mul2f(Y, C.invLy), C.magic), C.nmagic);
@@ -199,11 +201,22 @@ __device__ __forceinline__ void pair_sums_x2(unsigned long long X, unsigned long
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ic) : "f"(rc));
     const unsigned long long inv = pk2f(ia, ic);
     const unsigned long long s6 = mul2f(mul2f(inv, inv), inv);
-    const unsigned long long m = pk2f(ra <= rc2 ? 1.0f : 0.0f, rc <= rc2 ? 1.0f : 0.0f);
-    const unsigned long long s6m = mul2f(s6, m);
+    float sa, sc, ma, mc;
+    upk2f(s6, sa, sc);
+    // select + predicated integer increments (written out: the compiler's own form is an add and a predicated move
+    // per pair, and the move runs on the FP32 pipe)
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.le.f32 p, %5, %7;\n\t"
+        "setp.le.f32 q, %6, %7;\n\t"
+        "selp.f32 %0, %3, 0f00000000, p;\n\t"
+        "selp.f32 %1, %4, 0f00000000, q;\n\t"
+        "@p add.s32 %2, %2, 1;\n\t"
+        "@q add.s32 %2, %2, 1;\n\t}"
+        : "=f"(ma), "=f"(mc), "+r"(cnt)
+        : "f"(sa), "f"(sc), "f"(ra), "f"(rc), "f"(rc2));
+    const unsigned long long s6m = pk2f(ma, mc);
     a12 = fma2f(s6m, s6, a12);
     a6 = add2f(a6, s6m);
-    cnt = add2f(cnt, m);
 }
 
 template <int G>
@@ -248,7 +261,8 @@ __global__ void __launch_bounds__(256) energy_total_kernel_v2(const float* __res
         for (int i = t; i < N; i += G) {
             const float pix = X0[i], piy = Y0[i];
             const unsigned long long PX = pk2f(pix, pix), PY = pk2f(piy, piy);
-            unsigned long long b12 = 0ull, b6 = 0ull, bc = 0ull, c12 = 0ull, c6 = 0ull, cc = 0ull;   // +0.0f pairs
+            unsigned long long b12 = 0ull, b6 = 0ull, c12 = 0ull, c6 = 0ull;   // +0.0f pairs
+            int bc = 0, cc = 0;
             // partners j = i+1 .. i+half; (x[j], x[j+1]) is an aligned pair in X0 for even j, in X1 - 1 for odd j
             const bool odd = ((i + 1) & 1) != 0;
             const float* bx = odd ? X1 - 1 : X0;
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(256) energy_total_kernel_v2(const float* __res
             float s12, s6, sc, u, v;
             upk2f(add2f(b12, c12), u, v); s12 = u + v;
             upk2f(add2f(b6, c6), u, v); s6 = u + v;
-            upk2f(add2f(bc, cc), u, v); sc = u + v;
+            sc = (float)(bc + cc);
             if (k <= half)
                 pair_sums<false>(pix - X0[i + k], piy - Y0[i + k], P, hx, hy, s12, s6, sc, r2min);
             if ((N & 1) == 0 && i < N / 2)
@@ -390,10 +404,12 @@ extern "C" int fs_energy_total(const float* pos, int B, int N, float Lx, float L
     if (B == 0) return FS_OK;
     fs::PotDev P = fs::make_pot(pot, Lx, Ly);
     cudaStream_t s = (cudaStream_t)stream;
-    // group size: about half a particle per thread keeps the cyclic loops long enough
+    // group size
     static int g_forced = -1;                            // tuning knob (32 / 64 / 128 / 256)
     if (g_forced < 0) { const char* e = getenv("FS_ENERGY_G"); g_forced = e ? atoi(e) : 0; }
-    int G = N <= 48 ? 32 : (N <= 96 ? 64 : (N <= 192 ? 128 : 256));
+    // (measured, scripts/energy_sweep.py with FS_ENERGY_G: about four particles per thread is best - several
+    // configurations per block hide each other's load / reduction phases, and the smaller groups need fewer registers)
+    int G = N <= 160 ? 32 : (N <= 320 ? 64 : (N <= 768 ? 128 : 256));
     if (g_forced) G = g_forced;
     if (G == 32) return fs::launch_total<32>(pos, B, N, P, E, W, overlap, s);
     if (G == 64) return fs::launch_total<64>(pos, B, N, P, E, W, overlap, s);

@@ -7,8 +7,11 @@ The reference trains with plain eager autograd, one optimizer step per minibatch
     if loss is finite: loss.backward(); optimizer.step()
 
 Here the same step runs with
-  * the forward + backward pass of the forward-KL loss captured once per batch shape in a CUDA graph and replayed
-    (the pass is ~5 k small kernels for the K = 23 flow: launch-bound when issued eagerly);
+  * the forward-KL loss and all its gradients from the hand-written training kernels (fs_train_forward_kld,
+    drivers/_train_native.py: ~36 launches for the whole flow, gradients written straight into the flat bucket) whenever
+    the flow has that path (`native`); otherwise
+  * the forward + backward pass captured once per batch shape in a CUDA graph and replayed
+    (the autograd pass is ~5 k small kernels for the K = 23 flow: launch-bound when issued eagerly);
   * all gradients living in ONE flat float32 buffer (every p.grad is a view into it), so the multi-GPU gradient
     all-reduce is a single NCCL call on that buffer (SUM, then divided by the world size) with no flatten / unflatten
     copies - the hook point is between backward and optimizer.step (main_algorithm_2.py:450-451);
@@ -26,6 +29,8 @@ Adam skips them exactly like the reference's.
 import torch
 import torch.distributed as dist
 
+from . import _train_native
+
 
 def _world():
     if dist.is_available() and dist.is_initialized():
@@ -34,7 +39,8 @@ def _world():
 
 
 class FlowTrainer:
-    def __init__(self, model, lr, weight_decay=0.0, alpha=1.0, reverse_batch=256, use_graph=True, sync_bn=False):
+    def __init__(self, model, lr, weight_decay=0.0, alpha=1.0, reverse_batch=256, use_graph=True, sync_bn=False,
+                 native=True):
         self.sync_bn = bool(sync_bn) and _world() > 1
         if self.sync_bn:                                       # children are replaced in place; parameters are kept
             torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
@@ -44,6 +50,12 @@ class FlowTrainer:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.device = self.params[0].device
         self.use_graph = bool(use_graph) and self.device.type == "cuda" and alpha >= 1.0
+        # hand-written forward + backward (pure forward-KL steps on flows that have the path)
+        self.use_native = bool(native) and self.device.type == "cuda" and alpha >= 1.0 and not self.sync_bn \
+            and _train_native.supported(model)
+        self.native = None
+        self._native_checked = False
+        self._opt_kw = None
         self.flat = None                 # flat gradient bucket
         self.trainable = None            # parameters that receive gradients
         self.graphs = {}                 # batch rows -> (graph, static input, static loss)
@@ -81,17 +93,40 @@ class FlowTrainer:
             off += n
 
     def fresh_optimizer(self):
-        """A new Adam (zero moments, step 0) over every parameter, as the reference creates one per training cycle."""
+        """A new Adam (zero moments, step 0) over every parameter, as the reference creates one per training cycle
+        (main_algorithm_2.py:440).  After the first cycle the existing optimizer's state is zeroed in place - the same
+        state as a newly built one, in three multi-tensor launches instead of ~1.5 k allocations and fills."""
+        self._native_checked = False
+        if self.opt is not None and self._opt_kw == (self.lr, self.weight_decay):
+            bufs = [v for st in self.opt.state.values() for v in st.values() if torch.is_tensor(v)]
+            if bufs:
+                by_kind = {}
+                for v in bufs:
+                    by_kind.setdefault((v.dtype, v.device), []).append(v)
+                for vs in by_kind.values():
+                    torch._foreach_zero_(vs)
+            return self.opt
         kw = dict(lr=self.lr, weight_decay=self.weight_decay)
         if self.device.type == "cuda":
             kw["fused"] = True
         self.opt = torch.optim.Adam(self.params, **kw)
+        self._opt_kw = (self.lr, self.weight_decay)
         return self.opt
 
     # -- one minibatch ----------------------------------------------------------
     def _forward_backward(self, batch):
         """Fills the flat gradient bucket, returns the (device) loss."""
         rows = batch.shape[0]
+        if self.use_native and self.model.training:
+            if self.native is None or (not self._native_checked and not self.native.pointers_valid()):
+                try:
+                    self.native = _train_native.NativeForwardKL(self.model)
+                except _train_native._lib.FlowStateError:      # FS_ERR_UNSUPPORTED (e.g. odd N): autograd path
+                    self.use_native = False
+                    self.native = None
+            if self.native is not None:
+                self._native_checked = True                    # re-validated once per optimizer (training cycle)
+                return self.native.step(batch)[0]
         if not self.use_graph:
             self.flat.zero_()
             loss = self._loss(batch)

@@ -274,6 +274,40 @@ int fs_spline_train_bwd(const float* x, const float* theta, long long theta_row_
                         double bound, double scale, const float* grad_y, const float* grad_logdet,
                         float* grad_x, float* grad_theta, void* stream);
 
+/* ---- one forward-KL training step of the whole flow ------------------------------------------- */
+
+/* NormalizingFlow.forward_kld(x) + loss.backward() (NF/normflows/core.py:88-108; the minibatch step of
+ * hybrid_NF_MCMC/main_algorithm_1.py:297-320 and main_algorithm_2.py:437-452) for a flow of K
+ * CircularCoupledRationalQuadraticSpline layers (flows/neural_spline/wrapper.py:16-93, coupling.py:86-102) whose
+ * conditioner is the ResidualNet of nets/resnet.py:7-104 with BatchNorm1d in training mode and dropout 0:
+ *     loss = -mean_rows( sum_layers log|det J| ),  gradients of every trainable tensor WRITTEN (not accumulated).
+ * The descriptor holds HOST arrays of DEVICE pointers.  Per layer (flow index 0 .. K-1) PER = 2 + 8 n_blocks + 5 tensors:
+ *     initial_layer.weight [H, 2N], .bias [H],
+ *     per block: batch_norm_layers.0.weight, .bias [H], linear_layers.0.weight [H, H], .bias [H],
+ *                batch_norm_layers.1.weight, .bias,     linear_layers.1.weight,       .bias,
+ *     final_layer.weight [N (3 nb + 1), H], .bias,
+ *     unconditional_transform.unnormalized_widths [N, nb], .unnormalized_heights [N, nb], .unnormalized_derivatives [N, nb + 1];
+ * grads: the same order (e.g. views of one flat bucket); bn_running: per layer 4 n_blocks tensors
+ * (block b: batch_norm_layers.0.running_mean, .running_var, batch_norm_layers.1.running_mean, .running_var),
+ * updated in place with `bn_momentum` and the unbiased batch variance when update_running != 0 (num_batches_tracked is
+ * the caller's).  feature_scale: PeriodicFeaturesElementwise.scale (utils/nn.py:65-137).  The pointers must stay valid
+ * (optimizers update in place).  FS_ERR_UNSUPPORTED when the identity features are not closed under the roll by D/2
+ * (odd N) or N (3 nb + 1) is not a multiple of 4: the caller keeps the autograd path. */
+typedef struct fs_train fs_train;
+typedef struct fs_train_desc {
+    int K, N, H, n_blocks, nb;
+    double bound, feature_scale, bn_eps, bn_momentum;
+    const int* transform_features; /* host [N] */
+    const int* identity_features;  /* host [N] */
+    float* const* params;          /* host [K * PER] */
+    float* const* grads;           /* host [K * PER] */
+    float* const* bn_running;      /* host [K * 4 n_blocks] */
+} fs_train_desc;
+int fs_train_create(const fs_train_desc* desc, fs_train** out);
+void fs_train_destroy(fs_train* t);
+/* x [B, 2N] (centred coordinates), B >= 2; loss: one float on the device.  Repeatable bit for bit. */
+int fs_train_forward_kld(fs_train* t, const float* x, int B, float* loss, int update_running, void* stream);
+
 /* ---- affine (RealNVP) coupling and periodic shifts ----------------------------------------- */
 
 /* MaskedAffineFlow.forward / inverse (NF/normflows/flows/affine/coupling.py:163-229) and the element-wise half of

@@ -96,9 +96,96 @@ def test_graph_trainer_matches_eager_steps():
             for p in model.parameters():
                 p.add_(0.05 * torch.randn_like(p))
         model = model.cuda().train()
-        tr = FlowTrainer(model, 1e-3, 1e-4, 1.0, 48, use_graph=graph)
+        tr = FlowTrainer(model, 1e-3, 1e-4, 1.0, 48, use_graph=graph, native=False)
         losses = [tr.step(x) for x in xs]
         out[graph] = (losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone())
     la, lb = out[False][0], out[True][0]
     assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(la, lb)), (la, lb)
     assert (out[False][1] - out[True][1]).abs().max().item() < 1e-4
+
+
+def _perturbed(n, K, blocks, H, nb, bound, seed, sigma=0.05):
+    torch.manual_seed(seed)
+    model = _build(n, K, blocks, H, nb, bound)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(sigma * torch.randn_like(p))
+        for name, buf in model.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(0.1 * torch.randn_like(buf))
+            elif name.endswith("running_var"):
+                buf.copy_(0.5 + torch.rand_like(buf))
+    return model.cuda().train()
+
+
+@pytest.mark.parametrize("n,K,blocks,H,nb,B", [(8, 3, 2, 32, 8, 100), (64, 4, 2, 128, 15, 256), (32, 2, 3, 64, 32, 37)])
+def test_native_training_step_matches_autograd(n, K, blocks, H, nb, B):
+    """fs_train_forward_kld (the whole forward-KL step in hand-written kernels) against loss.backward() through the
+    module tree: loss, the gradient of every parameter, BatchNorm running statistics and counters; and bit-identical
+    when repeated.  Tolerance: 2e-4 of the largest gradient entry of a tensor's group (float32, different summation
+    order; the autograd path it is compared with is pinned on the reference in tests/test_host_cpu.py)."""
+    from flowstate_b200.drivers import _train_native as tn
+    bound = float(np.float32(np.sqrt(n / 0.3))) / 2
+    model = _perturbed(n, K, blocks, H, nb, bound, seed=5)
+    assert tn.supported(model)
+    x = ((torch.rand(B, 2 * n, generator=torch.Generator().manual_seed(2)) * 2 - 1) * bound).cuda()
+    x[0, 0] = 1.2 * bound                 # a coordinate outside the box: identity, zero log-det
+    bufs0 = {k: v.clone() for k, v in model.named_buffers()}
+    model.zero_grad()
+    loss_ref = model.forward_kld(x)
+    loss_ref.backward()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    bufs_ref = {k: v.clone() for k, v in model.named_buffers()}
+    with torch.no_grad():
+        for k, v in model.named_buffers():
+            v.copy_(bufs0[k])
+    for p in model.parameters():
+        if p.grad is not None:
+            p.grad = torch.full_like(p.grad, 7.0)          # the engine writes, it does not accumulate
+    eng = tn.NativeForwardKL(model)
+    loss = eng.step(x).clone()
+    got = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    loss_ref = loss_ref.detach()
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * max(1.0, abs(float(loss_ref))), (float(loss), float(loss_ref))
+    assert set(got) == set(ref)
+    worst = 0.0
+    top = max(v.abs().max().item() for v in ref.values())
+    for k in ref:
+        # (a Linear bias in front of a BatchNorm has a gradient of exactly zero up to rounding: judged on the absolute
+        # difference, like every tensor whose gradient is below 1e-3 of the largest one)
+        sc = max(ref[k].abs().max().item(), 1e-3 * top)
+        err = (got[k] - ref[k]).abs().max().item() / sc
+        worst = max(worst, err)
+        assert err < 2e-4, (k, err, sc)
+    for k, v in model.named_buffers():
+        if v.dtype.is_floating_point:
+            assert (v - bufs_ref[k]).abs().max().item() < 1e-5 * max(1.0, bufs_ref[k].abs().max().item()), k
+        else:
+            assert torch.equal(v, bufs_ref[k]), k
+    print("native step n=%d K=%d H=%d: loss %.6f vs %.6f, worst relative gradient error %.2e" %
+          (n, K, H, float(loss), float(loss_ref), worst))
+    eng.step(x, update_running=False)
+    again = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    assert all(torch.equal(again[k], got[k]) for k in got)
+
+
+def test_native_trainer_matches_autograd_trainer():
+    from flowstate_b200.drivers.training import FlowTrainer
+    n, K, blocks, H, nb, bound = 8, 3, 2, 32, 8, 6.0
+    xs = [((torch.rand(48, 2 * n, generator=torch.Generator().manual_seed(20 + i)) * 2 - 1) * bound).cuda()
+          for i in range(4)]
+    out = {}
+    for native in (False, True):
+        model = _perturbed(n, K, blocks, H, nb, bound, seed=1)
+        tr = FlowTrainer(model, 1e-3, 1e-4, 1.0, 48, use_graph=False, native=native)
+        losses = [tr.step(x) for x in xs]
+        assert (tr.native is not None) == native
+        out[native] = (losses, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone(),
+                       torch.cat([b.detach().double().reshape(-1) for b in model.buffers()]).clone())
+    la, lb = out[False][0], out[True][0]
+    assert all(abs(a - b) < 1e-4 * max(1.0, abs(a)) for a, b in zip(la, lb)), (la, lb)
+    assert (out[False][1] - out[True][1]).abs().max().item() < 2e-4
+    assert (out[False][2] - out[True][2]).abs().max().item() < 1e-4
+    # eval-mode sampling after the native steps sees the trained weights (device re-pack)
+    model.eval()
+    assert torch.isfinite(model.log_prob(xs[0])).all()

@@ -360,3 +360,30 @@ def test_initialisers_match_reference_golden(golden_dir):
     assert pos.shape == (5, 3, 2) and pos.dtype == np.float32
     assert np.array_equal(pos[0], left.astype(np.float32)) and np.array_equal(pos[1], right.astype(np.float32))
     assert np.array_equal(pos[2], pos[0]) and abs(box.box_size_x - 10.0) < 1e-12
+
+
+def test_trainer_optimizer_reset_equals_a_new_adam():
+    """FlowTrainer.fresh_optimizer zeroes the existing Adam state in place from the second cycle on; the updates that
+    follow must be those of a newly built optimizer (main_algorithm_2.py:440 builds one per cycle)."""
+    import flowstate_b200.normflows as NF
+    from flowstate_b200.drivers.training import FlowTrainer
+    n, bound = 4, 3.0
+    xs = [(torch.rand(16, 2 * n, generator=torch.Generator().manual_seed(i)) * 2 - 1) * bound for i in range(4)]
+    out = []
+    for reuse in (True, False):
+        torch.manual_seed(0)
+        base = NF.Energy.UniformParticle(n, 2, bound)
+        model = NF.NormalizingFlow(base, [NF.flows.CircularCoupledRationalQuadraticSpline(
+            2 * n, 1, 16, range(2 * n), num_bins=4, tail_bound=bound) for _ in range(2)]).train()
+        tr = FlowTrainer(model, 1e-2, 1e-4, 1.0, 16, use_graph=False)
+        tr.fresh_optimizer()
+        tr.step(xs[0]); tr.step(xs[1])
+        if reuse:
+            first = tr.opt
+            assert tr.fresh_optimizer() is first              # same object, state zeroed
+        else:
+            tr.opt = None
+            tr.fresh_optimizer()
+        tr.step(xs[2]); tr.step(xs[3])
+        out.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
+    assert torch.equal(out[0], out[1])
