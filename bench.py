@@ -434,6 +434,7 @@ class Harness:
         # one proposal energy and `local` local moves per chain.
         self.side = torch.cuda.Stream(device=dev)
         self.pending = {}
+        self.logq_from_sample = False      # True: the reported VARIANT (details.variant_logq_from_sampling_pass)
         self.trainer = None
         if w.get("train"):
             from flowstate_b200.drivers.training import FlowTrainer
@@ -449,11 +450,18 @@ class Harness:
             else:
                 z = torch.empty(self.B, 2 * self.n, dtype=torch.float32, device=self.dev)
                 z.copy_(z_host, non_blocking=True)
-            cfg = (self.model.forward(z).reshape(self.B, self.n, 2) + self.half32).contiguous()
+            lq_new = None
+            if self.logq_from_sample:                  # variant: log q(proposal) from the sampling pass itself
+                x, ld = self.model.forward_and_log_det(z)
+                lq_new = self.model.q0.log_prob(z) - ld
+                lq_new.record_stream(main)
+            else:
+                x = self.model.forward(z)
+            cfg = (x.reshape(self.B, self.n, 2) + self.half32).contiguous()
             ev = torch.cuda.Event()
             ev.record(self.side)
         cfg.record_stream(main)
-        self.pending["cfg"], self.pending["ev"] = cfg, ev
+        self.pending["cfg"], self.pending["ev"], self.pending["lq_new"] = cfg, ev, lq_new
 
     def train_cycle(self, z_host=None, timers=None):
         """One Algorithm-2 cycle (main_algorithm_2.py:393-548)."""
@@ -501,11 +509,11 @@ class Harness:
             return self.train_cycle(z_host)
         if "cfg" not in self.pending:
             self.launch_proposals(z_host)
-        cfg, ev = self.pending.pop("cfg"), self.pending.pop("ev")
+        cfg, ev, lq_new = self.pending.pop("cfg"), self.pending.pop("ev"), self.pending.pop("lq_new")
         self.launch_proposals(z_host)                  # next round's proposals, off the critical path
         self.eng.particle_displacement(self.w["local"])
         torch.cuda.current_stream(self.dev).wait_event(ev)
-        return self.eng.nf_big_move(cfg)
+        return self.eng.nf_big_move(cfg, logq_new=lq_new)
 
     # -- parity sample (checked by the oracle in the cpu_baseline subprocess) ---
     def dump_parity_sample(self, path, chains=6, steps=48, rows=6):
@@ -751,7 +759,9 @@ class Harness:
         u = torch.rand(B, dtype=torch.float64, device=dev)
         acc0 = int(eng.accepted.sum().item())
         lqo, lqn = lq[:B].contiguous(), lq[B:].contiguous()
-        timed("accept_global_ms", lambda: eng.nf_big_move(cfg, u=u, logq=(lqo, lqn)), reps=5)
+        timed("global_move_fused_ms", lambda: eng.nf_big_move(cfg, u=u, logq=(lqo, lqn)), reps=5)
+        # the stand-alone acceptance kernel on the same inputs (its HBM figure; the round runs the fused kernel above)
+        timed("accept_global_ms", lambda: eng.accept_global(cfg, E_new, W_new, lqo, lqn, u=u), reps=20)
         extra = {}
         if fp32:
             sw = sweep_flops_per_step(n) * B * w["local"] / (out["local_sweep_ms"] * 1e-3) / 1e12
@@ -765,13 +775,20 @@ class Harness:
         if peaks:
             # accept kernel: 8N bytes of proposal read + 8N written per accepted chain + ~40 bytes of scalars per chain
             # (the phase above re-ran the move 6 times on the same inputs: use its acceptance count)
-            frac_acc = (int(eng.accepted.sum().item()) - acc0) / (6.0 * B)
+            frac_acc = (int(eng.accepted.sum().item()) - acc0) / (27.0 * B)
             bytes_ = B * (8.0 * n * (1 + frac_acc) + 40)
             gbs = bytes_ / (out["accept_global_ms"] * 1e-3) / 1e9
             extra["accept_global"] = {"bound": "hbm", "kernel": "accept_global_kernel", "achieved": gbs,
                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                      "note": "launch-latency-bound at this size (%.1f KB in %.1f us)"
+                                      "note": "stand-alone fs_accept_global, %.1f KB in %.1f us (a launch is ~2 us: "
+                                              "latency-bound at this size); the round runs fs_accept_global_fused"
                                               % (bytes_ / 1e3, out["accept_global_ms"] * 1e3)}
+            if fp32:
+                gm = energy_flops(B, n) / (out["global_move_fused_ms"] * 1e-3) / 1e12
+                extra["global_move_fused"] = {"bound": "fp32", "kernel": "energy_total_kernel_v2<.., ACCEPT> (fs_accept_global_fused)",
+                                              "achieved": gm, "peak": fp32["peak"], "unit": "TFLOP/s",
+                                              "frac": gm / fp32["peak"],
+                                              "peak_source": "scripts/fp32_peak.cu measured in this run"}
         return out, extra
 
 
@@ -862,6 +879,22 @@ def main():
     fp32 = fp32_peak(local_rank) if rank == 0 else None
     roof = h.conditioner_roofline(peaks, peak_src)
     phases, extra = h.phases(fp32, peaks)
+    variant = None
+    if rank == 0 and world == 1 and h.trainer is None and not args.no_secondary:
+        # Not the headline: the same round with log q(proposal) taken from the sampling pass that produced the proposal
+        # (NormalizingFlow.sample_with_log_prob) instead of a second trip through the density pass - a third of the
+        # conditioner work of a round.  The headline keeps the reference's order (monte_carlo.py:262).
+        h.pending.clear()
+        h.logq_from_sample = True
+        v_steps = 12
+        ms_v, l_v = h.time_device(v_steps, 4)
+        h.logq_from_sample = False
+        h.pending.clear()
+        variant = {"value": w["chains"] * (w["local"] + 1) * v_steps / (ms_v * 1e-3), "unit": "chain-steps/s",
+                   "ms_per_step": ms_v / v_steps, "steps": v_steps, "gpu_launches": l_v,
+                   "note": "log q(new) = log q0(z) - log-det of the sampling pass; parity: "
+                           "tests/test_gpu_flow.py::test_sampling_pass_log_prob_equals_inverse_pass, "
+                           "tests/test_gpu_global.py::test_global_move_with_sampling_pass_log_density"}
 
     secondary = {}
     if rank == 0 and world == 1 and not args.no_secondary:
@@ -913,6 +946,7 @@ def main():
                     "pipelining": "proposals of round r+1 sampled on a side stream during round r",
                     "weight_broadcast_bytes": h.bcast_bytes,
                     "timed_region_ms": ms_total,
+                    "variant_logq_from_sampling_pass": variant,
                     "step_ms_min_median_max": [min(h.step_ms), sorted(h.step_ms)[len(h.step_ms) // 2], max(h.step_ms)]},
         "nf_proposals_per_s": world * B * args.steps / (ms_total * 1e-3),
         "gpu_launches": launches, "clocks": clk, "phases_ms": phases,

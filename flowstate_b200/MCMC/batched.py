@@ -90,6 +90,8 @@ class BatchedMonteCarlo:
             raise ValueError("rng must be 'pcg64', 'philox' or 'philox_ref'")
         self.nf_model = None
         self.launches = 0          # kernels launched through this object (bench bookkeeping)
+        self.fused_accept = True   # nf_big_move: proposal energy + acceptance + update in one kernel
+        self.proposal_energy = None
         self.refresh_energy()
 
     # -- plumbing ---------------------------------------------------------
@@ -174,21 +176,29 @@ class BatchedMonteCarlo:
         """MC-box -> flow coordinates, float64 subtraction stored float32 (monte_carlo.py:251-258)."""
         return (pos.double() - self.half_width).float().reshape(pos.shape[0], -1)
 
-    def nf_big_move(self, configs=None, u=None, logq=None):
+    def nf_big_move(self, configs=None, u=None, logq=None, logq_new=None):
         """One NF-proposed global move per chain (monte_carlo.py:235-303).
 
         configs: (B, N, 2) float32 CUDA tensor in MC-box coordinates; None draws
                  `nf_model.sample(B) + half_width` (main_algorithm_2.py:479-482).
         u:       optional float64 [B] uniforms (replay); default draws from the chain RNG.
         logq:    optional (logq_old, logq_new) float32 tensors to skip the flow.
+        logq_new: optional float32 [B] log q of the proposals when the caller already holds it (the sampling pass that
+                 produced them yields it: NormalizingFlow.sample_with_log_prob); only the chains' current states then go
+                 through the density pass.  The reference evaluates log_prob on the proposals again
+                 (monte_carlo.py:262) - the default here too.
         Returns the uint8 accept mask [B]."""
         B, dev = self.B, self.device
         if configs is None:
             z = self.nf_model.sample(B)
             configs = (z.reshape(B, self.num_particles, 2) + np.float32(self.half_width)).contiguous()
         configs = _lib.require_cuda(configs, "configs")
-        E_new, W_new, _ = self.total_energy_virial(configs)
-        if logq is None:
+        if configs.dtype != torch.float32 or not configs.is_contiguous():
+            raise _lib.FlowStateError("flowstate_b200: configurations must be contiguous float32")
+        if logq is None and logq_new is not None:
+            lq_old = self.nf_model.log_prob(self.centred(self.pos))
+            lq_new = _lib.require_cuda(logq_new, "logq_new").float().contiguous()
+        elif logq is None:
             both = torch.cat([self.centred(self.pos), self.centred(configs)], dim=0)
             lq = self.nf_model.log_prob(both)
             lq_old, lq_new = lq[:B].contiguous(), lq[B:].contiguous()
@@ -198,6 +208,30 @@ class BatchedMonteCarlo:
         rng = self._rng_struct()
         if u is not None:
             u = _lib.require_cuda(u, "u")
+        if self.fused_accept:
+            # energy of the proposal + acceptance rule + masked update in one kernel (fs_accept_global_fused)
+            E_new = torch.empty(B, dtype=torch.float32, device=dev)
+            W_new = torch.empty(B, dtype=torch.float32, device=dev)
+            Lx, Ly = self._L()
+            _lib.check(_lib.lib().fs_accept_global_fused(
+                _lib.ptr(self.pos), _lib.ptr(configs), _lib.ptr(self.E), _lib.ptr(self.W), _lib.ptr(E_new),
+                _lib.ptr(W_new), _lib.ptr(lq_old), _lib.ptr(lq_new), _lib.ptr(u), C.byref(rng), float(self.beta),
+                _lib.ptr(self.attempts), _lib.ptr(self.accepted), _lib.ptr(mask), B, self.num_particles,
+                Lx, Ly, self._pot, _lib.stream_ptr(dev)))
+            self.launches += 1
+        else:
+            E_new, W_new, _ = self.total_energy_virial(configs)
+            self.accept_global(configs, E_new, W_new, lq_old, lq_new, u=u, mask=mask)
+        self.proposal_energy = E_new
+        return mask
+
+    def accept_global(self, configs, E_new, W_new, lq_old, lq_new, u=None, mask=None):
+        """Steps 3-5 of nf_big_move alone (fs_accept_global): acceptance rule on given proposal energies and flow
+        log-densities, masked in-place update.  Returns the uint8 accept mask [B]."""
+        B, dev = self.B, self.device
+        if mask is None:
+            mask = torch.empty(B, dtype=torch.uint8, device=dev)
+        rng = self._rng_struct()
         _lib.check(_lib.lib().fs_accept_global(
             _lib.ptr(self.pos), _lib.ptr(configs), _lib.ptr(self.E), _lib.ptr(self.W), _lib.ptr(E_new),
             _lib.ptr(W_new), _lib.ptr(lq_old), _lib.ptr(lq_new), _lib.ptr(u), C.byref(rng), float(self.beta),

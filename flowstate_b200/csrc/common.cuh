@@ -120,12 +120,6 @@ __device__ __forceinline__ float well_term(float x, float y, int wi, const PotDe
     return P.V0[wi] / (1.0f + expf(a2));
 }
 
-__device__ __forceinline__ float wells(float x, float y, const PotDev& P) {
-    float v = 0.f;
-    if (P.num_wells >= 1) v += well_term(x, y, 0, P);
-    if (P.num_wells == 2) v += well_term(x, y, 1, P);
-    return v;
-}
 
 // The same term for the throughput sweep: parameters picked by selects (a dynamically indexed kernel parameter lives
 // in local memory), and on the wall the float64 geometry reuses the float32 image shift (no float64 division) when the
@@ -156,6 +150,16 @@ __device__ __forceinline__ float well_term_sel(float x, float y, int wi, const P
     if (rf > 0.0f) r = (double)rf + (r2 - (double)rf * (double)rf) * (double)(0.5f / rf);
     const float a2 = (float)(P.k2d * (r - P.r0d));
     return v0 / (1.0f + expf(a2));
+}
+
+// Sum over the wells (potential.py:95-112).  well_term_sel: same value as well_term (the float32 image shift equals
+// rint(dx / L) whenever the pre-test lets a particle through in a box wide enough - well_shift_ok), no float64
+// division on the wall.
+__device__ __forceinline__ float wells(float x, float y, const PotDev& P) {
+    float v = 0.f;
+    if (P.num_wells >= 1) v += well_term_sel(x, y, 0, P);
+    if (P.num_wells == 2) v += well_term_sel(x, y, 1, P);
+    return v;
 }
 
 // numpy float32 floor-mod (npy_divmodf), simulation_box.py:23-26 on a float32 state.

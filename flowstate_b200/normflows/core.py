@@ -115,6 +115,16 @@ class NormalizingFlow(nn.Module):
         z = self.q0(num_samples)
         return self.forward(z)
 
+    def sample_with_log_prob(self, num_samples=1):
+        """(x, log q(x)) from ONE sampling pass: x = f(z), log q(x) = log q0(z) - log|det J_f(z)| - what upstream
+        normflows' sample() returns (NF/normflows/core.py:178-196 forms log_q the same way; the fork's sample() keeps
+        x only).  MonteCarlo.nf_big_move can take it as the proposal's log-density instead of
+        running the proposal through the inverse pass again (logq_new=, MCMC/batched.py); the two values differ by the
+        round-off of inverting the flow (tests/test_gpu_flow.py::test_sampling_pass_log_prob_equals_inverse_pass)."""
+        z = self.q0(num_samples)
+        x, log_det = self.forward_and_log_det(z)
+        return x, self.q0.log_prob(z) - log_det
+
     def log_prob(self, x):
         if self._fusable() and hasattr(self.q0, "bound"):
             return self._cuda_pack().inverse(x, want_logq=True)[2]

@@ -129,6 +129,20 @@ int fs_accept_global(float* pos, const float* prop, double* E, double* W,
                      double beta, long long* attempts, long long* accepted,
                      unsigned char* accept_mask, int B, int N, void* stream);
 
+/* The whole tail of MonteCarlo.nf_big_move in ONE kernel (MCMC/monte_carlo.py:243-303): the energy and virial of the
+ * proposal (calculate_total_energy_virial, MCMC/energy_calculator.py:121-203, what fs_energy_total computes), the
+ * acceptance rule of fs_accept_global on it and the masked in-place update - the proposal is staged in shared memory
+ * once for its O(N^2) pair walk and an accepted one is written to `pos` from there.  E_new / W_new [B] (required)
+ * receive the proposals' energies and virials (inf on hard-core overlap -> the move is rejected).  `prop` must not
+ * alias `pos`.  Tiles beyond the packed kernel's shared-memory budget run as fs_energy_total + fs_accept_global. */
+int fs_accept_global_fused(float* pos, const float* prop, double* E, double* W,
+                           float* E_new, float* W_new,
+                           const float* logq_old, const float* logq_new,
+                           const double* u, const fs_rng* rng /*host, may be NULL if u*/,
+                           double beta, long long* attempts, long long* accepted,
+                           unsigned char* accept_mask, int B, int N,
+                           float Lx, float Ly, const fs_pot* pot /*host*/, void* stream);
+
 /* ---- flow (NF/normflows) -------------------------------------------------- */
 
 /* Parameters of one CircularCoupledRationalQuadraticSpline layer in the

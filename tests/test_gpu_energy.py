@@ -163,3 +163,25 @@ def test_empty_batch_and_bad_shapes():
     MC = _mc()
     with pytest.raises(ValueError):
         MC.BatchedMonteCarlo(np.zeros((2, 4, 2), np.float32), MC.SimulationBox(10.0), 1.0, 3)
+
+
+@pytest.mark.parametrize("n", [32, 64, 256, 1000, 4096])
+def test_fold_and_rint_minimum_image_agree(n):
+    """Configurations inside [0, L] take the fold form of the minimum image (min(|d|, L - |d|)), a configuration with a
+    particle outside the box the general d - L rint(d / L): the same configuration moved by one box length in one
+    particle's coordinate must give the same energy (the shift is exact in float32 only up to the rounding of
+    x - L, hence the tolerance, stated relative to the sum of the pair-term magnitudes)."""
+    B = 32 if n < 1000 else (6 if n < 4096 else 2)
+    pos, L = er.batch_lattices(B, n, 0.5, seed0=7 * n)
+    eng = _engine(pos, L)
+    E0, W0, _ = eng.total_energy_virial()
+    sh = pos.copy()
+    sh[:, 0, 0] -= np.float32(L)
+    sh[:, n // 2, 1] += np.float32(L)
+    E1, W1, _ = eng.total_energy_virial(torch.from_numpy(sh).cuda())
+    for b in range(B):
+        p64 = pos[b].astype(np.float64)
+        scale = 0.5 * sum(er.particle_energy_magnitude(p64, p, L, L, POT) for p in range(n))
+        assert abs(float(E0[b]) - float(E1[b])) <= 2e-5 * max(1.0, scale), (b, float(E0[b]), float(E1[b]), scale)
+        Er, Wr = er.total_energy_virial(p64, L, L, POT)
+        assert abs(float(E0[b]) - Er) <= RTOL * max(1.0, scale) and abs(float(E1[b]) - Er) <= 2e-5 * max(1.0, scale)

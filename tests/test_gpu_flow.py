@@ -447,6 +447,34 @@ def test_tensor_path_full_depth_vs_float64_oracle(tag, n, K, blocks, H, nb, sigm
     assert rel.max() < 1e-4, (tag, rel.max())
 
 
+@pytest.mark.parametrize("tag,n,K,blocks,H,nb,sigma,B,B_oracle", FULL)
+def test_sampling_pass_log_prob_equals_inverse_pass(tag, n, K, blocks, H, nb, sigma, B, B_oracle):
+    """NormalizingFlow.sample_with_log_prob: log q(x) = log q0(z) - log-det of the sampling pass, against what the
+    reference's nf_big_move computes for a proposal - log_prob of the sampled x through the inverse pass
+    (MCMC/monte_carlo.py:262) - at the full depth of the three BASELINE flows and on the path the bench runs.  The two
+    differ by the round-off of inverting the flow; required: within the 1e-4 relative log-density tolerance (and the
+    float64 oracle's log_prob of the same x as the arbiter on a subset of rows)."""
+    model, bound, g = _perturbed(n, K, blocks, H, nb, sigma)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    spec = fr.FlowSpec(sd, bound)
+    model = model.cuda().eval()
+    torch.manual_seed(5)
+    torch.cuda.manual_seed(5)
+    for prec in _precisions(model):
+        model.precision = prec
+        x, lq_s = model.sample_with_log_prob(B)
+        lq_i = model.log_prob(x)
+        model._cuda_pack().check_nan()
+        assert x.shape == (B, 2 * n) and torch.isfinite(lq_s).all() and torch.isfinite(lq_i).all()
+        rel = ((lq_s - lq_i).abs() / lq_i.abs()).max().item()
+        sel = torch.linspace(0, B - 1, min(B_oracle, 64)).long()
+        with torch.no_grad():
+            truth = fr.log_prob(sd, spec, x[sel].cpu().double(), dtype=torch.float64).numpy()
+        err = np.max(np.abs(lq_s[sel].cpu().numpy() - truth) / np.abs(truth))
+        print("%s %s: sampling-pass log q vs inverse pass %.2e, vs float64 oracle %.2e" % (tag, prec, rel, err))
+        assert rel < 1e-4 and err < 1e-4, (tag, prec, rel, err)
+
+
 def test_fp16_operand_range_is_guarded():
     """FP16 operands overflow at 65504.  A flow whose activations leave that range must not return silently wrong
     numbers from the tensor path: the NaN flag is raised (check_nan -> ValueError, the reference's error for a broken

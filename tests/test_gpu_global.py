@@ -206,3 +206,85 @@ def test_judge_and_bulk_judge_match_reference(golden_dir):
     acc, att = mc.bulk_judge_normalizing_flow([c.copy() for c in props[12:]], float(g["bulk_ref_energy"]))
     assert (acc, att) == (int(g["bulk_acc"]), int(g["bulk_att"]))
     assert mc.rng.random() == float(g["next_uniform"])              # same number of uniforms consumed
+
+
+@pytest.mark.parametrize("n,B,rho", [(3, 37, 0.03), (32, 301, 0.5), (45, 64, 0.4), (64, 257, 0.5), (256, 96, 0.5),
+                                     (300, 33, 0.3), (1000, 9, 0.5), (4000, 3, 0.5), (7500, 2, 0.5)])
+def test_fused_global_move_equals_energy_then_accept(n, B, rho):
+    """fs_accept_global_fused (proposal energy + acceptance + update in one kernel) against the two-kernel sequence
+    fs_energy_total -> fs_accept_global on identical inputs: bit-equal energies, masks, states and counters for every
+    group size of the energy kernel, ragged batch sizes, overlapping proposals (E = inf: rejected), proposals outside the
+    box (rint minimum image) and Philox as well as replayed uniforms.  N = 4000 runs the 1024-thread block of the packed
+    kernel, N = 7500 is beyond its tile and takes the entry point's two-kernel fallback."""
+    import flowstate_b200.MCMC as MC
+    pos, L = er.batch_lattices(B, n, rho, seed0=3 * n)
+    prop, _ = er.batch_lattices(B, n, rho, seed0=5 * n + 1)
+    if n > 3:
+        prop[1, 0] = prop[1, n - 1] + np.float32(0.3)          # overlapping proposal
+        prop[2, 1, 0] -= np.float32(L)                         # a proposal with a particle outside [0, L]
+    rs = np.random.default_rng(n)
+    lq_old = torch.from_numpy(rs.normal(-30, 2, B).astype(np.float32)).cuda()
+    lq_new = torch.from_numpy(rs.normal(-30, 2, B).astype(np.float32)).cuda()
+    u = torch.from_numpy(rs.random(B)).cuda()
+    tprop = torch.from_numpy(prop).cuda()
+    for draws in ("replay", "philox"):
+        engs = []
+        for fused in (True, False):
+            eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, n, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2,
+                                       k=15, rng="philox", seeds=11)
+            eng.fused_accept = fused
+            mask = eng.nf_big_move(tprop, u=u if draws == "replay" else None, logq=(lq_old, lq_new))
+            engs.append((eng, mask))
+        (a, ma), (b, mb) = engs
+        E_ref, W_ref, _ = b.total_energy_virial(tprop)
+        assert torch.equal(a.proposal_energy, E_ref) and torch.equal(b.proposal_energy, E_ref)
+        assert torch.equal(ma, mb) and torch.equal(a.pos, b.pos)
+        assert torch.equal(a.E, b.E) and torch.equal(a.W, b.W)
+        assert torch.equal(a.attempts, b.attempts) and torch.equal(a.accepted, b.accepted)
+        m = ma.bool().cpu().numpy()
+        out = a.pos.cpu().numpy()
+        assert np.array_equal(out[m], prop[m]) and np.array_equal(out[~m], pos[~m])
+        if n > 3:
+            assert not m[1] and torch.isinf(E_ref[1])
+        assert 0 < m.sum() < B or B < 8
+
+
+def test_global_move_with_sampling_pass_log_density(golden_dir):
+    """nf_big_move(configs, logq_new=...) with the proposals' log q from the sampling pass that produced them
+    (NormalizingFlow.sample_with_log_prob) against the default, which sends the proposals through the density pass
+    again like the reference (monte_carlo.py:262): same uniforms -> same decisions except where the acceptance ratio is
+    within the epsilon band of the threshold (|log ratio - log u| <= 1e-4 |log q|, the log-density tolerance)."""
+    import flowstate_b200.MCMC as MC
+    g = np.load(os.path.join(golden_dir, "mc_global.npz"))
+    tag = str(g["names"][0]).split("_")[0]
+    sd = _sd(g, tag + "__sd__")
+    bound, L = float(g[tag + "__bound"]), float(g[tag + "__L"])
+    n = g[str(g["names"][0]) + "__pos0"].shape[0]
+    model, spec = _model(sd, n, bound)
+    B = 512
+    pos, _ = er.batch_lattices(B, n, n / (L * L), seed0=41)
+    torch.manual_seed(3)
+    torch.cuda.manual_seed(3)
+    x, lq_new = model.sample_with_log_prob(B)
+    cfg = (x.reshape(B, n, 2) + np.float32(L / 2)).contiguous()
+    u = torch.rand(B, dtype=torch.float64, device="cuda")
+    res = []
+    for from_sample in (False, True):
+        eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, n, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15,
+                                   rng="philox", seeds=5)
+        eng.set_nf_model(model)
+        E_old = eng.E.clone()
+        mask = eng.nf_big_move(cfg, u=u, logq_new=lq_new if from_sample else None)
+        res.append((mask.bool().cpu().numpy(), eng, E_old))
+    (m0, e0, E_old), (m1, e1, _) = res
+    lq = model.log_prob(torch.cat([e0.centred(torch.from_numpy(pos).cuda()), e0.centred(cfg)]))
+    lq_old, lq_inv = lq[:B].double(), lq[B:].double()
+    assert ((lq_new.double() - lq_inv).abs() / lq_inv.abs()).max().item() < 1e-4
+    log_ratio = -(e0.proposal_energy.double() - E_old) - (lq_inv - lq_old)          # beta = 1
+    band = 1e-4 * lq_inv.abs() + 1e-9
+    margin = (log_ratio - torch.log(u)).abs()
+    differ = torch.from_numpy(m0 != m1).cuda()
+    assert not bool((differ & (margin > band) & (log_ratio < 0)).any()), int(differ.sum())
+    assert 0 < m0.sum() and torch.equal(e0.attempts, e1.attempts)
+    same = ~differ
+    assert torch.equal(e0.pos[same], e1.pos[same])
