@@ -484,7 +484,7 @@ class Harness:
         self.trainer.fresh_optimizer()                         # new Adam every cycle (main_algorithm_2.py:440)
         perm = torch.randperm(data.shape[0], device=self.dev)
         for bi in range(0, data.shape[0], t["batch"]):
-            self.trainer.step(data[perm[bi:bi + t["batch"]]])
+            self.trainer.step(data[perm[bi:bi + t["batch"]]], sync=False)   # loss and skip decision stay on the device
         model.eval()
         mark("train")
         if self.world > 1:

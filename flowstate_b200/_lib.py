@@ -64,6 +64,8 @@ _PROTOS = {
     "fs_adjust_displacement": (C.c_int, [_P, _P, _P, _P, _P, C.c_double, C.c_int, _P]),
     "fs_accept_global": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(FsRng), C.c_double, _P, _P, _P,
                                    C.c_int, C.c_int, _P]),
+    "fs_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_longlong, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float,
+                               C.c_float, _P]),
     "fs_accept_global_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(FsRng), C.c_double, _P, _P, _P,
                                          C.c_int, C.c_int, C.c_float, C.c_float, C.POINTER(FsPot), _P]),
     "fs_tc_debug_read": (C.c_int, [_P, C.c_int]),

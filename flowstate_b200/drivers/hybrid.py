@@ -185,11 +185,20 @@ def _train(model, data, cfg, epochs, trainer=None):
     for _ in range(epochs):
         perm = torch.randperm(data.shape[0], device=data.device)
         tot, nb = 0.0, 0
+        dev_losses = []
         for bi in range(n_batches):
-            loss = tr.step(data[perm[bi * cfg.batch_size:(bi + 1) * cfg.batch_size]])
+            batch = data[perm[bi * cfg.batch_size:(bi + 1) * cfg.batch_size]]
+            if tr.native_adam:                                 # no host wait per step: losses are read once per epoch
+                dev_losses.append(tr.step(batch, sync=False))
+                continue
+            loss = tr.step(batch)
             if loss is not None:
                 tot += loss
                 nb += 1
+        if dev_losses:
+            ls = torch.cat([l.reshape(1) for l in dev_losses])
+            ok = torch.isfinite(ls)                            # a skipped step shows as a non-finite loss
+            tot, nb = float(ls[ok].sum()), int(ok.sum())
         losses.append(tot / max(nb, 1))
     model.eval()
     if not tr.sync_bn:            # parameters followed the all-reduced gradients on every rank; the BatchNorm running

@@ -15,9 +15,13 @@ Here the same step runs with
   * all gradients living in ONE flat float32 buffer (every p.grad is a view into it), so the multi-GPU gradient
     all-reduce is a single NCCL call on that buffer (SUM, then divided by the world size) with no flatten / unflatten
     copies - the hook point is between backward and optimizer.step (main_algorithm_2.py:450-451);
-  * a fused multi-tensor Adam (torch.optim.Adam(fused=True)); a new optimizer per call of `fresh_optimizer`, like the
-    reference's new Adam every cycle (main_algorithm_2.py:440);
-  * the reference's "skip the step when the loss is NaN / Inf" decision taken collectively over the ranks;
+  * on CUDA, the parameters and both Adam moments in flat buffers as well (every Parameter's .data is a view, names and
+    state_dict untouched), so optimizer.step() is fs_adam_step: two launches, the same update as torch.optim.Adam
+    (tests/test_gpu_train.py), with the reference's "skip the step when the loss is NaN / Inf" decided on the device -
+    the host does not wait for the loss (`step(batch, sync=False)`); on CPU a torch.optim.Adam.  A new optimizer per
+    call of `fresh_optimizer` (zeroed moments and step count), like the reference's new Adam every cycle
+    (main_algorithm_2.py:440);
+  * the skip decision taken collectively over the ranks (MAX all-reduce of the flag);
   * optionally (sync_bn=True, N > 1 GPUs) train-mode BatchNorm statistics taken over the union of the ranks' batches
     (torch.nn.SyncBatchNorm, same state_dict keys): the N-GPU step then equals the single-process step on the
     concatenated batch; without it every rank normalises with its own batch (DDP's default semantics)
@@ -26,10 +30,13 @@ Here the same step runs with
 Parameters that never receive a gradient (PeriodicFeaturesElementwise.weights) keep grad = None, so
 Adam skips them exactly like the reference's.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
 from . import _train_native
+from .. import _lib
 
 
 def _world():
@@ -40,7 +47,7 @@ def _world():
 
 class FlowTrainer:
     def __init__(self, model, lr, weight_decay=0.0, alpha=1.0, reverse_batch=256, use_graph=True, sync_bn=False,
-                 native=True):
+                 native=True, native_adam=True):
         self.sync_bn = bool(sync_bn) and _world() > 1
         if self.sync_bn:                                       # children are replaced in place; parameters are kept
             torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
@@ -56,6 +63,9 @@ class FlowTrainer:
         self.native = None
         self._native_checked = False
         self._opt_kw = None
+        # flat Adam (fs_adam_step): parameters, moments and step state in flat device buffers
+        self.native_adam = bool(native_adam) and self.device.type == "cuda"
+        self.flat_p = self.exp_avg = self.exp_avg_sq = self.adam_state = None
         self.flat = None                 # flat gradient bucket
         self.trainable = None            # parameters that receive gradients
         self.graphs = {}                 # batch rows -> (graph, static input, static loss)
@@ -84,19 +94,36 @@ class FlowTrainer:
         else:
             self._loss(batch).backward()
         self.trainable = [p for p in self.params if p.grad is not None]
-        total = sum(p.numel() for p in self.trainable)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
-        off = 0
+        # every tensor starts on a 16-byte boundary of the flat buffers (the training kernels load float4)
+        offs, total = [], 0
         for p in self.trainable:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+        for p, off in zip(self.trainable, offs):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+        if self.native_adam:
+            self.flat_p = torch.zeros(total, dtype=torch.float32, device=self.device)
+            for p, off in zip(self.trainable, offs):
+                dst = self.flat_p[off:off + p.numel()].view_as(p)
+                dst.copy_(p.data)
+                p.data = dst                                   # same Parameter object, same state_dict entry
+            self.exp_avg = torch.zeros_like(self.flat_p)
+            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            self.adam_state = torch.zeros(4, dtype=torch.float32, device=self.device)
 
     def fresh_optimizer(self):
         """A new Adam (zero moments, step 0) over every parameter, as the reference creates one per training cycle
         (main_algorithm_2.py:440).  After the first cycle the existing optimizer's state is zeroed in place - the same
         state as a newly built one, in three multi-tensor launches instead of ~1.5 k allocations and fills."""
         self._native_checked = False
+        if self.native_adam:
+            if self.adam_state is not None:
+                self.exp_avg.zero_()
+                self.exp_avg_sq.zero_()
+                self.adam_state.zero_()
+            self.opt = "fs_adam_step"
+            return self.opt
         if self.opt is not None and self._opt_kw == (self.lr, self.weight_decay):
             bufs = [v for st in self.opt.state.values() for v in st.values() if torch.is_tensor(v)]
             if bufs:
@@ -158,15 +185,19 @@ class FlowTrainer:
         g.replay()
         return static_loss.detach()
 
-    def step(self, batch):
-        """One optimizer step on `batch`.  Returns the loss as a Python float, or None when the step was skipped
-        (fewer than two rows, or a non-finite loss on any rank)."""
+    def step(self, batch, sync=True):
+        """One optimizer step on `batch`.  sync=True returns the loss as a Python float, or None when the step was
+        skipped (fewer than two rows, or a non-finite loss on any rank).  sync=False (flat Adam only) never waits for the
+        device: it returns the loss as a 1-element device tensor (NaN for an unusable batch); a skipped step shows as
+        a non-finite loss."""
         if self.opt is None:
             self.fresh_optimizer()
         world = _world()
         usable = batch.shape[0] >= 2                           # BatchNorm needs two rows
         if usable and self.flat is None:
             self._prepare(batch)
+        if self.native_adam:
+            return self._step_flat(batch, usable, world, sync)
         loss = self._forward_backward(batch) if usable else None
         bad = torch.zeros(1, device=self.device)
         if not usable:
@@ -184,3 +215,37 @@ class FlowTrainer:
             self.allreduce_calls += 1
         self.opt.step()
         return float(loss)
+
+    def _step_flat(self, batch, usable, world, sync):
+        if self.flat is None:                                  # nothing prepared yet and this batch cannot prepare it
+            if world > 1:
+                raise RuntimeError("FlowTrainer: the first minibatch of a rank needs at least two rows")
+            return None if sync else torch.full((1,), float("nan"), device=self.device)
+        loss = self._forward_backward(batch).reshape(1) if usable else None
+        skip = None
+        if world > 1 or not usable:
+            skip = (~torch.isfinite(loss)).float() if usable else torch.ones(1, device=self.device)
+            if world > 1:
+                dist.all_reduce(skip, op=dist.ReduceOp.MAX)    # every rank skips this step together
+        if world > 1:                                          # same collectives on every rank whatever the decision
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)   # ONE collective on the flat bucket
+            self.flat.div_(world)
+            self.allreduce_bytes += self.flat.numel() * 4
+            self.allreduce_calls += 1
+        _lib.check(_lib.lib().fs_adam_step(
+            _lib.ptr(self.flat_p), _lib.ptr(self.flat), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+            int(self.flat_p.numel()), _lib.ptr(self.adam_state), _lib.ptr(skip), _lib.ptr(loss),
+            float(self.lr), 0.9, 0.999, 1e-8, float(self.weight_decay), _lib.stream_ptr(self.device)))
+        self._bump_versions()
+        if not sync:
+            return loss.clone() if usable else torch.full((1,), float("nan"), device=self.device)
+        if self.adam_state[1].item() == 0:
+            return None
+        return float(loss)
+
+    def _bump_versions(self):
+        """fs_adam_step writes the parameters behind autograd's back; one in-place no-op on the flat buffer's views
+        would cost a launch per tensor, so the model's inference pack is marked stale instead."""
+        repack = getattr(self.model, "repack", None)
+        if repack is not None:
+            repack()

@@ -322,6 +322,16 @@ void fs_train_destroy(fs_train* t);
 /* x [B, 2N] (centred coordinates), B >= 2; loss: one float on the device.  Repeatable bit for bit. */
 int fs_train_forward_kld(fs_train* t, const float* x, int B, float* loss, int update_running, void* stream);
 
+/* torch.optim.Adam(params, lr, weight_decay).step() on ONE flat float32 buffer (the optimizer of both drivers:
+ * hybrid_NF_MCMC/main_algorithm_1.py:297-320, main_algorithm_2.py:440-451): params / grads / exp_avg / exp_avg_sq [n]
+ * (16-byte aligned), L2 weight decay, bias-corrected moments.  state: 4 device floats - [0] steps applied so far (zero
+ * it, with the moments, for a new optimizer), [1] 1 if this call applied its step, [2] lr / bc1, [3] 1 / sqrt(bc2).
+ * The step is skipped ON THE DEVICE when *skip != 0 (nullable; e.g. a flag all-reduced over the ranks) or *loss is
+ * NaN / Inf (nullable; the reference's `if ~(isnan(loss) | isinf(loss))`, main_algorithm_2.py:449). */
+int fs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                 float* state, const float* skip, const float* loss, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, void* stream);
+
 /* ---- affine (RealNVP) coupling and periodic shifts ----------------------------------------- */
 
 /* MaskedAffineFlow.forward / inverse (NF/normflows/flows/affine/coupling.py:163-229) and the element-wise half of

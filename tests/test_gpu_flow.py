@@ -458,6 +458,7 @@ def test_sampling_pass_log_prob_equals_inverse_pass(tag, n, K, blocks, H, nb, si
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     spec = fr.FlowSpec(sd, bound)
     model = model.cuda().eval()
+    model.q0.device = "cuda"                      # the base distribution samples where it is told to (Energy/Uniform.py:18-22)
     torch.manual_seed(5)
     torch.cuda.manual_seed(5)
     for prec in _precisions(model):

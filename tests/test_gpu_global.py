@@ -209,7 +209,7 @@ def test_judge_and_bulk_judge_match_reference(golden_dir):
 
 
 @pytest.mark.parametrize("n,B,rho", [(3, 37, 0.03), (32, 301, 0.5), (45, 64, 0.4), (64, 257, 0.5), (256, 96, 0.5),
-                                     (300, 33, 0.3), (1000, 9, 0.5), (4000, 3, 0.5), (7500, 2, 0.5)])
+                                     (300, 33, 0.3), (1000, 9, 0.5), (4000, 3, 0.5), (7500, 3, 0.5)])
 def test_fused_global_move_equals_energy_then_accept(n, B, rho):
     """fs_accept_global_fused (proposal energy + acceptance + update in one kernel) against the two-kernel sequence
     fs_energy_total -> fs_accept_global on identical inputs: bit-equal energies, masks, states and counters for every
