@@ -5,7 +5,7 @@
 #    global accept, the two feature / unconditional-spline kernels)
 # Every ncu run is preceded by the same command without ncu (B200_PROFILING.md).
 set -u
-TAG=${1:-r02b}
+TAG=${1:-r02e}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary"
 OUT=gpurun_out
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
@@ -19,5 +19,5 @@ cap cond "tc_conditioner_kernel" 62 6
 cap sweep "local_sweep_fast_kernel" 3 1
 cap energy "energy_total_kernel" 3 1
 cap accept "accept_global_kernel" 3 1
-cap prep "prep_(inverse|forward)_v2" 40 2
+cap prep "prep_v3" 40 2
 ls -la $OUT/*$TAG*
