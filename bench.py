@@ -765,6 +765,8 @@ class Harness:
         mask_buf = torch.empty(B, dtype=torch.uint8, device=dev)
         acc_fn = lambda: eng.accept_global(cfg, E_new, W_new, lqo, lqn, u=u, mask=mask_buf)
         try:
+            if self.world > 1:                     # no stream capture next to a live NCCL communicator (its watchdog
+                raise RuntimeError("plain launches")   # thread queries events): plain launches there
             acc_fn()
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
