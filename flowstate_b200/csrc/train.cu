@@ -24,6 +24,7 @@
 // shared-parameter gradients, the loss) are fixed-order: the step is repeatable bit for bit.
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "spline_train.cuh"
@@ -319,6 +320,198 @@ __global__ void features_bwd(const float* __restrict__ x, const float* __restric
 // starts at 0 (the loss does not see z) and picks up inject[z][row, j] at every step (identity chain: dL/d(conditioner
 // input)).  SHARED: the parameters of a step are shared by all rows (unconditional spline).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// chain_lanes: the same coordinate chains with LPE (16 or 32) lanes per (row, coordinate) element - lane i owns bin i of
+// the element's spline (its width, height and derivative logits): the three parameter segments are coalesced loads, the
+// softmax normalisers are segmented shuffle reductions, the knots a segmented inclusive scan, the bin search a ballot,
+// and in the backward pass lane i writes the gradient of "its" three parameters (coalesced stores).  The thread-per-
+// element kernel above walks 46 parameters per layer through strided loads with 16 k threads in flight (3.5 warps per
+// SM: latency-bound, 45 % of the training step); here the same pass has 16 / 32 x the threads and no strided access.
+// The arithmetic per element is that of spline_point (spline_train.cuh) with the prefix sums taken in scan order.
+// nb <= LPE; the (nb + 1)-th derivative logit is read by every lane (broadcast).
+// ---------------------------------------------------------------------------
+template <int LPE>
+__device__ __forceinline__ float seg_max(float v) {
+#pragma unroll
+    for (int o = LPE / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, LPE));
+    return v;
+}
+template <int LPE>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+    for (int o = LPE / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, LPE);
+    return v;
+}
+template <int LPE>
+__device__ __forceinline__ float seg_scan(float v, int li) {      // inclusive prefix sum over the LPE lanes of a segment
+#pragma unroll
+    for (int o = 1; o < LPE; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, v, o, LPE);
+        if (li >= o) v += t;
+    }
+    return v;
+}
+
+// One axis (widths or heights) of one element: softmax probabilities p (0 on pad lanes), prefix sums ps, and for bin k
+// the knots lo / hi with the probability sums below them (p0, p1).  `k` < 0: the bin is searched on this axis (x given).
+template <int LPE>
+__device__ __forceinline__ void lane_axis(float logit, bool live, int li, int nb, float bound, float x, int& k, float& p,
+                                          float& lo, float& hi, float& p0, float& p1) {
+    const float c = 1.0f - kTMin * nb;
+    const float m = seg_max<LPE>(live ? logit : -3.0e38f);
+    const float e = live ? expf(logit - m) : 0.f;
+    const float rz = 1.0f / seg_sum<LPE>(e);
+    p = e * rz;
+    const float ps = seg_scan<LPE>(p, li);                                 // sum of p[0 .. li]
+    const float cum = __fmaf_rn(c, ps, kTMin * (float)(li + 1));          // cumulative size at knot li + 1
+    if (k < 0) {                                                           // utils/splines.py:11-13 on the interior knots
+        const bool ge = li < nb - 1 && x >= 2.0f * bound * cum - bound;
+        const unsigned seg = LPE == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+        k = __popc(__ballot_sync(0xffffffffu, ge) & seg);
+    }
+    const int base = (threadIdx.x & 31) & ~(LPE - 1);
+    const float c1 = __shfl_sync(0xffffffffu, cum, base + k);
+    const float q1 = __shfl_sync(0xffffffffu, ps, base + k);
+    const float c0 = __shfl_sync(0xffffffffu, cum, base + (k > 0 ? k - 1 : 0));
+    const float q0 = __shfl_sync(0xffffffffu, ps, base + (k > 0 ? k - 1 : 0));
+    p0 = k > 0 ? q0 : 0.f;
+    p1 = q1;
+    lo = (k == 0) ? -bound : 2.0f * bound * (k > 0 ? c0 : 0.f) - bound;
+    hi = (k == nb - 1) ? bound : 2.0f * bound * c1 - bound;
+}
+
+template <bool BWD, bool SHARED, int LPE>
+__global__ void __launch_bounds__(128) chain_lanes(const float* __restrict__ x0, int D, const int* __restrict__ cols,
+                                                   const int* __restrict__ tau, int rows, int N, int K, int nb, float bound,
+                                                   float scale, const float* __restrict__ theta, float* __restrict__ xs,
+                                                   float* __restrict__ ldsum, float gld, const float* __restrict__ inject,
+                                                   float* __restrict__ gtheta) {
+    const long long total = (long long)rows * N;
+    long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+    const bool valid = e < total;                      // whole segments: the grid covers total * LPE threads exactly or pads
+    if (!valid) e = total - 1;                         // padding segments shadow the last element (no stores)
+    const int li = threadIdx.x & (LPE - 1);
+    const int base = (threadIdx.x & 31) & ~(LPE - 1);
+    const int r = (int)(e / N);
+    int j = (int)(e % N);
+    const int P = 3 * nb + 1;
+    const size_t step = (size_t)rows * N;
+    const bool live = li < nb;
+    const float c = 1.0f - kTMin * nb, two_b = 2.0f * bound;
+    if (!BWD) {
+        float x = x0[(size_t)r * D + cols[j]], lds = 0.f;
+        for (int z = 0; z < K; ++z) {
+            const size_t o = z * step + (size_t)r * N + j;
+            if (valid && li == 0) xs[o] = x;
+            const float* u = SHARED ? theta + ((size_t)z * N + j) * P : theta + o * P;
+            const float uw = live ? u[li] * scale : 0.f, uh = live ? u[nb + li] * scale : 0.f;
+            const float ud = live ? u[2 * nb + li] : 0.f, ud_last = u[3 * nb];
+            const bool in = x >= -bound && x <= bound;                    // tails: identity (utils/splines.py:24-39)
+            const float xc = in ? x : 0.f;
+            int k = -1;
+            float pw, ph, xlo, xhi, ylo, yhi, a0, a1;
+            lane_axis<LPE>(uw, live, li, nb, bound, xc, k, pw, xlo, xhi, a0, a1);
+            lane_axis<LPE>(uh, live, li, nb, bound, xc, k, ph, ylo, yhi, a0, a1);
+            const float ud0 = __shfl_sync(0xffffffffu, ud, base + k);
+            const float udn = __shfl_sync(0xffffffffu, ud, base + (k + 1 < LPE ? k + 1 : k));
+            const float ud1 = (k + 1 < nb) ? udn : ud_last;
+            RqFwd f;
+            float y, ld;
+            rq_forward(xc, xlo, xhi, ylo, yhi, kTMin + softplus_acc(ud0), kTMin + softplus_acc(ud1), f, y, ld);
+            lds += in ? ld : 0.f;
+            x = in ? y : x;
+            j = tau[j];
+        }
+        if (valid && li == 0) ldsum[e] = lds;
+    } else {
+        float gy = 0.f;
+        for (int z = K - 1; z >= 0; --z) {
+            j = tau[j];                                            // tau here is the inverse table
+            const size_t o = z * step + (size_t)r * N + j;
+            const float* u = SHARED ? theta + ((size_t)z * N + j) * P : theta + o * P;
+            float* gt = gtheta + o * P;
+            const float x = xs[o];
+            const float uw = live ? u[li] * scale : 0.f, uh = live ? u[nb + li] * scale : 0.f;
+            const float ud = live ? u[2 * nb + li] : 0.f, ud_last = u[3 * nb];
+            const bool in = x >= -bound && x <= bound;
+            const float xc = in ? x : 0.f;
+            int k = -1;
+            float pw, ph, xlo, xhi, ylo, yhi, wp0, wp1, hp0, hp1;
+            lane_axis<LPE>(uw, live, li, nb, bound, xc, k, pw, xlo, xhi, wp0, wp1);
+            lane_axis<LPE>(uh, live, li, nb, bound, xc, k, ph, ylo, yhi, hp0, hp1);
+            const float ud0 = __shfl_sync(0xffffffffu, ud, base + k);
+            const float udn = __shfl_sync(0xffffffffu, ud, base + (k + 1 < LPE ? k + 1 : k));
+            const float ud1 = (k + 1 < nb) ? udn : ud_last;
+            RqFwd f;
+            float yv, lv;
+            rq_forward(xc, xlo, xhi, ylo, yhi, kTMin + softplus_acc(ud0), kTMin + softplus_acc(ud1), f, yv, lv);
+            // ---- reverse mode through the rational-quadratic formula (as spline_point<true>) ----
+            const float gyv = gy, gl = gld;
+            const float q = f.numA / f.den;
+            float hk_b = gyv * q;
+            const float q_b = gyv * f.hk;
+            const float numA_b = q_b / f.den;
+            float den_b = -q_b * q / f.den - 2.0f * gl / f.den;
+            float s_b = 2.0f * gl / f.s;
+            const float dn_b = gl / f.dn;
+            float d1_b = dn_b * f.th * f.th;
+            s_b += dn_b * 2.0f * f.tt;
+            float tt_b = dn_b * 2.0f * f.s;
+            float d0_b = dn_b * f.omt * f.omt;
+            float th_b = dn_b * 2.0f * f.d1 * f.th;
+            float omt_b = dn_b * 2.0f * f.d0 * f.omt;
+            s_b += numA_b * f.th * f.th;
+            th_b += numA_b * 2.0f * f.s * f.th;
+            d0_b += numA_b * f.tt;
+            tt_b += numA_b * f.d0;
+            s_b += den_b;
+            const float t_b = den_b * f.tt;
+            tt_b += den_b * f.t;
+            d0_b += t_b;
+            d1_b += t_b;
+            s_b -= 2.0f * t_b;
+            th_b += tt_b * f.omt;
+            omt_b += tt_b * f.th;
+            th_b -= omt_b;
+            const float x_b = th_b / f.wk;
+            float x0_b = -x_b;
+            float wk_b = -th_b * f.th / f.wk;
+            hk_b += s_b / f.wk;
+            wk_b += -s_b * f.s / f.wk;
+            const float x1_b = wk_b;
+            x0_b -= wk_b;
+            const float y1_b = hk_b;
+            const float y0_b = gyv - hk_b;
+            // ---- knots -> cumulative sizes -> softmax logits: lane li writes the gradients of its three logits ----
+            float gw = 0.f, gh = 0.f, gd = 0.f, gd_last = 0.f;
+            if (in) {
+                {
+                    const float G0 = (k == 0) ? 0.f : two_b * x0_b, G1 = (k == nb - 1) ? 0.f : two_b * x1_b;
+                    const float dot = G0 * wp0 + G1 * wp1;
+                    gw = scale * c * pw * ((li < k ? G0 : 0.f) + (li < k + 1 ? G1 : 0.f) - dot);
+                }
+                {
+                    const float G0 = (k == 0) ? 0.f : two_b * y0_b, G1 = (k == nb - 1) ? 0.f : two_b * y1_b;
+                    const float dot = G0 * hp0 + G1 * hp1;
+                    gh = scale * c * ph * ((li < k ? G0 : 0.f) + (li < k + 1 ? G1 : 0.f) - dot);
+                }
+                const float g0 = d0_b / (1.0f + expf(-ud0)), g1 = d1_b / (1.0f + expf(-ud1));   // d softplus = sigmoid
+                gd = (li == k) ? g0 : ((li == k + 1) ? g1 : 0.f);
+                gd_last = (k + 1 == nb) ? g1 : 0.f;
+            }
+            if (valid) {
+                if (live) {
+                    gt[li] = gw;
+                    gt[nb + li] = gh;
+                    gt[2 * nb + li] = gd;
+                }
+                if (li == 0) gt[3 * nb] = gd_last;
+            }
+            gy = (in ? x_b : gyv) + (inject ? inject[o] : 0.f);
+        }
+    }
+}
+
 template <bool BWD, bool SHARED>
 __global__ void __launch_bounds__(128) chain_kernel(const float* __restrict__ x0, int D, const int* __restrict__ cols,
                                                     const int* __restrict__ tau, int rows, int N, int K, int nb, float bound,
@@ -553,11 +746,26 @@ extern "C" int fs_train_forward_kld(fs_train* t, const float* x, int B, float* l
     auto grid2 = [&](int cols, int rows_) { return dim3((cols + 63) / 64, (rows_ + 63) / 64, K); };
     const dim3 bng((H + 31) / 32, K);
     int launches = 0;
+    // coordinate chains: lane-per-bin kernel for nb <= 32 (16 lanes per element up to nb = 16), else one thread per element
+    auto chain = [&](auto bwd, auto shared, const float* x0, const int* cols, const int* tau, float scale_, const float* th,
+                     float* xs_, float* lds_, float gld_, const float* inj, float* gth) {
+        constexpr bool BW = decltype(bwd)::value, SH = decltype(shared)::value;
+        if (nb <= 16 && !getenv("FS_TRAIN_CHAIN_SCALAR")) {
+            const unsigned g16 = (unsigned)(((long long)B * N * 16 + 127) / 128);
+            chain_lanes<BW, SH, 16><<<g16, 128, 0, s>>>(x0, t->D, cols, tau, B, N, K, nb, t->bound, scale_, th, xs_, lds_, gld_, inj, gth);
+        } else if (nb <= 32 && !getenv("FS_TRAIN_CHAIN_SCALAR")) {
+            const unsigned g32 = (unsigned)(((long long)B * N * 32 + 127) / 128);
+            chain_lanes<BW, SH, 32><<<g32, 128, 0, s>>>(x0, t->D, cols, tau, B, N, K, nb, t->bound, scale_, th, xs_, lds_, gld_, inj, gth);
+        } else {
+            chain_kernel<BW, SH><<<ce, 128, 0, s>>>(x0, t->D, cols, tau, B, N, K, nb, t->bound, scale_, th, xs_, lds_, gld_, inj, gth);
+        }
+    };
+    using std::true_type;
+    using std::false_type;
 
     // ---- forward ----
     gather_uncond<<<(unsigned)(((long long)K * NP + 255) / 256), 256, 0, s>>>(t->ptab, per, t_wf(nbk) + 2, K, N, nb, c.thI);
-    chain_kernel<false, true><<<ce, 128, 0, s>>>(x, t->D, colsI, tauI, B, N, K, nb, t->bound, 1.0f, c.thI, c.xsI, c.ldI, 0.f,
-                                                 nullptr, nullptr);
+    chain(false_type{}, true_type{}, x, colsI, tauI, 1.0f, c.thI, c.xsI, c.ldI, 0.f, nullptr, nullptr);
     features_fwd<<<(unsigned)((kbn + 255) / 256), 256, 0, s>>>(c.xsI, (long long)K * B, N, t->fscale, c.feat);
     gemm_nt<0, 0><<<grid2(H, B), 256, 0, s>>>(c.feat, B, 2 * N, H, t->ptab, per, T_W0, T_B0, nullptr, nullptr, nullptr, c.hs);
     launches += 4;
@@ -579,15 +787,14 @@ extern "C" int fs_train_forward_kld(fs_train* t, const float* x, int B, float* l
     float* hlast = c.hs + (size_t)nbk * KBH;
     gemm_nt<0, 0><<<grid2(NP, B), 256, 0, s>>>(hlast, B, H, NP, t->ptab, per, t_wf(nbk), t_wf(nbk) + 1, nullptr, nullptr,
                                                nullptr, c.theta);
-    chain_kernel<false, false><<<ce, 128, 0, s>>>(x, t->D, colsT, tauT, B, N, K, nb, t->bound, 1.0f / sqrtf((float)H), c.theta,
-                                                  c.xsT, c.ldT, 0.f, nullptr, nullptr);
+    chain(false_type{}, false_type{}, x, colsT, tauT, 1.0f / sqrtf((float)H), c.theta, c.xsT, c.ldT, 0.f, nullptr, nullptr);
     loss_kernel<<<1, 1024, 0, s>>>(c.ldI, c.ldT, (long long)B * N, B, loss);
     launches += 3;
 
     // ---- backward: d loss / d log-det = -1 / B for every element ----
     const float gld = -1.0f / (float)B;
-    chain_kernel<true, false><<<ce, 128, 0, s>>>(nullptr, t->D, nullptr, itauT, B, N, K, nb, t->bound, 1.0f / sqrtf((float)H),
-                                                 c.theta, c.xsT, nullptr, gld, nullptr, c.dtheta);
+    chain(true_type{}, false_type{}, nullptr, nullptr, itauT, 1.0f / sqrtf((float)H), c.theta, c.xsT, nullptr, gld, nullptr,
+          c.dtheta);
     gemm_tn<0><<<dim3((H + 63) / 64, (NP + 63) / 64, K), 256, 0, s>>>(c.dtheta, B, NP, H, hlast, nullptr, nullptr, t->gtab, per,
                                                                       t_wf(nbk), t_wf(nbk) + 1);
     gemm_nn<0><<<grid2(H, B), 256, 0, s>>>(c.dtheta, B, NP, H, t->ptab, per, t_wf(nbk), nullptr, nullptr, nullptr, c.dhA);
@@ -614,8 +821,7 @@ extern "C" int fs_train_forward_kld(fs_train* t, const float* x, int B, float* l
     gemm_nn<0><<<grid2(2 * N, B), 256, 0, s>>>(dA, B, H, 2 * N, t->ptab, per, T_W0, nullptr, nullptr, nullptr, c.dfeat);
     features_bwd<<<(unsigned)((kbn + 255) / 256), 256, 0, s>>>(c.xsI, c.dfeat, (long long)K * B, N, t->fscale, c.dident);
     // identity chain: the per-row parameter gradients reuse the dtheta buffer (the conditioners are done with it)
-    chain_kernel<true, true><<<ce, 128, 0, s>>>(nullptr, t->D, nullptr, itauI, B, N, K, nb, t->bound, 1.0f, c.thI, c.xsI, nullptr,
-                                                gld, c.dident, c.dtheta);
+    chain(true_type{}, true_type{}, nullptr, nullptr, itauI, 1.0f, c.thI, c.xsI, nullptr, gld, c.dident, c.dtheta);
     scatter_uncond<<<(unsigned)(((long long)K * NP + 255) / 256), 256, 0, s>>>(c.dtheta, B, t->gtab, per, t_wf(nbk) + 2, K, N, nb);
     launches += 5;
     count_launch(launches);
