@@ -50,6 +50,8 @@ def build(force=False, verbose=False):
                "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        for flag in os.environ.get("FS_NVCC_FLAGS", "").split():          # development: extra -D switches
+            cmd.insert(1, flag)
         if os.environ.get("FS_TC_TIMERS") in ("1", "2"):   # in-kernel timers for scripts/tc_debug.py (development only;
             cmd.insert(1, "-DFS_TC_TIMERS=" + os.environ["FS_TC_TIMERS"])   # 2: slots 11-13 hold a timeline instead)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

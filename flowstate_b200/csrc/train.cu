@@ -330,6 +330,40 @@ __global__ void features_bwd(const float* __restrict__ x, const float* __restric
 // The arithmetic per element is that of spline_point (spline_train.cuh) with the prefix sums taken in scan order.
 // nb <= LPE; the (nb + 1)-th derivative logit is read by every lane (broadcast).
 // ---------------------------------------------------------------------------
+// rq_forward / softplus of spline_train.cuh with approximate reciprocals (1-2 ulp): the chain kernels below are bound by
+// instruction issue, an IEEE division is ~8 instructions and log1pf ~30.  The log-det keeps logf.
+// FS_CHAIN_FAST bits (development switch, -DFS_CHAIN_FAST=n through FS_NVCC_FLAGS): 1 softplus, 2 rational-quadratic
+// forward, 4 softmax numerators with ex2.approx.  Bit 4 stays off: the gradient of the shared (unconditional) width
+// logits is a sum over the rows of terms that cancel to ~1e-3 of their size, and the same-sign 1e-7 errors of the
+// approximate exponential showed up as 1.8 % there (tests/test_gpu_train.py, N = 64 case); the others measure
+// <= 1.4e-4 like the exact forms.
+#ifndef FS_CHAIN_FAST
+#define FS_CHAIN_FAST 3
+#endif
+__device__ __forceinline__ float softplus_fast_t(float x) {
+    if (!(FS_CHAIN_FAST & 1)) return softplus_acc(x);
+    return fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(x)));
+}
+__device__ __forceinline__ void rq_forward_fast(float x, float x0, float x1, float y0, float y1, float d0, float d1, RqFwd& f,
+                                                float& y, float& ld) {
+    if (!(FS_CHAIN_FAST & 2)) { rq_forward(x, x0, x1, y0, y1, d0, d1, f, y, ld); return; }
+    f.wk = x1 - x0;
+    f.hk = y1 - y0;
+    const float rwk = __frcp_rn(f.wk);
+    f.s = f.hk * rwk;
+    f.th = (x - x0) * rwk;
+    f.omt = 1.0f - f.th;
+    f.tt = f.th * f.omt;
+    f.t = d0 + d1 - 2.0f * f.s;
+    f.den = f.s + f.t * f.tt;
+    f.numA = f.s * f.th * f.th + d0 * f.tt;
+    f.dn = d1 * f.th * f.th + 2.0f * f.s * f.tt + d0 * f.omt * f.omt;
+    f.d0 = d0;
+    f.d1 = d1;
+    y = y0 + f.hk * f.numA * __frcp_rn(f.den);
+    ld = logf(f.s * f.s * f.dn) - 2.0f * logf(f.den);             // utils/splines.py:214-222
+}
+
 template <int LPE>
 __device__ __forceinline__ float seg_max(float v) {
 #pragma unroll
@@ -359,8 +393,8 @@ __device__ __forceinline__ void lane_axis(float logit, bool live, int li, int nb
                                           float& lo, float& hi, float& p0, float& p1) {
     const float c = 1.0f - kTMin * nb;
     const float m = seg_max<LPE>(live ? logit : -3.0e38f);
-    const float e = live ? expf(logit - m) : 0.f;
-    const float rz = 1.0f / seg_sum<LPE>(e);
+    const float e = live ? ((FS_CHAIN_FAST & 4) ? __expf(logit - m) : expf(logit - m)) : 0.f;   // logit - m <= 0
+    const float rz = __frcp_rn(seg_sum<LPE>(e));
     p = e * rz;
     const float ps = seg_scan<LPE>(p, li);                                 // sum of p[0 .. li]
     const float cum = __fmaf_rn(c, ps, kTMin * (float)(li + 1));          // cumulative size at knot li + 1
@@ -417,7 +451,7 @@ __global__ void __launch_bounds__(128) chain_lanes(const float* __restrict__ x0,
             const float ud1 = (k + 1 < nb) ? udn : ud_last;
             RqFwd f;
             float y, ld;
-            rq_forward(xc, xlo, xhi, ylo, yhi, kTMin + softplus_acc(ud0), kTMin + softplus_acc(ud1), f, y, ld);
+            rq_forward_fast(xc, xlo, xhi, ylo, yhi, kTMin + softplus_fast_t(ud0), kTMin + softplus_fast_t(ud1), f, y, ld);
             lds += in ? ld : 0.f;
             x = in ? y : x;
             j = tau[j];
@@ -444,16 +478,17 @@ __global__ void __launch_bounds__(128) chain_lanes(const float* __restrict__ x0,
             const float ud1 = (k + 1 < nb) ? udn : ud_last;
             RqFwd f;
             float yv, lv;
-            rq_forward(xc, xlo, xhi, ylo, yhi, kTMin + softplus_acc(ud0), kTMin + softplus_acc(ud1), f, yv, lv);
+            rq_forward_fast(xc, xlo, xhi, ylo, yhi, kTMin + softplus_fast_t(ud0), kTMin + softplus_fast_t(ud1), f, yv, lv);
             // ---- reverse mode through the rational-quadratic formula (as spline_point<true>) ----
             const float gyv = gy, gl = gld;
-            const float q = f.numA / f.den;
+            const float rden = __frcp_rn(f.den), rwk = __frcp_rn(f.wk);
+            const float q = f.numA * rden;
             float hk_b = gyv * q;
             const float q_b = gyv * f.hk;
-            const float numA_b = q_b / f.den;
-            float den_b = -q_b * q / f.den - 2.0f * gl / f.den;
-            float s_b = 2.0f * gl / f.s;
-            const float dn_b = gl / f.dn;
+            const float numA_b = q_b * rden;
+            float den_b = (-q_b * q - 2.0f * gl) * rden;
+            float s_b = __fdividef(2.0f * gl, f.s);
+            const float dn_b = __fdividef(gl, f.dn);
             float d1_b = dn_b * f.th * f.th;
             s_b += dn_b * 2.0f * f.tt;
             float tt_b = dn_b * 2.0f * f.s;
@@ -473,11 +508,11 @@ __global__ void __launch_bounds__(128) chain_lanes(const float* __restrict__ x0,
             th_b += tt_b * f.omt;
             omt_b += tt_b * f.th;
             th_b -= omt_b;
-            const float x_b = th_b / f.wk;
+            const float x_b = th_b * rwk;
             float x0_b = -x_b;
-            float wk_b = -th_b * f.th / f.wk;
-            hk_b += s_b / f.wk;
-            wk_b += -s_b * f.s / f.wk;
+            float wk_b = -th_b * f.th * rwk;
+            hk_b += s_b * rwk;
+            wk_b += -s_b * f.s * rwk;
             const float x1_b = wk_b;
             x0_b -= wk_b;
             const float y1_b = hk_b;
@@ -495,7 +530,7 @@ __global__ void __launch_bounds__(128) chain_lanes(const float* __restrict__ x0,
                     const float dot = G0 * hp0 + G1 * hp1;
                     gh = scale * c * ph * ((li < k ? G0 : 0.f) + (li < k + 1 ? G1 : 0.f) - dot);
                 }
-                const float g0 = d0_b / (1.0f + expf(-ud0)), g1 = d1_b / (1.0f + expf(-ud1));   // d softplus = sigmoid
+                const float g0 = __fdividef(d0_b, 1.0f + __expf(-ud0)), g1 = __fdividef(d1_b, 1.0f + __expf(-ud1));   // d softplus = sigmoid
                 gd = (li == k) ? g0 : ((li == k + 1) ? g1 : 0.f);
                 gd_last = (k + 1 == nb) ? g1 : 0.f;
             }
