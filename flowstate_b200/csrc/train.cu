@@ -100,23 +100,31 @@ __global__ void __launch_bounds__(256) gemm_nt(const float* __restrict__ A, int 
 }
 
 // dX[m, k] = sum_n dY[m, n] W[n, k];  MASK = 1: times [X[m, k] sc[k] + of[k] > 0] (the ReLU behind the BatchNorm of X)
+// splits > 1 (MASK = 0 only): blockIdx.x = column tile * splits + part; part p sums its share of the n range and writes
+// dX + p * part_stride (partials, added up in fixed order by sum_parts: the step stays bit-repeatable).  The final
+// layer's dX has a reduction length of N (3 nb + 1) ~ 3 k against a 256 x 128 output per layer: without the split the
+// launch is 184 blocks of 184 dependent load -> compute iterations.
 template <int MASK>
 __global__ void __launch_bounds__(256) gemm_nn(const float* __restrict__ dY, int M, int Nout, int Kd, float* const* ptab,
                                                int per, int wi, const float* __restrict__ X, const float* __restrict__ sc,
-                                               const float* __restrict__ of, float* __restrict__ dX) {
+                                               const float* __restrict__ of, float* __restrict__ dX, int splits = 1,
+                                               size_t part_stride = 0) {
     __shared__ float As[16][68], Bs[16][68];
     const int z = blockIdx.z, tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
-    const int m0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int part = (int)blockIdx.x % splits;
+    const int m0 = blockIdx.y * 64, c0 = ((int)blockIdx.x / splits) * 64;
     dY += (size_t)z * M * Nout;
-    dX += (size_t)z * M * Kd;
+    dX += (size_t)z * M * Kd + (size_t)part * part_stride;
     const float* W = ptab[(size_t)z * per + wi];
     float acc[4][4] = {};
     const int lr = tid / 4, ln = (tid % 4) * 4;          // dY tile: row lr, 4 consecutive n
     const int wr = tid / 16, wc = (tid % 16) * 4;        // W tile: n-row wr, 4 consecutive columns
-    for (int n0 = 0; n0 < Nout; n0 += 16) {
+    const int nper = ((Nout + splits - 1) / splits + 15) / 16 * 16;
+    const int n_begin = part * nper, n_end = min(Nout, n_begin + nper);
+    for (int n0 = n_begin; n0 < n_end; n0 += 16) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), w = a;
-        if (m0 + lr < M && n0 + ln < Nout) a = *reinterpret_cast<const float4*>(dY + (size_t)(m0 + lr) * Nout + n0 + ln);
-        if (n0 + wr < Nout && c0 + wc < Kd) w = *reinterpret_cast<const float4*>(W + (size_t)(n0 + wr) * Kd + c0 + wc);
+        if (m0 + lr < M && n0 + ln < n_end) a = *reinterpret_cast<const float4*>(dY + (size_t)(m0 + lr) * Nout + n0 + ln);
+        if (n0 + wr < n_end && c0 + wc < Kd) w = *reinterpret_cast<const float4*>(W + (size_t)(n0 + wr) * Kd + c0 + wc);
         As[ln][lr] = a.x; As[ln + 1][lr] = a.y; As[ln + 2][lr] = a.z; As[ln + 3][lr] = a.w;
         *reinterpret_cast<float4*>(&Bs[wr][wc]) = w;
         __syncthreads();
@@ -137,6 +145,19 @@ __global__ void __launch_bounds__(256) gemm_nn(const float* __restrict__ dY, int
             dX[(size_t)m * Kd + c] = v;
         }
     }
+}
+
+// out[i] = parts[0][i] + parts[1][i] + ... in that order (float4 lanes)
+__global__ void __launch_bounds__(256) sum_parts(const float* __restrict__ parts, size_t part_stride, int splits, size_t n4,
+                                                 float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = reinterpret_cast<const float4*>(parts)[i];
+    for (int p = 1; p < splits; ++p) {
+        const float4 b = reinterpret_cast<const float4*>(parts + (size_t)p * part_stride)[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
 }
 
 // dW[n, k] = sum_m dY[m, n] pro(A[m, k]),  db[n] = sum_m dY[m, n]  (written, not accumulated)
@@ -643,8 +664,9 @@ struct fs_train {
 };
 
 namespace {
+static constexpr int FINAL_DX_SPLITS = 4;
 struct Carve {
-    float *thI, *xsI, *xsT, *ldI, *ldT, *feat, *hs, *ts, *st, *theta, *dtheta, *dhA, *dhB, *d1, *d2, *dfeat, *dident;
+    float *thI, *xsI, *xsT, *ldI, *ldT, *feat, *hs, *ts, *st, *theta, *dtheta, *dhA, *dhB, *d1, *d2, *dfeat, *dident, *parts;
 };
 size_t carve_train(const fs_train* t, int B, float* base, Carve* c) {
     size_t off = 0;
@@ -668,6 +690,7 @@ size_t carve_train(const fs_train* t, int B, float* base, Carve* c) {
     v.d2 = take(K * b * H);
     v.dfeat = take(K * b * 2 * N);
     v.dident = take(K * b * N);
+    v.parts = take((size_t)FINAL_DX_SPLITS * K * b * H);     // partials of the final layer's dX (split reduction)
     if (c) *c = v;
     return off * sizeof(float);
 }
@@ -832,7 +855,14 @@ extern "C" int fs_train_forward_kld(fs_train* t, const float* x, int B, float* l
           c.dtheta);
     gemm_tn<0><<<dim3((H + 63) / 64, (NP + 63) / 64, K), 256, 0, s>>>(c.dtheta, B, NP, H, hlast, nullptr, nullptr, t->gtab, per,
                                                                       t_wf(nbk), t_wf(nbk) + 1);
-    gemm_nn<0><<<grid2(H, B), 256, 0, s>>>(c.dtheta, B, NP, H, t->ptab, per, t_wf(nbk), nullptr, nullptr, nullptr, c.dhA);
+    if (NP >= 1024 && (KBH & 3) == 0) {                   // long reduction, small output: split it four ways
+        gemm_nn<0><<<dim3(((H + 63) / 64) * FINAL_DX_SPLITS, (B + 63) / 64, K), 256, 0, s>>>(
+            c.dtheta, B, NP, H, t->ptab, per, t_wf(nbk), nullptr, nullptr, nullptr, c.parts, FINAL_DX_SPLITS, KBH);
+        sum_parts<<<(unsigned)((KBH / 4 + 255) / 256), 256, 0, s>>>(c.parts, KBH, FINAL_DX_SPLITS, KBH / 4, c.dhA);
+        ++launches;
+    } else {
+        gemm_nn<0><<<grid2(H, B), 256, 0, s>>>(c.dtheta, B, NP, H, t->ptab, per, t_wf(nbk), nullptr, nullptr, nullptr, c.dhA);
+    }
     launches += 3;
     float *dA = c.dhA, *dB = c.dhB;
     for (int b = nbk - 1; b >= 0; --b) {
