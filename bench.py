@@ -440,6 +440,7 @@ class Harness:
             from flowstate_b200.drivers.training import FlowTrainer
             t = w["train"]
             self.trainer = FlowTrainer(self.model, t["lr"], t["wd"], 1.0, t["batch"], use_graph=True)
+            self.model.layer_parallel = "prefer"   # the cycle's sample / log_prob passes run alone (no side stream)
 
     # -- the round ----------------------------------------------------------
     def launch_proposals(self, z_host=None):

@@ -87,6 +87,7 @@ _PROTOS = {
     "fs_flow_coupling": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_coupling_all": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P, _P]),
     "fs_flow_uses_layer_parallel": (C.c_int, [_P, C.c_int, C.c_int]),
+    "fs_flow_set_layer_parallel": (C.c_int, [_P, C.c_int]),
     "fs_train_create": (C.c_int, [_P, _P]),
     "fs_train_destroy": (None, [_P]),
     "fs_train_forward_kld": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),

@@ -807,8 +807,15 @@ static bool layer_parallel_rows(const fs_flow* f, int precision, int rows) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    if (f->lp_mode == 2) return false;
     if (tiles > 96) return false;
     if (f->K * tiles <= sms) return true;
+    // "prefer" (fs_flow_set_layer_parallel): the caller runs its passes alone on the GPU, so thread blocks that wait
+    // for their predecessor step take nothing from anybody; with two whole steps resident the trunks of step s + 1
+    // overlap the spline chain of step s (Alg-2 flow, 23 layers x 32 / 64 tiles: passes 11 % faster).  Not the default:
+    // next to other streams (the hybrid round samples its next proposals beside the sweep) waiting blocks hold SMs
+    // the other kernels need, and the measured gain was nil.
+    if (f->lp_mode == 1 && 2 * tiles <= sms) return true;
     const double trunk = 2.0 * (2.0 * f->N) * f->H + 4.0 * f->n_blocks * (double)f->H * f->H;
     const double fin = 2.0 * f->H * (double)f->N * (3.0 * f->nb + 1.0);
     return (double)tiles / sms + trunk / (trunk + fin) >= 1.0;
@@ -1097,6 +1104,12 @@ extern "C" int fs_flow_inverse(fs_flow* f, const float* x, int B, double in_shif
     fs::count_launch();
         FS_CUDA(cudaGetLastError());
     }
+    return FS_OK;
+}
+
+extern "C" int fs_flow_set_layer_parallel(fs_flow* f, int mode) {
+    if (!f || mode < 0 || mode > 2) { set_error("fs_flow_set_layer_parallel: invalid argument"); return FS_ERR_INVALID; }
+    f->lp_mode = mode;
     return FS_OK;
 }
 

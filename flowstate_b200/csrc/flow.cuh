@@ -32,6 +32,7 @@ struct fs_flow {
     void* tc;   // tensor-core pack (flow_tc.cu), or nullptr
     int* tc_err;   // device error word written by the tensor kernel's watchdog
     int sm_count;
+    int lp_mode = 0;                   // fs_flow_set_layer_parallel: 0 auto, 1 prefer (the caller's passes run alone), 2 never
     void* repack_tab = nullptr;        // fs_flow_update: device table of per-layer pointers (repack.cu)
     double* repack_scratch = nullptr;  // ... and its float64 scratch
 };

@@ -278,6 +278,7 @@ def run_algorithm_2(cfg, device="cuda", log=print):
     eng, L = _init_chains(cfg, device)
     _local_phase(eng, cfg.equilibration_steps, cfg)
     model = _build_flow(cfg, L, device)
+    model.layer_parallel = "prefer"        # every sample / log_prob pass of a cycle runs alone on the GPU
     eng.set_nf_model(model)
     # initial training set: INITIAL_TRAINING_NUM_SAMPLES / (NUM_MC_RUNS / SAMPLING_FREQUENCY) steps per chain
     # (main_algorithm_2.py:240-252)

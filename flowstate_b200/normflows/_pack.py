@@ -310,6 +310,14 @@ class FlowPack:
                                                    _lib.stream_ptr(buf0.device)))
         return (buf1 if self.K & 1 else buf0), parts
 
+    def set_layer_parallel(self, mode):
+        """Scheduling hint (fs_flow_set_layer_parallel): "auto" | "prefer" (this flow's passes run alone on the GPU) |
+        "never"."""
+        code = {"auto": 0, "prefer": 1, "never": 2}[mode]
+        if getattr(self, "_lp_mode", 0) != code:
+            _lib.check(_lib.lib().fs_flow_set_layer_parallel(self._h, code))
+            self._lp_mode = code
+
     def uses_layer_parallel(self, rows):
         """True when log_prob / sample passes of `rows` rows run as one layer-parallel launch (fs_flow_uses_layer_parallel)."""
         return bool(_lib.lib().fs_flow_uses_layer_parallel(self._h, int(rows), _PREC[self.resolved_precision()]))

@@ -22,6 +22,9 @@ class NormalizingFlow(nn.Module):
         # "auto": tcgen05 tensor cores (TF32 operands, FP32 accumulation; log-density within ~5e-6 of float64)
         # when the flow shape has the tensor path, else the FP32 CUDA-core path | "fp32" | "tf32"
         self.precision = "auto"
+        # "auto" | "prefer" | "never": whether eval-mode passes launch all K layers at once (FlowPack.set_layer_parallel);
+        # "prefer" when nothing else runs beside the flow's passes (the Algorithm-2 driver sets it)
+        self.layer_parallel = "auto"
 
     # -- packing ----------------------------------------------------------
     def _fusable(self):
@@ -38,6 +41,7 @@ class NormalizingFlow(nn.Module):
             # (fs_flow_update) instead of packing on the host again - Algorithm 2 does this every cycle
             self._pack.update(layers)
         self._pack.precision = self.precision
+        self._pack.set_layer_parallel(self.layer_parallel)
         return self._pack
 
     def repack(self):

@@ -236,6 +236,13 @@ int fs_flow_coupling_all(fs_flow* flow, int direction, const float* features, fl
  * they launch layer by layer (no such path for the flow, or one launch per layer already fills the GPU). */
 int fs_flow_uses_layer_parallel(const fs_flow* flow, int rows, int precision);
 
+/* Scheduling hint for the passes of this flow: 0 = automatic (default: layer-parallel only when measured to pay next to
+ * concurrent streams), 1 = prefer - the caller's fs_flow_inverse / fs_flow_forward calls have the GPU to themselves
+ * (Algorithm 2's per-cycle sample / log_prob, hybrid_NF_MCMC/main_algorithm_2.py:476-500), so every pass with at
+ * least two whole layer steps resident runs layer-parallel, 2 = never.  Results do not depend on the mode beyond
+ * the summation order of the per-layer log-det partials. */
+int fs_flow_set_layer_parallel(fs_flow* flow, int mode);
+
 /* Feature layout of the tensor path.  fs_flow_inverse / fs_flow_forward keep the periodic features of a chunk in
  * 128-row tiles of quads, element (row b, feature k) at [b / 128][k / 4][b % 128][k % 4], so that the kernel's
  * row-per-thread loads are coalesced.  A caller of fs_flow_coupling that already holds the features in that layout

@@ -215,7 +215,7 @@ def test_prep_kernel_with_staged_tables_is_bit_identical(monkeypatch, n, H, nb):
 
 
 @pytest.mark.parametrize("n,K,blocks,H,nb,B", [(40, 5, 2, 256, 32, 300), (64, 4, 2, 128, 15, 700), (6, 7, 1, 128, 8, 129),
-                                                 (5, 3, 2, 128, 8, 200)])
+                                                 (5, 3, 2, 128, 8, 200), (64, 23, 2, 128, 15, 4096)])
 def test_layer_parallel_pass_matches_layer_by_layer(monkeypatch, n, K, blocks, H, nb, B):
     """Even N: the conditioners of all K layers run in ONE launch of K x tiles CTAs, the spline chain ordered by
     per-(tile, quadrant, pair) chunk counters in global memory; FS_NO_LP=1 keeps one launch per layer.
@@ -237,6 +237,21 @@ def test_layer_parallel_pass_matches_layer_by_layer(monkeypatch, n, K, blocks, H
     for _ in range(2):                                   # twice: the chunk counters are re-armed per pass
         z_lp, ld_lp = model.inverse_and_log_det(x)
         xs_lp, lds_lp = model.forward_and_log_det(z)
+    # the scheduling hint: "never" = one launch per layer; "prefer" = layer-parallel whenever two whole steps are resident
+    lp_auto = model._cuda_pack().uses_layer_parallel(B)
+    model.layer_parallel = "never"
+    assert not model._cuda_pack().uses_layer_parallel(B)
+    z_nv, ld_nv = model.inverse_and_log_det(x)
+    model.layer_parallel = "prefer"
+    lp_prefer = model._cuda_pack().uses_layer_parallel(B)
+    assert lp_prefer or not lp_auto
+    if n % 2 == 0:
+        assert lp_prefer                                 # every case here keeps two whole steps resident
+    z_pf, ld_pf = model.inverse_and_log_det(x)
+    model.layer_parallel = "auto"
+    assert torch.equal(z_nv, z_lp) and torch.equal(z_pf, z_lp)
+    assert (ld_nv - ld_lp).abs().max().item() < 2e-6 * (1.0 + ld_lp.abs().max().item())
+    assert (ld_pf - ld_lp).abs().max().item() < 2e-6 * (1.0 + ld_lp.abs().max().item())
     monkeypatch.setenv("FS_NO_LP", "1")
     z_seq, ld_seq = model.inverse_and_log_det(x)
     xs_seq, lds_seq = model.forward_and_log_det(z)
