@@ -239,15 +239,21 @@ __device__ __forceinline__ float np_mod_near(float a, float L) {
 // float2 apart (stride2 * 8 bytes = 64 mod 128, so the groups of a warp read disjoint banks).
 // TRACE adds the outputs of the parity tests (accept flag, particle index, e_old / e_new reduced separately); the
 // decision arithmetic is the same code either way, so a traced run follows the untraced trajectory bit for bit.
+// SKIP (dilute boxes) keeps ONLY (x, y) in shared memory and derives the centred copy of the few partners that pass the
+// cut-off pre-test on the fly (two selects + two adds): 8 bytes per particle instead of 16, so that - with the register
+// budget of seven 128-thread blocks per SM - all 1024 blocks of the N = 256 hybrid configuration (8192 chains) are
+// resident at once.  With both copies stored the launch was 1.38 waves of equally long blocks, i.e. two full block
+// times, the second one at a third of the occupancy and spread thinly over every SM.
 template <int LPC, bool TRACE, bool SKIP>
-__global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
+__global__ void __launch_bounds__(128, SKIP ? 7 : 5) local_sweep_fast_kernel(float* __restrict__ pos, double* __restrict__ E,
                                                                double* __restrict__ W,
                                                                const double* __restrict__ max_disp,
                                                                long long* __restrict__ attempts,
                                                                long long* __restrict__ accepted, int B, int N,
                                                                int steps, PotDev P, double beta,
                                                                unsigned long long seed, long long chain_id0,
-                                                               int stride2, unsigned char* __restrict__ trace_accept,
+                                                               int stride2, int slot2,
+                                                               unsigned char* __restrict__ trace_accept,
                                                                int* __restrict__ trace_idx,
                                                                float* __restrict__ trace_e) {
     constexpr int CPW = 32 / LPC;                 // chains per warp
@@ -267,12 +273,14 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
     // ulp(L) / r of relative accuracy on pairs that straddle the periodic boundary (1e-5 of r^-12 at L = 11).
     // (two float2 arrays per chain slot: the dilute-box variant reads the centred copy only for warp trips that hold a
     // pair inside the cut-off)
-    float2* sp = reinterpret_cast<float2*>(smem4) + (size_t)(wib * CPW + grp) * 2 * stride2;
-    float2* sc = sp + stride2;
+    const float hLx = 0.5f * P.Lx, hLy = 0.5f * P.Ly;
+    constexpr bool CEN = !SKIP;                  // centred copy stored (slot2 = 2 * stride2) or derived on the fly
+    float2* sp = reinterpret_cast<float2*>(smem4) + (size_t)(wib * CPW + grp) * slot2;
+    float2* sc = sp + stride2;                   // CEN only
+    auto centred = [&](float2 v) { return make_float2(v.x - (v.x > hLx ? P.Lx : 0.f), v.y - (v.y > hLy ? P.Ly : 0.f)); };
     float2* gp = reinterpret_cast<float2*>(pos) + (size_t)b * N;
     const int iters = (N + LPC - 1) / LPC;
     const float qnan = __int_as_float(0x7fc00000);
-    const float hLx = 0.5f * P.Lx, hLy = 0.5f * P.Ly;
     // Slots are padded to iters * LPC entries with NaN positions: a NaN r^2 fails the cut-off test (every term 0) and is
     // ignored by fminf, so neither the padding nor the moved particle itself (overwritten with NaN while its partners
     // are walked) needs a mask inside the pair loop.
@@ -280,10 +288,10 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         float2 v = make_float2(qnan, qnan), c = v;
         if (i < N) {
             v = gp[i];
-            c = make_float2(v.x - (v.x > hLx ? P.Lx : 0.f), v.y - (v.y > hLy ? P.Ly : 0.f));
+            c = centred(v);
         }
         sp[i] = v;
-        sc[i] = c;
+        if (CEN) sc[i] = c;
     }
     __syncwarp();
 
@@ -340,11 +348,11 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         const int p = p_n;
         const double ddx = dx_n, ddy = dy_n;
         const uint32_t r_u3 = u3_n;
-        const float2 old = sp[p], oldc = sc[p];
+        const float2 old = sp[p], oldc = CEN ? sc[p] : centred(old);
         __syncwarp();
         if (sub == 0) {                                        // the moved particle is not its own partner
             sp[p] = make_float2(qnan, qnan);
-            sc[p] = make_float2(qnan, qnan);
+            if (CEN) sc[p] = make_float2(qnan, qnan);
         }
         // new_positions[p] += displacement (float64 add, stored float32), then % L (monte_carlo.py:161-166)
         float nx = (float)((double)old.x + ddx);
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
                 if (!__any_sync(FULL, fminf(ta, tb) <= 1.0001f * rc2)) continue;
             }
             // both candidates of the minimum image per axis, squared; the smaller one is the image (see above)
-            const float2 qc = sc[sub + it * LPC];
+            const float2 qc = CEN ? sc[sub + it * LPC] : centred(q);     // NaN stays NaN (the comparison is false)
             const unsigned long long X1 = sub2s(PCX, pk2s(qc.x, qc.x)), Y1 = sub2s(PCY, pk2s(qc.y, qc.y));
             float ax0, bx0, ax1, bx1, ay0, by0, ay1, by1;
             upk2s(mul2s(X0, X0), ax0, bx0);
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(128) local_sweep_fast_kernel(float* __restrict
         }
         if (sub == 0) {
             sp[p] = ok ? make_float2(nx, ny) : old;
-            sc[p] = ok ? make_float2(cnx, cny) : oldc;
+            if (CEN) sc[p] = ok ? make_float2(cnx, cny) : oldc;
         }
         if (ok) {
             acc += 1;
@@ -512,9 +520,12 @@ static int launch_fast_t(float* pos, double* E, double* W, const double* md, lon
     constexpr int CPW = 32 / LPC;
     // slot stride (float4 units): N rounded up to whole trips of the lane group (room for the NaN padding)
     const int stride2 = (N + LPC - 1) / LPC * LPC;
+    // float2 units between two chains' slots: (x, y) and the centred copy, or (SKIP) the positions alone - then padded
+    // to 8 mod 16 for the 8-lane groups so that the two groups of a half-warp read different banks
+    const int slot2 = SKIP ? (LPC == 8 ? stride2 + ((8 - stride2 % 16) + 16) % 16 : stride2) : 2 * stride2;
     int wpc = 4;
-    while (wpc > 1 && (size_t)wpc * CPW * stride2 * sizeof(float4) > 200 * 1024) wpc >>= 1;
-    const size_t smem = (size_t)wpc * CPW * stride2 * sizeof(float4);
+    while (wpc > 1 && (size_t)wpc * CPW * slot2 * sizeof(float2) > 200 * 1024) wpc >>= 1;
+    const size_t smem = (size_t)wpc * CPW * slot2 * sizeof(float2);
     if (smem > 227 * 1024) {
         set_error("fs_local_sweep: N=%d does not fit in shared memory", N);
         return FS_ERR_UNSUPPORTED;
@@ -524,7 +535,7 @@ static int launch_fast_t(float* pos, double* E, double* W, const double* md, lon
                                      (int)smem));
     const int cpc = wpc * CPW;
     local_sweep_fast_kernel<LPC, TRACE, SKIP><<<(B + cpc - 1) / cpc, wpc * 32, smem, s>>>(
-        pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, stride2, ta, ti, te);
+        pos, E, W, md, att, acc, B, N, steps, P, beta, seed, chain_id0, stride2, slot2, ta, ti, te);
     fs::count_launch();
     return cuda_check(cudaGetLastError(), "local_sweep_fast_kernel");
 }
