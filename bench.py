@@ -819,8 +819,11 @@ class Harness:
             gbs = bytes_ / (out["accept_global_ms"] * 1e-3) / 1e9
             extra["accept_global"] = {"bound": "hbm", "kernel": "accept_global_kernel", "achieved": gbs,
                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                      "note": "stand-alone fs_accept_global replayed from a CUDA graph, %.1f KB in %.1f us "
-                                              "per launch; the round runs fs_accept_global_fused"
+                                      "note": "stand-alone fs_accept_global replayed from a CUDA graph on the same buffers "
+                                              "(17 MB of proposals stay in the 126 MB L2 between replays: an L2-assisted "
+                                              "figure; cold-cache ncu launch: 8.2 us, DRAM 26 %% of peak, "
+                                              "profiles/r02f_ncu_summary.md), %.1f KB in %.1f us per launch; the round runs "
+                                              "fs_accept_global_fused"
                                               % (bytes_ / 1e3, out["accept_global_ms"] * 1e3)}
             if fp32:
                 gm = energy_flops(B, n) / (out["global_move_fused_ms"] * 1e-3) / 1e12

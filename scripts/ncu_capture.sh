@@ -5,7 +5,7 @@
 #    global accept, the two feature / unconditional-spline kernels)
 # Every ncu run is preceded by the same command without ncu (B200_PROFILING.md).
 set -u
-TAG=${1:-r02e}
+TAG=${1:-r02f}
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary"
 OUT=gpurun_out
 $CMD > $OUT/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain_$TAG.log; exit 1; }
