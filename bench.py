@@ -600,28 +600,62 @@ class Harness:
         import torch.distributed as dist
         B, n, dev, eng = self.B, self.n, self.dev, self.eng
         h_z = torch.empty(B, 2 * n, dtype=torch.float32).uniform_(-self.bound, self.bound).pin_memory()
+        # Copies ride on their own streams (the copy engines run beside the SMs): the upload of step k + 1's chain batch
+        # is issued while step k computes, the download of step k's results while step k + 1 computes; device-side
+        # staging buffers decouple them from the engine's state.  Every step still moves its own inputs and results.
+        main = torch.cuda.current_stream(dev)
+        up, dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         hb = []
         for k in range(2):
             hp = torch.empty(B, n, 2, dtype=torch.float32).pin_memory()
             hp.copy_(eng.pos.cpu())
             hb.append({"pos": hp, "out_pos": torch.empty(B, n, 2, dtype=torch.float32).pin_memory(),
                        "out_E": torch.empty(B, dtype=torch.float64).pin_memory(),
-                       "out_mask": torch.empty(B, dtype=torch.uint8).pin_memory(), "ev": None})
+                       "out_mask": torch.empty(B, dtype=torch.uint8).pin_memory(),
+                       "d_in": torch.empty(B, n, 2, dtype=torch.float32, device=dev),
+                       "d_pos": torch.empty(B, n, 2, dtype=torch.float32, device=dev),
+                       "d_E": torch.empty(B, dtype=torch.float64, device=dev),
+                       "d_mask": torch.empty(B, dtype=torch.uint8, device=dev),
+                       "ev_up": None, "ev_used": None, "ev_dn": None})
+
+        def upload(k):
+            buf = hb[k % 2]
+            if buf["ev_dn"] is not None:                   # results of this batch's previous step have landed:
+                buf["ev_dn"].synchronize()                 # its output buffer becomes its next input
+                buf["pos"], buf["out_pos"] = buf["out_pos"], buf["pos"]
+            with torch.cuda.stream(up):
+                if buf["ev_used"] is not None:
+                    up.wait_event(buf["ev_used"])          # the engine has taken the previous content of the staging buffer
+                buf["d_in"].copy_(buf["pos"], non_blocking=True)
+                buf["ev_up"] = torch.cuda.Event()
+                buf["ev_up"].record(up)
 
         def e2e_round(k):
             buf = hb[k % 2]
-            if buf["ev"] is not None:                      # results of this batch's previous step have landed
-                buf["ev"].synchronize()
-                buf["pos"].copy_(buf["out_pos"])
-            eng.pos.copy_(buf["pos"], non_blocking=True)
+            main.wait_event(buf["ev_up"])
+            eng.pos.copy_(buf["d_in"])
+            buf["ev_used"] = torch.cuda.Event()
+            buf["ev_used"].record(main)
             eng.refresh_energy()
-            mask = self.one_round(h_z)                     # base noise comes from the host buffer
-            buf["out_pos"].copy_(eng.pos, non_blocking=True)
-            buf["out_E"].copy_(eng.E, non_blocking=True)
-            buf["out_mask"].copy_(mask, non_blocking=True)
-            buf["ev"] = torch.cuda.Event()
-            buf["ev"].record()
+            mask = self.one_round(h_z)                     # base noise comes from the host buffer (side stream)
+            if buf["ev_dn"] is not None:
+                main.wait_event(buf["ev_dn"])              # the previous download out of the staging buffers is done
+            buf["d_pos"].copy_(eng.pos)
+            buf["d_E"].copy_(eng.E)
+            buf["d_mask"].copy_(mask)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(dn):
+                dn.wait_event(done)
+                buf["out_pos"].copy_(buf["d_pos"], non_blocking=True)
+                buf["out_E"].copy_(buf["d_E"], non_blocking=True)
+                buf["out_mask"].copy_(buf["d_mask"], non_blocking=True)
+                buf["ev_dn"] = torch.cuda.Event()
+                buf["ev_dn"].record(dn)
+            upload(k + 1)                                  # after this step is queued: the host wait inside it (step
+                                                           # k - 1's results) overlaps this step's execution
 
+        upload(0)
         with quiet_host():
             for k in range(4):
                 e2e_round(k)

@@ -369,8 +369,12 @@ __global__ void __launch_bounds__(32 * FS_SPLINE_WARPS) prep_inverse_v2(
 // coordinate is word 32 k + lane: bank = lane whatever k, no conflicts.  Sums run over the same elements in the same
 // order as prep_*_v2 (lane-strided coordinates, then the warp tree): results are bit-identical.
 // DENSITY: true = prep_inverse (coupling.py:86-102), false = prep_forward (coupling.py:113-124).
+#ifndef FS_PREP3_WARPS
 #define FS_PREP3_WARPS 8
+#endif
+#ifndef FS_PREP3_ROWS
 #define FS_PREP3_ROWS 4
+#endif
 __device__ __forceinline__ void cp_async4(unsigned dst_smem, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
 }
