@@ -392,6 +392,42 @@ def fp32_peak(device_index):
     return out
 
 
+def time_graphed_round(h, steps):
+    """The same round issued as ONE CUDA-graph launch (flowstate_b200/drivers/rounds.HybridRound): a reported variant, the
+    headline stays the host-driven loop.  Returns None when the capture is refused."""
+    from flowstate_b200.drivers.rounds import HybridRound
+    try:
+        hr = HybridRound(h.eng, h.model, h.w["local"], use_graph=True)
+        with quiet_host():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(6):
+                hr.step()
+            b.record()
+            torch.cuda.synchronize()
+            per = max(a.elapsed_time(b) / 6, 1e-3)
+            for _ in range(max(0, min(200, int(200.0 / per) - 6))):
+                hr.step()
+            torch.cuda.synchronize()
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            marks[0].record()
+            for i in range(steps):
+                hr.step()
+                marks[i + 1].record()
+            torch.cuda.synchronize()
+        ms = marks[0].elapsed_time(marks[-1])
+        per_round = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+        return {"value": h.B * (h.w["local"] + 1) * steps / (ms * 1e-3), "unit": "chain-steps/s",
+                "ms_per_step": ms / steps, "steps": steps, "graph_launches_per_step": 1,
+                "kernels_per_graph": hr.launches_per_round,
+                "step_ms_min_median_max": [min(per_round), sorted(per_round)[len(per_round) // 2], max(per_round)],
+                "note": "whole round (forked sampling pass, sweep, log-densities, fused global move) replayed from a CUDA "
+                        "graph; bit-equal to the eager round: tests/test_gpu_drivers.py::"
+                        "test_graphed_hybrid_round_equals_eager_round"}
+    except Exception as ex:
+        return {"error": repr(ex)[:200]}
+
+
 class Harness:
     """One workload on this rank: engine + flow + the hybrid round, its timings and rooflines."""
 
@@ -975,6 +1011,9 @@ def main():
                            "tests/test_gpu_flow.py::test_sampling_pass_log_prob_equals_inverse_pass, "
                            "tests/test_gpu_global.py::test_global_move_with_sampling_pass_log_density"}
 
+    graphed = None
+    if rank == 0 and world == 1 and h.trainer is None and not args.no_secondary:
+        graphed = time_graphed_round(h, 20)
     secondary = {}
     if rank == 0 and world == 1 and not args.no_secondary:
         del h.model, h.eng
@@ -992,6 +1031,7 @@ def main():
             e2e_ss, h2d_s, d2h_s = hs.time_e2e(s_steps)
             tot = ws["chains"] * (ws["local"] + 1) * s_steps
             ph, ex = hs.phases(fp32, peaks)
+            gr_s = time_graphed_round(hs, s_steps) if hs.trainer is None else None
             secondary[name] = {"metric": "mh_chain_steps_per_s", "value": tot / (ms_s * 1e-3), "unit": "chain-steps/s",
                                "steps": s_steps, "warmup": hs.warmup_rounds, "ms_per_step": ms_s / s_steps, "gpu_launches": l_s,
                                "step_ms_min_median_max": [min(hs.step_ms), sorted(hs.step_ms)[len(hs.step_ms) // 2],
@@ -1000,7 +1040,7 @@ def main():
                                "e2e": {"value": tot / e2e_ss, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d_s,
                                        "d2h_bytes_per_step": d2h_s},
                                "roofline": hs.conditioner_roofline(peaks, peak_src), "phases_ms": ph,
-                               "other_rooflines": ex}
+                               "other_rooflines": ex, "variant_graphed_round": gr_s}
             del hs
             torch.cuda.empty_cache()
         try:
@@ -1029,6 +1069,7 @@ def main():
                     "timed_region_ms": ms_total,
                     "warmup_rounds_run": main_warmup,
                     "variant_logq_from_sampling_pass": variant,
+                    "variant_graphed_round": graphed,
                     "step_ms_min_median_max": [min(main_step_ms), sorted(main_step_ms)[len(main_step_ms) // 2],
                                                max(main_step_ms)]},
         "nf_proposals_per_s": world * B * args.steps / (ms_total * 1e-3),

@@ -89,3 +89,45 @@ def test_mcmc_only_small():
     from flowstate_b200.drivers import observables
     cls, _, _ = observables._classify(pos, L / 2, cfg.r0)
     assert np.array_equal(cls.cpu().numpy(), obr.classify(pos, L / 2, cfg.r0))
+
+
+def test_graphed_hybrid_round_equals_eager_round():
+    """drivers/rounds.HybridRound: the whole round (forked sampling pass of the next proposals, local sweep, both
+    log-densities, fused energy + acceptance) replayed from a CUDA graph against the same round issued eagerly - same
+    Philox streams, same base noise (torch's generator re-seeded) -> identical accept masks, positions, energies and
+    counters after every round, including the rounds that are replays."""
+    import flowstate_b200.MCMC as MC
+    import flowstate_b200.normflows as NF
+    from flowstate_b200.drivers.rounds import HybridRound
+    from oracle import energy_ref as er
+    n, B, rho = 32, 256, 0.3
+    L = float(np.float32(np.sqrt(n / rho)))
+    bound = L / 2
+    torch.manual_seed(0)
+    flows = [NF.flows.CircularCoupledRationalQuadraticSpline(2 * n, 2, 128, list(range(2 * n)), num_bins=8,
+                                                             tail_bound=bound) for _ in range(3)]
+    model = NF.NormalizingFlow(NF.Energy.UniformParticle(n, 2, bound, "cuda"), flows)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    model = model.cuda().eval()
+    pos, _ = er.batch_lattices(B, n, rho, seed0=3)
+    out = {}
+    for graph in (False, True):
+        eng = MC.BatchedMonteCarlo(pos, MC.SimulationBox(L), 1.0, n, num_wells=2, V0_list=[-10.0, -10.5], r0=1.2, k=15,
+                                   initial_max_displacement=0.4, rng="philox", seeds=9)
+        eng.set_nf_model(model)
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        hr = HybridRound(eng, model, 40, use_graph=graph)
+        hist = []
+        for r in range(6):
+            mask = hr.step()
+            hist.append((mask.clone(), eng.pos.clone(), eng.E.clone(), eng.accepted.clone()))
+        out[graph] = hist
+        if graph:
+            assert hr.graphs[0] is not None and hr.graphs[1] is not None and hr.launches_per_round > 0
+    for r, (a, b) in enumerate(zip(out[False], out[True])):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]), r
+    # the chains moved (local acceptances) and every round attempted its global move
+    assert int(out[True][-1][3].sum()) > 0 and not torch.equal(out[True][-1][1], out[True][0][1])
