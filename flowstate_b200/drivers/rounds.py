@@ -25,6 +25,8 @@ class HybridRound:
     def __init__(self, eng, model, local_steps, use_graph=True):
         if eng.nf_model is None:
             eng.set_nf_model(model)
+        elif eng.nf_model is not model:
+            raise ValueError("HybridRound: the engine already carries a different flow (set_nf_model)")
         self.eng, self.model, self.local_steps = eng, model, int(local_steps)
         self.use_graph = bool(use_graph)
         self.device = eng.device
