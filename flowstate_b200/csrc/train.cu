@@ -808,10 +808,11 @@ extern "C" int fs_train_forward_kld(fs_train* t, const float* x, int B, float* l
     auto chain = [&](auto bwd, auto shared, const float* x0, const int* cols, const int* tau, float scale_, const float* th,
                      float* xs_, float* lds_, float gld_, const float* inj, float* gth) {
         constexpr bool BW = decltype(bwd)::value, SH = decltype(shared)::value;
-        if (nb <= 16 && !getenv("FS_TRAIN_CHAIN_SCALAR")) {
+        static const bool scalar_chain = getenv("FS_TRAIN_CHAIN_SCALAR") != nullptr;   // development: thread-per-element kernel
+        if (nb <= 16 && !scalar_chain) {
             const unsigned g16 = (unsigned)(((long long)B * N * 16 + 127) / 128);
             chain_lanes<BW, SH, 16><<<g16, 128, 0, s>>>(x0, t->D, cols, tau, B, N, K, nb, t->bound, scale_, th, xs_, lds_, gld_, inj, gth);
-        } else if (nb <= 32 && !getenv("FS_TRAIN_CHAIN_SCALAR")) {
+        } else if (nb <= 32 && !scalar_chain) {
             const unsigned g32 = (unsigned)(((long long)B * N * 32 + 127) / 128);
             chain_lanes<BW, SH, 32><<<g32, 128, 0, s>>>(x0, t->D, cols, tau, B, N, K, nb, t->bound, scale_, th, xs_, lds_, gld_, inj, gth);
         } else {
