@@ -1001,7 +1001,12 @@ def main():
         h.pending.clear()
         h.logq_from_sample = True
         v_steps = 12
-        ms_v, l_v = h.time_device(v_steps, 4)
+        try:
+            ms_v, l_v = h.time_device(v_steps, 4)
+        except Exception as exv:                       # a variant must never take the line down
+            ms_v, l_v = float("nan"), 0
+            h.step_ms = [float("nan")]
+            variant_error = repr(exv)[:200]
         h.logq_from_sample = False
         h.pending.clear()
         variant = {"value": w["chains"] * (w["local"] + 1) * v_steps / (ms_v * 1e-3), "unit": "chain-steps/s",
@@ -1022,27 +1027,31 @@ def main():
         for name in WORKLOADS:
             if name == args.workload:
                 continue
-            ws = dict(WORKLOADS[name])
-            hs = Harness(name, ws, dev, 0, 1, args.precision)
-            # short rounds: enough of them that the pipeline refill after the bracketing synchronize (about four
-            # rounds, see time_device) weighs as little as in the headline run
-            s_steps = 12 if (ws.get("train") or ws["n"] >= 128) else 60
-            ms_s, l_s = hs.time_device(s_steps, 4)
-            e2e_ss, h2d_s, d2h_s = hs.time_e2e(s_steps)
-            tot = ws["chains"] * (ws["local"] + 1) * s_steps
-            ph, ex = hs.phases(fp32, peaks)
-            gr_s = time_graphed_round(hs, s_steps) if hs.trainer is None else None
-            secondary[name] = {"metric": "mh_chain_steps_per_s", "value": tot / (ms_s * 1e-3), "unit": "chain-steps/s",
-                               "steps": s_steps, "warmup": hs.warmup_rounds, "ms_per_step": ms_s / s_steps, "gpu_launches": l_s,
-                               "step_ms_min_median_max": [min(hs.step_ms), sorted(hs.step_ms)[len(hs.step_ms) // 2],
-                                                          max(hs.step_ms)],
-                               "config": workload_config(name, ws),
-                               "e2e": {"value": tot / e2e_ss, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d_s,
-                                       "d2h_bytes_per_step": d2h_s},
-                               "roofline": hs.conditioner_roofline(peaks, peak_src), "phases_ms": ph,
-                               "other_rooflines": ex, "variant_graphed_round": gr_s}
-            del hs
-            torch.cuda.empty_cache()
+            try:
+                ws = dict(WORKLOADS[name])
+                hs = Harness(name, ws, dev, 0, 1, args.precision)
+                # short rounds: enough of them that the pipeline refill after the bracketing synchronize (about four
+                # rounds, see time_device) weighs as little as in the headline run
+                s_steps = 12 if (ws.get("train") or ws["n"] >= 128) else 60
+                ms_s, l_s = hs.time_device(s_steps, 4)
+                e2e_ss, h2d_s, d2h_s = hs.time_e2e(s_steps)
+                tot = ws["chains"] * (ws["local"] + 1) * s_steps
+                ph, ex = hs.phases(fp32, peaks)
+                gr_s = time_graphed_round(hs, s_steps) if hs.trainer is None else None
+                secondary[name] = {"metric": "mh_chain_steps_per_s", "value": tot / (ms_s * 1e-3), "unit": "chain-steps/s",
+                                   "steps": s_steps, "warmup": hs.warmup_rounds, "ms_per_step": ms_s / s_steps, "gpu_launches": l_s,
+                                   "step_ms_min_median_max": [min(hs.step_ms), sorted(hs.step_ms)[len(hs.step_ms) // 2],
+                                                              max(hs.step_ms)],
+                                   "config": workload_config(name, ws),
+                                   "e2e": {"value": tot / e2e_ss, "unit": "chain-steps/s", "h2d_bytes_per_step": h2d_s,
+                                           "d2h_bytes_per_step": d2h_s},
+                                   "roofline": hs.conditioner_roofline(peaks, peak_src), "phases_ms": ph,
+                                   "other_rooflines": ex, "variant_graphed_round": gr_s}
+                del hs
+                torch.cuda.empty_cache()
+            except Exception as ex:      # a secondary entry must never take the line down
+                secondary[name] = {"error": repr(ex)[:300]}
+                torch.cuda.empty_cache()
         try:
             secondary["energy_sweep"] = energy_sweep(dev, fp32, MC)
         except Exception as ex:      # a secondary entry must never take the line down
