@@ -387,3 +387,30 @@ def test_trainer_optimizer_reset_equals_a_new_adam():
         tr.step(xs[2]); tr.step(xs[3])
         out.append(torch.cat([p.detach().reshape(-1) for p in model.parameters()]))
     assert torch.equal(out[0], out[1])
+
+
+def test_trainer_flat_bucket_layout():
+    """The gradient bucket of FlowTrainer: every trainable parameter's .grad is a view into ONE flat buffer, tensors
+    start on 16-byte boundaries (the training kernels load float4 through these pointers), the padding stays zero and
+    parameters without a gradient (PeriodicFeaturesElementwise.weights) are left alone."""
+    import flowstate_b200.normflows as NF
+    from flowstate_b200.drivers.training import FlowTrainer
+    n, bound = 3, 3.0                                       # N = 3, nb = 5: tensor sizes that are not multiples of 4
+    torch.manual_seed(0)
+    base = NF.Energy.UniformParticle(n, 2, bound)
+    model = NF.NormalizingFlow(base, [NF.flows.CircularCoupledRationalQuadraticSpline(
+        2 * n, 1, 10, range(2 * n), num_bins=5, tail_bound=bound) for _ in range(2)]).train()
+    tr = FlowTrainer(model, 1e-2, 0.0, 1.0, 8, use_graph=False)
+    x = (torch.rand(8, 2 * n) * 2 - 1) * bound
+    assert tr.step(x) is not None
+    assert not tr.native_adam and tr.flat_p is None         # CPU: torch.optim.Adam on the parameters where they are
+    lo, hi = tr.flat.data_ptr(), tr.flat.data_ptr() + tr.flat.numel() * 4
+    covered = torch.zeros(tr.flat.numel(), dtype=torch.bool)
+    for p in tr.trainable:
+        assert p.grad is not None and lo <= p.grad.data_ptr() < hi and (p.grad.data_ptr() - lo) % 16 == 0
+        off = (p.grad.data_ptr() - lo) // 4
+        assert not covered[off:off + p.numel()].any()
+        covered[off:off + p.numel()] = True
+    assert tr.flat.numel() % 4 == 0 and (tr.flat[~covered] == 0).all() and tr.flat[covered].abs().sum() > 0
+    skipped = [k for k, p in model.named_parameters() if p.grad is None]
+    assert skipped and all(k.endswith("preprocessing.weights") for k in skipped), skipped
